@@ -1,0 +1,117 @@
+/* isb.h -- C ABI of libisb.so, the B200 (sm_100a) implementation of the
+ * retrieval hot path of maxgreat/Instance-Search.
+ *
+ * The reference is pure Python over torch; it has no FFI of its own.  Its
+ * boundary for this path is the Python operator surface listed in SURVEY.md
+ * section 8b.  Each entry point below names the reference lines it replaces
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; the caller owns all
+ *     buffers, the library never allocates outputs; scratch memory comes in
+ *     through a workspace whose size the matching *_workspace_bytes() returns;
+ *   - tensors are dense row-major; fp32 = float, bf16 = uint16_t bit pattern,
+ *     indices int64_t (torch LongTensor) unless stated, masks/labels int32_t;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     calls are asynchronous on it and thread-safe per stream;
+ *   - return value: ISB_OK or an ISB_ERR_* code; isb_last_error() returns a
+ *     thread-local message for the last failing call on this thread;
+ *   - no entry point has a CPU fallback: without an sm_100 device they fail.
+ */
+#ifndef ISB_H_
+#define ISB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISB_OK 0
+#define ISB_ERR_INVALID_ARGUMENT 1
+#define ISB_ERR_CUDA 2
+#define ISB_ERR_WORKSPACE 3
+#define ISB_ERR_UNSUPPORTED_DEVICE 4
+
+#define ISB_ABI_VERSION 1
+
+/* Largest k (after the screening margin is added) one search call supports. */
+#define ISB_MAX_CANDIDATES 128
+
+int isb_abi_version(void);
+const char* isb_last_error(void);
+/* 0 when the current device is compute capability 10.x, else an error code. */
+int isb_check_device(void);
+
+/* ---------------------------------------------------------------- a1 / a5
+ * y[m, :] = x[m, :] / sqrt(sum_j x[m, j]^2 + eps)          (eps INSIDE the sqrt)
+ * replaces NormalizeL2Fun.forward, model/custom_modules.py:52-57 (module :70-76;
+ * used at model/siamese.py:178,182,222).  x and y may alias. */
+int isb_l2norm_rows(const float* x, int64_t M, int64_t F, float eps, float* y, void* stream);
+
+/* ---------------------------------------------------------------- a2
+ * y[m, j] = x[m, j] + param[j]
+ * replaces ShiftFun.forward, model/custom_modules.py:16-18 (module :28-39). */
+int isb_shift_rows(const float* x, const float* param, int64_t M, int64_t F, float* y,
+                   void* stream);
+
+/* fp32 [rows, cols] (leading dimension ldx) -> bf16 [rows, ldy], columns
+ * [cols, ldy) zero-filled.  ldy must be a multiple of 8 (16-byte rows for TMA).
+ * Data preparation for the tensor-core operands (database, queries, weights);
+ * `part` selects which bf16 term of the fp32 value is produced:
+ *   0: hi = bf16(x)     1: lo = bf16(x - hi)     2: lo2 = bf16(x - hi - lo)  */
+int isb_f32_to_bf16(const float* x, int64_t rows, int64_t cols, int64_t ldx, uint16_t* y,
+                    int64_t ldy, int part, void* stream);
+
+/* ---------------------------------------------------------------- a8 + a9/a10
+ * Cosine top-k:  for every query row, the k database rows with the largest
+ * q . db, best first -- the first k entries of the descending sort the
+ * reference takes of each row of  sim = torch.mm(Q, DB.t())
+ * (test/siamese_regions_test.py:76, utils/train_siamese.py:70, consumed by
+ * utils/metrics.py:11,13,33) without materialising the Q x N matrix.
+ *
+ *   stage 1  bf16 tcgen05 GEMM, fp32 accumulate, streaming per-row top-(k+margin)
+ *            filter fused into the TMEM epilogue        (db_bf16, ld_bf16)
+ *   stage 2  exact re-rank of the k+margin candidates: dot products of the
+ *            fp32 rows accumulated in fp64, sorted, ties -> lower index
+ *
+ * q        [Q, D] fp32           db_f32  [N, D] fp32
+ * db_bf16  [N, ld_bf16] bf16 made by isb_f32_to_bf16(part 0), ld_bf16 >= D, %8 == 0
+ * k + margin <= ISB_MAX_CANDIDATES;  k <= N;  N < 2^31
+ * idx_offset is added to every returned index (row offset of a database shard)
+ * out_scores [Q, k] fp32 (the fp64 dot rounded to fp32), out_idx [Q, k] int64 */
+size_t isb_topk_search_workspace_bytes(int64_t Q, int64_t N, int64_t D, int k, int margin);
+int isb_topk_search(const float* q, int64_t Q, const float* db_f32, const uint16_t* db_bf16,
+                    int64_t N, int64_t D, int64_t ld_bf16, int k, int margin,
+                    int64_t idx_offset, float* out_scores, int64_t* out_idx, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- (e) multi-GPU
+ * Merge R per-shard results (after the all-gather): cand_scores [R, Q, k],
+ * cand_idx [R, Q, k] (global indices) -> the k best per query, best first,
+ * ties -> lower index.  The reference has no multi-device code; this is the
+ * exchange step of the row-sharded search. */
+int isb_topk_merge(const float* cand_scores, const int64_t* cand_idx, int R, int64_t Q, int k,
+                   float* out_scores, int64_t* out_idx, void* stream);
+
+/* ---------------------------------------------------------------- dense contraction
+ * C[M, N] (fp32, leading dimension ldc) = A[M, K] . B[N, K]^T  (+ bias[N])
+ * A, B bf16 row-major with leading dimensions lda, ldb (multiples of 8).
+ * tcgen05 GEMM with fp32 accumulation; `splits` > 1 splits K across CTAs and
+ * reduces the partial tiles in a fixed order (deterministic).  bias may be NULL.
+ * Used for: all-pairs similarities  torch.mm(E, E.t())  utils/train_siamese.py:53,
+ * test/instance_avg.py:12;  the whitening projection  nn.Linear(100352, D)
+ * model/siamese.py:180;  the 1x1-conv window classifier  model/siamese.py:188.
+ * An fp32-grade result is obtained by concatenating the bf16 terms of
+ * isb_f32_to_bf16 along K:  [A_hi|A_lo|A_hi] . [B_hi|B_hi|B_lo]^T. */
+size_t isb_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K, int splits);
+int isb_gemm_nt(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, int64_t M,
+                int64_t N, int64_t K, const float* bias, float* C, int64_t ldc, int splits,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISB_H_ */

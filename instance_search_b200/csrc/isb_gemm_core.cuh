@@ -1,0 +1,183 @@
+// Warp-specialised tcgen05 GEMM mainloop for sm_100a:  acc[128 x 256] (fp32, TMEM)
+//   = A[m-block, K] (bf16, K-major) . B[n-tile, K]^T (bf16, K-major)
+//
+//   warp 0      TMA producer   (one lane): global -> 128B-swizzled smem ring
+//   warp 1      MMA issuer     (one lane): tcgen05.mma 128x256x16, 4 per k-block,
+//                              tcgen05.commit frees the smem slot / publishes the tile
+//   warps 2..5  epilogue       (128 threads = 128 TMEM lanes = 128 rows of the tile)
+//
+// TMEM holds two 256-column accumulators, so the epilogue of tile t overlaps the
+// MMAs of tile t+1.  Work is a list of SEGMENTS handed out round-robin to a
+// persistent grid (segment s -> CTA s % gridDim.x): a segment is one m-block
+// times a run of n-tiles times a k-block range.  What happens to a finished
+// accumulator tile is the Epilogue policy's business (streaming top-k filter,
+// fp32 store, ...).
+#pragma once
+
+#include "isb_ptx.cuh"
+
+namespace isb {
+
+constexpr int kBM = 128;      // rows of A per tile (= TMEM lanes)
+constexpr int kBN = 256;      // rows of B per tile (= TMEM columns per accumulator)
+constexpr int kBK = 64;       // bf16 per k-block = one 128-byte swizzle row
+constexpr int kStages = 4;    // smem ring depth
+constexpr int kUmmaK = 16;    // K of one tcgen05.mma kind::f16
+constexpr int kGemmThreads = 192;
+constexpr int kEpiWarp0 = 2;  // first epilogue warp
+constexpr uint32_t kTmemCols = 512;
+
+constexpr uint32_t kABytes = kBM * kBK * 2;                       // 16 KB
+constexpr uint32_t kBBytes = kBN * kBK * 2;                       // 32 KB
+constexpr uint32_t kStageBytes = kABytes + kBBytes;               // 48 KB
+constexpr uint32_t kRingBytes = kStages * kStageBytes;            // 192 KB
+constexpr uint32_t kGemmSmemBytes = kRingBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct Segment {
+  int m_block;   // rows [m_block*128, +128) of A
+  int nt_begin;  // n-tiles [nt_begin, nt_end) of B (256 rows each)
+  int nt_end;
+  int kb_begin;  // k-blocks [kb_begin, kb_end) (64 columns each)
+  int kb_end;
+  int aux;       // scheduler-defined (n-group id / k-split id)
+};
+
+struct GemmSmem {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+// Epilogue policy interface (all called by the 128 epilogue threads):
+//   Epi(params, row_in_tile)                    per-thread state
+//   void begin_segment(const Segment&)
+//   void tile(const Segment&, int nt, uint32_t tmem_acc, uint64_t* tmem_empty_bar)
+//        must read the accumulator (lane = row_in_tile, columns [0,256)) with
+//        tcgen05.ld, then tcgen05.fence::before + arrive on tmem_empty_bar
+//        (every epilogue thread arrives once per tile).
+//   void end_segment(const Segment&)
+template <class Sched, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const Sched sched, const typename Epi::Params ep) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment.
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  GemmSmem* bars = reinterpret_cast<GemmSmem*>(ring + kRingBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&bars->full[s], 1);
+      ptx::mbar_init(&bars->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&bars->tmem_full[b], 1);
+      ptx::mbar_init(&bars->tmem_empty[b], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<kTmemCols>(&bars->tmem_base);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  const int num_segments = sched.num_segments();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = blockIdx.x; s < num_segments; s += gridDim.x) {
+        const Segment seg = sched.segment(s);
+        for (int nt = seg.nt_begin; nt < seg.nt_end; ++nt) {
+          for (int kb = seg.kb_begin; kb < seg.kb_end; ++kb) {
+            ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+            uint8_t* sa = ring + stage * kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            ptx::mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
+            // A (queries / activations) is re-read for every n-tile: keep it in L2.
+            ptx::tma_load_2d(sa, &tmap_a, &bars->full[stage], kb * kBK, seg.m_block * kBM,
+                             ptx::kEvictLast);
+            ptx::tma_load_2d(sb, &tmap_b, &bars->full[stage], kb * kBK, nt * kBN,
+                             ptx::kEvictNormal);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(kBM, kBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t acc_iter = 0;
+      for (int s = blockIdx.x; s < num_segments; s += gridDim.x) {
+        const Segment seg = sched.segment(s);
+        for (int nt = seg.nt_begin; nt < seg.nt_end; ++nt, ++acc_iter) {
+          const uint32_t buf = acc_iter & 1;
+          const uint32_t acc_phase = (acc_iter >> 1) & 1;
+          ptx::mbar_wait(&bars->tmem_empty[buf], acc_phase ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t tmem_acc = tmem_base + buf * kBN;
+          for (int kb = seg.kb_begin; kb < seg.kb_end; ++kb) {
+            ptx::mbar_wait(&bars->full[stage], phase);
+            ptx::tc_fence_after();
+            const uint32_t sa = ptx::smem_u32(ring + stage * kStageBytes);
+            const uint64_t da = ptx::make_smem_desc_k_sw128(sa);
+            const uint64_t db = ptx::make_smem_desc_k_sw128(sa + kABytes);
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in
+              // the (addr >> 4) start-address field
+              ptx::umma_bf16(tmem_acc, da + 2 * k, db + 2 * k, idesc,
+                             (kb > seg.kb_begin || k > 0) ? 1u : 0u);
+            }
+            ptx::umma_commit(&bars->empty[stage]);  // smem slot free once these MMAs retire
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          ptx::umma_commit(&bars->tmem_full[buf]);  // accumulator complete
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    // A warp may only touch TMEM lanes [32*(warp%4), +32).
+    const int lane_group = warp & 3;
+    const int row_in_tile = lane_group * 32 + lane;
+    Epi epi(ep, row_in_tile);
+    uint32_t acc_iter = 0;
+    for (int s = blockIdx.x; s < num_segments; s += gridDim.x) {
+      const Segment seg = sched.segment(s);
+      epi.begin_segment(seg);
+      for (int nt = seg.nt_begin; nt < seg.nt_end; ++nt, ++acc_iter) {
+        const uint32_t buf = acc_iter & 1;
+        const uint32_t acc_phase = (acc_iter >> 1) & 1;
+        ptx::mbar_wait(&bars->tmem_full[buf], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + buf * kBN + (static_cast<uint32_t>(lane_group * 32) << 16);
+        epi.tile(seg, nt, tmem_acc, &bars->tmem_empty[buf]);
+      }
+      epi.end_segment(seg);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace isb

@@ -1,0 +1,448 @@
+// Cosine top-k search:  bf16 tcgen05 screen with fused streaming top-k  +
+// exact (fp64-accumulated) re-rank of the surviving candidates, and the R-way
+// merge used after the multi-GPU all-gather.
+//
+// replaces  sim = torch.mm(Q, DB.t())  (test/siamese_regions_test.py:76,
+// utils/train_siamese.py:70) + the descending sort / max / kthvalue that consume
+// it (utils/metrics.py:11,13,33) of the reference.
+#include "isb_host.cuh"
+#include "isb_topk.cuh"
+
+namespace isb {
+
+// ------------------------------------------------------------------ small kernels
+__global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    p[i] = v;
+}
+
+__device__ __forceinline__ uint16_t f32_to_bf16_rn(float f) {
+  // round-to-nearest-even; NaN stays NaN
+  uint32_t u = __float_as_uint(f);
+  if ((u & 0x7F800000u) == 0x7F800000u && (u & 0x007FFFFFu)) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+__device__ __forceinline__ float bf16_to_f32(uint16_t h) {
+  return __uint_as_float(static_cast<uint32_t>(h) << 16);
+}
+
+// one thread = 8 output columns (one 16-byte store)
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, int64_t rows, int64_t cols,
+                                   int64_t ldx, uint16_t* __restrict__ y, int64_t ldy, int part) {
+  const int64_t groups_per_row = ldy / 8;
+  const int64_t total = rows * groups_per_row;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / groups_per_row;
+    const int64_t c0 = (i - r * groups_per_row) * 8;
+    const float* src = x + r * ldx + c0;
+    float v[8];
+    if (c0 + 8 <= cols && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+      v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < cols) ? __ldg(src + j) : 0.f;
+    }
+    uint16_t h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f = v[j];
+      uint16_t b = f32_to_bf16_rn(f);
+      for (int t = 0; t < part; ++t) {  // peel `part` leading bf16 terms
+        f -= bf16_to_f32(b);
+        b = f32_to_bf16_rn(f);
+      }
+      h[j] = b;
+    }
+    uint4 o;
+    o.x = h[0] | (static_cast<uint32_t>(h[1]) << 16);
+    o.y = h[2] | (static_cast<uint32_t>(h[3]) << 16);
+    o.z = h[4] | (static_cast<uint32_t>(h[5]) << 16);
+    o.w = h[6] | (static_cast<uint32_t>(h[7]) << 16);
+    *reinterpret_cast<uint4*>(y + r * ldy + c0) = o;
+  }
+}
+
+// ------------------------------------------------------------------ exact re-rank
+// One CTA per query row.
+//   1. radix-select (4 x 8 bits) the kc best screen scores among the row's pool
+//      entries (<= n_groups * 128);
+//   2. exact score of each selected database row: fp32 products accumulated in
+//      fp64 (one warp per candidate, 16-byte loads);
+//   3. bitonic sort by (score desc, index asc); write the first k.
+constexpr int kRerankThreads = 256;
+
+struct SortEntry {
+  double score;
+  int col;
+};
+
+__device__ __forceinline__ bool entry_before(double sa, int ia, double sb, int ib) {
+  return (sa > sb) || (sa == sb && ia < ib);
+}
+
+__global__ void __launch_bounds__(kRerankThreads)
+rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, int n_groups,
+              const uint2* __restrict__ pool, const int* __restrict__ pool_cnt, int kc, int k,
+              int64_t idx_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+  extern __shared__ __align__(16) uint8_t rr_smem[];
+  float* qs = reinterpret_cast<float*>(rr_smem);  // [D]
+  __shared__ int hist[256];
+  __shared__ int s_total, s_sel, s_eq_taken;
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_remaining;
+  __shared__ double sel_score[kMaxCand];
+  __shared__ int sel_col[kMaxCand];
+
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int slots = n_groups * kMaxCand;
+  const uint2* rpool = pool + static_cast<size_t>(row) * slots;
+  const int* rcnt = pool_cnt + static_cast<size_t>(row) * n_groups;
+
+  for (int i = tid; i < D / 4; i += kRerankThreads)
+    reinterpret_cast<float4*>(qs)[i] = __ldg(reinterpret_cast<const float4*>(q + static_cast<size_t>(row) * D) + i);
+  if (tid == 0) {
+    int t = 0;
+    for (int g = 0; g < n_groups; ++g) t += rcnt[g];
+    s_total = t;
+    s_prefix = 0;
+    s_remaining = kc;
+    s_sel = 0;
+    s_eq_taken = 0;
+  }
+  __syncthreads();
+  const int total = s_total;
+  const int want = min(total, kc);
+
+  // ---- 1. threshold key T: the want-th largest key (only needed if total > kc)
+  uint32_t T = 0;
+  if (total > kc) {
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      hist[tid] = 0;  // kRerankThreads == 256 bins
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      const uint32_t pmask = (pass == 0) ? 0u : (0xFFFFFFFFu << (shift + 8));
+      for (int e = tid; e < slots; e += kRerankThreads) {
+        if ((e & (kMaxCand - 1)) < rcnt[e / kMaxCand]) {
+          const uint32_t key = f2key(rpool[e].x);
+          if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int rem = s_remaining;  // how many still to take from keys matching the prefix
+        int d = 255;
+        for (; d > 0; --d) {
+          if (hist[d] >= rem) break;
+          rem -= hist[d];
+        }
+        s_prefix = prefix | (static_cast<uint32_t>(d) << shift);
+        s_remaining = rem;
+      }
+      __syncthreads();
+    }
+    T = s_prefix;
+  }
+  // after the 4 passes s_remaining = how many entries with key == T to take
+  const int quota_eq = (total > kc) ? s_remaining : 0x7FFFFFFF;
+
+  // ---- collect
+  for (int e = tid; e < slots; e += kRerankThreads) {
+    if ((e & (kMaxCand - 1)) < rcnt[e / kMaxCand]) {
+      const uint2 ent = rpool[e];
+      const uint32_t key = f2key(ent.x);
+      bool take = key > T;
+      if (!take && key == T) take = atomicAdd(&s_eq_taken, 1) < quota_eq;
+      if (take) {
+        const int pos = atomicAdd(&s_sel, 1);
+        if (pos < kMaxCand) sel_col[pos] = static_cast<int>(ent.y);
+      }
+    }
+  }
+  __syncthreads();
+  const int n_sel = min(s_sel, want);
+
+  // ---- 2. exact scores
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int c = warp; c < kMaxCand; c += kRerankThreads / 32) {
+    if (c < n_sel) {
+      const float4* dr = reinterpret_cast<const float4*>(db + static_cast<size_t>(sel_col[c]) * D);
+      double acc = 0.0;
+      for (int i = lane; i < D / 4; i += 32) {
+        const float4 b = __ldg(dr + i);
+        const float4 a = reinterpret_cast<const float4*>(qs)[i];
+        acc = fma(static_cast<double>(a.x), static_cast<double>(b.x), acc);
+        acc = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc);
+        acc = fma(static_cast<double>(a.z), static_cast<double>(b.z), acc);
+        acc = fma(static_cast<double>(a.w), static_cast<double>(b.w), acc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) sel_score[c] = acc;
+    } else if (lane == 0) {
+      sel_score[c] = -INFINITY;
+      sel_col[c] = 0x7FFFFFFF;
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. bitonic sort of 128 entries (first 128 threads)
+  for (int size = 2; size <= kMaxCand; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (tid < kMaxCand) {
+        const int partner = tid ^ stride;
+        if (partner > tid) {
+          const bool up = (tid & size) == 0;  // "up" blocks sort best-first
+          const double sa = sel_score[tid], sb = sel_score[partner];
+          const int ia = sel_col[tid], ib = sel_col[partner];
+          const bool a_first = entry_before(sa, ia, sb, ib);
+          if (a_first != up) {
+            sel_score[tid] = sb; sel_score[partner] = sa;
+            sel_col[tid] = ib; sel_col[partner] = ia;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = tid; j < k; j += kRerankThreads) {
+    const bool ok = j < n_sel;
+    out_scores[static_cast<size_t>(row) * k + j] = ok ? static_cast<float>(sel_score[j]) : -INFINITY;
+    out_idx[static_cast<size_t>(row) * k + j] = ok ? static_cast<int64_t>(sel_col[j]) + idx_offset : -1;
+  }
+}
+
+// ------------------------------------------------------------------ R-way merge
+// cand_scores / cand_idx: [R, Q, k].  One CTA per query; bitonic sort of the
+// R*k (padded to a power of two <= kMergeMax) entries in shared memory.
+constexpr int kMergeMax = 4096;
+
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const float* __restrict__ cs, const int64_t* __restrict__ ci, int R, int64_t Q,
+                  int k, int n_pow2, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+  extern __shared__ __align__(16) uint8_t mg_smem[];
+  int64_t* sidx = reinterpret_cast<int64_t*>(mg_smem);           // [n_pow2]
+  float* sscore = reinterpret_cast<float*>(sidx + n_pow2);        // [n_pow2]
+  const int64_t row = blockIdx.x;
+  const int n = R * k;
+  for (int e = threadIdx.x; e < n_pow2; e += blockDim.x) {
+    if (e < n) {
+      const int r = e / k, j = e - r * k;
+      const size_t off = (static_cast<size_t>(r) * Q + row) * k + j;
+      sscore[e] = cs[off];
+      sidx[e] = ci[off];
+    } else {
+      sscore[e] = -INFINITY;
+      sidx[e] = INT64_MAX;
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < n_pow2; t += blockDim.x) {
+        const int partner = t ^ stride;
+        if (partner > t) {
+          const bool up = (t & size) == 0;
+          const float sa = sscore[t], sb = sscore[partner];
+          const int64_t ia = sidx[t], ib = sidx[partner];
+          // invalid (index < 0) entries sort last
+          const bool va = ia >= 0, vb = ib >= 0;
+          const bool a_first = (va != vb) ? va : ((sa > sb) || (sa == sb && ia < ib));
+          if (a_first != up) {
+            sscore[t] = sb; sscore[partner] = sa;
+            sidx[t] = ib; sidx[partner] = ia;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const bool ok = j < n && sidx[j] != INT64_MAX;
+    out_scores[row * k + j] = ok ? sscore[j] : -INFINITY;
+    out_idx[row * k + j] = ok ? sidx[j] : -1;
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct SearchPlan {
+  int m_blocks, n_tiles, k_blocks, n_groups, grid;
+  int64_t ldq;
+  size_t off_qbf16, off_cta_buf, off_gthr, off_pool, off_pool_cnt, total;
+};
+
+// Pick the number of n-groups so that m_blocks * n_groups segments fill whole
+// waves of the persistent grid (segments are handed out round-robin).
+static int pick_n_groups(int m_blocks, int n_tiles, int grid) {
+  int lo = (grid + m_blocks - 1) / m_blocks;
+  if (lo < 1) lo = 1;
+  if (lo > n_tiles) lo = n_tiles;
+  int hi = lo * 8 + 8;
+  if (hi > n_tiles) hi = n_tiles;
+  int best = lo;
+  double best_eff = -1.0;
+  for (int ng = lo; ng <= hi; ++ng) {
+    const long long segs = static_cast<long long>(m_blocks) * ng;
+    const long long waves = (segs + grid - 1) / grid;
+    const double eff = static_cast<double>(segs) / static_cast<double>(waves * grid);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = ng;
+    }
+  }
+  return best;
+}
+
+static SearchPlan make_search_plan(int64_t Q, int64_t N, int64_t D) {
+  SearchPlan p;
+  p.m_blocks = static_cast<int>((Q + kBM - 1) / kBM);
+  p.n_tiles = static_cast<int>((N + kBN - 1) / kBN);
+  p.k_blocks = static_cast<int>((D + kBK - 1) / kBK);
+  const int sms = device_sm_count();
+  const long long tiles = static_cast<long long>(p.m_blocks) * p.n_tiles;
+  p.grid = static_cast<int>(tiles < sms ? tiles : sms);
+  p.n_groups = pick_n_groups(p.m_blocks, p.n_tiles, p.grid);
+  p.ldq = static_cast<int64_t>(align_up(static_cast<size_t>(D), 8));
+  size_t off = 0;
+  p.off_qbf16 = off;    off = align_up(off + static_cast<size_t>(Q) * p.ldq * 2, 1024);
+  p.off_cta_buf = off;  off = align_up(off + static_cast<size_t>(p.grid) * kBM * kCap * sizeof(uint2), 1024);
+  p.off_gthr = off;     off = align_up(off + static_cast<size_t>(p.m_blocks) * kBM * 4, 1024);
+  p.off_pool = off;     off = align_up(off + static_cast<size_t>(Q) * p.n_groups * kMaxCand * sizeof(uint2), 1024);
+  p.off_pool_cnt = off; off = align_up(off + static_cast<size_t>(Q) * p.n_groups * 4, 1024);
+  p.total = off;
+  return p;
+}
+
+// Runs the screen (GEMM + streaming top-k) into the candidate pool.  Shared by
+// the search and the negative-mining entry points.
+int launch_topk_screen(const uint16_t* a_bf16, int64_t lda, int64_t Q, const uint16_t* b_bf16,
+                       int64_t ldb, int64_t N, int64_t D, int kc, const SearchPlan& plan,
+                       uint8_t* ws, const int* col_label, const int* row_label,
+                       const float* row_ub, float ub_slack, cudaStream_t st) {
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_k64(&ta, a_bf16, Q, D, lda, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_k64(&tb, b_bf16, N, D, ldb, kBN);
+  if (rc) return rc;
+
+  uint32_t* gthr = reinterpret_cast<uint32_t*>(ws + plan.off_gthr);
+  const size_t n_thr = static_cast<size_t>(plan.m_blocks) * kBM;
+  fill_u32_kernel<<<static_cast<int>((n_thr + 255) / 256), 256, 0, st>>>(gthr, n_thr, kKeyNegInf);
+
+  TopkSched sched{plan.m_blocks, plan.n_tiles, plan.n_groups, plan.k_blocks};
+  TopkEpiParams ep;
+  ep.Q = static_cast<int>(Q);
+  ep.N = static_cast<int>(N);
+  ep.n_groups = plan.n_groups;
+  ep.kc = kc;
+  ep.cta_buf = reinterpret_cast<uint2*>(ws + plan.off_cta_buf);
+  ep.gthr = gthr;
+  ep.pool = reinterpret_cast<uint2*>(ws + plan.off_pool);
+  ep.pool_cnt = reinterpret_cast<int*>(ws + plan.off_pool_cnt);
+  ep.col_label = col_label;
+  ep.row_label = row_label;
+  ep.row_ub = row_ub;
+  ep.ub_slack = ub_slack;
+
+  auto kern = gemm_tc_kernel<TopkSched, TopkEpilogue>;
+  ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+  kern<<<plan.grid, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, sched, ep);
+  ISB_CUDA(cudaGetLastError());
+  return ISB_OK;
+}
+
+}  // namespace isb
+
+using namespace isb;
+
+extern "C" int isb_f32_to_bf16(const float* x, int64_t rows, int64_t cols, int64_t ldx, uint16_t* y,
+                               int64_t ldy, int part, void* stream) {
+  ISB_CHECK_ARG(x && y, "isb_f32_to_bf16: null pointer");
+  ISB_CHECK_ARG(rows >= 0 && cols >= 0 && ldx >= cols && ldy >= cols, "isb_f32_to_bf16: bad shape");
+  ISB_CHECK_ARG(ldy % 8 == 0, "isb_f32_to_bf16: ldy (%lld) must be a multiple of 8", (long long)ldy);
+  ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "isb_f32_to_bf16: y must be 16-byte aligned");
+  ISB_CHECK_ARG(part >= 0 && part <= 2, "isb_f32_to_bf16: part must be 0, 1 or 2");
+  if (rows == 0 || ldy == 0) return ISB_OK;
+  const int64_t total = rows * (ldy / 8);
+  const int64_t blocks = (total + 255) / 256;
+  const int grid = static_cast<int>(blocks < 148 * 16 ? blocks : 148 * 16);
+  f32_to_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, cols, ldx, y, ldy, part);
+  ISB_CUDA(cudaGetLastError());
+  return ISB_OK;
+}
+
+extern "C" size_t isb_topk_search_workspace_bytes(int64_t Q, int64_t N, int64_t D, int k, int margin) {
+  (void)k; (void)margin;
+  if (Q <= 0 || N <= 0 || D <= 0) return 0;
+  return make_search_plan(Q, N, D).total;
+}
+
+extern "C" int isb_topk_search(const float* q, int64_t Q, const float* db_f32, const uint16_t* db_bf16,
+                               int64_t N, int64_t D, int64_t ld_bf16, int k, int margin,
+                               int64_t idx_offset, float* out_scores, int64_t* out_idx,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  ISB_CHECK_ARG(q && db_f32 && db_bf16 && out_scores && out_idx, "isb_topk_search: null pointer");
+  ISB_CHECK_ARG(Q > 0 && N > 0 && D > 0, "isb_topk_search: empty problem (Q=%lld N=%lld D=%lld)",
+                (long long)Q, (long long)N, (long long)D);
+  ISB_CHECK_ARG(N < (1ll << 31) && Q < (1ll << 31), "isb_topk_search: Q and N must be < 2^31 per call");
+  ISB_CHECK_ARG(D % 8 == 0, "isb_topk_search: D (%lld) must be a multiple of 8 (pad with zeros)", (long long)D);
+  ISB_CHECK_ARG(ld_bf16 >= D && ld_bf16 % 8 == 0, "isb_topk_search: bad ld_bf16");
+  ISB_CHECK_ARG(k >= 1 && margin >= 0 && k + margin <= ISB_MAX_CANDIDATES,
+                "isb_topk_search: need 1 <= k, k + margin <= %d (k=%d margin=%d)", ISB_MAX_CANDIDATES, k, margin);
+  ISB_CHECK_ARG(k <= N, "isb_topk_search: k (%d) > N (%lld)", k, (long long)N);
+  ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(db_f32) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(db_bf16) & 15) == 0, "isb_topk_search: inputs must be 16-byte aligned");
+  int rc = isb_check_device();
+  if (rc) return rc;
+  const SearchPlan plan = make_search_plan(Q, N, D);
+  if (workspace == nullptr || workspace_bytes < plan.total ||
+      (reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) {
+    set_error("isb_topk_search: workspace too small or not 1024-byte aligned (need %zu bytes, got %zu)",
+              plan.total, workspace_bytes);
+    return ISB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint16_t* q_bf16 = reinterpret_cast<uint16_t*>(ws + plan.off_qbf16);
+  rc = isb_f32_to_bf16(q, Q, D, D, q_bf16, plan.ldq, 0, stream);
+  if (rc) return rc;
+  int kc = k + margin;
+  if (kc > N) kc = static_cast<int>(N);
+  rc = launch_topk_screen(q_bf16, plan.ldq, Q, db_bf16, ld_bf16, N, D, kc, plan, ws, nullptr, nullptr,
+                          nullptr, 0.f, st);
+  if (rc) return rc;
+  const size_t smem = static_cast<size_t>(D) * 4;
+  ISB_CHECK_ARG(smem <= 160 * 1024, "isb_topk_search: D too large for the re-rank kernel");
+  if (smem > 48 * 1024)
+    ISB_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rerank_kernel<<<static_cast<unsigned>(Q), kRerankThreads, smem, st>>>(
+      q, db_f32, static_cast<int>(D), plan.n_groups, reinterpret_cast<const uint2*>(ws + plan.off_pool),
+      reinterpret_cast<const int*>(ws + plan.off_pool_cnt), kc, k, idx_offset, out_scores, out_idx);
+  ISB_CUDA(cudaGetLastError());
+  return ISB_OK;
+}
+
+extern "C" int isb_topk_merge(const float* cand_scores, const int64_t* cand_idx, int R, int64_t Q, int k,
+                              float* out_scores, int64_t* out_idx, void* stream) {
+  ISB_CHECK_ARG(cand_scores && cand_idx && out_scores && out_idx, "isb_topk_merge: null pointer");
+  ISB_CHECK_ARG(R >= 1 && Q >= 0 && k >= 1, "isb_topk_merge: bad shape");
+  ISB_CHECK_ARG(static_cast<int64_t>(R) * k <= kMergeMax, "isb_topk_merge: R*k (%lld) > %d",
+                (long long)R * k, kMergeMax);
+  if (Q == 0) return ISB_OK;
+  int n_pow2 = 2;
+  while (n_pow2 < R * k) n_pow2 <<= 1;
+  const size_t smem = static_cast<size_t>(n_pow2) * 12;
+  if (smem > 48 * 1024)
+    ISB_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topk_merge_kernel<<<static_cast<unsigned>(Q), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      cand_scores, cand_idx, R, Q, k, n_pow2, out_scores, out_idx);
+  ISB_CUDA(cudaGetLastError());
+  return ISB_OK;
+}

@@ -1,0 +1,238 @@
+// Streaming per-row top-k fused into the tcgen05 GEMM epilogue.
+//
+// Each epilogue thread owns one row (= one TMEM lane = one query).  It keeps a
+// threshold `thr` and a private candidate buffer of kCap (score, column) pairs
+// in global memory (L2-resident).  A score passes when score > thr; passing is
+// rare once thr has warmed up (expected k*ln(N/k) passes per row over N
+// columns).  When a row's buffer holds more than kTrig entries after a tile,
+// the warp compacts it cooperatively: a 32-step radix select finds the kc-th
+// largest key, the kc best are kept, thr becomes that key and is published with
+// atomicMax to a global per-row threshold that every CTA working on the same
+// rows re-reads at each tile.  At the end of a segment (one m-block x one group
+// of n-tiles) the surviving <= kc candidates are copied to the row's slot of a
+// candidate pool [row][group][kMaxCand] that the merge / re-rank kernel reads.
+#pragma once
+
+#include "isb_gemm_core.cuh"
+
+namespace isb {
+
+constexpr int kCap = 512;        // private buffer entries per row
+constexpr int kTrig = 256;       // compact when a row holds more than this after a tile
+constexpr int kMaxCand = 128;    // == ISB_MAX_CANDIDATES
+
+// order-preserving float <-> uint32 key (larger float <=> larger key)
+__host__ __device__ __forceinline__ uint32_t f2key(uint32_t bits) {
+  return bits ^ ((bits & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__host__ __device__ __forceinline__ uint32_t key2f(uint32_t key) {
+  return key ^ ((key & 0x80000000u) ? 0x80000000u : 0xFFFFFFFFu);
+}
+constexpr uint32_t kKeyNegInf = 0x007FFFFFu;  // f2key(bits(-inf))
+
+struct TopkEpiParams {
+  int Q;                 // valid rows
+  int N;                 // valid columns
+  int n_groups;          // pool slots per row
+  int kc;                // candidates kept per (row, group), <= kMaxCand
+  uint2* cta_buf;        // [gridDim.x][128][kCap]  (score bits, column)
+  uint32_t* gthr;        // [m_blocks*128] global per-row threshold keys
+  uint2* pool;           // [Q][n_groups][kMaxCand]
+  int* pool_cnt;         // [Q][n_groups]
+  // optional column mask (hard-negative mining): a column is a candidate only if
+  // col_label[col] != row_label[row] and score < row_ub[row] + ub_slack
+  const int* col_label;  // [N] or null
+  const int* row_label;  // [Q] or null
+  const float* row_ub;   // [Q] or null
+  float ub_slack;
+};
+
+// Warp-cooperative: keep the `keep` largest of buf[0..cnt) (cnt <= kCap), packed
+// to the front.  Returns the key of the keep-th largest.  All 32 lanes call it
+// with identical arguments.
+__device__ __forceinline__ uint32_t warp_compact_row(uint2* buf, int cnt, int keep, int lane) {
+  constexpr int kPer = kCap / 32;
+  uint32_t key[kPer], col[kPer];
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const int j = lane + 32 * i;
+    if (j < cnt) {
+      const uint2 e = buf[j];
+      key[i] = f2key(e.x);
+      col[i] = e.y;
+    } else {
+      key[i] = 0;
+      col[i] = 0;
+    }
+  }
+  __syncwarp();  // every load above is ordered before every store below
+  uint32_t T = 0;
+#pragma unroll 1
+  for (int b = 31; b >= 0; --b) {
+    const uint32_t trial = T | (1u << b);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) c += (key[i] >= trial) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= keep) T = trial;
+  }
+  int n_gt = 0;
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) n_gt += (key[i] > T) ? 1 : 0;
+  n_gt = __reduce_add_sync(0xffffffffu, n_gt);
+  const int quota_eq = keep - n_gt;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  int pos_gt = 0, pos_eq = 0;
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const bool gt = key[i] > T;
+    const bool eq = key[i] == T;
+    const uint32_t bgt = __ballot_sync(0xffffffffu, gt);
+    const uint32_t beq = __ballot_sync(0xffffffffu, eq);
+    if (gt) buf[pos_gt + __popc(bgt & lt_mask)] = make_uint2(key2f(key[i]), col[i]);
+    if (eq) {
+      const int p = pos_eq + __popc(beq & lt_mask);
+      if (p < quota_eq) buf[n_gt + p] = make_uint2(key2f(key[i]), col[i]);
+    }
+    pos_gt += __popc(bgt);
+    pos_eq += __popc(beq);
+  }
+  __syncwarp();
+  return T;
+}
+
+struct TopkEpilogue {
+  using Params = TopkEpiParams;
+  const Params& p;
+  const int row_in_tile;
+  const int lane;
+  uint2* my_buf;      // this row's private buffer
+  uint2* warp_buf;    // buffer of lane 0's row (rows of a warp are consecutive)
+  int row;            // global row
+  bool row_valid;
+  int cnt;
+  float thr;
+  int my_label;
+  float my_ub;
+
+  __device__ TopkEpilogue(const Params& p_, int row_in_tile_)
+      : p(p_), row_in_tile(row_in_tile_), lane(row_in_tile_ & 31) {
+    uint2* cta = p.cta_buf + static_cast<size_t>(blockIdx.x) * kBM * kCap;
+    my_buf = cta + static_cast<size_t>(row_in_tile) * kCap;
+    warp_buf = cta + static_cast<size_t>(row_in_tile - lane) * kCap;
+    row = 0; row_valid = false; cnt = 0; thr = 0.f; my_label = -1; my_ub = 0.f;
+  }
+
+  __device__ __forceinline__ void begin_segment(const Segment& seg) {
+    row = seg.m_block * kBM + row_in_tile;
+    row_valid = row < p.Q;
+    cnt = 0;
+    thr = row_valid ? __uint_as_float(key2f(kKeyNegInf)) : __uint_as_float(0x7F800000u);
+    if (p.col_label != nullptr && row_valid) {
+      my_label = p.row_label[row];
+      my_ub = (p.row_ub != nullptr) ? p.row_ub[row] + p.ub_slack : __uint_as_float(0x7F800000u);
+    }
+  }
+
+  __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int col0) {
+    float m = __uint_as_float(v[0]);
+#pragma unroll
+    for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+    if (m > thr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = __uint_as_float(v[j]);
+        const int col = col0 + j;
+        bool pass = (x > thr) && (col < p.N);
+        if (p.col_label != nullptr) {
+          // evaluated only for scores that beat the threshold
+          if (pass) pass = (x < my_ub) && (__ldg(p.col_label + col) != my_label);
+        }
+        if (pass) {
+          my_buf[cnt] = make_uint2(v[j], static_cast<uint32_t>(col));
+          ++cnt;
+        }
+      }
+    }
+  }
+
+  __device__ __forceinline__ void compact_rows(uint32_t need, int keep) {
+    while (need) {
+      const int r = __ffs(need) - 1;
+      need &= need - 1;
+      const int c = __shfl_sync(0xffffffffu, cnt, r);
+      const uint32_t T = warp_compact_row(warp_buf + static_cast<size_t>(r) * kCap, c, keep, lane);
+      if (lane == r) {
+        cnt = keep;
+        thr = fmaxf(thr, __uint_as_float(key2f(T)));
+        atomicMax(p.gthr + row, T);
+      }
+    }
+  }
+
+  __device__ __forceinline__ void tile(const Segment& seg, int nt, uint32_t tmem_acc,
+                                       uint64_t* tmem_empty_bar) {
+    if (row_valid) {
+      // thresholds published by the other CTAs that work on these rows
+      const uint32_t g = *reinterpret_cast<volatile uint32_t*>(p.gthr + row);
+      thr = fmaxf(thr, __uint_as_float(key2f(g)));
+    }
+    const int col0 = nt * kBN;
+    uint32_t v[2][32];
+    ptx::tmem_ld_32x32b_x32(tmem_acc, v[0]);
+#pragma unroll
+    for (int c = 0; c < kBN / 32; ++c) {
+      ptx::tmem_ld_wait();
+      if (c + 1 < kBN / 32) {
+        ptx::tmem_ld_32x32b_x32(tmem_acc + (c + 1) * 32, v[(c + 1) & 1]);
+      } else {
+        // the whole accumulator is in registers: hand the TMEM buffer back
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(tmem_empty_bar);
+      }
+      scan_chunk(v[c & 1], col0 + c * 32);
+      __syncwarp();
+    }
+    const uint32_t need = __ballot_sync(0xffffffffu, cnt > kTrig);
+    if (need) compact_rows(need, p.kc);
+  }
+
+  __device__ __forceinline__ void end_segment(const Segment& seg) {
+    const uint32_t need = __ballot_sync(0xffffffffu, cnt > p.kc);
+    if (need) compact_rows(need, p.kc);
+    __syncwarp();
+#pragma unroll 1
+    for (int r = 0; r < 32; ++r) {
+      const int c = __shfl_sync(0xffffffffu, cnt, r);
+      const int grow = __shfl_sync(0xffffffffu, row, r);
+      if (grow >= p.Q) continue;  // warp-uniform
+      const size_t slot = static_cast<size_t>(grow) * p.n_groups + seg.aux;
+      const uint2* src = warp_buf + static_cast<size_t>(r) * kCap;
+      uint2* dst = p.pool + slot * kMaxCand;
+      for (int j = lane; j < c; j += 32) dst[j] = src[j];
+      if (lane == 0) p.pool_cnt[slot] = c;
+    }
+    __syncwarp();
+  }
+};
+
+// m-blocks x n-groups segments; consecutive segment ids share an n-group so the
+// CTAs running concurrently stream the SAME database tiles (one HBM read, the
+// rest L2 hits) while the whole query matrix stays L2-resident.
+struct TopkSched {
+  int m_blocks, n_tiles, n_groups, k_blocks;
+  __device__ __forceinline__ int num_segments() const { return m_blocks * n_groups; }
+  __device__ __forceinline__ Segment segment(int s) const {
+    Segment seg;
+    const int g = s / m_blocks;
+    seg.m_block = s - g * m_blocks;
+    seg.nt_begin = static_cast<int>(static_cast<long long>(g) * n_tiles / n_groups);
+    seg.nt_end = static_cast<int>(static_cast<long long>(g + 1) * n_tiles / n_groups);
+    seg.kb_begin = 0;
+    seg.kb_end = k_blocks;
+    seg.aux = g;
+    return seg;
+  }
+};
+
+}  // namespace isb

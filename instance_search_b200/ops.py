@@ -1,0 +1,196 @@
+"""Tensor-level wrappers of the C ABI, registered as torch custom ops (``isb::*``).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every
+computation below happens in libisb.so.  CUDA tensors only -- a CPU tensor is
+an error, not a fallback.
+"""
+
+import torch
+
+from . import _lib
+from ._lib import IsbError
+
+DEFAULT_MARGIN = 28      # candidates screened beyond k (k + margin <= 128)
+MAX_CANDIDATES = 128
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise IsbError("instance_search_b200 ops take CUDA tensors only (got %s); "
+                           "there is no CPU fallback" % (getattr(t, "device", type(t)),))
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise IsbError("expected a float32 tensor, got %s" % t.dtype)
+    return t.contiguous()
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+# ---------------------------------------------------------------- row operators
+def l2norm_rows(x, eps=1e-10):
+    """y = x / sqrt(sum(x^2, 1) + eps). reference: model/custom_modules.py:52-57"""
+    _need_cuda(x)
+    if x.dim() != 2:
+        raise IsbError("l2norm_rows expects a 2-D tensor")
+    x = _f32c(x)
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().isb_l2norm_rows(x.data_ptr(), x.size(0), x.size(1), float(eps),
+                                          y.data_ptr(), _stream()), "isb_l2norm_rows")
+    return y
+
+
+def shift_rows(x, param):
+    """y = x + param. reference: model/custom_modules.py:16-18"""
+    _need_cuda(x, param)
+    if x.dim() != 2 or param.numel() != x.size(1):
+        raise IsbError("shift_rows: x [M, F] and param [F] expected")
+    x, param = _f32c(x), _f32c(param)
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().isb_shift_rows(x.data_ptr(), param.data_ptr(), x.size(0), x.size(1),
+                                         y.data_ptr(), _stream()), "isb_shift_rows")
+    return y
+
+
+def to_bf16(x, part=0, ld=None):
+    """fp32 [rows, cols] -> bf16 [rows, ld] (ld = cols rounded up to 8, zero padded).
+    part 0/1/2 = hi / lo / lo2 term of the bf16 expansion of x."""
+    _need_cuda(x)
+    x = _f32c(x)
+    rows, cols = x.shape
+    if ld is None:
+        ld = (cols + 7) // 8 * 8
+    y = torch.empty((rows, ld), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().isb_f32_to_bf16(x.data_ptr(), rows, cols, cols, y.data_ptr(), ld,
+                                          int(part), _stream()), "isb_f32_to_bf16")
+    return y
+
+
+def gemm_nt(a, b, bias=None, splits=1, k=None):
+    """C[M, N] fp32 = a[M, :K] . b[N, :K]^T (+ bias). a, b: bf16, row-major,
+    leading dimensions multiples of 8."""
+    _need_cuda(a, b, bias)
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
+        raise IsbError("gemm_nt takes bf16 operands (see to_bf16)")
+    a, b = a.contiguous(), b.contiguous()
+    K = min(a.size(1), b.size(1)) if k is None else k
+    M, N = a.size(0), b.size(0)
+    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    L = _lib.lib()
+    ws_bytes = L.isb_gemm_nt_workspace_bytes(M, N, K, splits)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=a.device)
+    if bias is not None:
+        bias = _f32c(bias)
+    _lib.check(L.isb_gemm_nt(a.data_ptr(), a.size(1), b.data_ptr(), b.size(1), M, N, K,
+                             _ptr(bias), c.data_ptr(), N, int(splits), ws.data_ptr(), ws_bytes,
+                             _stream()), "isb_gemm_nt")
+    return c
+
+
+# ---------------------------------------------------------------------- search
+def topk_search(q, db_f32, db_bf16, k, margin=None, idx_offset=0, workspace=None):
+    """Top-k rows of db by q . db (best first), index-exact w.r.t. fp64 scores.
+
+    replaces ``torch.mm(q, db.t())`` + sort/max (test/siamese_regions_test.py:76,
+    utils/metrics.py:11,13,33).  q [Q, D] fp32, db_f32 [N, D] fp32,
+    db_bf16 = to_bf16(db_f32).  Returns (scores [Q, k] fp32, idx [Q, k] int64).
+    """
+    _need_cuda(q, db_f32, db_bf16)
+    q, db_f32 = _f32c(q), _f32c(db_f32)
+    Q, D = q.shape
+    N = db_f32.size(0)
+    if db_f32.size(1) != D or db_bf16.size(0) != N or db_bf16.dtype != torch.bfloat16:
+        raise IsbError("topk_search: shape/dtype mismatch between q, db_f32 and db_bf16")
+    if margin is None:
+        margin = min(DEFAULT_MARGIN, MAX_CANDIDATES - k)
+    margin = max(0, min(margin, MAX_CANDIDATES - k))
+    scores = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+    if Q == 0:
+        return scores, idx
+    L = _lib.lib()
+    ws_bytes = L.isb_topk_search_workspace_bytes(Q, N, D, k, margin)
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+    _lib.check(L.isb_topk_search(q.data_ptr(), Q, db_f32.data_ptr(), db_bf16.data_ptr(), N, D,
+                                 db_bf16.size(1), int(k), int(margin), int(idx_offset),
+                                 scores.data_ptr(), idx.data_ptr(), workspace.data_ptr(),
+                                 workspace.numel(), _stream()), "isb_topk_search")
+    return scores, idx
+
+
+def topk_search_workspace(Q, N, D, k, margin, device):
+    n = _lib.lib().isb_topk_search_workspace_bytes(Q, N, D, k, margin)
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def topk_merge(cand_scores, cand_idx):
+    """[R, Q, k] per-shard results -> the k best per query (ties -> lower index)."""
+    _need_cuda(cand_scores, cand_idx)
+    cand_scores = _f32c(cand_scores)
+    cand_idx = cand_idx.contiguous()
+    if cand_idx.dtype != torch.int64 or cand_scores.shape != cand_idx.shape or cand_idx.dim() != 3:
+        raise IsbError("topk_merge: expected [R, Q, k] fp32 scores and int64 indices")
+    R, Q, k = cand_scores.shape
+    scores = torch.empty((Q, k), dtype=torch.float32, device=cand_scores.device)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=cand_scores.device)
+    _lib.check(_lib.lib().isb_topk_merge(cand_scores.data_ptr(), cand_idx.data_ptr(), R, Q, k,
+                                         scores.data_ptr(), idx.data_ptr(), _stream()),
+               "isb_topk_merge")
+    return scores, idx
+
+
+# ------------------------------------------------------- torch.library registration
+# The same entry points as dispatcher ops (CUDA only; no CPU kernel is registered,
+# so calling them with CPU tensors raises NotImplementedError from the dispatcher).
+def _register():
+    try:
+        from torch.library import custom_op
+    except ImportError:  # pragma: no cover
+        return
+
+    @custom_op("isb::l2norm_rows", mutates_args=(), device_types="cuda")
+    def _l2norm(x: torch.Tensor, eps: float) -> torch.Tensor:
+        return l2norm_rows(x, eps)
+
+    @_l2norm.register_fake
+    def _(x, eps):
+        return torch.empty_like(x)
+
+    @custom_op("isb::shift_rows", mutates_args=(), device_types="cuda")
+    def _shift(x: torch.Tensor, param: torch.Tensor) -> torch.Tensor:
+        return shift_rows(x, param)
+
+    @_shift.register_fake
+    def _(x, param):
+        return torch.empty_like(x)
+
+    @custom_op("isb::topk_search", mutates_args=(), device_types="cuda")
+    def _search(q: torch.Tensor, db_f32: torch.Tensor, db_bf16: torch.Tensor, k: int,
+                margin: int, idx_offset: int) -> tuple[torch.Tensor, torch.Tensor]:
+        return topk_search(q, db_f32, db_bf16, k, margin, idx_offset)
+
+    @_search.register_fake
+    def _(q, db_f32, db_bf16, k, margin, idx_offset):
+        return (q.new_empty((q.size(0), k)), q.new_empty((q.size(0), k), dtype=torch.int64))
+
+    @custom_op("isb::gemm_nt", mutates_args=(), device_types="cuda")
+    def _gemm(a: torch.Tensor, b: torch.Tensor, splits: int) -> torch.Tensor:
+        return gemm_nt(a, b, None, splits)
+
+    @_gemm.register_fake
+    def _(a, b, splits):
+        return a.new_empty((a.size(0), b.size(0)), dtype=torch.float32)
+
+
+_register()

@@ -1,0 +1,188 @@
+"""GPU parity tests of the core kernels through the C ABI (ctypes -> libisb.so):
+row operators, bf16 conversion, the tcgen05 GEMM and the top-k search."""
+
+import pytest
+import torch
+
+import oracle
+from conftest import load_golden
+from parity import check_topk_against_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from instance_search_b200 import ops as o
+    return o
+
+
+def _randn(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g)
+
+
+# ------------------------------------------------------------------ a1 / a2
+@pytest.mark.parametrize("shape", [(1, 1), (3, 7), (5, 100), (4, 2048), (6, 100352), (2, 100353),
+                                   (300, 512), (0, 16)])
+def test_l2norm_rows(ops, shape):
+    x = _randn(*shape, seed=1) if shape[0] else torch.zeros(shape)
+    want = oracle.normalize_l2(x) if shape[0] else x
+    got = ops.l2norm_rows(x.cuda()).cpu()
+    # fp32, different summation order than torch's: 1e-6 relative
+    assert torch.allclose(got, want, rtol=1e-6, atol=1e-9)
+
+
+def test_l2norm_eps_inside_sqrt(ops):
+    x = torch.zeros(2, 64)
+    x[1] = 1e-6
+    got = ops.l2norm_rows(x.cuda()).cpu()
+    assert torch.equal(got[0], torch.zeros(64))
+    assert torch.allclose(got, oracle.normalize_l2(x), rtol=1e-6, atol=0)
+
+
+def test_shift_rows(ops):
+    x, s = _randn(7, 333, seed=2), _randn(333, seed=3)
+    assert torch.equal(ops.shift_rows(x.cuda(), s.cuda()).cpu(), oracle.shift(x, s))
+
+
+# ------------------------------------------------------------------ bf16 terms
+def test_to_bf16_terms(ops):
+    x = _randn(37, 100, seed=4) * 3
+    hi = ops.to_bf16(x.cuda(), 0).cpu()
+    assert hi.shape == (37, 104) and hi.dtype == torch.bfloat16
+    assert torch.equal(hi[:, :100], x.to(torch.bfloat16))
+    assert torch.equal(hi[:, 100:].float(), torch.zeros(37, 4))
+    lo = ops.to_bf16(x.cuda(), 1).cpu()
+    r1 = x - hi[:, :100].float()
+    assert torch.equal(lo[:, :100], r1.to(torch.bfloat16))
+    lo2 = ops.to_bf16(x.cuda(), 2).cpu()
+    r2 = r1 - lo[:, :100].float()
+    assert torch.equal(lo2[:, :100], r2.to(torch.bfloat16))
+    # three terms reproduce fp32 to ~2^-24
+    rec = hi.float() + lo.float() + lo2.float()
+    assert torch.allclose(rec[:, :100], x, rtol=2e-7, atol=1e-30)
+
+
+# ------------------------------------------------------------------ tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K,splits", [
+    (128, 256, 64, 1),      # one tile, one k-block
+    (128, 256, 256, 1),     # ring wraps once
+    (128, 256, 1024, 1),    # ring wraps many times
+    (256, 512, 128, 1),     # 2x2 tiles
+    (200, 300, 136, 1),     # ragged M, N, K (TMA zero fill)
+    (1, 1, 8, 1),
+    (1000, 2000, 2048, 1),
+    (1536, 512, 6272, 4),   # split-K
+    (130, 258, 6400, 7),    # ragged + split-K
+    (4096, 4096, 512, 1),   # many tiles per CTA: TMEM double buffering
+])
+def test_gemm_nt(ops, M, N, K, splits):
+    a = _randn(M, K, seed=5).cuda()
+    b = _randn(N, K, seed=6).cuda()
+    bias = _randn(N, seed=7).cuda()
+    a16, b16 = ops.to_bf16(a), ops.to_bf16(b)
+    got = ops.gemm_nt(a16, b16, bias=bias, splits=splits, k=K)
+    # checker: the same bf16 values multiplied in fp64 on the GPU
+    want = (a16[:, :K].double() @ b16[:, :K].double().t() + bias.double())
+    err = (got.double() - want).abs().max().item()
+    scale = want.abs().max().item()
+    # fp32 accumulation of K exact products
+    assert err <= 2e-6 * scale * max(1.0, (K / 64) ** 0.5), (err, scale)
+
+
+def test_gemm_nt_fp32_grade_by_k_concat(ops):
+    # [A_hi|A_lo|A_hi] . [B_hi|B_hi|B_lo]^T ~ fp32-grade product (include/isb.h)
+    M, N, K = 256, 512, 1024
+    a, b = _randn(M, K, seed=8).cuda(), _randn(N, K, seed=9).cuda()
+    a_hi, a_lo = ops.to_bf16(a, 0), ops.to_bf16(a, 1)
+    b_hi, b_lo = ops.to_bf16(b, 0), ops.to_bf16(b, 1)
+    A = torch.cat([a_hi, a_lo, a_hi], 1).contiguous()
+    B = torch.cat([b_hi, b_hi, b_lo], 1).contiguous()
+    got = ops.gemm_nt(A, B)
+    want = a.double() @ b.double().t()
+    rel = (got.double() - want).abs().max().item() / want.abs().max().item()
+    assert rel < 3e-6, rel
+    one = ops.gemm_nt(a_hi, b_hi)
+    rel1 = (one.double() - want).abs().max().item() / want.abs().max().item()
+    assert rel1 > 20 * rel  # the split really buys precision
+
+
+# ------------------------------------------------------------------ top-k search
+def _search(ops, q, db, k, margin=None):
+    qd, dbd = q.cuda(), db.cuda()
+    s, i = ops.topk_search(qd, dbd, ops.to_bf16(dbd), k, margin)
+    torch.cuda.synchronize()
+    return s, i
+
+
+def test_topk_search_golden(ops):
+    g = load_golden("search_tiny")
+    s, i = _search(ops, g["q"], g["db"], 10)
+    assert torch.equal(i.cpu(), g["idx"])
+    assert torch.allclose(s.cpu(), g["scores"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("Q,N,D,k", [
+    (1, 1, 8, 1),            # degenerate
+    (3, 5, 8, 5),            # k == N
+    (40, 1500, 64, 10),
+    (130, 777, 72, 100),     # ragged everything, D not a multiple of 64
+    (300, 20000, 256, 100),
+    (64, 70000, 128, 100),   # many n-tiles per segment
+    (1000, 5000, 64, 20),    # several m-blocks
+])
+def test_topk_search_random(ops, Q, N, D, k):
+    q = oracle.normalize_l2(_randn(Q, D, seed=10))
+    db = oracle.normalize_l2(_randn(N, D, seed=11))
+    s, i = _search(ops, q, db, k)
+    check_topk_against_oracle(q, db, k, s, i)
+    assert (i >= 0).all() and (i < N).all()
+    # size-independent properties: sorted, no duplicates
+    assert (s[:, :-1] >= s[:, 1:]).all()
+    assert all(len(set(r)) == k for r in i.cpu().tolist()[:50])
+
+
+def test_topk_search_clustered_and_planted(ops):
+    # database with near-duplicate clusters + planted exact matches of each query
+    Q, N, D, k = 200, 30000, 128, 50
+    centers = _randn(300, D, seed=12)
+    lab = torch.randint(0, 300, (N,), generator=torch.Generator().manual_seed(13))
+    db = oracle.normalize_l2(centers[lab] + 0.05 * _randn(N, D, seed=14))
+    q = oracle.normalize_l2(centers[:Q] + 0.05 * _randn(Q, D, seed=15))
+    planted = torch.arange(Q) * 7 + 3
+    db[planted] = q
+    s, i = _search(ops, q, db, k)
+    assert torch.equal(i[:, 0].cpu(), planted)          # round trip: a row finds itself
+    assert torch.allclose(s[:, 0].cpu(), torch.ones(Q), atol=1e-6)
+    check_topk_against_oracle(q, db, k, s, i)
+
+
+def test_topk_search_idx_offset_and_merge(ops):
+    # row-sharded database: per-shard search + merge == single search  
+    Q, N, D, k = 150, 9000, 64, 30
+    q = oracle.normalize_l2(_randn(Q, D, seed=16))
+    db = oracle.normalize_l2(_randn(N, D, seed=17))
+    full_s, full_i = _search(ops, q, db, k)
+    R = 4
+    bounds = [0, 2000, 2500, 7000, 9000]  # uneven shards
+    cs, ci = [], []
+    for r in range(R):
+        shard = db[bounds[r]:bounds[r + 1]].cuda()
+        s, i = ops.topk_search(q.cuda(), shard, ops.to_bf16(shard), k, idx_offset=bounds[r])
+        cs.append(s), ci.append(i)
+    ms, mi = ops.topk_merge(torch.stack(cs), torch.stack(ci))
+    assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+
+
+def test_topk_search_errors(ops):
+    from instance_search_b200 import IsbError
+    q = torch.zeros(4, 16).cuda()
+    db = torch.zeros(10, 16).cuda()
+    with pytest.raises(IsbError):
+        ops.topk_search(q, db, ops.to_bf16(db), 11)          # k > N
+    with pytest.raises(IsbError):
+        ops.topk_search(q.cpu(), db, ops.to_bf16(db), 2)     # CPU tensor: no fallback
+    with pytest.raises(IsbError):
+        ops.topk_search(q[:, :12].contiguous(), db[:, :12].contiguous(),
+                        ops.to_bf16(db[:, :12].contiguous()), 2)  # D % 8 != 0
