@@ -351,9 +351,15 @@ int launch_topk_screen(const uint16_t* a_bf16, int64_t lda, int64_t Q, const uin
   ep.row_ub = row_ub;
   ep.ub_slack = ub_slack;
 
-  auto kern = gemm_tc_kernel<TopkSched, TopkEpilogue>;
-  ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
-  kern<<<plan.grid, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, sched, ep);
+  if (col_label != nullptr) {
+    auto kern = gemm_tc_kernel<TopkSched, TopkEpilogue<true>>;
+    ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    kern<<<plan.grid, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, sched, ep);
+  } else {
+    auto kern = gemm_tc_kernel<TopkSched, TopkEpilogue<false>>;
+    ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    kern<<<plan.grid, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, sched, ep);
+  }
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;
 }
@@ -381,7 +387,7 @@ extern "C" int isb_f32_to_bf16(const float* x, int64_t rows, int64_t cols, int64
 extern "C" size_t isb_topk_search_workspace_bytes(int64_t Q, int64_t N, int64_t D, int k, int margin) {
   (void)k; (void)margin;
   if (Q <= 0 || N <= 0 || D <= 0) return 0;
-  return make_search_plan(Q, N, D).total;
+  return make_search_plan(Q, N, D).total + 1024;  // slack: the base is aligned up to 1024
 }
 
 extern "C" int isb_topk_search(const float* q, int64_t Q, const float* db_f32, const uint16_t* db_bf16,
@@ -402,14 +408,14 @@ extern "C" int isb_topk_search(const float* q, int64_t Q, const float* db_f32, c
   int rc = isb_check_device();
   if (rc) return rc;
   const SearchPlan plan = make_search_plan(Q, N, D);
-  if (workspace == nullptr || workspace_bytes < plan.total ||
-      (reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) {
-    set_error("isb_topk_search: workspace too small or not 1024-byte aligned (need %zu bytes, got %zu)",
-              plan.total, workspace_bytes);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+  if (workspace == nullptr ||
+      ws + plan.total > static_cast<uint8_t*>(workspace) + workspace_bytes) {
+    set_error("isb_topk_search: workspace too small (need %zu bytes incl. alignment slack, got %zu)",
+              plan.total + 1024, workspace_bytes);
     return ISB_ERR_WORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  uint8_t* ws = static_cast<uint8_t*>(workspace);
   uint16_t* q_bf16 = reinterpret_cast<uint16_t*>(ws + plan.off_qbf16);
   rc = isb_f32_to_bf16(q, Q, D, D, q_bf16, plan.ldq, 0, stream);
   if (rc) return rc;

@@ -66,15 +66,26 @@ __device__ __forceinline__ uint32_t warp_compact_row(uint2* buf, int cnt, int ke
     }
   }
   __syncwarp();  // every load above is ordered before every store below
-  uint32_t T = 0;
-#pragma unroll 1
-  for (int b = 31; b >= 0; --b) {
-    const uint32_t trial = T | (1u << b);
-    int c = 0;
+  // The keys of one row share their leading bits (same sign / exponent): start the
+  // bit-by-bit select below the common prefix instead of at bit 31.
+  const uint32_t k0 = __shfl_sync(0xffffffffu, key[0], 0);  // entry 0 is valid (cnt > 0)
+  uint32_t diff = 0;
 #pragma unroll
-    for (int i = 0; i < kPer; ++i) c += (key[i] >= trial) ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= keep) T = trial;
+  for (int i = 0; i < kPer; ++i) diff |= (lane + 32 * i < cnt) ? (key[i] ^ k0) : 0u;
+  diff = __reduce_or_sync(0xffffffffu, diff);
+  uint32_t T = k0;
+  if (diff != 0) {
+    const int hb = 31 - __clz(diff);
+    T = (hb == 31) ? 0u : (k0 & ~((2u << hb) - 1u));
+#pragma unroll 1
+    for (int b = hb; b >= 0; --b) {
+      const uint32_t trial = T | (1u << b);
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) c += (key[i] >= trial) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= keep) T = trial;
+    }
   }
   int n_gt = 0;
 #pragma unroll
@@ -101,6 +112,7 @@ __device__ __forceinline__ uint32_t warp_compact_row(uint2* buf, int cnt, int ke
   return T;
 }
 
+template <bool kMasked>
 struct TopkEpilogue {
   using Params = TopkEpiParams;
   const Params& p;
@@ -128,31 +140,83 @@ struct TopkEpilogue {
     row_valid = row < p.Q;
     cnt = 0;
     thr = row_valid ? __uint_as_float(key2f(kKeyNegInf)) : __uint_as_float(0x7F800000u);
-    if (p.col_label != nullptr && row_valid) {
-      my_label = p.row_label[row];
-      my_ub = (p.row_ub != nullptr) ? p.row_ub[row] + p.ub_slack : __uint_as_float(0x7F800000u);
+    if (kMasked) {
+      my_label = row_valid ? p.row_label[row] : -1;
+      my_ub = (row_valid && p.row_ub != nullptr) ? p.row_ub[row] + p.ub_slack
+                                                  : __uint_as_float(0x7F800000u);
     }
   }
 
-  __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int col0) {
-    float m = __uint_as_float(v[0]);
+  // One accumulator value: append (score, column) to the row's buffer when it
+  // beats the threshold.  Branch-free predicated PTX -- the epilogue must stay a
+  // few KB of straight-line code (an unrolled, branchy version thrashed the
+  // instruction cache and made the MMA pipe wait for TMEM).
+  template <bool kRagged>
+  __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int col0, int rem,
+                                             uint2*& wp) {
 #pragma unroll
-    for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-    if (m > thr) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = __uint_as_float(v[j]);
-        const int col = col0 + j;
-        bool pass = (x > thr) && (col < p.N);
-        if (p.col_label != nullptr) {
-          // evaluated only for scores that beat the threshold
-          if (pass) pass = (x < my_ub) && (__ldg(p.col_label + col) != my_label);
-        }
-        if (pass) {
-          my_buf[cnt] = make_uint2(v[j], static_cast<uint32_t>(col));
-          ++cnt;
-        }
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      if (kMasked) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t.reg .s32 l;\n\t"
+            "setp.gt.f32 p, %1, %2;\n\t"
+            "setp.lt.and.f32 p, %1, %6, p;\n\t"
+            "setp.lt.and.s32 p, %7, %8, p;\n\t"
+            "mad.wide.s32 a, %4, 4, %5;\n\t"
+            "mov.s32 l, %9;\n\t"
+            "@p ld.global.nc.s32 l, [a];\n\t"
+            "setp.ne.and.s32 p, l, %9, p;\n\t"
+            "@p st.global.v2.b32 [%0], {%3, %4};\n\t"
+            "@p add.u64 %0, %0, 8;\n\t}"
+            : "+l"(wp)
+            : "f"(__uint_as_float(v[j])), "f"(thr), "r"(v[j]), "r"(col), "l"(p.col_label),
+              "f"(my_ub), "r"(j), "r"(rem), "r"(my_label)
+            : "memory");
+      } else if (kRagged) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.gt.f32 p, %1, %2;\n\t"
+            "setp.lt.and.s32 p, %5, %6, p;\n\t"
+            "@p st.global.v2.b32 [%0], {%3, %4};\n\t"
+            "@p add.u64 %0, %0, 8;\n\t}"
+            : "+l"(wp)
+            : "f"(__uint_as_float(v[j])), "f"(thr), "r"(v[j]), "r"(col), "r"(j), "r"(rem)
+            : "memory");
+      } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.gt.f32 p, %1, %2;\n\t"
+            "@p st.global.v2.b32 [%0], {%3, %4};\n\t"
+            "@p add.u64 %0, %0, 8;\n\t}"
+            : "+l"(wp)
+            : "f"(__uint_as_float(v[j])), "f"(thr), "r"(v[j]), "r"(col)
+            : "memory");
       }
+    }
+  }
+
+  // 256 accumulator columns = 4 iterations of two 32-column chunks, TMEM loads
+  // double-buffered against the scan of the previous chunk.
+  template <bool kRagged>
+  __device__ __forceinline__ void scan_tile(uint32_t tmem_acc, int col0, int rem,
+                                            uint64_t* tmem_empty_bar, uint2*& wp) {
+    uint32_t v0[32], v1[32];
+    ptx::tmem_ld_32x32b_x32(tmem_acc, v0);
+#pragma unroll 1
+    for (int it = 0; it < kBN / 64; ++it) {
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_32x32b_x32(tmem_acc + it * 64 + 32, v1);
+      scan_chunk<kRagged>(v0, col0 + it * 64, rem - it * 64, wp);
+      ptx::tmem_ld_wait();
+      if (it + 1 < kBN / 64) {
+        ptx::tmem_ld_32x32b_x32(tmem_acc + it * 64 + 64, v0);
+      } else {
+        // the whole accumulator is in registers: hand the TMEM buffer back
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(tmem_empty_bar);
+      }
+      scan_chunk<kRagged>(v1, col0 + it * 64 + 32, rem - it * 64 - 32, wp);
     }
   }
 
@@ -178,21 +242,12 @@ struct TopkEpilogue {
       thr = fmaxf(thr, __uint_as_float(key2f(g)));
     }
     const int col0 = nt * kBN;
-    uint32_t v[2][32];
-    ptx::tmem_ld_32x32b_x32(tmem_acc, v[0]);
-#pragma unroll
-    for (int c = 0; c < kBN / 32; ++c) {
-      ptx::tmem_ld_wait();
-      if (c + 1 < kBN / 32) {
-        ptx::tmem_ld_32x32b_x32(tmem_acc + (c + 1) * 32, v[(c + 1) & 1]);
-      } else {
-        // the whole accumulator is in registers: hand the TMEM buffer back
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(tmem_empty_bar);
-      }
-      scan_chunk(v[c & 1], col0 + c * 32);
-      __syncwarp();
-    }
+    const int rem = p.N - col0;  // valid columns of this tile
+    uint2* wp = my_buf + cnt;
+    if (kMasked || rem < kBN) scan_tile<true>(tmem_acc, col0, rem, tmem_empty_bar, wp);
+    else scan_tile<false>(tmem_acc, col0, rem, tmem_empty_bar, wp);
+    cnt = static_cast<int>(wp - my_buf);
+    __syncwarp();
     const uint32_t need = __ballot_sync(0xffffffffu, cnt > kTrig);
     if (need) compact_rows(need, p.kc);
   }
