@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Headline benchmark: cosine top-100 retrieval, 10k queries over a 1M x 2048-d
+database (BASELINE.json configs[3], the configuration `metric` is quoted on; it
+fits one B200: 8 GB fp32 + 4 GB bf16).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path
+
+A step = one pass of the hot path over one batch of synthetic queries: bf16
+tcgen05 screen with fused streaming top-k, exact fp64-accumulated re-rank, and
+for N > 1 (database row-sharded, one process per GPU) one NCCL all-gather of
+the per-shard candidates + merge.  Prints ONE JSON line on rank 0.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "queries/s top-100 over 1Mx2048-d DB"
+UNIT = "queries/s"
+Q_DEFAULT, N_DEFAULT, D_DEFAULT, K_DEFAULT = 10000, 1000000, 2048, 100
+SEED = 1234 + 4  # manual_seed(1234 + cfg)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--queries", type=int, default=Q_DEFAULT)
+    ap.add_argument("--db-rows", type=int, default=N_DEFAULT)
+    ap.add_argument("--dim", type=int, default=D_DEFAULT)
+    ap.add_argument("--k", type=int, default=K_DEFAULT)
+    ap.add_argument("--cpu-sample-queries", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    # B200_PROFILING.md fallback
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------ synthetic data
+def make_rows(n, d, seed, device, chunk=131072):
+    """normalize(randn(n, d)) rows, generated in chunks with a seeded generator.
+    SURVEY.md 8d: continuous Gaussians => no exact ties."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = torch.empty((n, d), dtype=torch.float32, device=device)
+    for s in range(0, n, chunk):
+        x = torch.randn((min(chunk, n - s), d), generator=g, device=device)
+        out[s:s + chunk] = x / x.norm(dim=1, keepdim=True)
+    return out
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2])), pw.append(float(r[3]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [c for c, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "samples": len(sm),
+                "power_w_max": max(pw), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ reference arm
+def cpu_topk(q, db, k, chunk=128):
+    """The reference's CPU path for this metric, via the oracle's restatement:
+    sim = torch.mm(q_chunk, db.t()) (test/siamese_regions_test.py:76) then the
+    best k of every row (utils/metrics.py:11,33).  torch fp32 on all host cores."""
+    import oracle  # the one place bench.py may execute oracle/ (cpu baseline)
+    out_s, out_i = [], []
+    for s in range(0, q.size(0), chunk):
+        sim = oracle.similarity(q[s:s + chunk], db)
+        v, i = sim.topk(k, dim=1)  # == first k of the descending sort, without the full sort
+        out_s.append(v), out_i.append(i)
+    return torch.cat(out_s), torch.cat(out_i)
+
+
+def time_cpu(q, db, k, repeats=1):
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        cpu_topk(q, db, k)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    g = torch.Generator().manual_seed(SEED)
+    # same distribution as the GPU arm; generated on the host in chunks
+    db = torch.empty((a.db_rows, a.dim), dtype=torch.float32)
+    for s in range(0, a.db_rows, 65536):
+        x = torch.randn((min(65536, a.db_rows - s), a.dim), generator=g)
+        db[s:s + 65536] = x / x.norm(dim=1, keepdim=True)
+    nq = a.cpu_sample_queries
+    qs = torch.randn((nq, a.dim), generator=g)
+    qs = qs / qs.norm(dim=1, keepdim=True)
+    for _ in range(max(1, min(a.warmup, 1))):
+        cpu_topk(qs[:32], db, a.k)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cpu_topk(qs, db, a.k)
+    dt = (time.perf_counter() - t0) / a.steps
+    qps = nq / dt
+    sample = "%d of %d queries per step over the full %d-row database, torch fp32 mm + topk(%d), chunks of 128" % (
+        nq, a.queries, a.db_rows, a.k)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, 1),
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, world):
+    return {"workload": "cosine top-%d retrieval, %d queries x %d-row x %d-d database (BASELINE configs[3])" %
+                        (a.k, a.queries, a.db_rows, a.dim),
+            "queries": a.queries, "db_rows": a.db_rows, "dim": a.dim, "k": a.k,
+            "db_sharding": "row-wise over %d GPU(s)" % world,
+            "l2_policy": "inputs larger than L2 (bf16 database shard %.2f GB > 126 MB)" %
+                         (a.db_rows / world * a.dim * 2 / 1e9)}
+
+
+# ------------------------------------------------------------------ B200 arm
+def run_b200(a, rank, world, local_rank):
+    import torch.distributed as dist
+    from instance_search_b200.search import ShardedIndex, shard_bounds
+    from instance_search_b200 import _lib
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.lib().isb_check_device(), "isb_check_device")  # no fallback
+
+    lo, hi = shard_bounds(a.db_rows, world)[rank]
+    # every rank draws the same global stream and keeps its rows (shards of ONE database)
+    shard = make_rows_slice(a.db_rows, a.dim, SEED, dev, lo, hi)
+    index = ShardedIndex(shard, a.db_rows, rank, world)
+    del shard
+    q_dev = make_rows(a.queries, a.dim, SEED + 100, dev)
+    q_host = q_dev.cpu().pin_memory()
+    out_s_host = torch.empty((a.queries, a.k), dtype=torch.float32).pin_memory()
+    out_i_host = torch.empty((a.queries, a.k), dtype=torch.int64).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    screen_events = []
+
+    def step_resident():
+        return index.search(q_dev, a.k, events=screen_events)
+
+    def step_e2e():
+        qd = q_host.to(dev, non_blocking=True)
+        s, i = index.search(qd, a.k)
+        out_s_host.copy_(s, non_blocking=True)
+        out_i_host.copy_(i, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller holds the results
+
+    for _ in range(a.warmup):
+        step_resident()
+    screen_events.clear()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_resident, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ev = list(screen_events)
+    screen_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev) / max(1, len(ev))
+    for _ in range(min(2, a.warmup)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+
+    ms_step = ms_total / a.steps
+    value = a.queries / (ms_step * 1e-3)
+    e2e_value = a.queries / (ms_e2e / a.steps * 1e-3)
+
+    # ---- roofline of the dominant kernel: gemm_tc_kernel<TopkSched, TopkEpilogue>
+    pk, pk_src = peaks()
+    rows_local = hi - lo
+    flops = 2.0 * a.queries * rows_local * a.dim          # 2*Q*N*D per launch
+    achieved = flops / (screen_ms * 1e-3) / 1e12
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])  # timed inside a long step
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None,
+                "kernel": "gemm_tc_kernel<TopkSched,TopkEpilogue> (tcgen05 screen + streaming top-k)",
+                "kernel_ms": screen_ms, "peak_source": pk_src + " bf16_tflops_sustained",
+                "frac_of_burst_peak": achieved / pk["bf16_tflops"]}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            nq = a.cpu_sample_queries
+            db_host = index.local.db_f32[:, :a.dim].cpu()
+            dt = time_cpu(q_host[:nq], db_host, a.k)
+            cpu = {"value": nq / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": "first %d of %d queries over the full %d-row database (%.1f s), torch fp32 "
+                             "mm + topk(%d) on the host" % (nq, a.queries, a.db_rows, dt, a.k)}
+            del db_host
+        launches_per_step = 4 + (1 if world > 1 else 0)  # bf16 cast, thr init, screen, rerank (+ merge)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16 screen + f64-accumulated f32 re-rank",
+            "data": "synthetic (seeded unit-norm Gaussian rows)", "config": workload_config(a, world),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": q_host.numel() * 4,
+                    "d2h_bytes_per_step": out_s_host.numel() * 4 + out_i_host.numel() * 8,
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": launches_per_step * a.steps * 2,  # resident + e2e timed regions
+            "clocks": clocks,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def make_rows_slice(n, d, seed, device, lo, hi, chunk=131072):
+    """Rows [lo, hi) of make_rows(n, d, seed): the global stream is drawn chunk by
+    chunk on every rank, only the local rows are kept."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = torch.empty((hi - lo, d), dtype=torch.float32, device=device)
+    for s in range(0, n, chunk):
+        e = min(s + chunk, n)
+        x = torch.randn((e - s, d), generator=g, device=device)
+        a, b = max(s, lo), min(e, hi)
+        if a < b:
+            rows = x[a - s:b - s]
+            out[a - lo:b - lo] = rows / rows.norm(dim=1, keepdim=True)
+        if e >= hi:
+            break
+    return out
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    if world != a.gpus and world == 1 and a.gpus > 1:
+        # launched without torchrun: re-exec under it
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               "--nproc-per-node", str(a.gpus), "--master-addr", "127.0.0.1", "--master-port", "29517",
+               os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_b200(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

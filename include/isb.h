@@ -88,6 +88,17 @@ int isb_topk_search(const float* q, int64_t Q, const float* db_f32, const uint16
                     int64_t idx_offset, float* out_scores, int64_t* out_idx, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* The two stages of isb_topk_search as separate calls sharing one workspace
+ * (isb_topk_search == screen then rerank).  The screen leaves, per query, the
+ * k+margin best bf16-scored candidates in the workspace; the rerank consumes
+ * them.  Exposed so a caller can time / overlap the stages. */
+int isb_topk_screen(const float* q, int64_t Q, const uint16_t* db_bf16, int64_t N, int64_t D,
+                    int64_t ld_bf16, int k, int margin, void* workspace, size_t workspace_bytes,
+                    void* stream);
+int isb_topk_rerank(const float* q, int64_t Q, const float* db_f32, int64_t N, int64_t D, int k,
+                    int margin, int64_t idx_offset, float* out_scores, int64_t* out_idx,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- (e) multi-GPU
  * Merge R per-shard results (after the all-gather): cand_scores [R, Q, k],
  * cand_idx [R, Q, k] (global indices) -> the k best per query, best first,

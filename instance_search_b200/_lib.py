@@ -27,6 +27,10 @@ SIGNATURES = {
     "isb_topk_search_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_int, c_int]),
     "isb_topk_search": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_int,
                                 c_i64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    "isb_topk_screen": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_int, c_int, c_ptr, c_size,
+                                c_ptr]),
+    "isb_topk_rerank": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_ptr, c_ptr,
+                                c_ptr, c_size, c_ptr]),
     "isb_topk_merge": (c_int, [c_ptr, c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
     "isb_gemm_nt_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_int]),
     "isb_gemm_nt": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64,

@@ -390,49 +390,83 @@ extern "C" size_t isb_topk_search_workspace_bytes(int64_t Q, int64_t N, int64_t 
   return make_search_plan(Q, N, D).total + 1024;  // slack: the base is aligned up to 1024
 }
 
-extern "C" int isb_topk_search(const float* q, int64_t Q, const float* db_f32, const uint16_t* db_bf16,
-                               int64_t N, int64_t D, int64_t ld_bf16, int k, int margin,
-                               int64_t idx_offset, float* out_scores, int64_t* out_idx,
-                               void* workspace, size_t workspace_bytes, void* stream) {
-  ISB_CHECK_ARG(q && db_f32 && db_bf16 && out_scores && out_idx, "isb_topk_search: null pointer");
-  ISB_CHECK_ARG(Q > 0 && N > 0 && D > 0, "isb_topk_search: empty problem (Q=%lld N=%lld D=%lld)",
-                (long long)Q, (long long)N, (long long)D);
-  ISB_CHECK_ARG(N < (1ll << 31) && Q < (1ll << 31), "isb_topk_search: Q and N must be < 2^31 per call");
-  ISB_CHECK_ARG(D % 8 == 0, "isb_topk_search: D (%lld) must be a multiple of 8 (pad with zeros)", (long long)D);
-  ISB_CHECK_ARG(ld_bf16 >= D && ld_bf16 % 8 == 0, "isb_topk_search: bad ld_bf16");
+static int check_search_args(const char* fn, int64_t Q, int64_t N, int64_t D, int k, int margin) {
+  ISB_CHECK_ARG(Q > 0 && N > 0 && D > 0, "%s: empty problem (Q=%lld N=%lld D=%lld)", fn, (long long)Q,
+                (long long)N, (long long)D);
+  ISB_CHECK_ARG(N < (1ll << 31) && Q < (1ll << 31), "%s: Q and N must be < 2^31 per call", fn);
+  ISB_CHECK_ARG(D % 8 == 0, "%s: D (%lld) must be a multiple of 8 (pad with zeros)", fn, (long long)D);
   ISB_CHECK_ARG(k >= 1 && margin >= 0 && k + margin <= ISB_MAX_CANDIDATES,
-                "isb_topk_search: need 1 <= k, k + margin <= %d (k=%d margin=%d)", ISB_MAX_CANDIDATES, k, margin);
-  ISB_CHECK_ARG(k <= N, "isb_topk_search: k (%d) > N (%lld)", k, (long long)N);
-  ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(db_f32) & 15) == 0 &&
-                (reinterpret_cast<uintptr_t>(db_bf16) & 15) == 0, "isb_topk_search: inputs must be 16-byte aligned");
-  int rc = isb_check_device();
-  if (rc) return rc;
-  const SearchPlan plan = make_search_plan(Q, N, D);
-  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
-  if (workspace == nullptr ||
-      ws + plan.total > static_cast<uint8_t*>(workspace) + workspace_bytes) {
-    set_error("isb_topk_search: workspace too small (need %zu bytes incl. alignment slack, got %zu)",
+                "%s: need 1 <= k, k + margin <= %d (k=%d margin=%d)", fn, ISB_MAX_CANDIDATES, k, margin);
+  ISB_CHECK_ARG(k <= N, "%s: k (%d) > N (%lld)", fn, k, (long long)N);
+  return isb_check_device();
+}
+
+static int carve_workspace(const char* fn, const SearchPlan& plan, void* workspace, size_t workspace_bytes,
+                           uint8_t** ws) {
+  *ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+  if (workspace == nullptr || *ws + plan.total > static_cast<uint8_t*>(workspace) + workspace_bytes) {
+    set_error("%s: workspace too small (need %zu bytes incl. alignment slack, got %zu)", fn,
               plan.total + 1024, workspace_bytes);
     return ISB_ERR_WORKSPACE;
   }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return ISB_OK;
+}
+
+extern "C" int isb_topk_screen(const float* q, int64_t Q, const uint16_t* db_bf16, int64_t N, int64_t D,
+                               int64_t ld_bf16, int k, int margin, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  ISB_CHECK_ARG(q && db_bf16, "isb_topk_screen: null pointer");
+  int rc = check_search_args("isb_topk_screen", Q, N, D, k, margin);
+  if (rc) return rc;
+  ISB_CHECK_ARG(ld_bf16 >= D && ld_bf16 % 8 == 0, "isb_topk_screen: bad ld_bf16");
+  ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(db_bf16) & 15) == 0,
+                "isb_topk_screen: inputs must be 16-byte aligned");
+  const SearchPlan plan = make_search_plan(Q, N, D);
+  uint8_t* ws;
+  rc = carve_workspace("isb_topk_screen", plan, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
   uint16_t* q_bf16 = reinterpret_cast<uint16_t*>(ws + plan.off_qbf16);
   rc = isb_f32_to_bf16(q, Q, D, D, q_bf16, plan.ldq, 0, stream);
   if (rc) return rc;
   int kc = k + margin;
   if (kc > N) kc = static_cast<int>(N);
-  rc = launch_topk_screen(q_bf16, plan.ldq, Q, db_bf16, ld_bf16, N, D, kc, plan, ws, nullptr, nullptr,
-                          nullptr, 0.f, st);
+  return launch_topk_screen(q_bf16, plan.ldq, Q, db_bf16, ld_bf16, N, D, kc, plan, ws, nullptr, nullptr,
+                            nullptr, 0.f, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int isb_topk_rerank(const float* q, int64_t Q, const float* db_f32, int64_t N, int64_t D, int k,
+                               int margin, int64_t idx_offset, float* out_scores, int64_t* out_idx,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  ISB_CHECK_ARG(q && db_f32 && out_scores && out_idx, "isb_topk_rerank: null pointer");
+  int rc = check_search_args("isb_topk_rerank", Q, N, D, k, margin);
   if (rc) return rc;
+  ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(db_f32) & 15) == 0,
+                "isb_topk_rerank: inputs must be 16-byte aligned");
+  const SearchPlan plan = make_search_plan(Q, N, D);
+  uint8_t* ws;
+  rc = carve_workspace("isb_topk_rerank", plan, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  int kc = k + margin;
+  if (kc > N) kc = static_cast<int>(N);
   const size_t smem = static_cast<size_t>(D) * 4;
-  ISB_CHECK_ARG(smem <= 160 * 1024, "isb_topk_search: D too large for the re-rank kernel");
+  ISB_CHECK_ARG(smem <= 160 * 1024, "isb_topk_rerank: D too large for the re-rank kernel");
   if (smem > 48 * 1024)
     ISB_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rerank_kernel<<<static_cast<unsigned>(Q), kRerankThreads, smem, st>>>(
+  rerank_kernel<<<static_cast<unsigned>(Q), kRerankThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       q, db_f32, static_cast<int>(D), plan.n_groups, reinterpret_cast<const uint2*>(ws + plan.off_pool),
       reinterpret_cast<const int*>(ws + plan.off_pool_cnt), kc, k, idx_offset, out_scores, out_idx);
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;
+}
+
+extern "C" int isb_topk_search(const float* q, int64_t Q, const float* db_f32, const uint16_t* db_bf16,
+                               int64_t N, int64_t D, int64_t ld_bf16, int k, int margin,
+                               int64_t idx_offset, float* out_scores, int64_t* out_idx,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = isb_topk_screen(q, Q, db_bf16, N, D, ld_bf16, k, margin, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return isb_topk_rerank(q, Q, db_f32, N, D, k, margin, idx_offset, out_scores, out_idx, workspace,
+                         workspace_bytes, stream);
 }
 
 extern "C" int isb_topk_merge(const float* cand_scores, const int64_t* cand_idx, int R, int64_t Q, int k,
