@@ -122,6 +122,51 @@ int isb_gemm_nt(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, 
                 int64_t N, int64_t K, const float* bias, float* C, int64_t ldc, int splits,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------- a3
+ * Window scoring + selection of RegionDescriptorNet.forward_single,
+ * model/siamese.py:186-217, for a batch of trunk feature maps (each image is
+ * treated exactly as the reference's batch-1 call, :184):
+ *   a = AvgPool2d((fh, fw), stride 1)(x)            (:164-166, :187)
+ *   c = Conv2d 1x1 (a) = cls_w . a + cls_b           (:188; model/nn_utils.py:26-39)
+ *   m = max over classes (:191); the k' = min(H'W', k) windows with the largest m,
+ *   best first (:193-194); cls_out[:, :, i] = c[:, :, window_i] (:216), zero beyond k'
+ * A bf16 tcgen05 GEMM with the class-max fused in its epilogue screens all
+ * windows; the k + margin best are re-scored exactly (fp32 products, fp64
+ * accumulation) and the final order / logits come from that exact pass.
+ *   x [B, C, H, W] fp32 (NCHW)    cls_w [ncls, C] fp32    cls_b [ncls] fp32
+ *   cls_w_bf16 [ncls, ld_w] = isb_f32_to_bf16(cls_w, part 0)
+ *   idx [B, k] int64: flat window index r * W' + c, -1 beyond k'    nsel [B] int32 = k'
+ *   cls_out [B, ncls, k] fp32      win_norm [B, k] fp32 = sqrt(||crop_i||^2 + 1e-10)
+ * k <= 32; windows re-scored per image = min(H'W', k + margin, 32). */
+size_t isb_region_select_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t ncls,
+                                         int fh, int fw, int k, int margin);
+int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H, int64_t W,
+                      const float* cls_w, const uint16_t* cls_w_bf16, int64_t ld_w,
+                      const float* cls_b, int64_t ncls, int fh, int fw, int k, int margin,
+                      int64_t* idx, int32_t* nsel, float* cls_out, float* win_norm,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- a4 (operand)
+ * u[b, :] = sum_{i < nsel[b]} crop_i / win_norm[b, i]  +  nsel[b] * shift
+ * where crop_i = x[b, :, r_i : r_i + fh, c_i : c_i + fw] flattened (C, fh, fw)
+ * -- NormalizeL2 + Shift of every selected region (model/siamese.py:218-219 via
+ * :178-179), summed BEFORE the projection (nn.Linear is linear; the reference
+ * sums after it, :220).  Written as bf16 terms for the tensor-core projection:
+ *   terms == 1: U[b] = [u_hi]            terms == 3: U[b] = [u_hi | u_lo | u_hi]
+ * (pair with W' = [W_hi] resp. [W_hi | W_hi | W_lo], see isb_gemm_nt).
+ * Each term occupies Kp = C*fh*fw rounded up to 8 columns (zero padded);
+ * ldu >= terms * Kp, % 8 == 0. */
+int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int fh, int fw,
+                      int k, const int64_t* idx, const int32_t* nsel, const float* win_norm,
+                      const float* shift, int terms, uint16_t* U, int64_t ldu, void* stream);
+
+/* ---------------------------------------------------------------- a4 (bias) + a5
+ * desc[b, :] = l2norm(y[b, :] + nsel[b] * bias)     (model/siamese.py:220-222)
+ * y = U . W'^T from isb_gemm_nt.  nsel == NULL means 1 (DescriptorNet, :117-122);
+ * bias may be NULL. */
+int isb_descriptor_finalize(const float* y, int64_t B, int64_t D, const float* bias,
+                            const int32_t* nsel, float eps, float* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

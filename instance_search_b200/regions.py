@@ -1,0 +1,147 @@
+"""Region-descriptor head on the GPU (functional form).
+
+Everything RegionDescriptorNet.forward_single does after the trunk
+(model/siamese.py:187-222), for a whole batch of feature maps at once; the
+result equals looping the reference's batch-1 forward over the images
+(train/siamese_regions.py:31-38).  All arithmetic is in libisb.so.
+"""
+
+import torch
+
+from . import _lib, ops
+from ._lib import IsbError
+
+WINDOW_MARGIN = 10   # windows re-scored exactly beyond k (k + margin <= 32)
+
+
+class HeadWeights(object):
+    """Device-resident, tensor-core-ready copies of the head's parameters.
+
+    cls_w [ncls, C], cls_b [ncls]    classifier.0.{weight,bias} (1x1 conv view)
+    shift [C*fh*fw]                  feature_reduc1.1.param
+    lin_w [D, C*fh*fw], lin_b [D]    feature_reduc1.2.{weight,bias}
+    terms: 1 = plain bf16 projection; 3 = [hi|hi|lo] K-concatenation, an
+    fp32-grade product (default: descriptors feed an index-exact search).
+    cls_w / lin_w may be None (DescriptorNet has no classifier).
+    """
+
+    def __init__(self, cls_w, cls_b, shift, lin_w, lin_b, terms=3):
+        if terms not in (1, 3):
+            raise IsbError("terms must be 1 or 3")
+        self.terms = terms
+        self.cls_w = None if cls_w is None else ops._f32c(cls_w.reshape(cls_w.size(0), -1))
+        self.cls_b = None if cls_b is None else ops._f32c(cls_b)
+        self.cls_w_bf16 = None if cls_w is None else ops.to_bf16(self.cls_w)
+        self.shift = ops._f32c(shift)
+        self.lin_b = None if lin_b is None else ops._f32c(lin_b)
+        lin_w = ops._f32c(lin_w)
+        self.D, self.Kin = lin_w.shape
+        self.KinP = (self.Kin + 7) // 8 * 8   # every bf16 term is zero-padded to 8 columns
+        hi = ops.to_bf16(lin_w, 0)
+        if terms == 1:
+            self.lin_w_bf16 = hi
+        else:
+            lo = ops.to_bf16(lin_w, 1)
+            self.lin_w_bf16 = torch.cat([hi, hi, lo], 1).contiguous()
+            del lo
+        del hi
+
+
+def _splits_for(M, N, K):
+    """Split K so the projection fills the 148 SMs (tiles are 128 x 256)."""
+    tiles = ((M + 127) // 128) * ((N + 255) // 256)
+    kb = (K + 63) // 64
+    return max(1, min(kb, 148 // max(1, tiles)))
+
+
+def region_select(x, hw, k, fsize, margin=WINDOW_MARGIN):
+    """a3: (idx [B,k] int64, nsel [B] int32, cls_out [B,ncls,k], win_norm [B,k])."""
+    ops._need_cuda(x)
+    x = ops._f32c(x)
+    B, C, H, W = x.shape
+    fh, fw = fsize
+    ncls = hw.cls_w.size(0)
+    margin = max(0, min(margin, 32 - k))
+    dev = x.device
+    idx = torch.empty((B, k), dtype=torch.int64, device=dev)
+    nsel = torch.empty((B,), dtype=torch.int32, device=dev)
+    cls_out = torch.empty((B, ncls, k), dtype=torch.float32, device=dev)
+    win_norm = torch.empty((B, k), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    nbytes = L.isb_region_select_workspace_bytes(B, C, H, W, ncls, fh, fw, k, margin)
+    ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+    _lib.check(L.isb_region_select(x.data_ptr(), B, C, H, W, hw.cls_w.data_ptr(),
+                                   hw.cls_w_bf16.data_ptr(), hw.cls_w_bf16.size(1),
+                                   hw.cls_b.data_ptr(), ncls, fh, fw, k, margin, idx.data_ptr(),
+                                   nsel.data_ptr(), cls_out.data_ptr(), win_norm.data_ptr(),
+                                   ws.data_ptr(), nbytes, ops._stream()), "isb_region_select")
+    return idx, nsel, cls_out, win_norm
+
+
+def region_aggregate(x, hw, k, fsize, idx, nsel, win_norm):
+    """a4 + a5: descriptors [B, D] of the selected windows."""
+    x = ops._f32c(x)
+    B, C, H, W = x.shape
+    fh, fw = fsize
+    if C * fh * fw != hw.Kin:
+        raise IsbError("feature map channels x window (%d) != projection in_features (%d)" %
+                       (C * fh * fw, hw.Kin))
+    L = _lib.lib()
+    ldu = hw.KinP * hw.terms
+    U = torch.empty((B, ldu), dtype=torch.bfloat16, device=x.device)
+    _lib.check(L.isb_region_gather(x.data_ptr(), B, C, H, W, fh, fw, k, idx.data_ptr(),
+                                   nsel.data_ptr(), win_norm.data_ptr(), hw.shift.data_ptr(),
+                                   hw.terms, U.data_ptr(), ldu, ops._stream()), "isb_region_gather")
+    y = ops.gemm_nt(U, hw.lin_w_bf16, splits=_splits_for(B, hw.D, ldu))
+    desc = torch.empty((B, hw.D), dtype=torch.float32, device=x.device)
+    _lib.check(L.isb_descriptor_finalize(y.data_ptr(), B, hw.D, ops._ptr(hw.lin_b), nsel.data_ptr(),
+                                         1e-10, desc.data_ptr(), ops._stream()),
+               "isb_descriptor_finalize")
+    return desc
+
+
+def region_descriptors(x, hw, k, fsize, margin=WINDOW_MARGIN):
+    """x [B, C, H, W] trunk feature maps -> (desc [B, D], cls_out [B, ncls, k],
+    idx [B, k], nsel [B]).  reference: model/siamese.py:187-223 per image."""
+    idx, nsel, cls_out, win_norm = region_select(x, hw, k, fsize, margin)
+    desc = region_aggregate(x, hw, k, fsize, idx, nsel, win_norm)
+    return desc, cls_out, idx, nsel
+
+
+def global_descriptors(x, hw):
+    """DescriptorNet head: flatten -> L2 -> Shift -> Linear -> L2.
+    reference: model/siamese.py:117-122.  x [B, C, fh, fw]."""
+    ops._need_cuda(x)
+    x = ops._f32c(x)
+    B = x.size(0)
+    flat = x.reshape(B, -1)
+    if flat.size(1) != hw.Kin:
+        raise IsbError("flattened features (%d) != projection in_features (%d)" % (flat.size(1), hw.Kin))
+    u = ops.shift_rows(ops.l2norm_rows(flat), hw.shift)
+    hi = ops.to_bf16(u, 0)
+    U = hi if hw.terms == 1 else torch.cat([hi, ops.to_bf16(u, 1), hi], 1).contiguous()
+    y = ops.gemm_nt(U, hw.lin_w_bf16, splits=_splits_for(B, hw.D, U.size(1)))
+    desc = torch.empty((B, hw.D), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().isb_descriptor_finalize(y.data_ptr(), B, hw.D, ops._ptr(hw.lin_b), 0, 1e-10,
+                                                  desc.data_ptr(), ops._stream()),
+               "isb_descriptor_finalize")
+    return desc
+
+
+def smoke_check(dev):
+    """Used by __graft_entry__.smoke(): tiny region batch vs the oracle."""
+    import oracle  # smoke() is one of the places allowed to use the checker
+    g = torch.Generator().manual_seed(3)
+    C, ncls, D, k, fs = 32, 5, 16, 6, (7, 7)
+    x = torch.relu(torch.randn(4, C, 9, 12, generator=g))
+    cls_w = torch.randn(ncls, C, generator=g) / C ** 0.5
+    cls_b = 0.01 * torch.randn(ncls, generator=g)
+    shift = 0.01 * torch.randn(C * 49, generator=g)
+    lin_w = torch.randn(D, C * 49, generator=g) / (C * 49) ** 0.5
+    lin_b = 0.01 * torch.randn(D, generator=g)
+    hw = HeadWeights(cls_w.to(dev), cls_b.to(dev), shift.to(dev), lin_w.to(dev), lin_b.to(dev))
+    d, c, i, n = region_descriptors(x.to(dev), hw, k, fs)
+    od, oc, oi, on = oracle.region_descriptor_forward(x, cls_w, cls_b, shift, lin_w, lin_b, k, fs)
+    assert torch.equal(i.cpu(), oi), "smoke: selected windows differ from the oracle"
+    assert torch.allclose(c.cpu(), oc, rtol=1e-5, atol=1e-6), "smoke: cls_out differs"
+    assert torch.allclose(d.cpu(), od, rtol=0, atol=2e-5), "smoke: descriptors differ"

@@ -1,0 +1,97 @@
+"""GPU parity: region-descriptor head (a3-a6) through the C ABI vs the oracle and
+the fixtures minted from the reference's own RegionDescriptorNet / DescriptorNet."""
+
+import pytest
+import torch
+
+import oracle
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+# descriptor components: the projection runs as a 3-product bf16 expansion
+# (fp32-grade, ~1e-5 relative); unit-norm rows => absolute tolerance
+DESC_ATOL = 3e-5
+CLS_RTOL = 1e-5   # cls_out comes from the exact (fp64-accumulated) re-score
+
+
+@pytest.fixture(scope="module")
+def R():
+    from instance_search_b200 import regions
+    return regions
+
+
+def _hw(R, g, dev="cuda", terms=3):
+    return R.HeadWeights(g["cls_w"].to(dev), g["cls_b"].to(dev), g["shift"].to(dev),
+                         g["lin_w"].to(dev), g["lin_b"].to(dev), terms=terms)
+
+
+@pytest.mark.parametrize("tag", ["7x7", "8x8", "9x12", "14x14"])
+def test_region_tiny_golden(R, tag):
+    g = load_golden("region_tiny")
+    fs = tuple(int(v) for v in g["fsize"])
+    hw = _hw(R, g)
+    d, c, i, n = R.region_descriptors(g["x_" + tag].cuda(), hw, g["k"], fs)
+    assert torch.equal(i.cpu(), g["idx_" + tag])                 # index-exact windows
+    assert torch.allclose(c.cpu(), g["cls_out_" + tag], rtol=CLS_RTOL, atol=1e-6)
+    assert torch.allclose(d.cpu(), g["desc_" + tag], rtol=0, atol=DESC_ATOL)
+    nw = (g["x_" + tag].size(2) - 6) * (g["x_" + tag].size(3) - 6)
+    assert n.tolist() == [min(nw, g["k"])] * 3
+    assert torch.allclose(d.norm(dim=1).cpu(), torch.ones(3), atol=1e-5)
+
+
+def test_region_resnet18_head_golden(R):
+    g = load_golden("region_resnet18_head")
+    hw = _hw(R, g)
+    d, c, i, n = R.region_descriptors(g["x"].cuda(), hw, g["k"], tuple(int(v) for v in g["fsize"]))
+    assert torch.equal(i.cpu(), g["idx"])
+    assert torch.allclose(c.cpu(), g["cls_out"], rtol=CLS_RTOL, atol=1e-6)
+    assert torch.allclose(d.cpu(), g["desc"], rtol=0, atol=DESC_ATOL)
+
+
+def test_descriptor_head_golden(R):
+    g = load_golden("descriptor_tiny")
+    hw = R.HeadWeights(None, None, g["shift"].cuda(), g["lin_w"].cuda(), g["lin_b"].cuda())
+    d = R.global_descriptors(g["x"].cuda(), hw)
+    assert torch.allclose(d.cpu(), g["desc"], rtol=0, atol=DESC_ATOL)
+
+
+def _synthetic(B, C, H, W, ncls, D, seed):
+    # relu(randn) maps, Wc ~ randn/sqrt(C), W ~ randn/sqrt(Kin)
+    g = torch.Generator().manual_seed(seed)
+    Kin = C * 49
+    return dict(x=torch.relu(torch.randn(B, C, H, W, generator=g)),
+                cls_w=torch.randn(ncls, C, generator=g) / C ** 0.5,
+                cls_b=0.01 * torch.randn(ncls, generator=g),
+                shift=0.01 * torch.randn(Kin, generator=g),
+                lin_w=torch.randn(D, Kin, generator=g) / Kin ** 0.5,
+                lin_b=0.01 * torch.randn(D, generator=g))
+
+
+@pytest.mark.parametrize("B,C,H,W,ncls,D,k", [
+    (5, 64, 14, 14, 20, 32, 6),
+    (3, 100, 10, 17, 7, 24, 6),      # C not a multiple of the channel block, ragged map
+    (2, 2048, 14, 14, 464, 64, 6),   # the reference's ResNet-152 head shape (config 2a), small D
+    (2, 256, 32, 32, 464, 32, 6),    # 676 windows per image (config 2b map size)
+    (4, 64, 9, 9, 10, 16, 12),       # k larger than the number of windows (9)
+])
+def test_region_random_vs_oracle(R, B, C, H, W, ncls, D, k):
+    s = _synthetic(B, C, H, W, ncls, D, seed=B * 1000 + C)
+    hw = _hw(R, s)
+    d, c, i, n = R.region_descriptors(s["x"].cuda(), hw, k, (7, 7))
+    od, oc, oi, on = oracle.region_descriptor_forward(s["x"], s["cls_w"], s["cls_b"], s["shift"],
+                                                      s["lin_w"], s["lin_b"], k, (7, 7))
+    assert torch.equal(n.cpu().long(), on)
+    assert torch.equal(i.cpu(), oi)
+    assert torch.allclose(c.cpu(), oc, rtol=CLS_RTOL, atol=1e-6)
+    assert torch.allclose(d.cpu(), od, rtol=0, atol=DESC_ATOL)
+
+
+def test_region_plain_bf16_projection_is_close(R):
+    # terms=1 (north_star's plain bf16 x bf16 projection): same windows, looser descriptors
+    s = _synthetic(4, 128, 14, 14, 30, 64, seed=77)
+    d3, _, i3, _ = R.region_descriptors(s["x"].cuda(), _hw(R, s, terms=3), 6, (7, 7))
+    d1, _, i1, _ = R.region_descriptors(s["x"].cuda(), _hw(R, s, terms=1), 6, (7, 7))
+    assert torch.equal(i1, i3)
+    assert (d1 - d3).abs().max().item() < 5e-3
+    assert (d1 * d3).sum(1).min().item() > 1 - 1e-4      # cosine between the two
