@@ -167,6 +167,32 @@ int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H, int64_t W
 int isb_descriptor_finalize(const float* y, int64_t B, int64_t D, const float* bias,
                             const int32_t* nsel, float eps, float* desc, void* stream);
 
+/* ---------------------------------------------------------------- a11 + a13
+ * Negative selection of create_batch, train/siamese_regions.py:106-129 (same
+ * code train/siamese_descriptor.py:108-131), for P positive couples at once and
+ * without materialising S = torch.mm(E, E.t()) (utils/train_siamese.py:53):
+ *   excl(j)  = label[j] == label[anchor]  ||  (semi_hard && S[anchor, j] >= S[anchor, positive])
+ *   neg      = argmax_{j : !excl(j)} S[anchor, j]        (-1 when every j is excluded;
+ *              the reference then draws a random negative on the host, :112-129)
+ * semi_hard is the reference's `epoch < P.train_epoch_switch`.
+ * The rows of a tcgen05 screen GEMM are the anchors; the masks are applied in its
+ * streaming top-k epilogue; the <= 128 survivors per couple are re-scored exactly
+ * (fp64 accumulation) and the exact conditions re-applied; a couple whose
+ * candidate list cannot be certified complete falls to an exhaustive exact pass
+ * (counted in *n_bruteforce when non-NULL).
+ *   emb [N, D] fp32 (unit rows); emb_a / emb_b [N, Kscr] bf16: the A-side / B-side
+ *   screen operands -- [hi] / [hi] (Kscr = D) or the fp32-grade
+ *   [hi|lo|hi] / [hi|hi|lo] (Kscr = 3 D), built with isb_f32_to_bf16;
+ *   screen_eps: absolute error bound of the screen scores (2e-5 for the 3-term form)
+ *   label [N] int32; anchors, positives [P] int64
+ *   neg_idx [P] int64; neg_sim [P] fp32 (-2 when none); pos_sim [P] fp32 */
+size_t isb_select_negatives_workspace_bytes(int64_t P, int64_t N, int64_t Kscr);
+int isb_select_negatives(const float* emb, const uint16_t* emb_a, const uint16_t* emb_b, int64_t Kscr,
+                         int64_t N, int64_t D, const int32_t* label, const int64_t* anchors,
+                         const int64_t* positives, int64_t P, int semi_hard, float screen_eps,
+                         int64_t* neg_idx, float* neg_sim, float* pos_sim, int32_t* n_bruteforce,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,9 @@ SIGNATURES = {
     "isb_region_gather": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_ptr, c_ptr,
                                   c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
     "isb_descriptor_finalize": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_f32, c_ptr, c_ptr]),
+    "isb_select_negatives_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
+    "isb_select_negatives": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64,
+                                     c_int, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     "isb_gemm_nt_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_int]),
     "isb_gemm_nt": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64,
                             c_int, c_ptr, c_size, c_ptr]),

@@ -86,94 +86,94 @@ __device__ __forceinline__ bool entry_before(double sa, int ia, double sb, int i
   return (sa > sb) || (sa == sb && ia < ib);
 }
 
-__global__ void __launch_bounds__(kRerankThreads)
-rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, int n_groups,
-              const uint2* __restrict__ pool, const int* __restrict__ pool_cnt, int kc, int k,
-              int64_t idx_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
-  extern __shared__ __align__(16) uint8_t rr_smem[];
-  float* qs = reinterpret_cast<float*>(rr_smem);  // [D]
-  __shared__ int hist[256];
-  __shared__ int s_total, s_sel, s_eq_taken;
-  __shared__ uint32_t s_prefix;
-  __shared__ int s_remaining;
-  __shared__ double sel_score[kMaxCand];
-  __shared__ int sel_col[kMaxCand];
+// Shared state of the candidate selection (one CTA = one row).
+struct SelectSmem {
+  int hist[256];
+  int total, sel, eq_taken, remaining;
+  uint32_t prefix;
+  uint32_t min_key;               // smallest screen key among the selected
+  double sel_score[kMaxCand];
+  int sel_col[kMaxCand];
+};
 
-  const int row = blockIdx.x;
+// Pick the kc best screen scores among the row's pool entries (4 x 8-bit radix
+// select), leave their columns in sm.sel_col[0..n) and return n = min(total, kc).
+// sm.total = number of pool entries; sm.min_key = key of the worst selected one.
+__device__ __forceinline__ int select_pool_candidates(SelectSmem& sm, const uint2* __restrict__ rpool,
+                                                      const int* __restrict__ rcnt, int n_groups, int kc) {
   const int tid = threadIdx.x;
   const int slots = n_groups * kMaxCand;
-  const uint2* rpool = pool + static_cast<size_t>(row) * slots;
-  const int* rcnt = pool_cnt + static_cast<size_t>(row) * n_groups;
-
-  for (int i = tid; i < D / 4; i += kRerankThreads)
-    reinterpret_cast<float4*>(qs)[i] = __ldg(reinterpret_cast<const float4*>(q + static_cast<size_t>(row) * D) + i);
   if (tid == 0) {
     int t = 0;
     for (int g = 0; g < n_groups; ++g) t += rcnt[g];
-    s_total = t;
-    s_prefix = 0;
-    s_remaining = kc;
-    s_sel = 0;
-    s_eq_taken = 0;
+    sm.total = t;
+    sm.prefix = 0;
+    sm.remaining = kc;
+    sm.sel = 0;
+    sm.eq_taken = 0;
+    sm.min_key = 0xFFFFFFFFu;
   }
   __syncthreads();
-  const int total = s_total;
+  const int total = sm.total;
   const int want = min(total, kc);
 
-  // ---- 1. threshold key T: the want-th largest key (only needed if total > kc)
+  // threshold key T: the want-th largest key (only needed if total > kc)
   uint32_t T = 0;
   if (total > kc) {
     for (int pass = 0; pass < 4; ++pass) {
       const int shift = 24 - 8 * pass;
-      hist[tid] = 0;  // kRerankThreads == 256 bins
+      sm.hist[tid] = 0;  // kRerankThreads == 256 bins
       __syncthreads();
-      const uint32_t prefix = s_prefix;
+      const uint32_t prefix = sm.prefix;
       const uint32_t pmask = (pass == 0) ? 0u : (0xFFFFFFFFu << (shift + 8));
       for (int e = tid; e < slots; e += kRerankThreads) {
         if ((e & (kMaxCand - 1)) < rcnt[e / kMaxCand]) {
           const uint32_t key = f2key(rpool[e].x);
-          if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+          if ((key & pmask) == prefix) atomicAdd(&sm.hist[(key >> shift) & 255], 1);
         }
       }
       __syncthreads();
       if (tid == 0) {
-        int rem = s_remaining;  // how many still to take from keys matching the prefix
+        int rem = sm.remaining;  // how many still to take from keys matching the prefix
         int d = 255;
         for (; d > 0; --d) {
-          if (hist[d] >= rem) break;
-          rem -= hist[d];
+          if (sm.hist[d] >= rem) break;
+          rem -= sm.hist[d];
         }
-        s_prefix = prefix | (static_cast<uint32_t>(d) << shift);
-        s_remaining = rem;
+        sm.prefix = prefix | (static_cast<uint32_t>(d) << shift);
+        sm.remaining = rem;
       }
       __syncthreads();
     }
-    T = s_prefix;
+    T = sm.prefix;
   }
-  // after the 4 passes s_remaining = how many entries with key == T to take
-  const int quota_eq = (total > kc) ? s_remaining : 0x7FFFFFFF;
-
-  // ---- collect
+  // after the 4 passes sm.remaining = how many entries with key == T to take
+  const int quota_eq = (total > kc) ? sm.remaining : 0x7FFFFFFF;
   for (int e = tid; e < slots; e += kRerankThreads) {
     if ((e & (kMaxCand - 1)) < rcnt[e / kMaxCand]) {
       const uint2 ent = rpool[e];
       const uint32_t key = f2key(ent.x);
       bool take = key > T;
-      if (!take && key == T) take = atomicAdd(&s_eq_taken, 1) < quota_eq;
+      if (!take && key == T) take = atomicAdd(&sm.eq_taken, 1) < quota_eq;
       if (take) {
-        const int pos = atomicAdd(&s_sel, 1);
-        if (pos < kMaxCand) sel_col[pos] = static_cast<int>(ent.y);
+        const int pos = atomicAdd(&sm.sel, 1);
+        if (pos < kMaxCand) sm.sel_col[pos] = static_cast<int>(ent.y);
+        atomicMin(&sm.min_key, key);
       }
     }
   }
   __syncthreads();
-  const int n_sel = min(s_sel, want);
+  return min(sm.sel, want);
+}
 
-  // ---- 2. exact scores
-  const int warp = tid >> 5, lane = tid & 31;
+// Exact scores of the n selected rows of `db` against the query in qs (smem):
+// fp32 products accumulated in fp64, one warp per candidate, 16-byte loads.
+__device__ __forceinline__ void exact_scores(SelectSmem& sm, const float* qs,
+                                             const float* __restrict__ db, int D, int n_sel) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int c = warp; c < kMaxCand; c += kRerankThreads / 32) {
     if (c < n_sel) {
-      const float4* dr = reinterpret_cast<const float4*>(db + static_cast<size_t>(sel_col[c]) * D);
+      const float4* dr = reinterpret_cast<const float4*>(db + static_cast<size_t>(sm.sel_col[c]) * D);
       double acc = 0.0;
       for (int i = lane; i < D / 4; i += 32) {
         const float4 b = __ldg(dr + i);
@@ -185,13 +185,32 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, 
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) sel_score[c] = acc;
+      if (lane == 0) sm.sel_score[c] = acc;
     } else if (lane == 0) {
-      sel_score[c] = -INFINITY;
-      sel_col[c] = 0x7FFFFFFF;
+      sm.sel_score[c] = -INFINITY;
+      sm.sel_col[c] = 0x7FFFFFFF;
     }
   }
   __syncthreads();
+}
+
+__global__ void __launch_bounds__(kRerankThreads)
+rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, int n_groups,
+              const uint2* __restrict__ pool, const int* __restrict__ pool_cnt, int kc, int k,
+              int64_t idx_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+  extern __shared__ __align__(16) uint8_t rr_smem[];
+  float* qs = reinterpret_cast<float*>(rr_smem);  // [D]
+  __shared__ SelectSmem sm;
+  double* sel_score = sm.sel_score;
+  int* sel_col = sm.sel_col;
+
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < D / 4; i += kRerankThreads)
+    reinterpret_cast<float4*>(qs)[i] = __ldg(reinterpret_cast<const float4*>(q + static_cast<size_t>(row) * D) + i);
+  const int n_sel = select_pool_candidates(sm, pool + static_cast<size_t>(row) * n_groups * kMaxCand,
+                                           pool_cnt + static_cast<size_t>(row) * n_groups, n_groups, kc);
+  exact_scores(sm, qs, db, D, n_sel);
 
   // ---- 3. bitonic sort of 128 entries (first 128 threads)
   for (int size = 2; size <= kMaxCand; size <<= 1) {
@@ -216,6 +235,154 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, 
     const bool ok = j < n_sel;
     out_scores[static_cast<size_t>(row) * k + j] = ok ? static_cast<float>(sel_score[j]) : -INFINITY;
     out_idx[static_cast<size_t>(row) * k + j] = ok ? static_cast<int64_t>(sel_col[j]) + idx_offset : -1;
+  }
+}
+
+// ------------------------------------------------------------------ negative mining
+// Per-couple (semi-)hard negative of train/siamese_regions.py:106-129 without the
+// N x N matrix: rows of the screen GEMM are the couples' anchors, columns all
+// items; the streaming top-k epilogue masks same-label columns and (semi-hard)
+// scores >= sim_pos; the survivors are re-checked exactly.
+
+// dst[p, :] = src[rows[p], :]  (bf16 rows, 16-byte copies); row_label[p] = label[rows[p]]
+__global__ void gather_rows_kernel(const uint16_t* __restrict__ src, int64_t ld,
+                                   const int64_t* __restrict__ rows, uint16_t* __restrict__ dst,
+                                   const int* __restrict__ label, int* __restrict__ row_label) {
+  const int64_t p = blockIdx.x;
+  const int64_t r = rows[p];
+  const uint4* s4 = reinterpret_cast<const uint4*>(src + r * ld);
+  uint4* d4 = reinterpret_cast<uint4*>(dst + p * ld);
+  for (int64_t i = threadIdx.x; i < ld / 8; i += blockDim.x) d4[i] = __ldg(s4 + i);
+  if (threadIdx.x == 0) row_label[p] = label[r];
+}
+
+// exact dot of every (anchor, positive) couple: one warp per couple
+__global__ void pair_dot_kernel(const float* __restrict__ emb, int D, const int64_t* __restrict__ a,
+                                const int64_t* __restrict__ b, int64_t P, double* __restrict__ out64,
+                                float* __restrict__ out32) {
+  const int64_t p = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= P) return;
+  const float4* x = reinterpret_cast<const float4*>(emb + a[p] * D);
+  const float4* y = reinterpret_cast<const float4*>(emb + b[p] * D);
+  double acc = 0.0;
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 u = __ldg(x + i), v = __ldg(y + i);
+    acc = fma(static_cast<double>(u.x), static_cast<double>(v.x), acc);
+    acc = fma(static_cast<double>(u.y), static_cast<double>(v.y), acc);
+    acc = fma(static_cast<double>(u.z), static_cast<double>(v.z), acc);
+    acc = fma(static_cast<double>(u.w), static_cast<double>(v.w), acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) { out64[p] = acc; out32[p] = static_cast<float>(acc); }
+}
+
+// block-wide "best valid": larger score first, ties -> lower column
+__device__ __forceinline__ void block_best(double& s, int& c, double* red_s, int* red_c) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double os = __shfl_xor_sync(0xffffffffu, s, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, c, o);
+    if (os > s || (os == s && oc < c)) { s = os; c = oc; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red_s[warp] = s; red_c[warp] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kRerankThreads / 32; ++w)
+      if (red_s[w] > red_s[0] || (red_s[w] == red_s[0] && red_c[w] < red_c[0])) {
+        red_s[0] = red_s[w]; red_c[0] = red_c[w];
+      }
+  }
+  __syncthreads();
+  s = red_s[0];
+  c = red_c[0];
+}
+
+__global__ void __launch_bounds__(kRerankThreads)
+mining_rerank_kernel(const float* __restrict__ emb, int D, const int64_t* __restrict__ anchors,
+                     int n_groups, const uint2* __restrict__ pool, const int* __restrict__ pool_cnt,
+                     int kc, const double* __restrict__ pos64, int semi_hard, float screen_eps,
+                     int64_t* __restrict__ neg_idx, float* __restrict__ neg_sim, int* __restrict__ flag) {
+  extern __shared__ __align__(16) uint8_t rr_smem[];
+  float* qs = reinterpret_cast<float*>(rr_smem);
+  __shared__ SelectSmem sm;
+  __shared__ double red_s[kRerankThreads / 32];
+  __shared__ int red_c[kRerankThreads / 32];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const float* qrow = emb + anchors[row] * D;
+  for (int i = tid; i < D / 4; i += kRerankThreads)
+    reinterpret_cast<float4*>(qs)[i] = __ldg(reinterpret_cast<const float4*>(qrow) + i);
+  const int n_sel = select_pool_candidates(sm, pool + static_cast<size_t>(row) * n_groups * kMaxCand,
+                                           pool_cnt + static_cast<size_t>(row) * n_groups, n_groups, kc);
+  exact_scores(sm, qs, emb, D, n_sel);
+  // reference: excluded if S[i1, j] >= S[i1, i2]  (train/siamese_regions.py:111)
+  double s = -INFINITY;
+  int c = 0x7FFFFFFF;
+  if (tid < n_sel) {
+    const double v = sm.sel_score[tid];
+    if (!semi_hard || v < pos64[row]) { s = v; c = sm.sel_col[tid]; }
+  }
+  block_best(s, c, red_s, red_c);
+  if (tid == 0) {
+    const bool found = c != 0x7FFFFFFF;
+    // Certificate: every column NOT selected has a screen score <= the worst
+    // selected one, hence an exact score <= that + screen_eps.
+    bool certified = true;
+    if (sm.total > kc) {
+      const float t_min = __uint_as_float(key2f(sm.min_key));
+      certified = found && (static_cast<double>(t_min) + static_cast<double>(screen_eps) < s);
+    }
+    neg_idx[row] = found ? static_cast<int64_t>(c) : -1;
+    neg_sim[row] = found ? static_cast<float>(s) : -2.f;  // the reference's fill value (:124)
+    flag[row] = certified ? 0 : 1;
+  }
+}
+
+// Exhaustive exact pass for the (rare) rows the certificate rejected.
+__global__ void __launch_bounds__(kRerankThreads)
+mining_bruteforce_kernel(const float* __restrict__ emb, int N, int D, const int* __restrict__ label,
+                         const int64_t* __restrict__ anchors, const double* __restrict__ pos64,
+                         int semi_hard, const int* __restrict__ flag, int64_t* __restrict__ neg_idx,
+                         float* __restrict__ neg_sim, int* __restrict__ n_brute) {
+  const int row = blockIdx.x;
+  if (flag[row] == 0) return;
+  extern __shared__ __align__(16) uint8_t rr_smem[];
+  float* qs = reinterpret_cast<float*>(rr_smem);
+  __shared__ double red_s[kRerankThreads / 32];
+  __shared__ int red_c[kRerankThreads / 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t a = anchors[row];
+  for (int i = tid; i < D / 4; i += kRerankThreads)
+    reinterpret_cast<float4*>(qs)[i] = __ldg(reinterpret_cast<const float4*>(emb + a * D) + i);
+  __syncthreads();
+  const int lab = label[a];
+  const double ub = pos64[row];
+  double best = -INFINITY;
+  int best_c = 0x7FFFFFFF;
+  for (int j = warp; j < N; j += kRerankThreads / 32) {
+    if (label[j] == lab) continue;  // warp-uniform
+    const float4* dr = reinterpret_cast<const float4*>(emb + static_cast<size_t>(j) * D);
+    double acc = 0.0;
+    for (int i = lane; i < D / 4; i += 32) {
+      const float4 b = __ldg(dr + i);
+      const float4 q4 = reinterpret_cast<const float4*>(qs)[i];
+      acc = fma(static_cast<double>(q4.x), static_cast<double>(b.x), acc);
+      acc = fma(static_cast<double>(q4.y), static_cast<double>(b.y), acc);
+      acc = fma(static_cast<double>(q4.z), static_cast<double>(b.z), acc);
+      acc = fma(static_cast<double>(q4.w), static_cast<double>(b.w), acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((!semi_hard || acc < ub) && (acc > best || (acc == best && j < best_c))) { best = acc; best_c = j; }
+  }
+  block_best(best, best_c, red_s, red_c);
+  if (tid == 0) {
+    const bool found = best_c != 0x7FFFFFFF;
+    neg_idx[row] = found ? static_cast<int64_t>(best_c) : -1;
+    neg_sim[row] = found ? static_cast<float>(best) : -2.f;
+    if (n_brute != nullptr) atomicAdd(n_brute, 1);
   }
 }
 
@@ -483,6 +650,86 @@ extern "C" int isb_topk_merge(const float* cand_scores, const int64_t* cand_idx,
     ISB_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   topk_merge_kernel<<<static_cast<unsigned>(Q), 256, smem, static_cast<cudaStream_t>(stream)>>>(
       cand_scores, cand_idx, R, Q, k, n_pow2, out_scores, out_idx);
+  ISB_CUDA(cudaGetLastError());
+  return ISB_OK;
+}
+
+// ------------------------------------------------------------------ a13 entry point
+struct MiningPlan {
+  SearchPlan sp;
+  size_t off_row_label, off_pos64, off_pos32, off_flag, total;
+};
+
+static MiningPlan make_mining_plan(int64_t P, int64_t N, int64_t Kscr) {
+  MiningPlan m;
+  m.sp = make_search_plan(P, N, Kscr);
+  size_t off = m.sp.total;
+  m.off_row_label = off; off = align_up(off + static_cast<size_t>(P) * 4, 1024);
+  m.off_pos64 = off;     off = align_up(off + static_cast<size_t>(P) * 8, 1024);
+  m.off_pos32 = off;     off = align_up(off + static_cast<size_t>(P) * 4, 1024);
+  m.off_flag = off;      off = align_up(off + static_cast<size_t>(P) * 4, 1024);
+  m.total = off;
+  return m;
+}
+
+extern "C" size_t isb_select_negatives_workspace_bytes(int64_t P, int64_t N, int64_t Kscr) {
+  if (P <= 0 || N <= 0 || Kscr <= 0) return 0;
+  return make_mining_plan(P, N, Kscr).total + 1024;
+}
+
+extern "C" int isb_select_negatives(const float* emb, const uint16_t* emb_a, const uint16_t* emb_b,
+                                    int64_t Kscr, int64_t N, int64_t D, const int32_t* label,
+                                    const int64_t* anchors, const int64_t* positives, int64_t P,
+                                    int semi_hard, float screen_eps, int64_t* neg_idx, float* neg_sim,
+                                    float* pos_sim, int32_t* n_bruteforce, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  ISB_CHECK_ARG(emb && emb_a && emb_b && label && anchors && positives && neg_idx && neg_sim && pos_sim,
+                "isb_select_negatives: null pointer");
+  ISB_CHECK_ARG(P > 0 && N > 0 && D > 0 && N < (1ll << 31) && P < (1ll << 31), "isb_select_negatives: bad shape");
+  ISB_CHECK_ARG(D % 8 == 0 && Kscr % 8 == 0 && Kscr >= D, "isb_select_negatives: D and Kscr must be multiples of 8");
+  ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(emb) & 15) == 0 && (reinterpret_cast<uintptr_t>(emb_a) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(emb_b) & 15) == 0, "isb_select_negatives: inputs must be 16-byte aligned");
+  int rc = isb_check_device();
+  if (rc) return rc;
+  const MiningPlan mp = make_mining_plan(P, N, Kscr);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+  if (workspace == nullptr || ws + mp.total > static_cast<uint8_t*>(workspace) + workspace_bytes) {
+    set_error("isb_select_negatives: workspace too small (need %zu bytes, got %zu)", mp.total + 1024, workspace_bytes);
+    return ISB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint16_t* a_rows = reinterpret_cast<uint16_t*>(ws + mp.sp.off_qbf16);   // [P, Kscr]
+  int* row_label = reinterpret_cast<int*>(ws + mp.off_row_label);
+  double* pos64 = reinterpret_cast<double*>(ws + mp.off_pos64);
+  float* pos32 = reinterpret_cast<float*>(ws + mp.off_pos32);
+  int* flag = reinterpret_cast<int*>(ws + mp.off_flag);
+
+  gather_rows_kernel<<<static_cast<unsigned>(P), 128, 0, st>>>(emb_a, Kscr, anchors, a_rows, label, row_label);
+  ISB_CUDA(cudaGetLastError());
+  pair_dot_kernel<<<static_cast<unsigned>((P * 32 + 255) / 256), 256, 0, st>>>(emb, (int)D, anchors, positives, P, pos64, pos32);
+  ISB_CUDA(cudaGetLastError());
+  ISB_CUDA(cudaMemcpyAsync(pos_sim, pos32, static_cast<size_t>(P) * 4, cudaMemcpyDeviceToDevice, st));
+  if (n_bruteforce != nullptr) ISB_CUDA(cudaMemsetAsync(n_bruteforce, 0, 4, st));
+
+  int kc = kMaxCand;
+  if (kc > N) kc = static_cast<int>(N);
+  // semi-hard: columns scoring >= sim_pos (+ the screen's error bound) are masked in the epilogue
+  rc = launch_topk_screen(a_rows, Kscr, P, emb_b, Kscr, N, Kscr, kc, mp.sp, ws, label, row_label,
+                          semi_hard ? pos32 : nullptr, screen_eps, st);
+  if (rc) return rc;
+  const size_t smem = static_cast<size_t>(D) * 4;
+  ISB_CHECK_ARG(smem <= 160 * 1024, "isb_select_negatives: D too large");
+  if (smem > 48 * 1024) {
+    ISB_CUDA(cudaFuncSetAttribute(mining_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ISB_CUDA(cudaFuncSetAttribute(mining_bruteforce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  mining_rerank_kernel<<<static_cast<unsigned>(P), kRerankThreads, smem, st>>>(
+      emb, (int)D, anchors, mp.sp.n_groups, reinterpret_cast<const uint2*>(ws + mp.sp.off_pool),
+      reinterpret_cast<const int*>(ws + mp.sp.off_pool_cnt), kc, pos64, semi_hard, screen_eps, neg_idx,
+      neg_sim, flag);
+  ISB_CUDA(cudaGetLastError());
+  mining_bruteforce_kernel<<<static_cast<unsigned>(P), kRerankThreads, smem, st>>>(
+      emb, (int)N, (int)D, label, anchors, pos64, semi_hard, flag, neg_idx, neg_sim, n_bruteforce);
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;
 }

@@ -1,0 +1,112 @@
+"""All-pairs similarities and (semi-)hard negative selection on the GPU.
+
+Host-side mirror of utils/train_siamese.py:14-55 and the mining block of
+train/siamese_regions.py:106-129 (same code train/siamese_descriptor.py:108-131).
+"""
+
+import torch
+
+from . import _lib, ops
+from ._lib import IsbError
+
+SCREEN_EPS_3TERM = 2e-5   # absolute error bound of the [hi|lo|hi].[hi|hi|lo] screen, unit rows
+SCREEN_EPS_1TERM = 4e-3   # worst case 2^-8 for plain bf16 operands
+
+
+def label_ids(dataset):
+    """Dense int ids of the labels of a reference-style dataset (list of
+    (tensor, label, name) triples), in first-appearance order, + the label list."""
+    seen, ids = {}, []
+    for _, lab, _ in dataset:
+        ids.append(seen.setdefault(lab, len(seen)))
+    return torch.tensor(ids, dtype=torch.int32), list(seen.keys())
+
+
+def get_lab_indicators(dataset, device):
+    """{label: uint8 mask [N]} -- reference: utils/train_siamese.py:14-25.
+    device >= 0 -> current CUDA device, < 0 -> CPU (utils/general.py:94-98)."""
+    ids, labels = label_ids(dataset)
+    if device >= 0:
+        ids = ids.cuda()
+    return {lab: (ids == i).to(torch.uint8) for i, lab in enumerate(labels)}
+
+
+def embeddings_device_dim(P, net, n, sim_matrix=False):
+    """Placement rule of the reference -- utils/train_siamese.py:30-43."""
+    device = P.cuda_device
+    out_size = P.feature_dim
+    if hasattr(net, 'feature_size') and out_size <= 0:
+        out_size = net.feature_size
+    if n * out_size * 4 > P.embeddings_cuda_size:
+        device = -1
+    if sim_matrix and n * n * 4 > P.embeddings_cuda_size:
+        device = -1
+    return device, out_size
+
+
+def _terms(x, side, terms):
+    """bf16 screen operand of fp32 rows: side 'a' -> [hi|lo|hi], 'b' -> [hi|hi|lo]."""
+    hi = ops.to_bf16(x, 0)
+    if terms == 1:
+        return hi
+    lo = ops.to_bf16(x, 1)
+    return torch.cat([hi, lo, hi] if side == "a" else [hi, hi, lo], 1).contiguous()
+
+
+def all_pairs_similarities(emb, terms=3):
+    """S = E . E^T, fp32 [N, N] -- reference: utils/train_siamese.py:53
+    (also test/instance_avg.py:12).  terms=3: fp32-grade 3-product expansion."""
+    ops._need_cuda(emb)
+    emb = ops._f32c(emb)
+    return ops.gemm_nt(_terms(emb, "a", terms), _terms(emb, "b", terms))
+
+
+class MiningIndex(object):
+    """Embeddings of the reference set prepared for negative selection."""
+
+    def __init__(self, emb, labels, terms=3):
+        ops._need_cuda(emb)
+        emb = ops._f32c(emb)
+        self.N, self.dim = emb.shape
+        pad = (-self.dim) % 8
+        if pad:
+            emb = torch.nn.functional.pad(emb, (0, pad))
+        self.emb = emb.contiguous()
+        self.labels = labels.to(device=emb.device, dtype=torch.int32).contiguous()
+        if self.labels.numel() != self.N:
+            raise IsbError("one label id per embedding expected")
+        self.emb_a = _terms(self.emb, "a", terms)
+        self.emb_b = _terms(self.emb, "b", terms)
+        self.eps = SCREEN_EPS_3TERM if terms == 3 else SCREEN_EPS_1TERM
+        self.last_bruteforce = None
+
+    def select_negatives(self, anchors, positives, semi_hard):
+        """One negative per positive couple (anchors[p], positives[p]).
+
+        reference: train/siamese_regions.py:106-129.  Returns (neg_idx [P] int64,
+        -1 where every item is excluded -> caller draws a random negative as the
+        reference does; neg_sim [P]; pos_sim [P]).
+        """
+        dev = self.emb.device
+        anchors = torch.as_tensor(anchors, dtype=torch.int64, device=dev).contiguous()
+        positives = torch.as_tensor(positives, dtype=torch.int64, device=dev).contiguous()
+        P = anchors.numel()
+        neg_idx = torch.empty(P, dtype=torch.int64, device=dev)
+        neg_sim = torch.empty(P, dtype=torch.float32, device=dev)
+        pos_sim = torch.empty(P, dtype=torch.float32, device=dev)
+        if P == 0:
+            return neg_idx, neg_sim, pos_sim
+        nb = torch.zeros(1, dtype=torch.int32, device=dev)
+        L = _lib.lib()
+        Kscr = self.emb_a.size(1)
+        nbytes = L.isb_select_negatives_workspace_bytes(P, self.N, Kscr)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(L.isb_select_negatives(self.emb.data_ptr(), self.emb_a.data_ptr(),
+                                          self.emb_b.data_ptr(), Kscr, self.N, self.emb.size(1),
+                                          self.labels.data_ptr(), anchors.data_ptr(),
+                                          positives.data_ptr(), P, 1 if semi_hard else 0, self.eps,
+                                          neg_idx.data_ptr(), neg_sim.data_ptr(), pos_sim.data_ptr(),
+                                          nb.data_ptr(), ws.data_ptr(), nbytes, ops._stream()),
+                   "isb_select_negatives")
+        self.last_bruteforce = nb
+        return neg_idx, neg_sim, pos_sim
