@@ -126,22 +126,3 @@ def global_descriptors(x, hw):
                                                   desc.data_ptr(), ops._stream()),
                "isb_descriptor_finalize")
     return desc
-
-
-def smoke_check(dev):
-    """Used by __graft_entry__.smoke(): tiny region batch vs the oracle."""
-    import oracle  # smoke() is one of the places allowed to use the checker
-    g = torch.Generator().manual_seed(3)
-    C, ncls, D, k, fs = 32, 5, 16, 6, (7, 7)
-    x = torch.relu(torch.randn(4, C, 9, 12, generator=g))
-    cls_w = torch.randn(ncls, C, generator=g) / C ** 0.5
-    cls_b = 0.01 * torch.randn(ncls, generator=g)
-    shift = 0.01 * torch.randn(C * 49, generator=g)
-    lin_w = torch.randn(D, C * 49, generator=g) / (C * 49) ** 0.5
-    lin_b = 0.01 * torch.randn(D, generator=g)
-    hw = HeadWeights(cls_w.to(dev), cls_b.to(dev), shift.to(dev), lin_w.to(dev), lin_b.to(dev))
-    d, c, i, n = region_descriptors(x.to(dev), hw, k, fs)
-    od, oc, oi, on = oracle.region_descriptor_forward(x, cls_w, cls_b, shift, lin_w, lin_b, k, fs)
-    assert torch.equal(i.cpu(), oi), "smoke: selected windows differ from the oracle"
-    assert torch.allclose(c.cpu(), oc, rtol=1e-5, atol=1e-6), "smoke: cls_out differs"
-    assert torch.allclose(d.cpu(), od, rtol=0, atol=2e-5), "smoke: descriptors differ"

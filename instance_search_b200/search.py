@@ -146,8 +146,9 @@ class ShardedIndex(object):
         gs = torch.empty((self.world_size, Q, k), dtype=s.dtype, device=s.device)
         gi = torch.empty((self.world_size, Q, k), dtype=i.dtype, device=i.device)
         # the one exchange step of the path: k candidates per query per shard
-        dist.all_gather_into_tensor(gs, s.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(gi, i.contiguous(), group=self.group)
+        # (concatenated [R*Q, k] view: the layout both the NCCL and the gloo backend accept)
+        dist.all_gather_into_tensor(gs.view(-1, k), s.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(gi.view(-1, k), i.contiguous(), group=self.group)
         ms, mi = self._merge(gs, gi)
         kk = min(k, self.n_total)
         return ms[:, :kk], mi[:, :kk]

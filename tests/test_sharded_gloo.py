@@ -1,0 +1,100 @@
+"""CPU, world_size 2 and 3 over gloo: the host-side plumbing of the row-sharded
+search (shard bounds, global index offsets, padding of short shards, the ONE
+all-gather, merge order) -- SURVEY.md section 8e.  The GPU kernels are replaced
+through ShardedIndex's hooks by the oracle (local search) and a torch sort
+(merge), so what is exercised is exactly the code bench.py runs at N > 1 minus
+the kernels, which tests/test_gpu_core.py covers on the device."""
+
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_total, k, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    from instance_search_b200.search import ShardedIndex, shard_bounds
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(7)
+    db = oracle.normalize_l2(torch.randn(n_total, 32, generator=g))
+    q = oracle.normalize_l2(torch.randn(17, 32, generator=g))
+
+    class HostShard(object):
+        def __init__(self, rows, off):
+            self.rows, self.off = rows, off
+
+    class CpuSharded(ShardedIndex):
+        def _make_local(self, local_db, row_offset):
+            return HostShard(local_db, row_offset)
+
+        def _local_search(self, q, k, events=None):
+            s, i = oracle.topk_search(q, self.local.rows, k)
+            return s, i + self.local.off
+
+        def _merge(self, cs, ci):
+            # same contract as isb_topk_merge: best first, ties -> lower index, idx < 0 last
+            R, Q, kk = cs.shape
+            s = cs.permute(1, 0, 2).reshape(Q, R * kk).clone()
+            i = ci.permute(1, 0, 2).reshape(Q, R * kk)
+            s[i < 0] = float("-inf")
+            key = i.clone()
+            key[i < 0] = torch.iinfo(torch.int64).max
+            o1 = key.argsort(dim=1, stable=True)
+            s1, i1 = s.gather(1, o1), i.gather(1, o1)
+            o2 = s1.argsort(dim=1, descending=True, stable=True)
+            return s1.gather(1, o2)[:, :kk], i1.gather(1, o2)[:, :kk]
+
+    lo, hi = shard_bounds(n_total, world)[rank]
+    index = CpuSharded(db[lo:hi], n_total, rank, world)
+    s, i = index.search(q, k)
+    want_s, want_i = oracle.topk_search(q, db, k)
+    ok = torch.equal(i, want_i) and torch.equal(s, want_s)
+    # every rank holds the full merged answer
+    flags = [torch.zeros(1) for _ in range(world)]
+    dist.all_gather(flags, torch.tensor([1.0 if ok else 0.0]))
+    with open(os.path.join(out_dir, "rank%d" % rank), "w") as f:
+        f.write("ok" if ok and all(float(x) == 1.0 for x in flags) else
+                "mismatch %s vs %s" % (i[0].tolist(), want_i[0].tolist()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_total,k", [
+    (2, 1001, 10),     # uneven split
+    (2, 12, 10),       # shards (6 rows) smaller than k: padded with invalid entries
+    (3, 500, 25),
+])
+def test_sharded_search_plumbing(tmp_path, world, n_total, k):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_total, k, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert (tmp_path / ("rank%d" % r)).read_text() == "ok"
+
+
+def test_shard_bounds():
+    from instance_search_b200.search import shard_bounds
+    for n, w in [(10, 1), (10, 3), (1000000, 8), (5, 8), (0, 2)]:
+        b = shard_bounds(n, w)
+        assert len(b) == w and b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 1
