@@ -35,7 +35,7 @@ extern "C" {
 #define ISB_ERR_WORKSPACE 3
 #define ISB_ERR_UNSUPPORTED_DEVICE 4
 
-#define ISB_ABI_VERSION 1
+#define ISB_ABI_VERSION 2
 
 /* Largest k (after the screening margin is added) one search call supports. */
 #define ISB_MAX_CANDIDATES 128
@@ -76,16 +76,27 @@ int isb_f32_to_bf16(const float* x, int64_t rows, int64_t cols, int64_t ldx, uin
  *            filter fused into the TMEM epilogue        (db_bf16, ld_bf16)
  *   stage 2  exact re-rank of the k+margin candidates: dot products of the
  *            fp32 rows accumulated in fp64, sorted, ties -> lower index
+ *   stage 2b completeness certificate per query: every database row outside the
+ *            candidate list has a screen score <= t_min (the worst candidate's),
+ *            so the list provably contains the true top k when
+ *               exact_kth - t_min  >  8 * sigma + 4e-7 * |score|
+ *            with sigma = rms(screen - exact) MEASURED on the row's own
+ *            candidates.  Rows that fail are appended to uncertified_rows and
+ *            counted in *n_uncertified (both device memory, may both be NULL to
+ *            skip the test); the caller resolves them with isb_topk_resolve and,
+ *            if still uncertified, isb_topk_exhaustive.
  *
  * q        [Q, D] fp32           db_f32  [N, D] fp32
  * db_bf16  [N, ld_bf16] bf16 made by isb_f32_to_bf16(part 0), ld_bf16 >= D, %8 == 0
  * k + margin <= ISB_MAX_CANDIDATES;  k <= N;  N < 2^31
  * idx_offset is added to every returned index (row offset of a database shard)
- * out_scores [Q, k] fp32 (the fp64 dot rounded to fp32), out_idx [Q, k] int64 */
+ * out_scores [Q, k] fp32 (the fp64 dot rounded to fp32), out_idx [Q, k] int64
+ * uncertified_rows [Q] int32 (order unspecified), n_uncertified [1] int32 */
 size_t isb_topk_search_workspace_bytes(int64_t Q, int64_t N, int64_t D, int k, int margin);
 int isb_topk_search(const float* q, int64_t Q, const float* db_f32, const uint16_t* db_bf16,
                     int64_t N, int64_t D, int64_t ld_bf16, int k, int margin,
-                    int64_t idx_offset, float* out_scores, int64_t* out_idx, void* workspace,
+                    int64_t idx_offset, float* out_scores, int64_t* out_idx,
+                    int32_t* uncertified_rows, int32_t* n_uncertified, void* workspace,
                     size_t workspace_bytes, void* stream);
 
 /* The two stages of isb_topk_search as separate calls sharing one workspace
@@ -97,7 +108,32 @@ int isb_topk_screen(const float* q, int64_t Q, const uint16_t* db_bf16, int64_t 
                     void* stream);
 int isb_topk_rerank(const float* q, int64_t Q, const float* db_f32, int64_t N, int64_t D, int k,
                     int margin, int64_t idx_offset, float* out_scores, int64_t* out_idx,
-                    void* workspace, size_t workspace_bytes, void* stream);
+                    int32_t* uncertified_rows, int32_t* n_uncertified, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* Second line for the rows a bf16 screen could not certify (near-duplicate-dense
+ * neighbourhoods): the same screen with fp32-grade split operands
+ *   score = q_hi.db_hi + q_lo.db_hi + q_hi.db_lo      (three bf16 tcgen05 products,
+ * error ~1e-6 on unit rows), exact re-rank and the same certificate.  Results of
+ * the listed rows are (re)written to out_scores / out_idx [Q, k] at their own row;
+ * rows still uncertified are listed in uncertified_rows / n_uncertified.
+ *   rows [n_rows] int32 device: query rows to resolve (from isb_topk_search)
+ *   db_lo_bf16 = isb_f32_to_bf16(db_f32, part 1), same leading dimension as db_bf16 */
+size_t isb_topk_resolve_workspace_bytes(int64_t n_rows, int64_t N, int64_t D);
+int isb_topk_resolve(const float* q, const float* db_f32, const uint16_t* db_bf16,
+                     const uint16_t* db_lo_bf16, int64_t N, int64_t D, int64_t ld_bf16, int k,
+                     int margin, int64_t idx_offset, const int32_t* rows, int64_t n_rows,
+                     float* out_scores, int64_t* out_idx, int32_t* uncertified_rows,
+                     int32_t* n_uncertified, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Last line: exhaustive exact (fp64-accumulated) scoring of the whole database
+ * for the listed rows -- what torch.mm + sort does, ties -> lower index.  Needed
+ * only when more than `margin` database rows tie with the k-th score within fp32
+ * noise (e.g. duplicated database entries). */
+size_t isb_topk_exhaustive_workspace_bytes(int64_t n_rows, int64_t N, int k);
+int isb_topk_exhaustive(const float* q, const float* db_f32, int64_t N, int64_t D, int k,
+                        int64_t idx_offset, const int32_t* rows, int64_t n_rows, float* out_scores,
+                        int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- (e) multi-GPU
  * Merge R per-shard results (after the all-gather): cand_scores [R, Q, k],
@@ -115,12 +151,18 @@ int isb_topk_merge(const float* cand_scores, const int64_t* cand_idx, int R, int
  * Used for: all-pairs similarities  torch.mm(E, E.t())  utils/train_siamese.py:53,
  * test/instance_avg.py:12;  the whitening projection  nn.Linear(100352, D)
  * model/siamese.py:180;  the 1x1-conv window classifier  model/siamese.py:188.
- * An fp32-grade result is obtained by concatenating the bf16 terms of
- * isb_f32_to_bf16 along K:  [A_hi|A_lo|A_hi] . [B_hi|B_hi|B_lo]^T. */
+ * isb_gemm_nt_split: fp32-grade product of two fp32 matrices given as split
+ * operands (isb_f32_to_bf16 parts 0 and 1, same leading dimension per side):
+ *   C = A_hi.B_hi^T + A_lo.B_hi^T + A_hi.B_lo^T   accumulated in ONE TMEM tile
+ * (the TMA producer switches tensor maps per term; nothing is K-concatenated). */
 size_t isb_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K, int splits);
 int isb_gemm_nt(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, int64_t M,
                 int64_t N, int64_t K, const float* bias, float* C, int64_t ldc, int splits,
                 void* workspace, size_t workspace_bytes, void* stream);
+int isb_gemm_nt_split(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda, const uint16_t* B_hi,
+                      const uint16_t* B_lo, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                      const float* bias, float* C, int64_t ldc, int splits, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- a3
  * Window scoring + selection of RegionDescriptorNet.forward_single,
@@ -151,18 +193,18 @@ int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H, int64_t W
  * where crop_i = x[b, :, r_i : r_i + fh, c_i : c_i + fw] flattened (C, fh, fw)
  * -- NormalizeL2 + Shift of every selected region (model/siamese.py:218-219 via
  * :178-179), summed BEFORE the projection (nn.Linear is linear; the reference
- * sums after it, :220).  Written as bf16 terms for the tensor-core projection:
- *   terms == 1: U[b] = [u_hi]            terms == 3: U[b] = [u_hi | u_lo | u_hi]
- * (pair with W' = [W_hi] resp. [W_hi | W_hi | W_lo], see isb_gemm_nt).
- * Each term occupies Kp = C*fh*fw rounded up to 8 columns (zero padded);
- * ldu >= terms * Kp, % 8 == 0. */
+ * sums after it, :220).  Written as the tensor-core operand of the projection:
+ *   U_hi[b] = bf16(u)      U_lo[b] = bf16(u - U_hi)   (U_lo may be NULL)
+ * U_hi alone pairs with isb_gemm_nt (plain bf16 projection); U_hi + U_lo pair
+ * with isb_gemm_nt_split (fp32-grade).  Rows hold C*fh*fw values zero padded to a
+ * multiple of 8; ldu >= that, % 8 == 0. */
 int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int fh, int fw,
                       int k, const int64_t* idx, const int32_t* nsel, const float* win_norm,
-                      const float* shift, int terms, uint16_t* U, int64_t ldu, void* stream);
+                      const float* shift, uint16_t* U_hi, uint16_t* U_lo, int64_t ldu, void* stream);
 
 /* ---------------------------------------------------------------- a4 (bias) + a5
  * desc[b, :] = l2norm(y[b, :] + nsel[b] * bias)     (model/siamese.py:220-222)
- * y = U . W'^T from isb_gemm_nt.  nsel == NULL means 1 (DescriptorNet, :117-122);
+ * y = U . W^T from isb_gemm_nt / isb_gemm_nt_split.  nsel == NULL means 1 (DescriptorNet, :117-122);
  * bias may be NULL. */
 int isb_descriptor_finalize(const float* y, int64_t B, int64_t D, const float* bias,
                             const int32_t* nsel, float eps, float* desc, void* stream);
@@ -180,14 +222,14 @@ int isb_descriptor_finalize(const float* y, int64_t B, int64_t D, const float* b
  * (fp64 accumulation) and the exact conditions re-applied; a couple whose
  * candidate list cannot be certified complete falls to an exhaustive exact pass
  * (counted in *n_bruteforce when non-NULL).
- *   emb [N, D] fp32 (unit rows); emb_a / emb_b [N, Kscr] bf16: the A-side / B-side
- *   screen operands -- [hi] / [hi] (Kscr = D) or the fp32-grade
- *   [hi|lo|hi] / [hi|hi|lo] (Kscr = 3 D), built with isb_f32_to_bf16;
- *   screen_eps: absolute error bound of the screen scores (2e-5 for the 3-term form)
+ *   emb [N, D] fp32 (unit rows); emb_hi / emb_lo [N, ld] bf16 = isb_f32_to_bf16 parts
+ *   0 / 1 of emb: the split operands of the fp32-grade screen
+ *   (a_hi.b_hi + a_lo.b_hi + a_hi.b_lo).  emb_lo == NULL: plain bf16 screen.
+ *   screen_eps: absolute error bound of the screen scores (2e-5 split, 4e-3 plain)
  *   label [N] int32; anchors, positives [P] int64
  *   neg_idx [P] int64; neg_sim [P] fp32 (-2 when none); pos_sim [P] fp32 */
-size_t isb_select_negatives_workspace_bytes(int64_t P, int64_t N, int64_t Kscr);
-int isb_select_negatives(const float* emb, const uint16_t* emb_a, const uint16_t* emb_b, int64_t Kscr,
+size_t isb_select_negatives_workspace_bytes(int64_t P, int64_t N, int64_t D, int split);
+int isb_select_negatives(const float* emb, const uint16_t* emb_hi, const uint16_t* emb_lo, int64_t ld,
                          int64_t N, int64_t D, const int32_t* label, const int64_t* anchors,
                          const int64_t* positives, int64_t P, int semi_hard, float screen_eps,
                          int64_t* neg_idx, float* neg_sim, float* pos_sim, int32_t* n_bruteforce,

@@ -16,6 +16,8 @@ c_f32 = ctypes.c_float
 c_ptr = ctypes.c_void_p
 c_size = ctypes.c_size_t
 
+ABI_VERSION = 2   # == ISB_ABI_VERSION in include/isb.h
+
 # name -> (restype, argtypes); mirrors include/isb.h one to one
 SIGNATURES = {
     "isb_abi_version": (c_int, []),
@@ -26,11 +28,17 @@ SIGNATURES = {
     "isb_f32_to_bf16": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_int, c_ptr]),
     "isb_topk_search_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_int, c_int]),
     "isb_topk_search": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_int,
-                                c_i64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+                                c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    "isb_topk_resolve_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
+    "isb_topk_resolve": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_int, c_i64,
+                                 c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    "isb_topk_exhaustive_workspace_bytes": (c_size, [c_i64, c_i64, c_int]),
+    "isb_topk_exhaustive": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_i64, c_ptr, c_i64, c_ptr,
+                                    c_ptr, c_ptr, c_size, c_ptr]),
     "isb_topk_screen": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_int, c_int, c_ptr, c_size,
                                 c_ptr]),
     "isb_topk_rerank": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_ptr, c_ptr,
-                                c_ptr, c_size, c_ptr]),
+                                c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     "isb_topk_merge": (c_int, [c_ptr, c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
     "isb_region_select_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int,
                                                   c_int, c_int]),
@@ -38,14 +46,16 @@ SIGNATURES = {
                                   c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size,
                                   c_ptr]),
     "isb_region_gather": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_ptr, c_ptr,
-                                  c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
+                                  c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "isb_descriptor_finalize": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_f32, c_ptr, c_ptr]),
-    "isb_select_negatives_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
+    "isb_select_negatives_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_int]),
     "isb_select_negatives": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64,
                                      c_int, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     "isb_gemm_nt_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_int]),
     "isb_gemm_nt": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64,
                             c_int, c_ptr, c_size, c_ptr]),
+    "isb_gemm_nt_split": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr,
+                                  c_ptr, c_i64, c_int, c_ptr, c_size, c_ptr]),
 }
 
 
@@ -71,7 +81,7 @@ def lib():
         fn = getattr(l, name)  # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if l.isb_abi_version() != 1:
+    if l.isb_abi_version() != ABI_VERSION:
         raise IsbError("libisb.so ABI version mismatch")
     _lib = l
     return l

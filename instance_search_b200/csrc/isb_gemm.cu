@@ -120,32 +120,45 @@ extern "C" size_t isb_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K, i
   return align_up(static_cast<size_t>(splits) * M * ldp * 4, 1024);
 }
 
-extern "C" int isb_gemm_nt(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, int64_t M,
-                           int64_t N, int64_t K, const float* bias, float* C, int64_t ldc, int splits,
-                           void* workspace, size_t workspace_bytes, void* stream) {
-  ISB_CHECK_ARG(A && B && C, "isb_gemm_nt: null pointer");
-  ISB_CHECK_ARG(M > 0 && N > 0 && K > 0, "isb_gemm_nt: empty problem");
-  ISB_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "isb_gemm_nt: dimension >= 2^31");
-  ISB_CHECK_ARG(lda >= K && ldb >= K && lda % 8 == 0 && ldb % 8 == 0, "isb_gemm_nt: lda/ldb must be >= K and multiples of 8");
-  ISB_CHECK_ARG(ldc >= N, "isb_gemm_nt: ldc < N");
+static int gemm_nt_impl(const char* fn, const uint16_t* A, const uint16_t* A_lo, int64_t lda,
+                        const uint16_t* B, const uint16_t* B_lo, int64_t ldb, int64_t M, int64_t N,
+                        int64_t K, const float* bias, float* C, int64_t ldc, int splits, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  ISB_CHECK_ARG(A && B && C, "%s: null pointer", fn);
+  ISB_CHECK_ARG((A_lo == nullptr) == (B_lo == nullptr), "%s: A_lo and B_lo go together", fn);
+  ISB_CHECK_ARG(M > 0 && N > 0 && K > 0, "%s: empty problem", fn);
+  ISB_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 29), "%s: dimension too large", fn);
+  ISB_CHECK_ARG(lda >= K && ldb >= K && lda % 8 == 0 && ldb % 8 == 0,
+                "%s: lda/ldb must be >= K and multiples of 8", fn);
+  ISB_CHECK_ARG(ldc >= N, "%s: ldc < N", fn);
   int rc = isb_check_device();
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool split_ops = A_lo != nullptr;
   const int m_blocks = static_cast<int>((M + kBM - 1) / kBM);
   const int n_tiles = static_cast<int>((N + kBN - 1) / kBN);
-  const int k_blocks = static_cast<int>((K + kBK - 1) / kBK);
+  const int kb_term = static_cast<int>((K + kBK - 1) / kBK);
+  const int k_blocks = split_ops ? 3 * kb_term : kb_term;
   if (splits < 1) splits = 1;
   if (splits > k_blocks) splits = k_blocks;
   const size_t need = isb_gemm_nt_workspace_bytes(M, N, K, splits);
   if (splits > 1 && (workspace == nullptr || workspace_bytes < need)) {
-    set_error("isb_gemm_nt: workspace too small (need %zu bytes, got %zu)", need, workspace_bytes);
+    set_error("%s: workspace too small (need %zu bytes, got %zu)", fn, need, workspace_bytes);
     return ISB_ERR_WORKSPACE;
   }
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, ta_lo, tb_lo;
   rc = make_tmap_bf16_k64(&ta, A, M, K, lda, kBM);
   if (rc) return rc;
   rc = make_tmap_bf16_k64(&tb, B, N, K, ldb, kBN);
   if (rc) return rc;
+  ta_lo = ta;
+  tb_lo = tb;
+  if (split_ops) {
+    rc = make_tmap_bf16_k64(&ta_lo, A_lo, M, K, lda, kBM);
+    if (rc) return rc;
+    rc = make_tmap_bf16_k64(&tb_lo, B_lo, N, K, ldb, kBN);
+    if (rc) return rc;
+  }
 
   PlainSched sched{m_blocks, n_tiles, k_blocks, splits};
   StoreEpiParams ep;
@@ -170,7 +183,8 @@ extern "C" int isb_gemm_nt(const uint16_t* A, int64_t lda, const uint16_t* B, in
   const int grid = static_cast<int>(segs < sms ? segs : sms);
   auto kern = gemm_tc_kernel<PlainSched, StoreEpilogue>;
   ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
-  kern<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, sched, ep);
+  kern<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, ta_lo, tb_lo, split_ops ? kb_term : kSingleTerm,
+                                                   sched, ep);
   ISB_CUDA(cudaGetLastError());
   if (splits > 1) {
     const long long total = static_cast<long long>(M) * N;
@@ -180,4 +194,20 @@ extern "C" int isb_gemm_nt(const uint16_t* A, int64_t lda, const uint16_t* B, in
     ISB_CUDA(cudaGetLastError());
   }
   return ISB_OK;
+}
+
+extern "C" int isb_gemm_nt(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, int64_t M,
+                           int64_t N, int64_t K, const float* bias, float* C, int64_t ldc, int splits,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  return gemm_nt_impl("isb_gemm_nt", A, nullptr, lda, B, nullptr, ldb, M, N, K, bias, C, ldc, splits,
+                      workspace, workspace_bytes, stream);
+}
+
+extern "C" int isb_gemm_nt_split(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda,
+                                 const uint16_t* B_hi, const uint16_t* B_lo, int64_t ldb, int64_t M,
+                                 int64_t N, int64_t K, const float* bias, float* C, int64_t ldc,
+                                 int splits, void* workspace, size_t workspace_bytes, void* stream) {
+  ISB_CHECK_ARG(A_lo && B_lo, "isb_gemm_nt_split: null pointer");
+  return gemm_nt_impl("isb_gemm_nt_split", A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, bias, C, ldc,
+                      splits, workspace, workspace_bytes, stream);
 }

@@ -26,6 +26,7 @@ constexpr int kUmmaK = 16;    // K of one tcgen05.mma kind::f16
 constexpr int kGemmThreads = 192;
 constexpr int kEpiWarp0 = 2;  // first epilogue warp
 constexpr uint32_t kTmemCols = 512;
+constexpr int kSingleTerm = 0x7FFFFFFF;  // kb_per_term of a plain (one bf16 term) GEMM
 
 constexpr uint32_t kABytes = kBM * kBK * 2;                       // 16 KB
 constexpr uint32_t kBBytes = kBN * kBK * 2;                       // 32 KB
@@ -58,9 +59,18 @@ struct GemmSmem {
 //        tcgen05.ld, then tcgen05.fence::before + arrive on tmem_empty_bar
 //        (every epilogue thread arrives once per tile).
 //   void end_segment(const Segment&)
+//
+// Split operands: an fp32-grade product of fp32 matrices is the sum of three bf16
+// products  A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  (isb_f32_to_bf16 parts 0 / 1).  The
+// k-block index of a segment then runs over 3 * kb_per_term blocks and the
+// producer switches tensor maps per term -- term 1 reads A from tmap_a_lo, term 2
+// reads B from tmap_b_lo -- so neither operand is ever stored K-concatenated.
+// Single-term callers pass kb_per_term = INT_MAX (and any valid maps for *_lo).
 template <class Sched, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_a_lo,
+               const __grid_constant__ CUtensorMap tmap_b_lo, const int kb_per_term,
                const Sched sched, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -74,6 +84,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
     ptx::prefetch_tensormap(&tmap_b);
+    if (kb_per_term != kSingleTerm) {
+      ptx::prefetch_tensormap(&tmap_a_lo);
+      ptx::prefetch_tensormap(&tmap_b_lo);
+    }
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&bars->full[s], 1);
       ptx::mbar_init(&bars->empty[s], 1);
@@ -105,10 +119,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint8_t* sa = ring + stage * kStageBytes;
             uint8_t* sb = sa + kABytes;
             ptx::mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
+            const int term = kb / kb_per_term;          // 0 unless split operands
+            const int kk = kb - term * kb_per_term;
+            const CUtensorMap* ma = (term == 1) ? &tmap_a_lo : &tmap_a;
+            const CUtensorMap* mb = (term == 2) ? &tmap_b_lo : &tmap_b;
             // A (queries / activations) is re-read for every n-tile: keep it in L2.
-            ptx::tma_load_2d(sa, &tmap_a, &bars->full[stage], kb * kBK, seg.m_block * kBM,
+            ptx::tma_load_2d(sa, ma, &bars->full[stage], kk * kBK, seg.m_block * kBM,
                              ptx::kEvictLast);
-            ptx::tma_load_2d(sb, &tmap_b, &bars->full[stage], kb * kBK, nt * kBN,
+            ptx::tma_load_2d(sb, mb, &bars->full[stage], kk * kBK, nt * kBN,
                              ptx::kEvictNormal);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }

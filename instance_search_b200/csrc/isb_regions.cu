@@ -11,8 +11,8 @@
 //                               cls_out (:216), ||crop||_2 of the chosen windows
 //   4. region_gather_kernel     u[b] = sum_i crop_i / ||crop_i|| + nsel * shift
 //                               (NormalizeL2 + Shift, :218-219, summed BEFORE the
-//                               projection -- the Linear is linear) -> bf16 terms
-//   5. isb_gemm_nt              u . W^T   (nn.Linear(100352, D), :180)
+//                               projection -- the Linear is linear) -> bf16 hi (+ lo)
+//   5. isb_gemm_nt[_split]      u . W^T   (nn.Linear(100352, D), :180)
 //   6. descriptor_finalize      desc = l2norm(y + nsel * bias)   (:220-222)
 #include "isb_host.cuh"
 #include "isb_gemm_core.cuh"
@@ -338,8 +338,8 @@ region_select_kernel(const float* __restrict__ x, int C, int H, int W, int fh, i
 __global__ void __launch_bounds__(256)
 region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh, int fw, int k,
                      const int64_t* __restrict__ idx, const int* __restrict__ nsel_in,
-                     const float* __restrict__ win_norm, const float* __restrict__ shift, int terms,
-                     uint16_t* __restrict__ U, int64_t ldu) {
+                     const float* __restrict__ win_norm, const float* __restrict__ shift,
+                     uint16_t* __restrict__ U_hi, uint16_t* __restrict__ U_lo, int64_t ldu) {
   __shared__ int s_off[kSelMaxCand];
   __shared__ float s_norm[kSelMaxCand];
   const int b = blockIdx.y;
@@ -353,7 +353,7 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh, i
     s_norm[threadIdx.x] = win_norm[static_cast<size_t>(b) * k + threadIdx.x];
   }
   __syncthreads();
-  const int KinP = (Kin + 7) & ~7;  // terms are laid out KinP apart (zero padded)
+  const int KinP = (Kin + 7) & ~7;  // rows are zero padded to 8 columns
   const int e0 = (blockIdx.x * 256 + threadIdx.x) * 8;
   if (e0 >= KinP) return;
   const float* xb = x + static_cast<size_t>(b) * C * HW;
@@ -377,12 +377,9 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh, i
   vh.z = hi[4] | (uint32_t(hi[5]) << 16); vh.w = hi[6] | (uint32_t(hi[7]) << 16);
   vl.x = lo[0] | (uint32_t(lo[1]) << 16); vl.y = lo[2] | (uint32_t(lo[3]) << 16);
   vl.z = lo[4] | (uint32_t(lo[5]) << 16); vl.w = lo[6] | (uint32_t(lo[7]) << 16);
-  uint16_t* row = U + static_cast<size_t>(b) * ldu;
-  *reinterpret_cast<uint4*>(row + e0) = vh;
-  if (terms == 3) {  // K-concatenation [hi | lo | hi] against W' = [hi | hi | lo]
-    *reinterpret_cast<uint4*>(row + KinP + e0) = vl;
-    *reinterpret_cast<uint4*>(row + 2 * static_cast<size_t>(KinP) + e0) = vh;
-  }
+  *reinterpret_cast<uint4*>(U_hi + static_cast<size_t>(b) * ldu + e0) = vh;
+  if (U_lo != nullptr)  // split operand for the fp32-grade projection (isb_gemm_nt_split)
+    *reinterpret_cast<uint4*>(U_lo + static_cast<size_t>(b) * ldu + e0) = vl;
 }
 
 // ------------------------------------------------------------------ 6. finalize
@@ -506,7 +503,7 @@ extern "C" int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H
   auto kern = gemm_tc_kernel<RowSched, RowMaxEpilogue>;
   ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
   const int sms = device_sm_count();
-  kern<<<sched.m_blocks < sms ? sched.m_blocks : sms, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, sched, ep);
+  kern<<<sched.m_blocks < sms ? sched.m_blocks : sms, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, ta, tb, kSingleTerm, sched, ep);
   ISB_CUDA(cudaGetLastError());
 
   ISB_CUDA(cudaFuncSetAttribute(region_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.sel_smem));
@@ -519,20 +516,19 @@ extern "C" int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H
 
 extern "C" int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int fh,
                                  int fw, int k, const int64_t* idx, const int32_t* nsel,
-                                 const float* win_norm, const float* shift, int terms, uint16_t* U,
-                                 int64_t ldu, void* stream) {
-  ISB_CHECK_ARG(x && idx && nsel && win_norm && shift && U, "isb_region_gather: null pointer");
+                                 const float* win_norm, const float* shift, uint16_t* U_hi,
+                                 uint16_t* U_lo, int64_t ldu, void* stream) {
+  ISB_CHECK_ARG(x && idx && nsel && win_norm && shift && U_hi, "isb_region_gather: null pointer");
   ISB_CHECK_ARG(B > 0 && C > 0 && fh > 0 && fw > 0 && H >= fh && W >= fw, "isb_region_gather: bad shape");
   ISB_CHECK_ARG(k >= 1 && k <= kSelMaxCand, "isb_region_gather: need 1 <= k <= %d", kSelMaxCand);
-  ISB_CHECK_ARG(terms == 1 || terms == 3, "isb_region_gather: terms must be 1 or 3");
   const int64_t Kin = C * fh * fw;
   const int64_t KinP = (Kin + 7) / 8 * 8;
   ISB_CHECK_ARG(Kin < (1ll << 30), "isb_region_gather: C*fh*fw too large");
-  ISB_CHECK_ARG(ldu >= KinP * terms && ldu % 8 == 0 && (reinterpret_cast<uintptr_t>(U) & 15) == 0,
-                "isb_region_gather: bad ldu / alignment");
+  ISB_CHECK_ARG(ldu >= KinP && ldu % 8 == 0 && (reinterpret_cast<uintptr_t>(U_hi) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(U_lo) & 15) == 0, "isb_region_gather: bad ldu / alignment");
   dim3 grid(static_cast<unsigned>((KinP / 8 + 255) / 256), static_cast<unsigned>(B));
   region_gather_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, (int)C, (int)H, (int)W, fh, fw, k, idx, nsel, win_norm, shift, terms, U, ldu);
+      x, (int)C, (int)H, (int)W, fh, fw, k, idx, nsel, win_norm, shift, U_hi, U_lo, ldu);
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;
 }

@@ -76,6 +76,7 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ x, int64_t rows, in
 //      fp64 (one warp per candidate, 16-byte loads);
 //   3. bitonic sort by (score desc, index asc); write the first k.
 constexpr int kRerankThreads = 256;
+constexpr float kCertZ = 8.f;   // certificate: the k-th exact score must clear t_min by kCertZ sigma
 
 struct SortEntry {
   double score;
@@ -94,6 +95,7 @@ struct SelectSmem {
   uint32_t min_key;               // smallest screen key among the selected
   double sel_score[kMaxCand];
   int sel_col[kMaxCand];
+  float sel_screen[kMaxCand];     // screen score of each selected candidate
 };
 
 // Pick the kc best screen scores among the row's pool entries (4 x 8-bit radix
@@ -157,7 +159,10 @@ __device__ __forceinline__ int select_pool_candidates(SelectSmem& sm, const uint
       if (!take && key == T) take = atomicAdd(&sm.eq_taken, 1) < quota_eq;
       if (take) {
         const int pos = atomicAdd(&sm.sel, 1);
-        if (pos < kMaxCand) sm.sel_col[pos] = static_cast<int>(ent.y);
+        if (pos < kMaxCand) {
+          sm.sel_col[pos] = static_cast<int>(ent.y);
+          sm.sel_screen[pos] = __uint_as_float(ent.x);
+        }
         atomicMin(&sm.min_key, key);
       }
     }
@@ -194,23 +199,60 @@ __device__ __forceinline__ void exact_scores(SelectSmem& sm, const float* qs,
   __syncthreads();
 }
 
+// Completeness certificate of a screened row.  Every database row that is NOT
+// among the selected candidates has a screen score <= t_min (the worst selected
+// one): the streaming filter only ever drops a score that is <= the kc-th best
+// seen so far.  Its exact score is therefore <= t_min + (screen error).  The
+// screen error is measured, not assumed: sigma = rms(screen - exact) over the
+// row's own candidates.  The row is certified when the exact k-th best score
+// clears t_min by z sigma plus an fp32 accumulation floor; otherwise the caller
+// re-screens it with fp32-grade operands (isb_topk_resolve) or exhaustively.
+__device__ __forceinline__ bool row_certified(const SelectSmem& sm, int kc, double sigma2_sum, int n_sel,
+                                              double kth_exact, float cert_z) {
+  if (sm.total < kc) return true;  // nothing was ever dropped for this row
+  const double sigma = sqrt(sigma2_sum / static_cast<double>(n_sel > 0 ? n_sel : 1));
+  const double t_min = static_cast<double>(__uint_as_float(key2f(sm.min_key)));
+  const double floor_ = 4e-7 * fmax(fabs(kth_exact), fabs(t_min)) + 1e-30;
+  return kth_exact - t_min > static_cast<double>(cert_z) * sigma + floor_;
+}
+
+// One CTA per listed row.  row_map == nullptr: CTA p handles query row p and pool
+// row p.  Otherwise (resolve pass) pool row p belongs to query row row_map[p].
 __global__ void __launch_bounds__(kRerankThreads)
 rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, int n_groups,
               const uint2* __restrict__ pool, const int* __restrict__ pool_cnt, int kc, int k,
-              int64_t idx_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+              int64_t idx_offset, const int* __restrict__ row_map, float cert_z,
+              int* __restrict__ unc_rows, int* __restrict__ unc_count,
+              float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
   extern __shared__ __align__(16) uint8_t rr_smem[];
   float* qs = reinterpret_cast<float*>(rr_smem);  // [D]
   __shared__ SelectSmem sm;
+  __shared__ double s_sig2;
   double* sel_score = sm.sel_score;
   int* sel_col = sm.sel_col;
 
-  const int row = blockIdx.x;
+  const int prow = blockIdx.x;
+  const int row = (row_map != nullptr) ? row_map[prow] : prow;
   const int tid = threadIdx.x;
+  if (tid == 0) s_sig2 = 0.0;
   for (int i = tid; i < D / 4; i += kRerankThreads)
     reinterpret_cast<float4*>(qs)[i] = __ldg(reinterpret_cast<const float4*>(q + static_cast<size_t>(row) * D) + i);
-  const int n_sel = select_pool_candidates(sm, pool + static_cast<size_t>(row) * n_groups * kMaxCand,
-                                           pool_cnt + static_cast<size_t>(row) * n_groups, n_groups, kc);
+  const int n_sel = select_pool_candidates(sm, pool + static_cast<size_t>(prow) * n_groups * kMaxCand,
+                                           pool_cnt + static_cast<size_t>(prow) * n_groups, n_groups, kc);
   exact_scores(sm, qs, db, D, n_sel);
+
+  // screen noise of this row: sum over its candidates of (screen - exact)^2
+  if (unc_count != nullptr) {
+    double d2 = 0.0;
+    if (tid < n_sel) {
+      const double d = static_cast<double>(sm.sel_screen[tid]) - sel_score[tid];
+      d2 = d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    if ((tid & 31) == 0 && tid < kMaxCand) atomicAdd(&s_sig2, d2);
+  }
+  __syncthreads();
 
   // ---- 3. bitonic sort of 128 entries (first 128 threads)
   for (int size = 2; size <= kMaxCand; size <<= 1) {
@@ -235,6 +277,148 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, 
     const bool ok = j < n_sel;
     out_scores[static_cast<size_t>(row) * k + j] = ok ? static_cast<float>(sel_score[j]) : -INFINITY;
     out_idx[static_cast<size_t>(row) * k + j] = ok ? static_cast<int64_t>(sel_col[j]) + idx_offset : -1;
+  }
+  if (unc_count != nullptr && tid == 0) {
+    const bool ok = (k <= n_sel) && row_certified(sm, kc, s_sig2, n_sel, sel_score[k - 1], cert_z);
+    if (!ok) unc_rows[atomicAdd(unc_count, 1)] = row;
+  }
+}
+
+// ------------------------------------------------------------------ resolve pass operands
+// a_hi[p, :], a_lo[p, :] = the two leading bf16 terms of q[rows[p], :]
+__global__ void gather_q_terms_kernel(const float* __restrict__ q, const int* __restrict__ rows, int D,
+                                      int64_t ldq, uint16_t* __restrict__ a_hi,
+                                      uint16_t* __restrict__ a_lo) {
+  const int p = blockIdx.x;
+  const float* src = q + static_cast<size_t>(rows[p]) * D;
+  for (int j = threadIdx.x; j < ldq; j += blockDim.x) {
+    const float f = (j < D) ? __ldg(src + j) : 0.f;
+    const uint16_t h = f32_to_bf16_rn(f);
+    a_hi[p * ldq + j] = h;
+    a_lo[p * ldq + j] = f32_to_bf16_rn(f - bf16_to_f32(h));
+  }
+}
+
+// ------------------------------------------------------------------ exhaustive exact search
+// For rows no screen can certify (dozens of database rows within fp32 noise of
+// the k-th score, e.g. duplicated entries).  grid (chunks, rows): every CTA
+// scores its chunk of the database exactly (fp64 accumulation) and keeps the
+// chunk's k best in shared memory; exhaustive_merge_kernel then sorts the
+// chunks * k survivors of a row.  Ties -> lower index.
+struct ExhEntry {
+  double score;
+  int col;
+  int pad;
+};
+
+__global__ void __launch_bounds__(kRerankThreads)
+exhaustive_chunk_kernel(const float* __restrict__ q, const float* __restrict__ db, int N, int D, int k,
+                        const int* __restrict__ rows, ExhEntry* __restrict__ part) {
+  extern __shared__ __align__(16) uint8_t rr_smem[];
+  float* qs = reinterpret_cast<float*>(rr_smem);  // [D]
+  __shared__ double best_s[kMaxCand];
+  __shared__ int best_c[kMaxCand];
+  __shared__ int worst_pos;      // position of the current worst entry
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunks = gridDim.x, chunk = blockIdx.x, prow = blockIdx.y;
+  const int row = rows[prow];
+  for (int i = tid; i < D / 4; i += kRerankThreads)
+    reinterpret_cast<float4*>(qs)[i] = __ldg(reinterpret_cast<const float4*>(q + static_cast<size_t>(row) * D) + i);
+  for (int i = tid; i < kMaxCand; i += kRerankThreads) { best_s[i] = -INFINITY; best_c[i] = 0x7FFFFFFF; }
+  if (tid == 0) worst_pos = 0;
+  __syncthreads();
+  const int lo = static_cast<int>(static_cast<long long>(chunk) * N / chunks);
+  const int hi = static_cast<int>(static_cast<long long>(chunk + 1) * N / chunks);
+  constexpr int kWarps = kRerankThreads / 32;
+  for (int j0 = lo; j0 < hi; j0 += kWarps) {
+    const int j = j0 + warp;
+    double acc = -INFINITY;
+    if (j < hi) {
+      const float4* dr = reinterpret_cast<const float4*>(db + static_cast<size_t>(j) * D);
+      acc = 0.0;
+      for (int i = lane; i < D / 4; i += 32) {
+        const float4 b = __ldg(dr + i);
+        const float4 a = reinterpret_cast<const float4*>(qs)[i];
+        acc = fma(static_cast<double>(a.x), static_cast<double>(b.x), acc);
+        acc = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc);
+        acc = fma(static_cast<double>(a.z), static_cast<double>(b.z), acc);
+        acc = fma(static_cast<double>(a.w), static_cast<double>(b.w), acc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    }
+    // insert in index order (warp w handles row j0 + w): deterministic
+    for (int w = 0; w < kWarps; ++w) {
+      __syncthreads();
+      if (warp == w && j < hi) {
+        const int wp = worst_pos;
+        if (entry_before(acc, j, best_s[wp], best_c[wp])) {
+          if (lane == 0) { best_s[wp] = acc; best_c[wp] = j; }
+          __syncwarp();
+          // new worst among the first k slots
+          double ws = INFINITY; int wc = -1, wpos = 0;
+          for (int i = lane; i < k; i += 32) {
+            const double s_ = best_s[i]; const int c_ = best_c[i];
+            if (wc == -1 || entry_before(ws, wc, s_, c_)) { ws = s_; wc = c_; wpos = i; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double os = __shfl_xor_sync(0xffffffffu, ws, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, wc, o);
+            const int op = __shfl_xor_sync(0xffffffffu, wpos, o);
+            if (oc != -1 && (wc == -1 || entry_before(ws, wc, os, oc))) { ws = os; wc = oc; wpos = op; }
+          }
+          if (lane == 0) worst_pos = wpos;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  ExhEntry* dst = part + (static_cast<size_t>(prow) * chunks + chunk) * k;
+  for (int i = tid; i < k; i += kRerankThreads) {
+    ExhEntry e; e.score = best_s[i]; e.col = best_c[i]; e.pad = 0;
+    dst[i] = e;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+exhaustive_merge_kernel(const ExhEntry* __restrict__ part, int chunks, int k, int n_pow2,
+                        const int* __restrict__ rows, int64_t idx_offset,
+                        float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+  extern __shared__ __align__(16) uint8_t mg_smem[];
+  double* ss = reinterpret_cast<double*>(mg_smem);        // [n_pow2]
+  int* sc = reinterpret_cast<int*>(ss + n_pow2);          // [n_pow2]
+  const int prow = blockIdx.x, row = rows[prow];
+  const int n = chunks * k;
+  for (int e = threadIdx.x; e < n_pow2; e += blockDim.x) {
+    if (e < n) {
+      const ExhEntry x = part[static_cast<size_t>(prow) * n + e];
+      ss[e] = x.score; sc[e] = x.col;
+    } else {
+      ss[e] = -INFINITY; sc[e] = 0x7FFFFFFF;
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < n_pow2; t += blockDim.x) {
+        const int partner = t ^ stride;
+        if (partner > t) {
+          const bool up = (t & size) == 0;
+          const double sa = ss[t], sb = ss[partner];
+          const int ia = sc[t], ib = sc[partner];
+          if (entry_before(sa, ia, sb, ib) != up) {
+            ss[t] = sb; ss[partner] = sa; sc[t] = ib; sc[partner] = ia;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const bool ok = sc[j] != 0x7FFFFFFF;
+    out_scores[static_cast<size_t>(row) * k + j] = ok ? static_cast<float>(ss[j]) : -INFINITY;
+    out_idx[static_cast<size_t>(row) * k + j] = ok ? static_cast<int64_t>(sc[j]) + idx_offset : -1;
   }
 }
 
@@ -467,18 +651,18 @@ static int pick_n_groups(int m_blocks, int n_tiles, int grid) {
   return best;
 }
 
-static SearchPlan make_search_plan(int64_t Q, int64_t N, int64_t D) {
+static SearchPlan make_search_plan(int64_t Q, int64_t N, int64_t D, int terms = 1) {
   SearchPlan p;
   p.m_blocks = static_cast<int>((Q + kBM - 1) / kBM);
   p.n_tiles = static_cast<int>((N + kBN - 1) / kBN);
-  p.k_blocks = static_cast<int>((D + kBK - 1) / kBK);
+  p.k_blocks = terms * static_cast<int>((D + kBK - 1) / kBK);
   const int sms = device_sm_count();
   const long long tiles = static_cast<long long>(p.m_blocks) * p.n_tiles;
   p.grid = static_cast<int>(tiles < sms ? tiles : sms);
   p.n_groups = pick_n_groups(p.m_blocks, p.n_tiles, p.grid);
   p.ldq = static_cast<int64_t>(align_up(static_cast<size_t>(D), 8));
   size_t off = 0;
-  p.off_qbf16 = off;    off = align_up(off + static_cast<size_t>(Q) * p.ldq * 2, 1024);
+  p.off_qbf16 = off;    off = align_up(off + static_cast<size_t>(Q) * p.ldq * 2 * (terms == 3 ? 2 : 1), 1024);
   p.off_cta_buf = off;  off = align_up(off + static_cast<size_t>(p.grid) * kBM * kCap * sizeof(uint2), 1024);
   p.off_gthr = off;     off = align_up(off + static_cast<size_t>(p.m_blocks) * kBM * 4, 1024);
   p.off_pool = off;     off = align_up(off + static_cast<size_t>(Q) * p.n_groups * kMaxCand * sizeof(uint2), 1024);
@@ -489,15 +673,27 @@ static SearchPlan make_search_plan(int64_t Q, int64_t N, int64_t D) {
 
 // Runs the screen (GEMM + streaming top-k) into the candidate pool.  Shared by
 // the search and the negative-mining entry points.
-int launch_topk_screen(const uint16_t* a_bf16, int64_t lda, int64_t Q, const uint16_t* b_bf16,
-                       int64_t ldb, int64_t N, int64_t D, int kc, const SearchPlan& plan,
-                       uint8_t* ws, const int* col_label, const int* row_label,
-                       const float* row_ub, float ub_slack, cudaStream_t st) {
-  CUtensorMap ta, tb;
+// a_lo / b_lo non-null: split operands, scores = a_hi.b_hi + a_lo.b_hi + a_hi.b_lo
+// (plan.k_blocks must then be 3 * the k-blocks of one term).
+int launch_topk_screen(const uint16_t* a_bf16, const uint16_t* a_lo, int64_t lda, int64_t Q,
+                       const uint16_t* b_bf16, const uint16_t* b_lo, int64_t ldb, int64_t N, int64_t D,
+                       int kc, const SearchPlan& plan, uint8_t* ws, const int* col_label,
+                       const int* row_label, const float* row_ub, float ub_slack, cudaStream_t st) {
+  CUtensorMap ta, tb, ta_lo, tb_lo;
   int rc = make_tmap_bf16_k64(&ta, a_bf16, Q, D, lda, kBM);
   if (rc) return rc;
   rc = make_tmap_bf16_k64(&tb, b_bf16, N, D, ldb, kBN);
   if (rc) return rc;
+  ta_lo = ta;
+  tb_lo = tb;
+  int kb_per_term = kSingleTerm;
+  if (a_lo != nullptr && b_lo != nullptr) {
+    rc = make_tmap_bf16_k64(&ta_lo, a_lo, Q, D, lda, kBM);
+    if (rc) return rc;
+    rc = make_tmap_bf16_k64(&tb_lo, b_lo, N, D, ldb, kBN);
+    if (rc) return rc;
+    kb_per_term = plan.k_blocks / 3;
+  }
 
   uint32_t* gthr = reinterpret_cast<uint32_t*>(ws + plan.off_gthr);
   const size_t n_thr = static_cast<size_t>(plan.m_blocks) * kBM;
@@ -521,11 +717,11 @@ int launch_topk_screen(const uint16_t* a_bf16, int64_t lda, int64_t Q, const uin
   if (col_label != nullptr) {
     auto kern = gemm_tc_kernel<TopkSched, TopkEpilogue<true>>;
     ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
-    kern<<<plan.grid, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, sched, ep);
+    kern<<<plan.grid, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, ta_lo, tb_lo, kb_per_term, sched, ep);
   } else {
     auto kern = gemm_tc_kernel<TopkSched, TopkEpilogue<false>>;
     ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
-    kern<<<plan.grid, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, sched, ep);
+    kern<<<plan.grid, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, ta_lo, tb_lo, kb_per_term, sched, ep);
   }
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;
@@ -597,14 +793,34 @@ extern "C" int isb_topk_screen(const float* q, int64_t Q, const uint16_t* db_bf1
   if (rc) return rc;
   int kc = k + margin;
   if (kc > N) kc = static_cast<int>(N);
-  return launch_topk_screen(q_bf16, plan.ldq, Q, db_bf16, ld_bf16, N, D, kc, plan, ws, nullptr, nullptr,
-                            nullptr, 0.f, static_cast<cudaStream_t>(stream));
+  return launch_topk_screen(q_bf16, nullptr, plan.ldq, Q, db_bf16, nullptr, ld_bf16, N, D, kc, plan, ws,
+                            nullptr, nullptr, nullptr, 0.f, static_cast<cudaStream_t>(stream));
+}
+
+static int launch_rerank(const char* fn, const float* q, const float* db_f32, int64_t D, int64_t n_rows,
+                         const SearchPlan& plan, uint8_t* ws, int kc, int k, int64_t idx_offset,
+                         const int* row_map, int32_t* unc_rows, int32_t* unc_count, float* out_scores,
+                         int64_t* out_idx, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(D) * 4;
+  ISB_CHECK_ARG(smem <= 160 * 1024, "%s: D too large for the re-rank kernel", fn);
+  if (smem > 48 * 1024)
+    ISB_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (unc_count != nullptr) ISB_CUDA(cudaMemsetAsync(unc_count, 0, 4, st));
+  rerank_kernel<<<static_cast<unsigned>(n_rows), kRerankThreads, smem, st>>>(
+      q, db_f32, static_cast<int>(D), plan.n_groups, reinterpret_cast<const uint2*>(ws + plan.off_pool),
+      reinterpret_cast<const int*>(ws + plan.off_pool_cnt), kc, k, idx_offset, row_map, kCertZ, unc_rows,
+      unc_count, out_scores, out_idx);
+  ISB_CUDA(cudaGetLastError());
+  return ISB_OK;
 }
 
 extern "C" int isb_topk_rerank(const float* q, int64_t Q, const float* db_f32, int64_t N, int64_t D, int k,
                                int margin, int64_t idx_offset, float* out_scores, int64_t* out_idx,
-                               void* workspace, size_t workspace_bytes, void* stream) {
+                               int32_t* uncertified_rows, int32_t* n_uncertified, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   ISB_CHECK_ARG(q && db_f32 && out_scores && out_idx, "isb_topk_rerank: null pointer");
+  ISB_CHECK_ARG((uncertified_rows == nullptr) == (n_uncertified == nullptr),
+                "isb_topk_rerank: uncertified_rows and n_uncertified go together");
   int rc = check_search_args("isb_topk_rerank", Q, N, D, k, margin);
   if (rc) return rc;
   ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(db_f32) & 15) == 0,
@@ -615,25 +831,102 @@ extern "C" int isb_topk_rerank(const float* q, int64_t Q, const float* db_f32, i
   if (rc) return rc;
   int kc = k + margin;
   if (kc > N) kc = static_cast<int>(N);
-  const size_t smem = static_cast<size_t>(D) * 4;
-  ISB_CHECK_ARG(smem <= 160 * 1024, "isb_topk_rerank: D too large for the re-rank kernel");
-  if (smem > 48 * 1024)
-    ISB_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rerank_kernel<<<static_cast<unsigned>(Q), kRerankThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      q, db_f32, static_cast<int>(D), plan.n_groups, reinterpret_cast<const uint2*>(ws + plan.off_pool),
-      reinterpret_cast<const int*>(ws + plan.off_pool_cnt), kc, k, idx_offset, out_scores, out_idx);
-  ISB_CUDA(cudaGetLastError());
-  return ISB_OK;
+  return launch_rerank("isb_topk_rerank", q, db_f32, D, Q, plan, ws, kc, k, idx_offset, nullptr,
+                       uncertified_rows, n_uncertified, out_scores, out_idx, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int isb_topk_search(const float* q, int64_t Q, const float* db_f32, const uint16_t* db_bf16,
                                int64_t N, int64_t D, int64_t ld_bf16, int k, int margin,
                                int64_t idx_offset, float* out_scores, int64_t* out_idx,
-                               void* workspace, size_t workspace_bytes, void* stream) {
+                               int32_t* uncertified_rows, int32_t* n_uncertified, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   int rc = isb_topk_screen(q, Q, db_bf16, N, D, ld_bf16, k, margin, workspace, workspace_bytes, stream);
   if (rc) return rc;
-  return isb_topk_rerank(q, Q, db_f32, N, D, k, margin, idx_offset, out_scores, out_idx, workspace,
-                         workspace_bytes, stream);
+  return isb_topk_rerank(q, Q, db_f32, N, D, k, margin, idx_offset, out_scores, out_idx, uncertified_rows,
+                         n_uncertified, workspace, workspace_bytes, stream);
+}
+
+// ---- second line: fp32-grade (split-operand) re-screen of the listed rows
+extern "C" size_t isb_topk_resolve_workspace_bytes(int64_t n_rows, int64_t N, int64_t D) {
+  if (n_rows <= 0 || N <= 0 || D <= 0) return 0;
+  return make_search_plan(n_rows, N, D, 3).total + 1024;
+}
+
+extern "C" int isb_topk_resolve(const float* q, const float* db_f32, const uint16_t* db_bf16,
+                                const uint16_t* db_lo_bf16, int64_t N, int64_t D, int64_t ld_bf16, int k,
+                                int margin, int64_t idx_offset, const int32_t* rows, int64_t n_rows,
+                                float* out_scores, int64_t* out_idx, int32_t* uncertified_rows,
+                                int32_t* n_uncertified, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  ISB_CHECK_ARG(q && db_f32 && db_bf16 && db_lo_bf16 && rows && out_scores && out_idx && uncertified_rows &&
+                n_uncertified, "isb_topk_resolve: null pointer");
+  int rc = check_search_args("isb_topk_resolve", n_rows, N, D, k, margin);
+  if (rc) return rc;
+  ISB_CHECK_ARG(ld_bf16 >= D && ld_bf16 % 8 == 0, "isb_topk_resolve: bad ld_bf16");
+  const SearchPlan plan = make_search_plan(n_rows, N, D, 3);
+  uint8_t* ws;
+  rc = carve_workspace("isb_topk_resolve", plan, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint16_t* a_hi = reinterpret_cast<uint16_t*>(ws + plan.off_qbf16);
+  uint16_t* a_lo = a_hi + static_cast<size_t>(n_rows) * plan.ldq;
+  gather_q_terms_kernel<<<static_cast<unsigned>(n_rows), 256, 0, st>>>(q, rows, (int)D, plan.ldq, a_hi, a_lo);
+  ISB_CUDA(cudaGetLastError());
+  int kc = k + margin;
+  if (kc > N) kc = static_cast<int>(N);
+  rc = launch_topk_screen(a_hi, a_lo, plan.ldq, n_rows, db_bf16, db_lo_bf16, ld_bf16, N, D, kc, plan, ws,
+                          nullptr, nullptr, nullptr, 0.f, st);
+  if (rc) return rc;
+  return launch_rerank("isb_topk_resolve", q, db_f32, D, n_rows, plan, ws, kc, k, idx_offset, rows,
+                       uncertified_rows, n_uncertified, out_scores, out_idx, st);
+}
+
+// ---- last line: exhaustive exact search of the listed rows
+static int exhaustive_chunks(int64_t n_rows, int64_t N) {
+  long long c = (148ll * 4 + n_rows - 1) / n_rows;
+  if (c > 32) c = 32;
+  if (c > N) c = N;
+  if (c < 1) c = 1;
+  return static_cast<int>(c);
+}
+
+extern "C" size_t isb_topk_exhaustive_workspace_bytes(int64_t n_rows, int64_t N, int k) {
+  if (n_rows <= 0 || N <= 0 || k <= 0) return 0;
+  return align_up(static_cast<size_t>(n_rows) * exhaustive_chunks(n_rows, N) * k * sizeof(ExhEntry), 1024) + 1024;
+}
+
+extern "C" int isb_topk_exhaustive(const float* q, const float* db_f32, int64_t N, int64_t D, int k,
+                                   int64_t idx_offset, const int32_t* rows, int64_t n_rows,
+                                   float* out_scores, int64_t* out_idx, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  ISB_CHECK_ARG(q && db_f32 && rows && out_scores && out_idx, "isb_topk_exhaustive: null pointer");
+  int rc = check_search_args("isb_topk_exhaustive", n_rows, N, D, k, 0);
+  if (rc) return rc;
+  const size_t need = isb_topk_exhaustive_workspace_bytes(n_rows, N, k);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+  if (workspace == nullptr || ws + need - 1024 > static_cast<uint8_t*>(workspace) + workspace_bytes) {
+    set_error("isb_topk_exhaustive: workspace too small (need %zu bytes, got %zu)", need, workspace_bytes);
+    return ISB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int chunks = exhaustive_chunks(n_rows, N);
+  const size_t smem = static_cast<size_t>(D) * 4;
+  ISB_CHECK_ARG(smem <= 160 * 1024, "isb_topk_exhaustive: D too large");
+  if (smem > 48 * 1024)
+    ISB_CUDA(cudaFuncSetAttribute(exhaustive_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ExhEntry* part = reinterpret_cast<ExhEntry*>(ws);
+  exhaustive_chunk_kernel<<<dim3(chunks, static_cast<unsigned>(n_rows)), kRerankThreads, smem, st>>>(
+      q, db_f32, (int)N, (int)D, k, rows, part);
+  ISB_CUDA(cudaGetLastError());
+  int n_pow2 = 2;
+  while (n_pow2 < chunks * k) n_pow2 <<= 1;
+  const size_t msmem = static_cast<size_t>(n_pow2) * 12;
+  if (msmem > 48 * 1024)
+    ISB_CUDA(cudaFuncSetAttribute(exhaustive_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+  exhaustive_merge_kernel<<<static_cast<unsigned>(n_rows), 256, msmem, st>>>(part, chunks, k, n_pow2, rows,
+                                                                            idx_offset, out_scores, out_idx);
+  ISB_CUDA(cudaGetLastError());
+  return ISB_OK;
 }
 
 extern "C" int isb_topk_merge(const float* cand_scores, const int64_t* cand_idx, int R, int64_t Q, int k,
@@ -660,9 +953,9 @@ struct MiningPlan {
   size_t off_row_label, off_pos64, off_pos32, off_flag, total;
 };
 
-static MiningPlan make_mining_plan(int64_t P, int64_t N, int64_t Kscr) {
+static MiningPlan make_mining_plan(int64_t P, int64_t N, int64_t D, int split) {
   MiningPlan m;
-  m.sp = make_search_plan(P, N, Kscr);
+  m.sp = make_search_plan(P, N, D, split ? 3 : 1);
   size_t off = m.sp.total;
   m.off_row_label = off; off = align_up(off + static_cast<size_t>(P) * 4, 1024);
   m.off_pos64 = off;     off = align_up(off + static_cast<size_t>(P) * 8, 1024);
@@ -672,40 +965,47 @@ static MiningPlan make_mining_plan(int64_t P, int64_t N, int64_t Kscr) {
   return m;
 }
 
-extern "C" size_t isb_select_negatives_workspace_bytes(int64_t P, int64_t N, int64_t Kscr) {
-  if (P <= 0 || N <= 0 || Kscr <= 0) return 0;
-  return make_mining_plan(P, N, Kscr).total + 1024;
+extern "C" size_t isb_select_negatives_workspace_bytes(int64_t P, int64_t N, int64_t D, int split) {
+  if (P <= 0 || N <= 0 || D <= 0) return 0;
+  return make_mining_plan(P, N, D, split).total + 1024;
 }
 
-extern "C" int isb_select_negatives(const float* emb, const uint16_t* emb_a, const uint16_t* emb_b,
-                                    int64_t Kscr, int64_t N, int64_t D, const int32_t* label,
+extern "C" int isb_select_negatives(const float* emb, const uint16_t* emb_hi, const uint16_t* emb_lo,
+                                    int64_t ld, int64_t N, int64_t D, const int32_t* label,
                                     const int64_t* anchors, const int64_t* positives, int64_t P,
                                     int semi_hard, float screen_eps, int64_t* neg_idx, float* neg_sim,
                                     float* pos_sim, int32_t* n_bruteforce, void* workspace,
                                     size_t workspace_bytes, void* stream) {
-  ISB_CHECK_ARG(emb && emb_a && emb_b && label && anchors && positives && neg_idx && neg_sim && pos_sim,
+  ISB_CHECK_ARG(emb && emb_hi && label && anchors && positives && neg_idx && neg_sim && pos_sim,
                 "isb_select_negatives: null pointer");
   ISB_CHECK_ARG(P > 0 && N > 0 && D > 0 && N < (1ll << 31) && P < (1ll << 31), "isb_select_negatives: bad shape");
-  ISB_CHECK_ARG(D % 8 == 0 && Kscr % 8 == 0 && Kscr >= D, "isb_select_negatives: D and Kscr must be multiples of 8");
-  ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(emb) & 15) == 0 && (reinterpret_cast<uintptr_t>(emb_a) & 15) == 0 &&
-                (reinterpret_cast<uintptr_t>(emb_b) & 15) == 0, "isb_select_negatives: inputs must be 16-byte aligned");
+  ISB_CHECK_ARG(D % 8 == 0 && ld % 8 == 0 && ld >= D, "isb_select_negatives: D and ld must be multiples of 8, ld >= D");
+  ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(emb) & 15) == 0 && (reinterpret_cast<uintptr_t>(emb_hi) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(emb_lo) & 15) == 0, "isb_select_negatives: inputs must be 16-byte aligned");
   int rc = isb_check_device();
   if (rc) return rc;
-  const MiningPlan mp = make_mining_plan(P, N, Kscr);
+  const int split = emb_lo != nullptr ? 1 : 0;
+  const MiningPlan mp = make_mining_plan(P, N, D, split);
+  ISB_CHECK_ARG(mp.sp.ldq == ld, "isb_select_negatives: ld (%lld) must equal D rounded up to 8", (long long)ld);
   uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
   if (workspace == nullptr || ws + mp.total > static_cast<uint8_t*>(workspace) + workspace_bytes) {
     set_error("isb_select_negatives: workspace too small (need %zu bytes, got %zu)", mp.total + 1024, workspace_bytes);
     return ISB_ERR_WORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  uint16_t* a_rows = reinterpret_cast<uint16_t*>(ws + mp.sp.off_qbf16);   // [P, Kscr]
+  uint16_t* a_hi = reinterpret_cast<uint16_t*>(ws + mp.sp.off_qbf16);   // [P, ld] anchors' rows
+  uint16_t* a_lo = split ? a_hi + static_cast<size_t>(P) * ld : nullptr;
   int* row_label = reinterpret_cast<int*>(ws + mp.off_row_label);
   double* pos64 = reinterpret_cast<double*>(ws + mp.off_pos64);
   float* pos32 = reinterpret_cast<float*>(ws + mp.off_pos32);
   int* flag = reinterpret_cast<int*>(ws + mp.off_flag);
 
-  gather_rows_kernel<<<static_cast<unsigned>(P), 128, 0, st>>>(emb_a, Kscr, anchors, a_rows, label, row_label);
+  gather_rows_kernel<<<static_cast<unsigned>(P), 128, 0, st>>>(emb_hi, ld, anchors, a_hi, label, row_label);
   ISB_CUDA(cudaGetLastError());
+  if (split) {
+    gather_rows_kernel<<<static_cast<unsigned>(P), 128, 0, st>>>(emb_lo, ld, anchors, a_lo, label, row_label);
+    ISB_CUDA(cudaGetLastError());
+  }
   pair_dot_kernel<<<static_cast<unsigned>((P * 32 + 255) / 256), 256, 0, st>>>(emb, (int)D, anchors, positives, P, pos64, pos32);
   ISB_CUDA(cudaGetLastError());
   ISB_CUDA(cudaMemcpyAsync(pos_sim, pos32, static_cast<size_t>(P) * 4, cudaMemcpyDeviceToDevice, st));
@@ -714,7 +1014,7 @@ extern "C" int isb_select_negatives(const float* emb, const uint16_t* emb_a, con
   int kc = kMaxCand;
   if (kc > N) kc = static_cast<int>(N);
   // semi-hard: columns scoring >= sim_pos (+ the screen's error bound) are masked in the epilogue
-  rc = launch_topk_screen(a_rows, Kscr, P, emb_b, Kscr, N, Kscr, kc, mp.sp, ws, label, row_label,
+  rc = launch_topk_screen(a_hi, a_lo, ld, P, emb_hi, emb_lo, ld, N, D, kc, mp.sp, ws, label, row_label,
                           semi_hard ? pos32 : nullptr, screen_eps, st);
   if (rc) return rc;
   const size_t smem = static_cast<size_t>(D) * 4;

@@ -44,21 +44,16 @@ def embeddings_device_dim(P, net, n, sim_matrix=False):
     return device, out_size
 
 
-def _terms(x, side, terms):
-    """bf16 screen operand of fp32 rows: side 'a' -> [hi|lo|hi], 'b' -> [hi|hi|lo]."""
-    hi = ops.to_bf16(x, 0)
-    if terms == 1:
-        return hi
-    lo = ops.to_bf16(x, 1)
-    return torch.cat([hi, lo, hi] if side == "a" else [hi, hi, lo], 1).contiguous()
-
-
 def all_pairs_similarities(emb, terms=3):
     """S = E . E^T, fp32 [N, N] -- reference: utils/train_siamese.py:53
-    (also test/instance_avg.py:12).  terms=3: fp32-grade 3-product expansion."""
+    (also test/instance_avg.py:12).  terms=3: fp32-grade split-operand product."""
     ops._need_cuda(emb)
     emb = ops._f32c(emb)
-    return ops.gemm_nt(_terms(emb, "a", terms), _terms(emb, "b", terms))
+    hi = ops.to_bf16(emb, 0)
+    if terms == 1:
+        return ops.gemm_nt(hi, hi)
+    lo = ops.to_bf16(emb, 1)
+    return ops.gemm_nt_split(hi, lo, hi, lo)
 
 
 class MiningIndex(object):
@@ -75,8 +70,8 @@ class MiningIndex(object):
         self.labels = labels.to(device=emb.device, dtype=torch.int32).contiguous()
         if self.labels.numel() != self.N:
             raise IsbError("one label id per embedding expected")
-        self.emb_a = _terms(self.emb, "a", terms)
-        self.emb_b = _terms(self.emb, "b", terms)
+        self.emb_hi = ops.to_bf16(self.emb, 0)
+        self.emb_lo = ops.to_bf16(self.emb, 1) if terms == 3 else None
         self.eps = SCREEN_EPS_3TERM if terms == 3 else SCREEN_EPS_1TERM
         self.last_bruteforce = None
 
@@ -98,11 +93,11 @@ class MiningIndex(object):
             return neg_idx, neg_sim, pos_sim
         nb = torch.zeros(1, dtype=torch.int32, device=dev)
         L = _lib.lib()
-        Kscr = self.emb_a.size(1)
-        nbytes = L.isb_select_negatives_workspace_bytes(P, self.N, Kscr)
+        D = self.emb.size(1)
+        nbytes = L.isb_select_negatives_workspace_bytes(P, self.N, D, 0 if self.emb_lo is None else 1)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _lib.check(L.isb_select_negatives(self.emb.data_ptr(), self.emb_a.data_ptr(),
-                                          self.emb_b.data_ptr(), Kscr, self.N, self.emb.size(1),
+        _lib.check(L.isb_select_negatives(self.emb.data_ptr(), self.emb_hi.data_ptr(),
+                                          ops._ptr(self.emb_lo), self.emb_hi.size(1), self.N, D,
                                           self.labels.data_ptr(), anchors.data_ptr(),
                                           positives.data_ptr(), P, 1 if semi_hard else 0, self.eps,
                                           neg_idx.data_ptr(), neg_sim.data_ptr(), pos_sim.data_ptr(),

@@ -97,13 +97,77 @@ def gemm_nt(a, b, bias=None, splits=1, k=None):
     return c
 
 
+def gemm_nt_split(a_hi, a_lo, b_hi, b_lo, bias=None, splits=1, k=None):
+    """fp32-grade C[M, N] = A . B^T from split operands (to_bf16 parts 0 and 1):
+    a_hi.b_hi + a_lo.b_hi + a_hi.b_lo accumulated in one TMEM tile."""
+    _need_cuda(a_hi, a_lo, b_hi, b_lo, bias)
+    for t in (a_hi, a_lo, b_hi, b_lo):
+        if t.dtype != torch.bfloat16 or not t.is_contiguous():
+            raise IsbError("gemm_nt_split takes contiguous bf16 operands (see to_bf16)")
+    if a_hi.shape != a_lo.shape or b_hi.shape != b_lo.shape:
+        raise IsbError("gemm_nt_split: hi/lo shape mismatch")
+    K = min(a_hi.size(1), b_hi.size(1)) if k is None else k
+    M, N = a_hi.size(0), b_hi.size(0)
+    c = torch.empty((M, N), dtype=torch.float32, device=a_hi.device)
+    L = _lib.lib()
+    ws_bytes = L.isb_gemm_nt_workspace_bytes(M, N, K, splits)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=a_hi.device)
+    if bias is not None:
+        bias = _f32c(bias)
+    _lib.check(L.isb_gemm_nt_split(a_hi.data_ptr(), a_lo.data_ptr(), a_hi.size(1), b_hi.data_ptr(),
+                                   b_lo.data_ptr(), b_hi.size(1), M, N, K, _ptr(bias), c.data_ptr(), N,
+                                   int(splits), ws.data_ptr(), ws_bytes, _stream()), "isb_gemm_nt_split")
+    return c
+
+
 # ---------------------------------------------------------------------- search
-def topk_search(q, db_f32, db_bf16, k, margin=None, idx_offset=0, workspace=None):
+def resolve_uncertified(q, db_f32, db_bf16, db_lo, k, margin, idx_offset, scores, idx, unc_rows, n_unc,
+                        stats=None):
+    """Host side of the exactness guarantee (include/isb.h, stage 2b): read the
+    number of rows the bf16 screen could not certify (ONE 4-byte D2H read; it is 0
+    on ordinary data), re-screen those with fp32-grade split operands, and search
+    exhaustively whatever is still uncertified.  db_lo: bf16 lo term of db_f32 or a
+    zero-argument callable that builds it on first need.  Returns db_lo (built or not)."""
+    L = _lib.lib()
+    n1 = int(n_unc.item())
+    n2 = 0
+    N, D = db_f32.shape
+    if n1 > 0:
+        if callable(db_lo):
+            db_lo = db_lo()
+        rows = unc_rows[:n1].clone()
+        nb = L.isb_topk_resolve_workspace_bytes(n1, N, D)
+        ws = torch.empty(nb, dtype=torch.uint8, device=q.device)
+        _lib.check(L.isb_topk_resolve(q.data_ptr(), db_f32.data_ptr(), db_bf16.data_ptr(), db_lo.data_ptr(),
+                                      N, D, db_bf16.size(1), int(k), int(margin), int(idx_offset),
+                                      rows.data_ptr(), n1, scores.data_ptr(), idx.data_ptr(),
+                                      unc_rows.data_ptr(), n_unc.data_ptr(), ws.data_ptr(), nb, _stream()),
+                   "isb_topk_resolve")
+        n2 = int(n_unc.item())
+        if n2 > 0:
+            rows = unc_rows[:n2].clone()
+            nb = L.isb_topk_exhaustive_workspace_bytes(n2, N, int(k))
+            ws = torch.empty(nb, dtype=torch.uint8, device=q.device)
+            _lib.check(L.isb_topk_exhaustive(q.data_ptr(), db_f32.data_ptr(), N, D, int(k), int(idx_offset),
+                                             rows.data_ptr(), n2, scores.data_ptr(), idx.data_ptr(),
+                                             ws.data_ptr(), nb, _stream()), "isb_topk_exhaustive")
+    if stats is not None:
+        stats["rows"] = stats.get("rows", 0) + q.size(0)
+        stats["resolved_fp32_grade"] = stats.get("resolved_fp32_grade", 0) + n1
+        stats["resolved_exhaustive"] = stats.get("resolved_exhaustive", 0) + n2
+    return db_lo
+
+
+def topk_search(q, db_f32, db_bf16, k, margin=None, idx_offset=0, workspace=None, exact=True,
+                db_lo=None, stats=None):
     """Top-k rows of db by q . db (best first), index-exact w.r.t. fp64 scores.
 
     replaces ``torch.mm(q, db.t())`` + sort/max (test/siamese_regions_test.py:76,
     utils/metrics.py:11,13,33).  q [Q, D] fp32, db_f32 [N, D] fp32,
     db_bf16 = to_bf16(db_f32).  Returns (scores [Q, k] fp32, idx [Q, k] int64).
+    exact=True (default) runs the completeness certificate and resolves the rows
+    that fail it (one 4-byte device->host read per call); exact=False returns the
+    re-ranked screen result without the guarantee and without any host sync.
     """
     _need_cuda(q, db_f32, db_bf16)
     q, db_f32 = _f32c(q), _f32c(db_f32)
@@ -122,10 +186,17 @@ def topk_search(q, db_f32, db_bf16, k, margin=None, idx_offset=0, workspace=None
     ws_bytes = L.isb_topk_search_workspace_bytes(Q, N, D, k, margin)
     if workspace is None or workspace.numel() < ws_bytes:
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+    unc_rows = torch.empty(Q, dtype=torch.int32, device=q.device) if exact else None
+    n_unc = torch.zeros(1, dtype=torch.int32, device=q.device) if exact else None
     _lib.check(L.isb_topk_search(q.data_ptr(), Q, db_f32.data_ptr(), db_bf16.data_ptr(), N, D,
                                  db_bf16.size(1), int(k), int(margin), int(idx_offset),
-                                 scores.data_ptr(), idx.data_ptr(), workspace.data_ptr(),
-                                 workspace.numel(), _stream()), "isb_topk_search")
+                                 scores.data_ptr(), idx.data_ptr(), _ptr(unc_rows), _ptr(n_unc),
+                                 workspace.data_ptr(), workspace.numel(), _stream()), "isb_topk_search")
+    if exact:
+        if db_lo is None:
+            db_lo = lambda: to_bf16(db_f32, 1, ld=db_bf16.size(1))  # noqa: E731
+        resolve_uncertified(q, db_f32, db_bf16, db_lo, k, margin, idx_offset, scores, idx, unc_rows,
+                            n_unc, stats)
     return scores, idx
 
 
@@ -179,6 +250,15 @@ def _register():
     def _search(q: torch.Tensor, db_f32: torch.Tensor, db_bf16: torch.Tensor, k: int,
                 margin: int, idx_offset: int) -> tuple[torch.Tensor, torch.Tensor]:
         return topk_search(q, db_f32, db_bf16, k, margin, idx_offset)
+
+    @custom_op("isb::gemm_nt_split", mutates_args=(), device_types="cuda")
+    def _gemm_split(a_hi: torch.Tensor, a_lo: torch.Tensor, b_hi: torch.Tensor, b_lo: torch.Tensor,
+                    splits: int) -> torch.Tensor:
+        return gemm_nt_split(a_hi, a_lo, b_hi, b_lo, None, splits)
+
+    @_gemm_split.register_fake
+    def _(a_hi, a_lo, b_hi, b_lo, splits):
+        return a_hi.new_empty((a_hi.size(0), b_hi.size(0)), dtype=torch.float32)
 
     @_search.register_fake
     def _(q, db_f32, db_bf16, k, margin, idx_offset):

@@ -20,8 +20,9 @@ class HeadWeights(object):
     cls_w [ncls, C], cls_b [ncls]    classifier.0.{weight,bias} (1x1 conv view)
     shift [C*fh*fw]                  feature_reduc1.1.param
     lin_w [D, C*fh*fw], lin_b [D]    feature_reduc1.2.{weight,bias}
-    terms: 1 = plain bf16 projection; 3 = [hi|hi|lo] K-concatenation, an
-    fp32-grade product (default: descriptors feed an index-exact search).
+    terms: 1 = plain bf16 projection; 3 = split operands (hi + lo bf16 terms, three
+    tcgen05 products per tile), an fp32-grade product (default: descriptors feed an
+    index-exact search).
     cls_w / lin_w may be None (DescriptorNet has no classifier).
     """
 
@@ -37,14 +38,8 @@ class HeadWeights(object):
         lin_w = ops._f32c(lin_w)
         self.D, self.Kin = lin_w.shape
         self.KinP = (self.Kin + 7) // 8 * 8   # every bf16 term is zero-padded to 8 columns
-        hi = ops.to_bf16(lin_w, 0)
-        if terms == 1:
-            self.lin_w_bf16 = hi
-        else:
-            lo = ops.to_bf16(lin_w, 1)
-            self.lin_w_bf16 = torch.cat([hi, hi, lo], 1).contiguous()
-            del lo
-        del hi
+        self.lin_w_hi = ops.to_bf16(lin_w, 0)
+        self.lin_w_lo = ops.to_bf16(lin_w, 1) if terms == 3 else None
 
 
 def _splits_for(M, N, K):
@@ -52,6 +47,14 @@ def _splits_for(M, N, K):
     tiles = ((M + 127) // 128) * ((N + 255) // 256)
     kb = (K + 63) // 64
     return max(1, min(kb, 148 // max(1, tiles)))
+
+
+def _project(U_hi, U_lo, hw, B):
+    """y = u . W^T  (nn.Linear(100352, D) without the bias, model/siamese.py:180)"""
+    splits = _splits_for(B, hw.D, hw.KinP * hw.terms)
+    if hw.terms == 1:
+        return ops.gemm_nt(U_hi, hw.lin_w_hi, splits=splits)
+    return ops.gemm_nt_split(U_hi, U_lo, hw.lin_w_hi, hw.lin_w_lo, splits=splits)
 
 
 def region_select(x, hw, k, fsize, margin=WINDOW_MARGIN):
@@ -87,12 +90,13 @@ def region_aggregate(x, hw, k, fsize, idx, nsel, win_norm):
         raise IsbError("feature map channels x window (%d) != projection in_features (%d)" %
                        (C * fh * fw, hw.Kin))
     L = _lib.lib()
-    ldu = hw.KinP * hw.terms
-    U = torch.empty((B, ldu), dtype=torch.bfloat16, device=x.device)
+    U_hi = torch.empty((B, hw.KinP), dtype=torch.bfloat16, device=x.device)
+    U_lo = torch.empty_like(U_hi) if hw.terms == 3 else None
     _lib.check(L.isb_region_gather(x.data_ptr(), B, C, H, W, fh, fw, k, idx.data_ptr(),
                                    nsel.data_ptr(), win_norm.data_ptr(), hw.shift.data_ptr(),
-                                   hw.terms, U.data_ptr(), ldu, ops._stream()), "isb_region_gather")
-    y = ops.gemm_nt(U, hw.lin_w_bf16, splits=_splits_for(B, hw.D, ldu))
+                                   U_hi.data_ptr(), ops._ptr(U_lo), hw.KinP, ops._stream()),
+               "isb_region_gather")
+    y = _project(U_hi, U_lo, hw, B)
     desc = torch.empty((B, hw.D), dtype=torch.float32, device=x.device)
     _lib.check(L.isb_descriptor_finalize(y.data_ptr(), B, hw.D, ops._ptr(hw.lin_b), nsel.data_ptr(),
                                          1e-10, desc.data_ptr(), ops._stream()),
@@ -118,9 +122,7 @@ def global_descriptors(x, hw):
     if flat.size(1) != hw.Kin:
         raise IsbError("flattened features (%d) != projection in_features (%d)" % (flat.size(1), hw.Kin))
     u = ops.shift_rows(ops.l2norm_rows(flat), hw.shift)
-    hi = ops.to_bf16(u, 0)
-    U = hi if hw.terms == 1 else torch.cat([hi, ops.to_bf16(u, 1), hi], 1).contiguous()
-    y = ops.gemm_nt(U, hw.lin_w_bf16, splits=_splits_for(B, hw.D, U.size(1)))
+    y = _project(ops.to_bf16(u, 0), ops.to_bf16(u, 1) if hw.terms == 3 else None, hw, B)
     desc = torch.empty((B, hw.D), dtype=torch.float32, device=x.device)
     _lib.check(_lib.lib().isb_descriptor_finalize(y.data_ptr(), B, hw.D, ops._ptr(hw.lin_b), 0, 1e-10,
                                                   desc.data_ptr(), ops._stream()),

@@ -47,8 +47,10 @@ class DescriptorIndex(object):
             db = torch.nn.functional.pad(db, (0, self.pad))
         self.db_f32 = db.contiguous()
         self.db_bf16 = ops.to_bf16(self.db_f32)
+        self._db_lo = None            # lo bf16 term, built the first time a row needs resolving
         self.row_offset = int(row_offset)
         self._ws = None
+        self.stats = {}               # rows searched / resolved fp32-grade / resolved exhaustively
 
     def __len__(self):
         return self.db_f32.size(0)
@@ -68,8 +70,17 @@ class DescriptorIndex(object):
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.db_f32.device)
         return self._ws
 
-    def search(self, q, k, margin=None, events=None):
+    def _lo(self):
+        if self._db_lo is None:
+            self._db_lo = ops.to_bf16(self.db_f32, 1, ld=self.db_bf16.size(1))
+        return self._db_lo
+
+    def search(self, q, k, margin=None, events=None, exact=True):
         """(scores [Q, k] fp32, idx [Q, k] int64 global), best first.
+
+        exact=True: rows whose candidate list the bf16 screen cannot certify
+        complete are re-screened with fp32-grade operands / exhaustively
+        (ops.resolve_uncertified); costs one 4-byte device->host read per call.
 
         events: optional list; when given, CUDA events bracketing the screen
         stage (the tcgen05 GEMM + streaming top-k) are appended as a pair so a
@@ -99,9 +110,15 @@ class DescriptorIndex(object):
         if events is not None:
             e1.record()
             events.append((e0, e1))
+        unc_rows = torch.empty(Q, dtype=torch.int32, device=q.device) if exact else None
+        n_unc = torch.zeros(1, dtype=torch.int32, device=q.device) if exact else None
         ops._lib.check(L.isb_topk_rerank(q.data_ptr(), Q, self.db_f32.data_ptr(), N, D, k_eff, margin,
                                          self.row_offset, scores.data_ptr(), idx.data_ptr(),
+                                         ops._ptr(unc_rows), ops._ptr(n_unc),
                                          ws.data_ptr(), ws.numel(), st), "isb_topk_rerank")
+        if exact:
+            ops.resolve_uncertified(q, self.db_f32, self.db_bf16, self._lo, k_eff, margin, self.row_offset,
+                                    scores, idx, unc_rows, n_unc, self.stats)
         return scores, idx
 
 

@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported_and_bound(L):
 
 
 def test_abi_version(L):
-    assert L.isb_abi_version() == 1
+    assert L.isb_abi_version() == 2
 
 
 def test_argument_errors_need_no_gpu(L):
@@ -52,7 +52,7 @@ def test_argument_errors_need_no_gpu(L):
     assert rc == 1 and b"empty" in L.isb_last_error()
     # k + margin beyond the candidate budget
     rc = L.isb_topk_search(ctypes.c_void_p(16), 1, ctypes.c_void_p(16), ctypes.c_void_p(16), 1000, 64, 64,
-                           100, 29, 0, ctypes.c_void_p(16), ctypes.c_void_p(16), None, 0, None)
+                           100, 29, 0, ctypes.c_void_p(16), ctypes.c_void_p(16), None, None, None, 0, None)
     assert rc == 1 and b"k + margin" in L.isb_last_error()
 
 
@@ -64,8 +64,8 @@ def test_no_device_is_an_error_not_a_fallback(L):
     assert L.isb_last_error()
     # a well-formed search call fails loudly on the device check
     rc = L.isb_topk_search(ctypes.c_void_p(16), 1, ctypes.c_void_p(16), ctypes.c_void_p(16), 1000, 64, 64,
-                           10, 5, 0, ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(1024),
-                           1 << 30, None)
+                           10, 5, 0, ctypes.c_void_p(16), ctypes.c_void_p(16), None, None,
+                           ctypes.c_void_p(1024), 1 << 30, None)
     assert rc == 4
 
 
@@ -76,7 +76,9 @@ def test_workspace_queries(L):
     assert L.isb_gemm_nt_workspace_bytes(256, 2048, 100352, 1) == 0
     assert L.isb_gemm_nt_workspace_bytes(256, 2048, 100352, 4) == 4 * 256 * 2048 * 4
     assert L.isb_region_select_workspace_bytes(2, 2048, 14, 14, 464, 7, 7, 6, 10) > 2 * 64 * 2048 * 2
-    assert L.isb_select_negatives_workspace_bytes(100, 1000, 384) > 0
+    assert L.isb_select_negatives_workspace_bytes(100, 1000, 128, 1) > L.isb_select_negatives_workspace_bytes(100, 1000, 128, 0) > 0
+    assert L.isb_topk_resolve_workspace_bytes(5, 100000, 256) > 0
+    assert L.isb_topk_exhaustive_workspace_bytes(5, 100000, 100) >= 5 * 32 * 100 * 16
 
 
 def test_ops_reject_cpu_tensors():

@@ -108,10 +108,30 @@ def test_gemm_nt_fp32_grade_by_k_concat(ops):
     assert rel1 > 20 * rel  # the split really buys precision
 
 
+@pytest.mark.parametrize("M,N,K,splits", [(256, 512, 1024, 1), (130, 300, 200, 1), (64, 256, 6400, 5)])
+def test_gemm_nt_split_operands(ops, M, N, K, splits):
+    # a_hi.b_hi + a_lo.b_hi + a_hi.b_lo in one TMEM accumulator == the K-concatenated form
+    a, b = _randn(M, K, seed=18).cuda(), _randn(N, K, seed=19).cuda()
+    bias = _randn(N, seed=20).cuda()
+    a_hi, a_lo = ops.to_bf16(a, 0), ops.to_bf16(a, 1)
+    b_hi, b_lo = ops.to_bf16(b, 0), ops.to_bf16(b, 1)
+    got = ops.gemm_nt_split(a_hi, a_lo, b_hi, b_lo, bias=bias, splits=splits, k=K)
+    want = a.double() @ b.double().t() + bias.double()
+    rel = (got.double() - want).abs().max().item() / want.abs().max().item()
+    assert rel < 2e-5, rel
+    if splits == 1:
+        cat = ops.gemm_nt(torch.cat([a_hi, a_lo, a_hi], 1).contiguous(),
+                          torch.cat([b_hi, b_hi, b_lo], 1).contiguous(), bias=bias)
+        if K % 64 == 0:   # same k-block sequence => bit-identical accumulation
+            assert torch.equal(got, cat)
+        else:
+            assert torch.allclose(got, cat, rtol=1e-6, atol=1e-6)
+
+
 # ------------------------------------------------------------------ top-k search
-def _search(ops, q, db, k, margin=None):
+def _search(ops, q, db, k, margin=None, stats=None, exact=True):
     qd, dbd = q.cuda(), db.cuda()
-    s, i = ops.topk_search(qd, dbd, ops.to_bf16(dbd), k, margin)
+    s, i = ops.topk_search(qd, dbd, ops.to_bf16(dbd), k, margin, stats=stats, exact=exact)
     torch.cuda.synchronize()
     return s, i
 
@@ -152,10 +172,63 @@ def test_topk_search_clustered_and_planted(ops):
     q = oracle.normalize_l2(centers[:Q] + 0.05 * _randn(Q, D, seed=15))
     planted = torch.arange(Q) * 7 + 3
     db[planted] = q
-    s, i = _search(ops, q, db, k)
+    stats = {}
+    s, i = _search(ops, q, db, k, stats=stats)
     assert torch.equal(i[:, 0].cpu(), planted)          # round trip: a row finds itself
     assert torch.allclose(s[:, 0].cpu(), torch.ones(Q), atol=1e-6)
     check_topk_against_oracle(q, db, k, s, i)
+    # ~100 near-duplicates per cluster, score spacing far below bf16 noise: the
+    # certificate must have sent (most of) these rows to the fp32-grade re-screen
+    assert stats["rows"] == Q and stats["resolved_fp32_grade"] > Q // 2
+    assert stats["resolved_exhaustive"] == 0
+
+
+def test_topk_search_certificate_is_silent_on_ordinary_data(ops):
+    Q, N, D, k = 256, 50000, 256, 100
+    q = oracle.normalize_l2(_randn(Q, D, seed=21))
+    db = oracle.normalize_l2(_randn(N, D, seed=22))
+    stats = {}
+    s, i = _search(ops, q, db, k, stats=stats)
+    check_topk_against_oracle(q, db, k, s, i)
+    assert stats == {"rows": Q, "resolved_fp32_grade": 0, "resolved_exhaustive": 0}
+    s2, i2 = _search(ops, q, db, k, exact=False)      # the sync-free variant: same answer here
+    assert torch.equal(i2, i) and torch.equal(s2, s)
+
+
+def test_topk_search_duplicated_database_rows(ops):
+    # 300 exact copies of one row: more ties at the k-th score than any margin holds
+    # -> fp32-grade re-screen cannot certify either -> exhaustive pass; ties -> lower index
+    Q, N, D, k = 20, 4000, 64, 40
+    q = oracle.normalize_l2(_randn(Q, D, seed=23))
+    db = oracle.normalize_l2(_randn(N, D, seed=24))
+    dup = torch.randperm(N, generator=torch.Generator().manual_seed(25))[:300]
+    db[dup] = q[3]
+    stats = {}
+    s, i = _search(ops, q, db, k, stats=stats)
+    want = dup.sort().values[:k]
+    assert torch.equal(i[3].cpu(), want)
+    assert torch.allclose(s[3].cpu(), torch.ones(k), atol=1e-6)
+    assert stats["resolved_exhaustive"] >= 1
+    a_s, a_i = oracle.topk_search_f64(q, db, k)
+    assert torch.equal(i.cpu(), a_i)
+
+
+def test_topk_exhaustive_matches_screened_search(ops):
+    # the last-line kernel alone, on every row, against the normal path
+    from instance_search_b200 import _lib
+    Q, N, D, k = 33, 7001, 72, 25
+    q = oracle.normalize_l2(_randn(Q, D, seed=26)).cuda()
+    db = oracle.normalize_l2(_randn(N, D, seed=27)).cuda()
+    s, i = ops.topk_search(q, db, ops.to_bf16(db), k)
+    L = _lib.lib()
+    rows = torch.arange(Q, dtype=torch.int32, device="cuda")
+    s2, i2 = torch.empty_like(s), torch.empty_like(i)
+    nb = L.isb_topk_exhaustive_workspace_bytes(Q, N, k)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    _lib.check(L.isb_topk_exhaustive(q.data_ptr(), db.data_ptr(), N, D, k, 0, rows.data_ptr(), Q,
+                                     s2.data_ptr(), i2.data_ptr(), ws.data_ptr(), nb, None), "exhaustive")
+    torch.cuda.synchronize()
+    assert torch.equal(i2, i) and torch.equal(s2, s)
 
 
 def test_topk_search_idx_offset_and_merge(ops):
