@@ -235,6 +235,53 @@ int isb_select_negatives(const float* emb, const uint16_t* emb_hi, const uint16_
                          int64_t* neg_idx, float* neg_sim, float* pos_sim, int32_t* n_bruteforce,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------- a9 (reduction)
+ * precision1's row reduction, utils/metrics.py:11-13:  kth <= 1 -> sim.max(1);
+ * kth > 1 -> sim.kthvalue(N - kth + 1, 1), i.e. the kth LARGEST entry of each row
+ * and its column.  sim [Q, N] fp32 with leading dimension ld; val [Q]; idx [Q]
+ * int64.  Ties -> lower column first.  1 <= kth <= min(64, N). */
+int isb_row_kth_largest(const float* sim, int64_t Q, int64_t N, int64_t ld, int kth, float* val,
+                        int64_t* idx, void* stream);
+
+/* ---------------------------------------------------------------- a10 (ranking)
+ * What avg_precision needs from  sim[i].sort(descending=True)  (utils/metrics.py:33):
+ * the position of the query's positives in that ranking.  For every row q and
+ * every listed column c = cols[q, p] (p < P; c < 0 marks an unused slot):
+ *   rank[q, p] = #{ j : sim[q, j] > sim[q, c]  or  (sim[q, j] == sim[q, c] and j < c) }
+ * (unused slots get -1).  One streaming pass per row, no sort of the row.
+ * cols, rank [Q, P] int32; 1 <= P <= 8192. */
+int isb_row_ranks(const float* sim, int64_t Q, int64_t N, int64_t ld, const int32_t* cols, int P,
+                  int32_t* rank, void* stream);
+
+/* ---------------------------------------------------------------- (f1) DBA
+ * instance_avg, test/instance_avg.py:7-33: out[i] = agg / (||agg|| + 1e-10),
+ * agg = emb[i] + sum_{j < nn} ((nn - j) / (nn + 1)) * emb[nbr_j], nbr = the other
+ * items of label[i] by decreasing emb[i].emb[nbr], nn = their number (capped by k
+ * when k >= 0); nn <= 0 -> out[i] = emb[i].  No N x N matrix: only same-label
+ * similarities are computed (exactly).  *overflow counts rows whose label has more
+ * than 2048 other members (not supported; result uses the first 2048 by index). */
+int isb_instance_avg(const float* emb, const int32_t* label, int64_t N, int64_t D, int k, float* out,
+                     int32_t* overflow, void* stream);
+
+/* ---------------------------------------------------------------- (f3) training-side operators
+ * NormalizeL2Fun.backward, model/custom_modules.py:59-67:
+ *   grad_in = (norm2 * g - x * <x, g>) / (norm2 * sqrt(norm2)),  norm2 = sum x^2 + eps */
+int isb_l2norm_rows_backward(const float* x, const float* grad_out, int64_t M, int64_t F, float eps,
+                             float* grad_in, void* stream);
+/* ShiftFun.backward, model/custom_modules.py:20-25: grad_param[j] = sum_m g[m, j]
+ * (grad_input is grad_output itself). */
+int isb_col_sums(const float* g, int64_t M, int64_t F, float* out, void* stream);
+/* TripletLossFun.forward, model/custom_modules.py:153-171.  row_loss [B] (after the
+ * clamp), clamp [B] uint8 (1 where the row's loss was <= 0), loss [1]. */
+int isb_triplet_loss_forward(const float* anchor, const float* pos, const float* neg, int64_t B,
+                             int64_t D, float margin, int size_average, int normalized, float* loss,
+                             float* row_loss, uint8_t* clamp, void* stream);
+/* TripletLossFun.backward, model/custom_modules.py:173-203.  grad_out [1] device. */
+int isb_triplet_loss_backward(const float* anchor, const float* pos, const float* neg, int64_t B,
+                              int64_t D, const uint8_t* clamp, const float* grad_out, int size_average,
+                              int normalized, float* grad_anchor, float* grad_pos, float* grad_neg,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,15 @@ SIGNATURES = {
     "isb_select_negatives_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_int]),
     "isb_select_negatives": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64,
                                      c_int, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    "isb_row_kth_largest": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
+    "isb_row_ranks": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_int, c_ptr, c_ptr]),
+    "isb_instance_avg": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
+    "isb_l2norm_rows_backward": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_f32, c_ptr, c_ptr]),
+    "isb_col_sums": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
+    "isb_triplet_loss_forward": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_int, c_int, c_ptr,
+                                         c_ptr, c_ptr, c_ptr]),
+    "isb_triplet_loss_backward": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_int, c_int,
+                                          c_ptr, c_ptr, c_ptr, c_ptr]),
     "isb_gemm_nt_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_int]),
     "isb_gemm_nt": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64,
                             c_int, c_ptr, c_size, c_ptr]),

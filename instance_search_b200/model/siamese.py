@@ -1,0 +1,188 @@
+"""Drop-in for the descriptor nets of the reference's ``model/siamese.py``.
+
+    DescriptorNet          model/siamese.py:92-130
+    RegionDescriptorNet    model/siamese.py:133-231
+
+Same constructor arguments, attributes (``k``, ``feature_size``,
+``feature_size2d``, ``features``, ``feature_reduc``, ``classifier``,
+``feature_reduc1``, ``feature_reduc2``), state-dict keys
+(``classifier.0.{weight,bias}``, ``feature_reduc1.1.param``,
+``feature_reduc1.2.{weight,bias}``) and forward contract, so the reference's
+checkpoints load and its callers run unchanged.  The trunk (``features``) stays
+in PyTorch.  Everything after it runs, without autograd, as the fused CUDA head
+of ``instance_search_b200.regions`` for the WHOLE batch at once -- the result
+equals the reference's batch-1 forward (:184) looped over the images.  When a
+gradient is required (training), the head is composed per image exactly as the
+reference composes it (:185-223), from this package's NormalizeL2 / Shift
+(CUDA forward + backward kernels) and torch's conv / linear autograd.
+"""
+
+import torch
+import torch.nn as nn
+
+from .. import regions
+from .custom_modules import NormalizeL2, Shift
+from .nn_utils import convolutionalize, extract_layers, get_feature_size, set_untrained_blocks
+
+
+class _HeadCache(object):
+    """Tensor-core-ready copies of the head parameters, rebuilt when any of them
+    changes (in-place updates bump ``_version``; re-assignment changes data_ptr)."""
+
+    def __init__(self):
+        self.key, self.hw = None, None
+
+    def get(self, params, terms, build):
+        key = (terms,) + tuple((None if p is None else (p.data_ptr(), p._version)) for p in params)
+        if key != self.key:
+            self.hw = build()
+            self.key = key
+        return self.hw
+
+
+class DescriptorNet(nn.Module):
+    """Global descriptor: trunk -> flatten -> L2 -> Shift -> Linear -> L2.
+    reference: model/siamese.py:92-130"""
+
+    projection_terms = 3   # 3: fp32-grade split-operand projection; 1: plain bf16
+
+    def __init__(self, net, feature_dim, feature_size2d, untrained=-1):
+        super(DescriptorNet, self).__init__()
+        self.features, _, classifier = extract_layers(net)
+        set_untrained_blocks([self.features], untrained)
+        factor = feature_size2d[0] * feature_size2d[1]
+        in_features = get_feature_size(self.features, factor)
+        if feature_dim <= 0:
+            self.feature_size = get_feature_size(classifier)
+        else:
+            self.feature_size = feature_dim
+        self.feature_reduc1 = nn.Sequential(
+            NormalizeL2(),
+            Shift(in_features),
+            nn.Linear(in_features, self.feature_size)
+        )
+        self.feature_reduc2 = NormalizeL2()
+        self._cache = _HeadCache()
+
+    def _head(self):
+        shift, lin = self.feature_reduc1[1], self.feature_reduc1[2]
+        return self._cache.get(
+            (shift.param, lin.weight, lin.bias), self.projection_terms,
+            lambda: regions.HeadWeights(None, None, shift.param.data, lin.weight.data,
+                                        None if lin.bias is None else lin.bias.data,
+                                        terms=self.projection_terms))
+
+    def forward_single(self, x):
+        x = self.features(x)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.feature_reduc1.parameters())):
+            x = x.reshape(x.size(0), -1)                 # :119-121
+            x = self.feature_reduc1(x)
+            return self.feature_reduc2(x)
+        return regions.global_descriptors(x.detach(), self._head())
+
+    def forward(self, x1, x2=None, x3=None):
+        if self.training and x3 is not None:
+            return self.forward_single(x1), self.forward_single(x2), self.forward_single(x3)
+        elif self.training:
+            return self.forward_single(x1), self.forward_single(x2)
+        else:
+            return self.forward_single(x1)
+
+
+class RegionDescriptorNet(nn.Module):
+    """Top-k region descriptor. reference: model/siamese.py:133-231"""
+
+    projection_terms = 3
+
+    def __init__(self, net, k, feature_dim, feature_size2d, untrained=-1):
+        super(RegionDescriptorNet, self).__init__()
+        self.k = k
+        self.feature_size2d = tuple(feature_size2d)
+        self.features, self.feature_reduc, self.classifier = extract_layers(net)
+        factor = feature_size2d[0] * feature_size2d[1]
+        in_features = get_feature_size(self.features, factor)
+        if feature_dim <= 0:
+            self.feature_size = get_feature_size(self.classifier)
+        else:
+            self.feature_size = feature_dim
+        reduc_count = sum(1 for _ in self.feature_reduc)
+        if reduc_count > 0:
+            # ResNet-like: sliding mean over feature_size2d windows, stride 1 (:161-166)
+            self.feature_reduc = nn.Sequential(nn.AvgPool2d(self.feature_size2d, stride=1))
+        count = 0
+        for name, module in self.classifier._modules.items():   # :167-175
+            if isinstance(module, nn.Linear):
+                size2d = self.feature_size2d
+                if reduc_count > 0 or count > 0:
+                    size2d = (1, 1)
+                self.classifier._modules[name] = convolutionalize(module, size2d)
+                count += 1
+        set_untrained_blocks([self.features, self.classifier], untrained)
+        self.feature_reduc1 = nn.Sequential(
+            NormalizeL2(),
+            Shift(in_features),
+            nn.Linear(in_features, self.feature_size)
+        )
+        self.feature_reduc2 = NormalizeL2()
+        self._cache = _HeadCache()
+
+    # ---- fused CUDA head -------------------------------------------------------
+    def _fusable(self):
+        """AvgPool(window, stride 1) + ONE 1x1 conv: the ResNet case of the reference."""
+        mods = list(self.classifier)
+        return (len(list(self.feature_reduc)) == 1 and isinstance(self.feature_reduc[0], nn.AvgPool2d) and
+                len(mods) == 1 and isinstance(mods[0], nn.Conv2d) and tuple(mods[0].kernel_size) == (1, 1) and
+                mods[0].bias is not None)
+
+    def _head(self):
+        conv = self.classifier[0]
+        shift, lin = self.feature_reduc1[1], self.feature_reduc1[2]
+        return self._cache.get(
+            (conv.weight, conv.bias, shift.param, lin.weight, lin.bias), self.projection_terms,
+            lambda: regions.HeadWeights(conv.weight.data, conv.bias.data, shift.param.data, lin.weight.data,
+                                        None if lin.bias is None else lin.bias.data,
+                                        terms=self.projection_terms))
+
+    def _needs_grad(self, x):
+        return torch.is_grad_enabled() and (
+            x.requires_grad or any(p.requires_grad for p in self.classifier.parameters()) or
+            any(p.requires_grad for p in self.feature_reduc1.parameters()))
+
+    # ---- reference composition, one image (:185-223), autograd-capable ---------
+    def _forward_single_composed(self, x):
+        c = self.feature_reduc(x)
+        c = self.classifier(c)
+        c_maxv, _ = c.max(1)
+        c_maxv = c_maxv.reshape(-1)
+        k = min(c_maxv.size(0), self.k)
+        _, flat_idx = c_maxv.topk(k)
+        fh, fw = self.feature_size2d
+        acc = x.new_zeros(c.size(0), self.feature_size)
+        cls_cols = []
+        for fi in flat_idx.tolist():
+            r, col = fi // c.size(3), fi % c.size(3)
+            cls_cols.append(c[:, :, r, col])
+            region = x[:, :, r:r + fh, col:col + fw].contiguous().view(x.size(0), -1)
+            acc = acc + self.feature_reduc1(region)
+        cls_out = torch.stack(cls_cols, 2)
+        if k < self.k:   # zero-padded to k slots (:207-208)
+            cls_out = torch.cat([cls_out, cls_out.new_zeros(c.size(0), c.size(1), self.k - k)], 2)
+        return self.feature_reduc2(acc), cls_out
+
+    def forward_single(self, x):
+        """x: [B, 3, h, w] images -> (desc [B, D], cls_out [B, ncls, k]); every image is
+        treated as the reference's batch-1 call (model/siamese.py:184)."""
+        x = self.features(x)
+        if self._needs_grad(x) or not self._fusable():
+            outs = [self._forward_single_composed(x[b:b + 1]) for b in range(x.size(0))]
+            return torch.cat([d for d, _ in outs], 0), torch.cat([c for _, c in outs], 0)
+        desc, cls_out, _, _ = regions.region_descriptors(x.detach(), self._head(), self.k, self.feature_size2d)
+        return desc, cls_out
+
+    def forward(self, x1, x2=None, x3=None):
+        if self.training and x3 is not None:
+            return self.forward_single(x1), self.forward_single(x2), self.forward_single(x3)
+        elif self.training:
+            return self.forward_single(x1), self.forward_single(x2)
+        else:
+            return self.forward_single(x1)[0]

@@ -221,6 +221,105 @@ def topk_merge(cand_scores, cand_idx):
     return scores, idx
 
 
+# --------------------------------------------------------------------- metrics
+def row_kth_largest(sim, kth=1):
+    """(val [Q], idx [Q] int64): the kth largest entry of every row of sim and its
+    column -- sim.max(1) / sim.kthvalue(N - kth + 1, 1) of utils/metrics.py:11-13."""
+    _need_cuda(sim)
+    if sim.dim() != 2 or sim.dtype != torch.float32 or sim.stride(1) != 1:
+        raise IsbError("row_kth_largest: [Q, N] float32 rows expected")
+    Q, N = sim.shape
+    val = torch.empty(Q, dtype=torch.float32, device=sim.device)
+    idx = torch.empty(Q, dtype=torch.int64, device=sim.device)
+    _lib.check(_lib.lib().isb_row_kth_largest(sim.data_ptr(), Q, N, sim.stride(0), int(kth), val.data_ptr(),
+                                              idx.data_ptr(), _stream()), "isb_row_kth_largest")
+    return val, idx
+
+
+def row_ranks(sim, cols):
+    """rank [Q, P] int32 of the listed columns (cols [Q, P] int32, -1 = unused) in
+    the descending sort of their row -- utils/metrics.py:33 without the sort."""
+    _need_cuda(sim, cols)
+    if sim.dim() != 2 or sim.dtype != torch.float32 or sim.stride(1) != 1:
+        raise IsbError("row_ranks: [Q, N] float32 rows expected")
+    cols = cols.to(torch.int32).contiguous()
+    Q, N = sim.shape
+    if cols.dim() != 2 or cols.size(0) != Q:
+        raise IsbError("row_ranks: cols must be [Q, P]")
+    rank = torch.empty_like(cols)
+    _lib.check(_lib.lib().isb_row_ranks(sim.data_ptr(), Q, N, sim.stride(0), cols.data_ptr(), cols.size(1),
+                                        rank.data_ptr(), _stream()), "isb_row_ranks")
+    return rank
+
+
+def instance_avg(emb, label_ids, k=-1):
+    """DBA of test/instance_avg.py:7-33 on device; label_ids [N] int32."""
+    _need_cuda(emb, label_ids)
+    emb = _f32c(emb)
+    label_ids = label_ids.to(torch.int32).contiguous()
+    out = torch.empty_like(emb)
+    ovf = torch.zeros(1, dtype=torch.int32, device=emb.device)
+    _lib.check(_lib.lib().isb_instance_avg(emb.data_ptr(), label_ids.data_ptr(), emb.size(0), emb.size(1),
+                                           int(k), out.data_ptr(), ovf.data_ptr(), _stream()),
+               "isb_instance_avg")
+    if int(ovf.item()):
+        raise IsbError("instance_avg: an instance has more than 2048 other members")
+    return out
+
+
+# ------------------------------------------------------------- training-side ops
+def l2norm_rows_backward(x, grad_out, eps=1e-10):
+    """reference: model/custom_modules.py:59-67"""
+    _need_cuda(x, grad_out)
+    x, grad_out = _f32c(x), _f32c(grad_out)
+    gx = torch.empty_like(x)
+    _lib.check(_lib.lib().isb_l2norm_rows_backward(x.data_ptr(), grad_out.data_ptr(), x.size(0), x.size(1),
+                                                   float(eps), gx.data_ptr(), _stream()),
+               "isb_l2norm_rows_backward")
+    return gx
+
+
+def col_sums(g):
+    """grad_param of Shift: model/custom_modules.py:23-24"""
+    _need_cuda(g)
+    g = _f32c(g)
+    out = torch.empty(g.size(1), dtype=torch.float32, device=g.device)
+    _lib.check(_lib.lib().isb_col_sums(g.data_ptr(), g.size(0), g.size(1), out.data_ptr(), _stream()),
+               "isb_col_sums")
+    return out
+
+
+def triplet_loss_forward(anchor, pos, neg, margin, size_average=True, normalized=True):
+    """(loss [1], clamp [B] uint8). reference: model/custom_modules.py:153-171"""
+    _need_cuda(anchor, pos, neg)
+    anchor, pos, neg = _f32c(anchor), _f32c(pos), _f32c(neg)
+    B, D = anchor.shape
+    loss = torch.empty(1, dtype=torch.float32, device=anchor.device)
+    row_loss = torch.empty(B, dtype=torch.float32, device=anchor.device)
+    clamp = torch.empty(B, dtype=torch.uint8, device=anchor.device)
+    _lib.check(_lib.lib().isb_triplet_loss_forward(anchor.data_ptr(), pos.data_ptr(), neg.data_ptr(), B, D,
+                                                   float(margin), int(bool(size_average)),
+                                                   int(bool(normalized)), loss.data_ptr(),
+                                                   row_loss.data_ptr(), clamp.data_ptr(), _stream()),
+               "isb_triplet_loss_forward")
+    return loss, clamp
+
+
+def triplet_loss_backward(anchor, pos, neg, clamp, grad_out, size_average=True, normalized=True):
+    """reference: model/custom_modules.py:173-203"""
+    _need_cuda(anchor, pos, neg, clamp, grad_out)
+    anchor, pos, neg = _f32c(anchor), _f32c(pos), _f32c(neg)
+    grad_out = _f32c(grad_out.reshape(1))
+    B, D = anchor.shape
+    ga, gp, gn = torch.empty_like(anchor), torch.empty_like(anchor), torch.empty_like(anchor)
+    _lib.check(_lib.lib().isb_triplet_loss_backward(anchor.data_ptr(), pos.data_ptr(), neg.data_ptr(), B, D,
+                                                    clamp.data_ptr(), grad_out.data_ptr(),
+                                                    int(bool(size_average)), int(bool(normalized)),
+                                                    ga.data_ptr(), gp.data_ptr(), gn.data_ptr(), _stream()),
+               "isb_triplet_loss_backward")
+    return ga, gp, gn
+
+
 # ------------------------------------------------------- torch.library registration
 # The same entry points as dispatcher ops (CUDA only; no CPU kernel is registered,
 # so calling them with CPU tensors raises NotImplementedError from the dispatcher).

@@ -1,0 +1,70 @@
+"""Hot-path functions of the reference's ``train/siamese_regions.py``:
+
+    get_embeddings              train/siamese_regions.py:26-41
+    negative selection          train/siamese_regions.py:106-129 (create_batch)
+
+The reference embeds ONE image per forward (``fold_batches(..., 1)``, an H2D copy
+and a Python iteration per image).  Here consecutive images of identical size
+are stacked from pinned host memory and go through the trunk and the fused CUDA
+head as a batch; the descriptors equal the per-image ones (the head treats every
+image as the reference's batch-1 call).
+"""
+
+import torch
+
+from .. import mining
+
+
+def get_embeddings(net, dataset, device, out_size, batch_size=32, transform=None):
+    """Descriptors [len(dataset), out_size] of a reference-style data set (list of
+    ``(image tensor [3, h, w], label, name)``), stored on ``device`` (>= 0: current
+    CUDA device, < 0: host -- utils/general.py:94-98).
+    reference: train/siamese_regions.py:26-41 (net must be in eval mode)."""
+    n = len(dataset)
+    out = torch.empty((n, out_size), dtype=torch.float32, device="cuda")
+    i = 0
+    with torch.no_grad():
+        while i < n:
+            first = dataset[i][0] if transform is None else transform(dataset[i][0])
+            batch = [first]
+            j = i + 1
+            while j < n and len(batch) < batch_size:
+                im = dataset[j][0] if transform is None else transform(dataset[j][0])
+                if im.shape != first.shape:
+                    break
+                batch.append(im)
+                j += 1
+            x = torch.stack(batch)
+            if not x.is_cuda:
+                x = x.pin_memory().cuda(non_blocking=True)
+            desc = net(x)
+            if isinstance(desc, tuple):          # a net left in train mode returns (desc, cls_out)
+                desc = desc[0]
+            out[i:j] = desc
+            i = j
+    return out if device >= 0 else out.cpu()
+
+
+class NegativeSelector(object):
+    """Batched form of the mining block of create_batch (train/siamese_regions.py:106-129).
+
+    Built once per epoch from the embeddings ``get_similarities`` would have
+    multiplied (utils/train_siamese.py:52-53); ``select`` answers, for any number
+    of positive couples at once, what the reference computes per training sample
+    from a row of the N x N matrix -- which is never materialised here.
+    """
+
+    def __init__(self, embeddings, dataset):
+        ids, self.labels = mining.label_ids(dataset)
+        self.index = mining.MiningIndex(embeddings.cuda(), ids)
+
+    def select(self, couples, epoch, train_epoch_switch):
+        """couples: sequence of (i1, i2).  Returns a list with, per couple, the index
+        of the chosen negative or None when every item is excluded (the reference
+        then falls back to choose_rand_neg, utils/dataset.py:57-61)."""
+        if len(couples) == 0:
+            return []
+        a = torch.tensor([c[0] for c in couples], dtype=torch.int64)
+        b = torch.tensor([c[1] for c in couples], dtype=torch.int64)
+        neg, _, _ = self.index.select_negatives(a, b, epoch < train_epoch_switch)   # :107
+        return [None if v < 0 else v for v in neg.tolist()]

@@ -1,0 +1,102 @@
+"""Stage-by-stage timing of the region-descriptor head (BASELINE configs[1]):
+B x 2048 x H x W fp32 feature maps -> [B, D] descriptors.  Prints one JSON line per
+map size with per-stage CUDA-event times, region descriptors/s, the HBM fraction of
+the bandwidth-bound stages and the tensor fraction of the projection.
+Synthetic inputs per SURVEY.md 8d.  Development / profiling probe; the contract
+bench is bench.py."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from instance_search_b200 import _lib, ops, regions  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--B", type=int, default=256)
+ap.add_argument("--C", type=int, default=2048)
+ap.add_argument("--sizes", default="14,32")
+ap.add_argument("--ncls", type=int, default=464)
+ap.add_argument("--D", type=int, default=2048)
+ap.add_argument("--k", type=int, default=6)
+ap.add_argument("--terms", type=int, default=3)
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--warmup", type=int, default=3)
+a = ap.parse_args()
+
+dev = torch.device("cuda:0")
+peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+pp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+if os.path.exists(pp):
+    peaks = json.load(open(pp))
+
+g = torch.Generator(device=dev).manual_seed(1234 + 2)
+Kin = a.C * 49
+cls_w = torch.randn(a.ncls, a.C, device=dev, generator=g) / a.C ** 0.5
+cls_b = 0.01 * torch.randn(a.ncls, device=dev, generator=g)
+shift = 0.01 * torch.randn(Kin, device=dev, generator=g)
+lin_w = torch.randn(a.D, Kin, device=dev, generator=g) / Kin ** 0.5
+lin_b = 0.01 * torch.randn(a.D, device=dev, generator=g)
+hw = regions.HeadWeights(cls_w, cls_b, shift, lin_w, lin_b, terms=a.terms)
+del lin_w
+flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > L2
+
+
+def ev():
+    return torch.cuda.Event(enable_timing=True)
+
+
+for hw_size in [int(s) for s in a.sizes.split(",")]:
+    H = W = hw_size
+    x = torch.relu(torch.randn(a.B, a.C, H, W, device=dev, generator=g))
+    stages = {"select": [], "gather": [], "project": [], "finalize": [], "total": []}
+    for it in range(a.warmup + a.iters):
+        flush.zero_()   # L2 flush between iterations (x at 14x14 is 411 MB, at 32x32 2.1 GB)
+        e = [ev() for _ in range(5)]
+        e[0].record()
+        idx, nsel, cls_out, win_norm = regions.region_select(x, hw, a.k, (7, 7))
+        e[1].record()
+        L = _lib.lib()
+        U_hi = torch.empty((a.B, hw.KinP), dtype=torch.bfloat16, device=dev)
+        U_lo = torch.empty_like(U_hi) if hw.terms == 3 else None
+        _lib.check(L.isb_region_gather(x.data_ptr(), a.B, a.C, H, W, 7, 7, a.k, idx.data_ptr(), nsel.data_ptr(),
+                                       win_norm.data_ptr(), hw.shift.data_ptr(), U_hi.data_ptr(),
+                                       ops._ptr(U_lo), hw.KinP, ops._stream()), "gather")
+        e[2].record()
+        y = regions._project(U_hi, U_lo, hw, a.B)
+        e[3].record()
+        desc = torch.empty((a.B, hw.D), dtype=torch.float32, device=dev)
+        _lib.check(L.isb_descriptor_finalize(y.data_ptr(), a.B, hw.D, ops._ptr(hw.lin_b), nsel.data_ptr(), 1e-10,
+                                             desc.data_ptr(), ops._stream()), "finalize")
+        e[4].record()
+        torch.cuda.synchronize()
+        if it >= a.warmup:
+            for n, (s, t) in zip(["select", "gather", "project", "finalize"], zip(e[:-1], e[1:])):
+                stages[n].append(s.elapsed_time(t))
+            stages["total"].append(e[0].elapsed_time(e[4]))
+    med = {n: sorted(v)[len(v) // 2] for n, v in stages.items()}
+    nwin = (H - 6) * (W - 6)
+    kk = min(nwin, a.k)
+    units = a.B * kk                                  # region descriptors per batch (SURVEY 8d unit)
+    # algorithmic bytes of the bandwidth-bound part (sum-before-projection form):
+    #   x read once + classifier weights + the bf16 operand written once (hi, + lo when terms == 3)
+    op_bytes = 2 * a.B * Kin * (2 if a.terms == 3 else 1)
+    bw_bytes = 4 * a.B * a.C * H * W + 4 * a.ncls * a.C + op_bytes
+    bw_ms = med["select"] + med["gather"]
+    proj_flops = 2.0 * a.B * Kin * a.D * a.terms     # tensor-pipe flops actually issued
+    alg_flops = 2.0 * a.B * Kin * a.D                # one fp32-grade product
+    print(json.dumps({
+        "workload": "region descriptors, B=%d C=%d %dx%d map, ncls=%d, D=%d, k=%d, terms=%d" %
+                    (a.B, a.C, H, W, a.ncls, a.D, a.k, a.terms),
+        "ms": med, "region_desc_per_s": units / (med["total"] * 1e-3),
+        "images_per_s": a.B / (med["total"] * 1e-3),
+        "pool_select_gather": {"algorithmic_bytes": bw_bytes, "ms": bw_ms,
+                               "achieved_gbs": bw_bytes / (bw_ms * 1e-3) / 1e9,
+                               "frac_of_measured_hbm": bw_bytes / (bw_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+        "projection": {"issued_tflops": proj_flops / (med["project"] * 1e-3) / 1e12,
+                       "algorithmic_tflops": alg_flops / (med["project"] * 1e-3) / 1e12,
+                       "frac_of_measured_bf16_burst": proj_flops / (med["project"] * 1e-3) / 1e12 / peaks["bf16_tflops"]},
+    }), flush=True)
+    del x
