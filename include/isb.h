@@ -173,20 +173,55 @@ int isb_gemm_nt_split(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda, c
  *   m = max over classes (:191); the k' = min(H'W', k) windows with the largest m,
  *   best first (:193-194); cls_out[:, :, i] = c[:, :, window_i] (:216), zero beyond k'
  * A bf16 tcgen05 GEMM with the class-max fused in its epilogue screens all
- * windows; the k + margin best are re-scored exactly (fp32 products, fp64
- * accumulation) and the final order / logits come from that exact pass.
+ * windows; the k + margin best of every image are re-scored with fp32-grade
+ * split operands (window means as bf16 hi + lo against cls_w hi + lo, three
+ * tcgen05 products, ~1e-6) and the final order / logits come from that pass.
+ * Completeness certificate as for the search: every non-candidate window has a
+ * screen value <= t_min; an image whose k-th exact class-max does not clear t_min
+ * by 8 sigma (sigma = rms(screen - exact) over its candidates) is counted in
+ * *n_uncertified (device int32, may be NULL); the caller re-runs such a batch
+ * with a larger margin (margin = 32 - k scores up to 32 windows exactly).
+ * The logits of this pass are fp32-GRADE, not fp32: cls_out here is a preview
+ * (abs. error ~1e-5 x logit scale); isb_region_logits recomputes the selected
+ * windows' logits in true fp32, fixes their order and closes the certificate.
+ * approx_max [B, k] (class-max of the selected windows as seen here) and
+ * runner_up [B] (class-max of the best window NOT selected, -inf if none) feed it;
+ * both may be NULL.
+ * exact_mode != 0: second line for uncertified batches -- the candidates (use
+ * margin = 32 - k) are re-scored from the fp32 inputs with fp64 accumulation; slow,
+ * exact, cls_out final.
  *   x [B, C, H, W] fp32 (NCHW)    cls_w [ncls, C] fp32    cls_b [ncls] fp32
- *   cls_w_bf16 [ncls, ld_w] = isb_f32_to_bf16(cls_w, part 0)
+ *   cls_w_hi / cls_w_lo [ncls, ld_w] = isb_f32_to_bf16(cls_w, part 0 / 1)
  *   idx [B, k] int64: flat window index r * W' + c, -1 beyond k'    nsel [B] int32 = k'
  *   cls_out [B, ncls, k] fp32      win_norm [B, k] fp32 = sqrt(||crop_i||^2 + 1e-10)
  * k <= 32; windows re-scored per image = min(H'W', k + margin, 32). */
 size_t isb_region_select_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t ncls,
                                          int fh, int fw, int k, int margin);
-int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H, int64_t W,
-                      const float* cls_w, const uint16_t* cls_w_bf16, int64_t ld_w,
+int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, const float* cls_w,
+                      const uint16_t* cls_w_hi, const uint16_t* cls_w_lo, int64_t ld_w,
                       const float* cls_b, int64_t ncls, int fh, int fw, int k, int margin,
-                      int64_t* idx, int32_t* nsel, float* cls_out, float* win_norm,
-                      void* workspace, size_t workspace_bytes, void* stream);
+                      int exact_mode, int64_t* idx, int32_t* nsel, float* cls_out, float* win_norm,
+                      float* approx_max, float* runner_up, int32_t* n_uncertified, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* a3 / a4, closing stage.  isb_region_select is called with ke = k + 2 (the k windows
+ * plus two runner-ups), isb_region_gather sums the first k into the operand and
+ * leaves the exact fp32 mean of all ke windows in win_mean [B, ke, C]; this call
+ * computes their logits in true fp32,  cls_w . mean + cls_b  (model/siamese.py:188),
+ * orders the ke windows exactly (class-max desc, window asc, :191-194) and writes
+ * the final k: idx_out [B, k], norm_out [B, k], nsel_out [B], cls_out [B, ncls, k]
+ * (:216).  Images where a runner-up displaced one of the first k are appended to
+ * changed_list / n_changed (device; may be NULL): their operand rows must be
+ * re-gathered (isb_region_gather with image_list).  Certificate: the k-th exact
+ * class-max must clear runner_up[b] -- the best fp32-grade value among the windows
+ * NOT scored here -- by 8 sigma, sigma = rms(approx_max - exact) over the ke windows;
+ * failures are counted in *n_uncertified (NULL: no certificate). */
+int isb_region_logits(const float* win_mean, const float* cls_w, const float* cls_b, int64_t B,
+                      int64_t C, int64_t ncls, int ke, int k, const int32_t* nsel_in,
+                      const float* approx_max, const float* runner_up, const int64_t* idx_in,
+                      const float* norm_in, int64_t* idx_out, float* norm_out, int32_t* nsel_out,
+                      float* cls_out, int32_t* changed_list, int32_t* n_changed,
+                      int32_t* n_uncertified, void* stream);
 
 /* ---------------------------------------------------------------- a4 (operand)
  * u[b, :] = sum_{i < nsel[b]} crop_i / win_norm[b, i]  +  nsel[b] * shift
@@ -197,10 +232,16 @@ int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H, int64_t W
  *   U_hi[b] = bf16(u)      U_lo[b] = bf16(u - U_hi)   (U_lo may be NULL)
  * U_hi alone pairs with isb_gemm_nt (plain bf16 projection); U_hi + U_lo pair
  * with isb_gemm_nt_split (fp32-grade).  Rows hold C*fh*fw values zero padded to a
- * multiple of 8; ldu >= that, % 8 == 0. */
+ * multiple of 8; ldu >= that, % 8 == 0.  idx / win_norm are [B, k]; only the first
+ * min(nsel[b], k_sum) windows are summed.  win_mean [B, k, C] fp32 (may be NULL): the
+ * exact mean of ALL nsel[b] listed windows, by-product for isb_region_logits.
+ * image_list / n_list (device, may be NULL): process only the images
+ * image_list[0 .. *n_list) -- the fix-up pass after isb_region_logits. */
 int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int fh, int fw,
-                      int k, const int64_t* idx, const int32_t* nsel, const float* win_norm,
-                      const float* shift, uint16_t* U_hi, uint16_t* U_lo, int64_t ldu, void* stream);
+                      int k, int k_sum, const int32_t* image_list, const int32_t* n_list,
+                      const int64_t* idx, const int32_t* nsel, const float* win_norm,
+                      const float* shift, uint16_t* U_hi, uint16_t* U_lo, int64_t ldu, float* win_mean,
+                      void* stream);
 
 /* ---------------------------------------------------------------- a4 (bias) + a5
  * desc[b, :] = l2norm(y[b, :] + nsel[b] * bias)     (model/siamese.py:220-222)

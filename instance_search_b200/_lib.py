@@ -42,11 +42,14 @@ SIGNATURES = {
     "isb_topk_merge": (c_int, [c_ptr, c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
     "isb_region_select_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int,
                                                   c_int, c_int]),
-    "isb_region_select": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_i64,
-                                  c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size,
+    "isb_region_select": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr,
+                                  c_i64, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+                                  c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    "isb_region_logits": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr,
+                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                   c_ptr]),
-    "isb_region_gather": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_ptr, c_ptr,
-                                  c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "isb_region_gather": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_ptr,
+                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "isb_descriptor_finalize": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_f32, c_ptr, c_ptr]),
     "isb_select_negatives_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_int]),
     "isb_select_negatives": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64,

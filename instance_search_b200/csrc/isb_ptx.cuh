@@ -96,6 +96,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 1-D bulk copy global -> shared through the TMA engine (SASS UBLKCP): `bytes`
+// contiguous bytes, both addresses 16-byte aligned, bytes % 16 == 0; completion
+// is signalled on the mbarrier as complete_tx.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // L2 eviction-priority policies (createpolicy encodings used by TMA hints).
 static constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 static constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;

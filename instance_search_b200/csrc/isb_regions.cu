@@ -1,14 +1,16 @@
 // Region-descriptor aggregation of RegionDescriptorNet.forward_single
 // (model/siamese.py:185-223) for a whole batch of trunk feature maps.
 //
-//   1. region_pool_kernel       x[B,C,H,W] fp32 -> window means P[B*H'W', C] bf16
+//   1. region_pool_kernel       x[B,C,H,W] fp32 -> window means P[B*H'W', C] as bf16 hi + lo
 //                               (AvgPool2d(fh x fw, stride 1), :164-166,187) and
 //                               per-pixel channel energy partials (for the crop norms)
-//   2. gemm_tc_kernel<RowMax>   P . Wc^T + bc  (the 1x1-conv classifier, :188) with
-//                               the class-max (:191) fused into the TMEM epilogue
-//   3. region_select_kernel     top-(k+margin) windows by the bf16 screen, exact
-//                               (fp64-accumulated) re-score of those, top-k (:194),
-//                               cls_out (:216), ||crop||_2 of the chosen windows
+//   2. gemm_tc_kernel<RowMax>   P_hi . Wc_hi^T + bc  (the 1x1-conv classifier, :188) with
+//                               the class-max (:191) fused into the TMEM epilogue: the screen
+//   3. region_candidates_kernel top-(k+margin) windows of every image by the screen; their
+//                               pooled rows gathered as split operands
+//      isb_gemm_nt_split        fp32-grade logits of the candidates (three tcgen05 products)
+//      region_finalize_select   class-max, final top-k (:194), cls_out (:216), ||crop||_2 of
+//                               the chosen windows, completeness certificate of the screen
 //   4. region_gather_kernel     u[b] = sum_i crop_i / ||crop_i|| + nsel * shift
 //                               (NormalizeL2 + Shift, :218-219, summed BEFORE the
 //                               projection -- the Linear is linear) -> bf16 hi (+ lo)
@@ -27,88 +29,442 @@ __device__ __forceinline__ uint16_t bf16_rn(float f) {
 }
 __device__ __forceinline__ float bf16_f(uint16_t h) { return __uint_as_float(static_cast<uint32_t>(h) << 16); }
 
-// ------------------------------------------------------------------ 1. pooling
-// One CTA = one image x CB channels.  The CB planes are contiguous in NCHW, so
-// the load is one coalesced stream; the 2-D window sum is separable (fw-wide
-// row sums, then fh-tall column sums) out of shared memory; the output is
-// written channel-contiguous (the K-major operand layout the classifier GEMM
-// wants), CB consecutive bf16 per window.  Plane strides are odd so that lanes
-// that differ in channel hit different banks.
-template <int CB>
-__global__ void __launch_bounds__(256)
-region_pool_kernel(const float* __restrict__ x, int C, int H, int W, int fh, int fw,
-                   uint16_t* __restrict__ P, int ldp, float* __restrict__ e_part) {
-  extern __shared__ float pool_smem[];
-  const int HW = H * W, Wo = W - fw + 1, Ho = H - fh + 1;
-  const int HWp = HW | 1, HRp = (H * Wo) | 1;
-  float* plane = pool_smem;               // [CB][HWp]
-  float* R = pool_smem + CB * HWp;        // [CB][HRp]
-  const int b = blockIdx.y, blk = blockIdx.x, c0 = blk * CB;
-  const int nblk = gridDim.x;
-  const float* src = x + (static_cast<size_t>(b) * C + c0) * HW;
-  const int cvalid = min(CB, C - c0);
-  const int tid = threadIdx.x;
+// ------------------------------------------------------------------ staging
+// Channel planes of one image are contiguous in NCHW, so a block of planes is ONE
+// contiguous byte range: it is staged into shared memory with a single 1-D bulk
+// copy through the TMA engine (cp.async.bulk, SASS UBLKCP) completing on an
+// mbarrier, double-buffered against the arithmetic on the previous block.  When
+// the range is not 16-byte aligned / sized (odd H*W with an odd channel count) the
+// same bytes are fetched with plain coalesced loads instead.
+constexpr int kPoolThreads = 512;
+constexpr int kMaxWinPerThread = 6;   // windows per thread in the horizontal pass (nwin <= 6 * 512)
+constexpr int kEParts = 4;   // energy partial planes per CTA (summed in a fixed order)
 
-  const int total = cvalid * HW;
-  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-    for (int i = tid * 4; i < total; i += 256 * 4) {
-      if (i + 4 <= total) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
-        const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int cb = (i + t) / HW, p = (i + t) - cb * HW;
-          plane[cb * HWp + p] = vv[t];
-        }
-      } else {
-        for (int t = i; t < total; ++t) {
-          const int cb = t / HW, p = t - cb * HW;
-          plane[cb * HWp + p] = __ldg(src + t);
-        }
+struct PoolParams {
+  const float* x;
+  int C, H, W, fh, fw;
+  int CB;        // channels per block (multiple of 4)
+  int G;         // channel blocks per CTA (one energy partial per CTA)
+  int nblk;      // ceil(C / CB)
+  int ngroups;   // ceil(nblk / G)
+  uint16_t* P_hi;   // [B * nwin, ldp]  bf16(mean)
+  uint16_t* P_lo;   // [B * nwin, ldp]  bf16(mean - hi)
+  int ldp;
+  float* e_part;    // [B][ngroups][H*W]
+};
+
+__device__ __forceinline__ void stage_planes(float* dst, const float* src, int n_floats, uint64_t* bar,
+                                             bool bulk) {
+  // called by every thread; returns after the copy has been ISSUED (bulk) or DONE (plain)
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      ptx::fence_proxy_async();  // earlier generic-proxy writes to dst are ordered before the async write
+      // one copy instruction moves at most 2^20 - 16 bytes: split larger ranges
+      const uint32_t bytes = static_cast<uint32_t>(n_floats) * 4u;
+      ptx::mbar_arrive_expect_tx(bar, bytes);
+      uint32_t off = 0;
+      while (off < bytes) {
+        const uint32_t chunk = (bytes - off) > 65536u ? 65536u : (bytes - off);
+        ptx::bulk_load_1d(reinterpret_cast<uint8_t*>(dst) + off, reinterpret_cast<const uint8_t*>(src) + off,
+                          chunk, bar);
+        off += chunk;
       }
     }
   } else {
-    for (int i = tid; i < total; i += 256) {
-      const int cb = i / HW, p = i - cb * HW;
-      plane[cb * HWp + p] = __ldg(src + i);
-    }
+    for (int i = threadIdx.x; i < n_floats; i += blockDim.x) dst[i] = __ldg(src + i);
   }
-  for (int i = total + tid; i < CB * HW; i += 256) {  // channels past C (ragged last block)
-    const int cb = i / HW, p = i - cb * HW;
-    plane[cb * HWp + p] = 0.f;
+}
+
+// ------------------------------------------------------------------ 1. pooling
+// One CTA = one image x G blocks of CB channels.  Per block, out of shared memory:
+//   A  per-pixel energy  sum_c x^2                       (for the crop norms)
+//   B  vertical fh-sums, in place (one thread per column, fh-register ring)
+//   C  horizontal fw-sums -> window mean -> bf16 hi / lo  into a [window][channel]
+//      staging tile (odd word stride: conflict-free for lanes that differ in window)
+//   D  staging tile -> P_hi / P_lo rows, CB consecutive channels per window
+//      (the K-major operand layout of the classifier GEMM), 4-byte coalesced stores
+template <int FH>
+__global__ void __launch_bounds__(kPoolThreads, 1)
+region_pool_generic_kernel(const PoolParams p) {
+  extern __shared__ __align__(128) uint8_t pool_smem_raw[];
+  const int HW = p.H * p.W, Wo = p.W - p.fw + 1, Ho = p.H - p.fh + 1, nwin = Ho * Wo;
+  const int CB = p.CB;
+  const int plane_floats = CB * HW;
+  float* X0 = reinterpret_cast<float*>(pool_smem_raw);
+  float* X1 = X0 + plane_floats;
+  float* E = X1 + plane_floats;                                   // [kEParts][HW]
+  uint32_t* O = reinterpret_cast<uint32_t*>(E + kEParts * HW);    // [nwin][CB + 1] words
+  uint64_t* bars = reinterpret_cast<uint64_t*>(O + static_cast<size_t>(nwin) * (CB + 1) + ((nwin * (CB + 1)) & 1));
+  uint16_t* O16 = reinterpret_cast<uint16_t*>(O);
+  const int ostride16 = 2 * (CB + 1);
+
+  const int b = blockIdx.y, grp = blockIdx.x, tid = threadIdx.x;
+  const int blk0 = grp * p.G;
+  const int blk1 = min(blk0 + p.G, p.nblk);
+  const float* xb = p.x + static_cast<size_t>(b) * p.C * HW;
+
+  for (int i = tid; i < kEParts * HW; i += kPoolThreads) E[i] = 0.f;
+  if (tid == 0) {
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::fence_barrier_init();
   }
   __syncthreads();
 
-  // per-pixel energy of these CB channels (summed over blocks, in block order, later)
-  for (int p = tid; p < HW; p += 256) {
-    float s = 0.f;
-#pragma unroll 8
-    for (int cb = 0; cb < CB; ++cb) {
-      const float v = plane[cb * HWp + p];
-      s = fmaf(v, v, s);
-    }
-    e_part[(static_cast<size_t>(b) * nblk + blk) * HW + p] = s;
+  auto block_src = [&](int blk, int& cvalid) -> const float* {
+    const int c0 = blk * CB;
+    cvalid = min(CB, p.C - c0);
+    return xb + static_cast<size_t>(c0) * HW;
+  };
+  auto can_bulk = [&](const float* src, int n) -> bool {
+    return ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((n & 3) == 0);
+  };
+
+  int cv;
+  const float* src = block_src(blk0, cv);
+  bool bulk_cur = can_bulk(src, cv * HW);
+  stage_planes(X0, src, cv * HW, &bars[0], bulk_cur);
+  uint32_t ph0 = 0u, ph1 = 0u;   // mbarrier phase parity of each buffer
+
+  const float inv_area = 1.f / static_cast<float>(p.fh * p.fw);
+  const int eparts = min(kEParts, max(1, kPoolThreads / HW));
+  // pass C thread grid: TW threads along the windows (a multiple of 32), TC channel slices
+  const int TW = min(kPoolThreads, (nwin + 31) & ~31);
+  const int TC = kPoolThreads / TW;
+  const int tw = tid % TW, tc = (tid / TW < TC) ? tid / TW : CB;   // threads beyond TW * TC idle in pass C
+  const int JW = (nwin + TW - 1) / TW;
+  int win_in[kMaxWinPerThread];
+#pragma unroll
+  for (int j = 0; j < kMaxWinPerThread; ++j) {
+    const int win = tw + j * TW;
+    win_in[j] = (j < JW && win < nwin) ? (win / Wo) * p.W + (win % Wo) : -1;
   }
-  // horizontal fw-sums
-  for (int i = tid; i < CB * H * Wo; i += 256) {
-    const int cb = i % CB, t = i / CB;
-    const int h = t / Wo, w = t - h * Wo;
-    const float* r = plane + cb * HWp + h * W + w;
-    float s = 0.f;
-    for (int dx = 0; dx < fw; ++dx) s += r[dx];
-    R[cb * HRp + h * Wo + w] = s;
+  int lgCB = 0;
+  while ((1 << lgCB) < CB) ++lgCB;
+
+  for (int blk = blk0; blk < blk1; ++blk) {
+    const int s = (blk - blk0) & 1;
+    float* X = s ? X1 : X0;
+    const int c0 = blk * CB;
+    const int cvalid = min(CB, p.C - c0);
+    // prefetch the next block into the other buffer (free since the barrier that ended iteration blk-1)
+    bool bulk_next = false;
+    if (blk + 1 < blk1) {
+      int cvn;
+      const float* nsrc = block_src(blk + 1, cvn);
+      bulk_next = can_bulk(nsrc, cvn * HW);
+      if (bulk_next) stage_planes(s ? X0 : X1, nsrc, cvn * HW, &bars[s ^ 1], true);
+    }
+    if (bulk_cur) {
+      ptx::mbar_wait(&bars[s], s ? ph1 : ph0);
+      if (s) ph1 ^= 1u; else ph0 ^= 1u;
+    }
+    for (int i = cvalid * HW + tid; i < plane_floats; i += kPoolThreads) X[i] = 0.f;   // ragged last block
+    __syncthreads();
+
+    // ---- A: per-pixel energy of these channels
+    {
+      const int cb_per = (cvalid + eparts - 1) / eparts;
+      for (int i = tid; i < eparts * HW; i += kPoolThreads) {
+        const int part = i / HW, px = i - part * HW;
+        const int cb_lo = part * cb_per, cb_hi = min(cvalid, cb_lo + cb_per);
+        float acc = 0.f;
+#pragma unroll 4
+        for (int cb = cb_lo; cb < cb_hi; ++cb) {
+          const float v = X[cb * HW + px];
+          acc = fmaf(v, v, acc);
+        }
+        E[part * HW + px] += acc;
+      }
+    }
+    __syncthreads();
+    // ---- B: vertical sums, in place: X[cb][ho][w] = sum_dy x[cb][ho + dy][w]
+    for (int i = tid; i < CB * p.W; i += kPoolThreads) {
+      const int cb = i / p.W, w = i - cb * p.W;
+      float* col = X + cb * HW + w;
+      if (FH == 7) {
+        float r[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) r[j] = col[j * p.W];
+        col[0] = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + r[6]);
+        for (int ho0 = 1; ho0 < Ho; ho0 += 7) {
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {
+            const int ho = ho0 + j;   // (ho - 1) % 7 == j: slot j leaves the window, x[ho + 6] enters
+            if (ho < Ho) {
+              r[j] = col[(ho + 6) * p.W];
+              col[ho * p.W] = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + r[6]);
+            }
+          }
+        }
+      } else {
+        for (int ho = 0; ho < Ho; ++ho) {   // rows < ho are already overwritten, rows >= ho are raw
+          float sum = 0.f;
+          for (int dy = 0; dy < p.fh; ++dy) sum += col[(ho + dy) * p.W];
+          col[ho * p.W] = sum;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- C: horizontal sums -> mean -> bf16 hi / lo into the staging tile.  Threads are a
+    // (window, channel-slice) grid fixed for the whole kernel: no index arithmetic in the loop.
+    for (int cb = tc; cb < CB; cb += TC) {
+      const float* xp = X + cb * HW;
+#pragma unroll
+      for (int j = 0; j < kMaxWinPerThread; ++j) {
+        if (j < JW && win_in[j] >= 0) {
+          const float* r = xp + win_in[j];
+          float sum;
+          if (FH == 7) {   // fw == 7 (checked on the host for this instantiation)
+            sum = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + r[6]);
+          } else {
+            sum = 0.f;
+            for (int dx = 0; dx < p.fw; ++dx) sum += r[dx];
+          }
+          const float mean = sum * inv_area;
+          const uint16_t hi = bf16_rn(mean);
+          uint16_t* o = O16 + (tw + j * TW) * ostride16 + cb;
+          o[0] = hi;
+          o[CB] = bf16_rn(mean - bf16_f(hi));
+        }
+      }
+    }
+    __syncthreads();
+    // ---- D: rows of the staging tile -> global (CB/2 words of hi, CB/2 words of lo per window)
+    {
+      const size_t row0 = static_cast<size_t>(b) * nwin;
+      const int half = CB >> 1;
+      const int valid_words = (cvalid + 1) >> 1;
+      const int wd = tid & (CB - 1);             // CB is a power of two
+      const bool lo = wd >= half;
+      const int k2 = lo ? wd - half : wd;
+      if (k2 < valid_words) {
+        uint16_t* base = (lo ? p.P_lo : p.P_hi) + row0 * p.ldp + c0;
+        for (int win = tid >> lgCB; win < nwin; win += kPoolThreads >> lgCB)
+          reinterpret_cast<uint32_t*>(base + static_cast<size_t>(win) * p.ldp)[k2] = O[win * (CB + 1) + wd];
+      }
+    }
+    // the non-bulk path fetches the next block only now (buffer s^1 is idle, nothing to overlap with)
+    if (blk + 1 < blk1 && !bulk_next) {
+      int cvn;
+      const float* nsrc = block_src(blk + 1, cvn);
+      stage_planes(s ? X0 : X1, nsrc, cvn * HW, &bars[s ^ 1], false);
+    }
+    bulk_cur = bulk_next;
+    __syncthreads();
+  }
+  float* eo = p.e_part + (static_cast<size_t>(b) * p.ngroups + grp) * HW;
+  for (int px = tid; px < HW; px += kPoolThreads) {
+    float t = 0.f;
+    for (int part = 0; part < eparts; ++part) t += E[part * HW + px];
+    eo[px] = t;
+  }
+}
+
+// ------------------------------------------------------------------ 1b. pooling, fast path
+// 7 x 7 windows on maps up to 32 x 32 (the reference's ResNet maps: 14 x 14 at 448 px
+// input, up to 32 x 32 at 1024 px).  Same staging, far fewer instructions per element:
+//   A  per-pixel energy (as above)
+//   B  one thread per (channel, column): the column goes to registers, the 7-tap
+//      vertical sums slide down it (add the entering row, subtract the leaving one),
+//      and are written back IN PLACE transposed, VT[cb][w][ho], with an odd ho-pitch
+//      and a per-plane skew that puts plane cb on bank (cb % 32) -- both passes are
+//      then bank-conflict free
+//   C  one thread per (channel, output row, row segment): 7-tap horizontal sliding
+//      sums out of VT, mean -> bf16 hi / lo (cvt.rn.bf16.f32), stored straight to
+//      P_hi / P_lo with the 32 lanes of a warp on 32 consecutive channels (full
+//      32-byte sectors; no staging tile, no fourth pass)
+constexpr int kFastThreads = 1024;
+
+__device__ __forceinline__ uint16_t cvt_bf16(float f) {
+  uint16_t h;
+  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(f));
+  return h;
+}
+
+struct FastGeom {
+  int Hop;    // odd pitch of the ho index in VT
+  int Q;      // output rows per warp-channel group: 32 / min(32, CB)
+  int nseg;   // row segments per output row
+  int segw;   // outputs per segment
+};
+
+__device__ __forceinline__ int vt_base(int cb, int HW, int Q) {
+  const int target = (cb % (32 / Q)) * Q;                // bank of VT[cb][0][0]
+  return cb * HW + ((target - cb * HW) & 31);
+}
+
+template <int HMAX>
+__global__ void __launch_bounds__(kFastThreads, 1)
+region_pool_fast_kernel(const PoolParams p, const FastGeom g) {
+  extern __shared__ __align__(128) uint8_t pool_smem_raw[];
+  constexpr int FH = 7;
+  const int HW = p.H * p.W, Wo = p.W - 6, Ho = p.H - 6, nwin = Ho * Wo;
+  const int CB = p.CB;
+  const int plane_floats = CB * HW;
+  float* X0 = reinterpret_cast<float*>(pool_smem_raw);
+  float* X1 = X0 + plane_floats;
+  float* E = X1 + plane_floats;                                   // [kEParts][HW]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(E + kEParts * HW + ((kEParts * HW) & 1));
+
+  const int b = blockIdx.y, grp = blockIdx.x, tid = threadIdx.x;
+  const int blk0 = grp * p.G;
+  const int blk1 = min(blk0 + p.G, p.nblk);
+  const float* xb = p.x + static_cast<size_t>(b) * p.C * HW;
+
+  for (int i = tid; i < kEParts * HW; i += kFastThreads) E[i] = 0.f;
+  if (tid == 0) {
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::fence_barrier_init();
   }
   __syncthreads();
-  // vertical fh-sums, mean, bf16, channel-contiguous store
-  const float inv_area = 1.f / static_cast<float>(fh * fw);
-  const size_t row0 = static_cast<size_t>(b) * Ho * Wo;
-  for (int i = tid; i < CB * Ho * Wo; i += 256) {
-    const int cb = i % CB, win = i / CB;
-    const int h = win / Wo, w = win - h * Wo;
-    const float* r = R + cb * HRp + h * Wo + w;
-    float s = 0.f;
-    for (int dy = 0; dy < fh; ++dy) s += r[dy * Wo];
-    if (cb < cvalid) P[(row0 + win) * ldp + c0 + cb] = bf16_rn(s * inv_area);
+
+  // ---- fixed thread roles
+  // pass B: column (cb_b, w_b)
+  const bool colv = tid < CB * p.W;
+  const int cb_b = tid / p.W, w_b = tid - cb_b * p.W;
+  const int col_in = cb_b * HW + w_b;
+  const int col_out = vt_base(colv ? cb_b : 0, HW, g.Q) + w_b * g.Hop;
+  // pass C: lane -> (channel, q), warp -> (channel group, ho block, segment)
+  const int lane = tid & 31, warp = tid >> 5;
+  const int cpw = 32 / g.Q;                       // channels per warp
+  const int cgroups = (CB + cpw - 1) / cpw;
+  const int hoblks = (Ho + g.Q - 1) / g.Q;
+  const int cg = warp % cgroups;
+  const int hb = (warp / cgroups) % hoblks;
+  const int seg = warp / (cgroups * hoblks);
+  const int cb_c = cg * cpw + lane / g.Q;
+  const int ho_c = hb * g.Q + (lane % g.Q);
+  const int wo0 = seg * g.segw;
+  const int wo1 = min(Wo, wo0 + g.segw);
+  const bool rowv = seg < g.nseg && cb_c < CB && ho_c < Ho && wo0 < wo1;
+  const int row_in = vt_base(cb_c < CB ? cb_c : 0, HW, g.Q) + ho_c;
+  const float inv_area = 1.f / 49.f;
+  const int eparts = min(kEParts, max(1, kFastThreads / HW));
+
+  int cv;
+  auto block_src = [&](int blk, int& cvalid) -> const float* {
+    const int c0 = blk * CB;
+    cvalid = min(CB, p.C - c0);
+    return xb + static_cast<size_t>(c0) * HW;
+  };
+  auto can_bulk = [&](const float* src, int n) -> bool {
+    return ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((n & 3) == 0);
+  };
+  const float* src = block_src(blk0, cv);
+  bool bulk_cur = can_bulk(src, cv * HW);
+  stage_planes(X0, src, cv * HW, &bars[0], bulk_cur);
+  uint32_t ph0 = 0u, ph1 = 0u;
+
+  for (int blk = blk0; blk < blk1; ++blk) {
+    const int s = (blk - blk0) & 1;
+    float* X = s ? X1 : X0;
+    const int c0 = blk * CB;
+    const int cvalid = min(CB, p.C - c0);
+    bool bulk_next = false;
+    if (blk + 1 < blk1) {
+      int cvn;
+      const float* nsrc = block_src(blk + 1, cvn);
+      bulk_next = can_bulk(nsrc, cvn * HW);
+      if (bulk_next) stage_planes(s ? X0 : X1, nsrc, cvn * HW, &bars[s ^ 1], true);
+    }
+    if (bulk_cur) {
+      ptx::mbar_wait(&bars[s], s ? ph1 : ph0);
+      if (s) ph1 ^= 1u; else ph0 ^= 1u;
+    } else {
+      __syncthreads();
+    }
+    // ---- A: per-pixel energy
+    {
+      const int cb_per = (cvalid + eparts - 1) / eparts;
+      for (int i = tid; i < eparts * HW; i += kFastThreads) {
+        const int part = i / HW, px = i - part * HW;
+        const int cb_lo = part * cb_per, cb_hi = min(cvalid, cb_lo + cb_per);
+        const float* xp = X + px;
+        float a0 = 0.f, a1 = 0.f;
+        int cb = cb_lo;
+        for (; cb + 1 < cb_hi; cb += 2) {
+          const float v0 = xp[cb * HW], v1 = xp[(cb + 1) * HW];
+          a0 = fmaf(v0, v0, a0);
+          a1 = fmaf(v1, v1, a1);
+        }
+        if (cb < cb_hi) { const float v0 = xp[cb * HW]; a0 = fmaf(v0, v0, a0); }
+        E[part * HW + px] += a0 + a1;
+      }
+    }
+    // ---- B: vertical sliding sums down the column (7-register ring), kept in registers
+    float o[HMAX - FH + 1];
+    if (colv) {
+      const float* col = X + col_in;
+      float r[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) r[j] = col[j * p.W];
+      float sum = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + r[6]);
+      o[0] = sum;
+#pragma unroll
+      for (int ho = 1; ho < HMAX - FH + 1; ++ho) {
+        if (ho < Ho) {
+          const float nv = col[(ho + FH - 1) * p.W];
+          sum += nv - r[(ho - 1) % 7];      // row ho - 1 leaves the window, row ho + 6 enters
+          r[(ho - 1) % 7] = nv;
+          o[ho] = sum;
+        }
+      }
+    }
+    __syncthreads();   // every raw value has been read: the planes may be overwritten
+    if (colv) {
+#pragma unroll
+      for (int ho = 0; ho < HMAX - FH + 1; ++ho)
+        if (ho < Ho) X[col_out + ho] = o[ho];
+    }
+    __syncthreads();
+    // ---- C: horizontal sliding sums -> mean -> bf16 hi / lo -> global
+    if (rowv && cb_c < cvalid) {
+      const float* r = X + row_in;
+      const int pitch = g.Hop;
+      uint16_t* ohi = p.P_hi + (static_cast<size_t>(b) * nwin + ho_c * Wo) * p.ldp + c0 + cb_c;
+      uint16_t* olo = p.P_lo + (static_cast<size_t>(b) * nwin + ho_c * Wo) * p.ldp + c0 + cb_c;
+      float q[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) q[j] = r[(wo0 + j) * pitch];
+      float sum = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + q[6]);
+      {
+        const float mean = sum * inv_area;
+        const uint16_t hi = cvt_bf16(mean);
+        ohi[static_cast<size_t>(wo0) * p.ldp] = hi;
+        olo[static_cast<size_t>(wo0) * p.ldp] = cvt_bf16(mean - __uint_as_float(static_cast<uint32_t>(hi) << 16));
+      }
+      for (int base = wo0 + 1; base < wo1; base += 7) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          const int wo = base + j;            // (wo - wo0 - 1) % 7 == j: slot j leaves, column wo + 6 enters
+          if (wo < wo1) {
+            const float nv = r[(wo + 6) * pitch];
+            sum += nv - q[j];
+            q[j] = nv;
+            const float mean = sum * inv_area;
+            const uint16_t hi = cvt_bf16(mean);
+            ohi[static_cast<size_t>(wo) * p.ldp] = hi;
+            olo[static_cast<size_t>(wo) * p.ldp] = cvt_bf16(mean - __uint_as_float(static_cast<uint32_t>(hi) << 16));
+          }
+        }
+      }
+    }
+    if (blk + 1 < blk1 && !bulk_next) {
+      __syncthreads();
+      int cvn;
+      const float* nsrc = block_src(blk + 1, cvn);
+      stage_planes(s ? X0 : X1, nsrc, cvn * HW, &bars[s ^ 1], false);
+    }
+    bulk_cur = bulk_next;
+    __syncthreads();
+  }
+  float* eo = p.e_part + (static_cast<size_t>(b) * p.ngroups + grp) * HW;
+  for (int px = tid; px < HW; px += kFastThreads) {
+    float t = 0.f;
+    for (int part = 0; part < eparts; ++part) t += E[part * HW + px];
+    eo[px] = t;
   }
 }
 
@@ -173,10 +529,9 @@ struct RowSched {
   }
 };
 
-// ------------------------------------------------------------------ 3. selection
+// ------------------------------------------------------------------ 3. candidates
 constexpr int kSelThreads = 256;
 constexpr int kSelMaxCand = 32;   // k + margin
-constexpr int kSelChunk = 8;      // candidates re-scored per pass over the classifier weights
 
 __device__ __forceinline__ void block_argmax(float v, int i, float* s_val, int* s_idx, float& out_v,
                                              int& out_i) {
@@ -207,13 +562,166 @@ __device__ __forceinline__ void block_argmax(float v, int i, float* s_val, int* 
   __syncthreads();
 }
 
+// One CTA per image: the ncand best windows of the bf16 screen (value desc, index
+// asc), and their pooled rows copied out of P_hi / P_lo into the operand of the
+// fp32-grade re-score GEMM: A_hi / A_lo [B * ncand_max, ldp], rows beyond the
+// image's candidates zeroed.
 __global__ void __launch_bounds__(kSelThreads)
-region_select_kernel(const float* __restrict__ x, int C, int H, int W, int fh, int fw,
+region_candidates_kernel(const float* __restrict__ screen, int nwin, int ncand, int ncand_max,
+                         const uint16_t* __restrict__ P_hi, const uint16_t* __restrict__ P_lo, int ldp,
+                         int* __restrict__ cand_out, float* __restrict__ cand_screen,
+                         uint16_t* __restrict__ A_hi, uint16_t* __restrict__ A_lo) {
+  extern __shared__ __align__(16) uint8_t sel_smem_raw[];
+  float* sc = reinterpret_cast<float*>(sel_smem_raw);   // [nwin]
+  __shared__ float s_val[kSelThreads / 32];
+  __shared__ int s_idx[kSelThreads / 32];
+  __shared__ int cand[kSelMaxCand];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < nwin; i += kSelThreads) sc[i] = screen[static_cast<size_t>(b) * nwin + i];
+  __syncthreads();
+  for (int c = 0; c < ncand; ++c) {
+    float v = -INFINITY;
+    int vi = 0x7FFFFFFF;
+    for (int i = tid; i < nwin; i += kSelThreads) {
+      const float s = sc[i];
+      if (s > v || (s == v && i < vi)) { v = s; vi = i; }
+    }
+    float bv; int bi;
+    block_argmax(v, vi, s_val, s_idx, bv, bi);
+    if (tid == 0) {
+      cand[c] = bi;
+      cand_out[b * ncand_max + c] = bi;
+      cand_screen[b * ncand_max + c] = bv;
+      sc[bi] = -INFINITY;
+    }
+    __syncthreads();
+  }
+  if (tid < ncand_max - ncand) {
+    cand_out[b * ncand_max + ncand + tid] = -1;
+    cand_screen[b * ncand_max + ncand + tid] = -INFINITY;
+  }
+  const int vec = ldp / 8;   // 16-byte chunks per row
+  for (int i = tid; i < ncand_max * vec; i += kSelThreads) {
+    const int c = i / vec, j = i - c * vec;
+    const size_t dst = (static_cast<size_t>(b) * ncand_max + c) * ldp;
+    uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
+    if (c < ncand) {
+      const size_t srcrow = (static_cast<size_t>(b) * nwin + cand[c]) * ldp;
+      h = __ldg(reinterpret_cast<const uint4*>(P_hi + srcrow) + j);
+      l = __ldg(reinterpret_cast<const uint4*>(P_lo + srcrow) + j);
+    }
+    reinterpret_cast<uint4*>(A_hi + dst)[j] = h;
+    reinterpret_cast<uint4*>(A_lo + dst)[j] = l;
+  }
+}
+
+// ------------------------------------------------------------------ 4. final selection
+// One CTA per image, from the fp32-grade logits [ncand_max, ldl] of its candidates:
+// class-max per candidate (model/siamese.py:191), order (value desc, window asc),
+// the k' = min(nwin, k) best (:193-194), cls_out (:216), crop norms, and the
+// completeness flag of the screen (see region_select in include/isb.h).
+__global__ void __launch_bounds__(kSelThreads)
+region_finalize_select_kernel(const float* __restrict__ logits, int ldl, int ncls, const int* __restrict__ cand_in,
+                              const float* __restrict__ cand_screen, int nwin, int ncand, int ncand_max,
+                              const float* __restrict__ e_part, int ngroups, int H, int W, int fh, int fw,
+                              int k, float eps, int64_t* __restrict__ idx, int* __restrict__ nsel_out,
+                              float* __restrict__ cls_out, float* __restrict__ win_norm,
+                              float* __restrict__ approx_max, float* __restrict__ runner_up,
+                              int* __restrict__ n_uncertified) {
+  __shared__ int cand[kSelMaxCand];
+  __shared__ float cand_max[kSelMaxCand];
+  __shared__ int order[kSelMaxCand];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Wo = W - fw + 1, HW = H * W;
+  const float* lg = logits + static_cast<size_t>(b) * ncand_max * ldl;
+  if (tid < ncand) cand[tid] = cand_in[b * ncand_max + tid];
+  for (int c = warp; c < ncand; c += kSelThreads / 32) {
+    float m = -INFINITY;
+    for (int j = lane; j < ncls; j += 32) m = fmaxf(m, lg[static_cast<size_t>(c) * ldl + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) cand_max[c] = m;
+  }
+  __syncthreads();
+  const int nsel = min(nwin, k);
+  if (tid == 0) {
+    for (int c = 0; c < ncand; ++c) order[c] = c;
+    for (int i = 1; i < ncand; ++i) {   // insertion sort of <= 32 entries
+      const int o = order[i];
+      int j = i - 1;
+      while (j >= 0 && (cand_max[order[j]] < cand_max[o] ||
+                        (cand_max[order[j]] == cand_max[o] && cand[order[j]] > cand[o]))) {
+        order[j + 1] = order[j];
+        --j;
+      }
+      order[j + 1] = o;
+    }
+    nsel_out[b] = nsel;
+    if (approx_max != nullptr) {
+      for (int i = 0; i < k; ++i) approx_max[static_cast<size_t>(b) * k + i] = (i < nsel) ? cand_max[order[i]] : 0.f;
+      runner_up[b] = (ncand > nsel) ? cand_max[order[nsel]] : -INFINITY;
+    }
+    // Certificate: every window that is not a candidate has a screen value <= t_min (the
+    // worst candidate's); with sigma = rms(screen - exact) over the candidates, the k
+    // selected windows are provably the top k when  exact_k - t_min > 8 sigma.
+    if (nwin > ncand && n_uncertified != nullptr) {
+      float t_min = INFINITY, s2 = 0.f;
+      for (int c = 0; c < ncand; ++c) {
+        const float sv = cand_screen[b * ncand_max + c];
+        t_min = fminf(t_min, sv);
+        const float d = sv - cand_max[c];
+        s2 += d * d;
+      }
+      const float sigma = sqrtf(s2 / static_cast<float>(ncand));
+      const float kth = cand_max[order[nsel - 1]];
+      if (!(kth - t_min > 8.f * sigma + 4e-7f * fmaxf(fabsf(kth), fabsf(t_min)))) atomicAdd(n_uncertified, 1);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < k; i += kSelThreads)
+    idx[static_cast<size_t>(b) * k + i] = (i < nsel) ? static_cast<int64_t>(cand[order[i]]) : -1;
+  // cls_out[b, cls, i]  (zero beyond nsel, model/siamese.py:207-208)
+  for (int t = tid; t < ncls * k; t += kSelThreads) {
+    const int j = t / k, i = t - j * k;
+    cls_out[(static_cast<size_t>(b) * ncls + j) * k + i] =
+        (i < nsel) ? lg[static_cast<size_t>(order[i]) * ldl + j] : 0.f;
+  }
+  // ||crop||: sqrt(sum over the window of the per-pixel energy + eps)
+  for (int i = warp; i < k; i += kSelThreads / 32) {
+    if (i < nsel) {
+      const int win = cand[order[i]];
+      const int h = win / Wo, w = win - h * Wo;
+      double s = 0.0;
+      for (int t = lane; t < fh * fw * ngroups; t += 32) {
+        const int g = t / (fh * fw), r = t - g * (fh * fw);
+        const int dy = r / fw, dx = r - dy * fw;
+        s += static_cast<double>(e_part[(static_cast<size_t>(b) * ngroups + g) * HW + (h + dy) * W + w + dx]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) win_norm[static_cast<size_t>(b) * k + i] = sqrtf(static_cast<float>(s) + eps);
+    } else if (lane == 0) {
+      win_norm[static_cast<size_t>(b) * k + i] = 1.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ 4b. exact selection (second line)
+// For batches the fast path could not certify: one CTA per image re-scores up to 32
+// candidates of the screen EXACTLY -- window means and logits from the fp32 inputs
+// with fp64 accumulation -- and selects from those.  Slow (each CTA streams the whole
+// classifier), used only when isb_region_select / isb_region_logits report
+// uncertified images.
+constexpr int kSelChunk = 8;      // candidates re-scored per pass over the classifier weights
+
+__global__ void __launch_bounds__(kSelThreads)
+region_select_exact_kernel(const float* __restrict__ x, int C, int H, int W, int fh, int fw,
                      const float* __restrict__ cls_w, const float* __restrict__ cls_b, int ncls,
                      const float* __restrict__ screen,   // [B*HoWo] class-max by the bf16 GEMM
                      const float* __restrict__ e_part, int nblk, int k, int ncand, float eps,
                      int64_t* __restrict__ idx, int* __restrict__ nsel_out,
-                     float* __restrict__ cls_out, float* __restrict__ win_norm) {
+                     float* __restrict__ cls_out, float* __restrict__ win_norm,
+                     int* __restrict__ n_uncertified) {
   extern __shared__ __align__(16) uint8_t sel_smem_raw[];
   const int Ho = H - fh + 1, Wo = W - fw + 1, nwin = Ho * Wo, HW = H * W;
   float* sc = reinterpret_cast<float*>(sel_smem_raw);          // [nwin]
@@ -224,6 +732,7 @@ region_select_kernel(const float* __restrict__ x, int C, int H, int W, int fh, i
   __shared__ int cand[kSelMaxCand];
   __shared__ float cand_max[kSelMaxCand];
   __shared__ int order[kSelMaxCand];
+  __shared__ float cand_scr[kSelMaxCand];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* xb = x + static_cast<size_t>(b) * C * HW;
 
@@ -239,7 +748,7 @@ region_select_kernel(const float* __restrict__ x, int C, int H, int W, int fh, i
     }
     float bv; int bi;
     block_argmax(v, vi, s_val, s_idx, bv, bi);
-    if (tid == 0) { cand[c] = bi; sc[bi] = -INFINITY; }
+    if (tid == 0) { cand[c] = bi; cand_scr[c] = bv; sc[bi] = -INFINITY; }
     __syncthreads();
   }
   // ---- exact logits of the candidates (fp64 accumulation of fp32 products)
@@ -303,6 +812,17 @@ region_select_kernel(const float* __restrict__ x, int C, int H, int W, int fh, i
       order[j + 1] = o;
     }
     nsel_out[b] = nsel;
+    if (nwin > ncand && n_uncertified != nullptr) {   // completeness of the screen's candidate list
+      float t_min = INFINITY, s2 = 0.f;
+      for (int c = 0; c < ncand; ++c) {
+        t_min = fminf(t_min, cand_scr[c]);
+        const float d = cand_scr[c] - cand_max[c];
+        s2 += d * d;
+      }
+      const float sigma = sqrtf(s2 / static_cast<float>(ncand));
+      const float kth = cand_max[order[nsel - 1]];
+      if (!(kth - t_min > 8.f * sigma + 4e-7f * fmaxf(fabsf(kth), fabsf(t_min)))) atomicAdd(n_uncertified, 1);
+    }
   }
   __syncthreads();
   for (int i = tid; i < k; i += kSelThreads)
@@ -332,54 +852,244 @@ region_select_kernel(const float* __restrict__ x, int C, int H, int W, int fh, i
   }
 }
 
-// ------------------------------------------------------------------ 4. gather
-// One thread = 8 consecutive elements of the C*fh*fw region vector (one 16-byte
-// bf16 store per term).  u[e] = sum_i x[b, c, h_i+dy, w_i+dx] / norm_i + nsel*shift[e].
-__global__ void __launch_bounds__(256)
-region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh, int fw, int k,
-                     const int64_t* __restrict__ idx, const int* __restrict__ nsel_in,
+
+// ------------------------------------------------------------------ 5. gather
+// One CTA = one image x CBg channels.  Only the rows [r0, r1) of each plane that the
+// image's selected windows touch are staged in shared memory (one bulk copy per
+// plane when aligned); every thread then produces two consecutive elements of
+//   u[e] = sum_i x[b, c, h_i + dy, w_i + dx] / norm_i + nsel * shift[e],  e = (c, dy, dx)
+// -- the CBg * fh * fw outputs of a CTA are one contiguous run of the operand row.
+constexpr int kGatherThreads = 256;
+
+template <int FHW>   // FHW = 7: 7 x 7 window with compile-time index arithmetic; 0: generic
+__global__ void __launch_bounds__(kGatherThreads)
+region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, int fw_, int k, int k_sum,
+                     int CBg, int row_align, const int* __restrict__ image_list,
+                     const int* __restrict__ n_list, const int64_t* __restrict__ idx,
+                     const int* __restrict__ nsel_in,
                      const float* __restrict__ win_norm, const float* __restrict__ shift,
-                     uint16_t* __restrict__ U_hi, uint16_t* __restrict__ U_lo, int64_t ldu) {
+                     uint16_t* __restrict__ U_hi, uint16_t* __restrict__ U_lo, int64_t ldu,
+                     float* __restrict__ win_mean) {
+  extern __shared__ __align__(128) uint8_t gat_smem_raw[];
+  float* X = reinterpret_cast<float*>(gat_smem_raw);
   __shared__ int s_off[kSelMaxCand];
   __shared__ float s_norm[kSelMaxCand];
-  const int b = blockIdx.y;
+  __shared__ int s_r0, s_r1;
+  __shared__ __align__(8) uint64_t bar;
+  const int fh = FHW ? FHW : fh_, fw = FHW ? FHW : fw_;
+  // optional image list (fix-up pass): grid.y covers the whole batch, rows beyond *n_list exit
+  if (image_list != nullptr && static_cast<int>(blockIdx.y) >= *n_list) return;
+  const int b = (image_list != nullptr) ? image_list[blockIdx.y] : blockIdx.y;
+  const int c0 = blockIdx.x * CBg, tid = threadIdx.x;
   const int Wo = W - fw + 1, HW = H * W, area = fh * fw;
-  const int Kin = C * area;
-  const int nsel = nsel_in[b];
-  if (threadIdx.x < nsel) {
-    const int win = static_cast<int>(idx[static_cast<size_t>(b) * k + threadIdx.x]);
-    const int h = win / Wo, w = win - h * Wo;
-    s_off[threadIdx.x] = h * W + w;
-    s_norm[threadIdx.x] = win_norm[static_cast<size_t>(b) * k + threadIdx.x];
+  const int cvalid = min(CBg, C - c0);
+  const int nall = nsel_in[b];                 // windows listed for this image (means are taken of all)
+  const int nsel = min(nall, k_sum);           // leading windows summed into the operand
+  if (tid == 0) {
+    int r0 = H, r1 = 0;
+    for (int i = 0; i < nall; ++i) {
+      const int win = static_cast<int>(idx[static_cast<size_t>(b) * k + i]);
+      const int h = win / Wo;
+      r0 = min(r0, h);
+      r1 = max(r1, h + fh);
+    }
+    if (nall == 0) { r0 = 0; r1 = 0; }
+    r0 = (r0 / row_align) * row_align;                       // keep every plane's range 16-byte aligned
+    r1 = min(H, ((r1 + row_align - 1) / row_align) * row_align);
+    s_r0 = r0; s_r1 = r1;
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_barrier_init();
   }
   __syncthreads();
-  const int KinP = (Kin + 7) & ~7;  // rows are zero padded to 8 columns
-  const int e0 = (blockIdx.x * 256 + threadIdx.x) * 8;
-  if (e0 >= KinP) return;
-  const float* xb = x + static_cast<size_t>(b) * C * HW;
-  uint16_t hi[8], lo[8];
-#pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const int e = e0 + t;
-    float u = 0.f;
-    if (e < Kin) {
-      const int c = e / area, r = e - c * area;
-      const int dy = r / fw, dx = r - dy * fw;
-      const float* pl = xb + static_cast<size_t>(c) * HW + dy * W + dx;
-      for (int i = 0; i < nsel; ++i) u += __ldg(pl + s_off[i]) / s_norm[i];
-      u += static_cast<float>(nsel) * __ldg(shift + e);
-    }
-    hi[t] = bf16_rn(u);
-    lo[t] = bf16_rn(u - bf16_f(hi[t]));
+  const int r0 = s_r0, nrows = s_r1 - s_r0;
+  const int pl = nrows * W;                                  // floats staged per plane
+  if (tid < nall) {
+    const int win = static_cast<int>(idx[static_cast<size_t>(b) * k + tid]);
+    const int h = win / Wo, w = win - h * Wo;
+    s_off[tid] = (h - r0) * W + w;
+    // the operand is rounded to bf16 hi + lo (2^-17) below: a reciprocal multiply instead of the
+    // reference's division (model/custom_modules.py:56) changes nothing that survives that rounding
+    s_norm[tid] = 1.f / win_norm[static_cast<size_t>(b) * k + tid];
   }
-  uint4 vh, vl;
-  vh.x = hi[0] | (uint32_t(hi[1]) << 16); vh.y = hi[2] | (uint32_t(hi[3]) << 16);
-  vh.z = hi[4] | (uint32_t(hi[5]) << 16); vh.w = hi[6] | (uint32_t(hi[7]) << 16);
-  vl.x = lo[0] | (uint32_t(lo[1]) << 16); vl.y = lo[2] | (uint32_t(lo[3]) << 16);
-  vl.z = lo[4] | (uint32_t(lo[5]) << 16); vl.w = lo[6] | (uint32_t(lo[7]) << 16);
-  *reinterpret_cast<uint4*>(U_hi + static_cast<size_t>(b) * ldu + e0) = vh;
-  if (U_lo != nullptr)  // split operand for the fp32-grade projection (isb_gemm_nt_split)
-    *reinterpret_cast<uint4*>(U_lo + static_cast<size_t>(b) * ldu + e0) = vl;
+  const float* src0 = x + (static_cast<size_t>(b) * C + c0) * HW + r0 * W;
+  const bool bulk = ((reinterpret_cast<uintptr_t>(src0) & 15) == 0) && ((HW & 3) == 0) && ((pl & 3) == 0) && pl > 0;
+  if (bulk) {
+    if (tid < 32) {
+      if (tid == 0) ptx::mbar_arrive_expect_tx(&bar, static_cast<uint32_t>(cvalid) * pl * 4u);
+      __syncwarp();
+      for (int cb = tid; cb < cvalid; cb += 32)
+        ptx::bulk_load_1d(X + cb * pl, src0 + static_cast<size_t>(cb) * HW, static_cast<uint32_t>(pl) * 4u, &bar);
+    }
+    ptx::mbar_wait(&bar, 0);
+  } else {
+    for (int i = tid; i < cvalid * pl; i += kGatherThreads) {
+      const int cb = i / pl, o = i - cb * pl;
+      X[i] = __ldg(src0 + static_cast<size_t>(cb) * HW + o);
+    }
+  }
+  __syncthreads();
+  // by-product: the exact fp32 mean of every selected window (row-major sum, then / area --
+  // AvgPool2d's own arithmetic, model/siamese.py:187), input of isb_region_logits
+  if (win_mean != nullptr) {
+    const float farea = static_cast<float>(area);
+    for (int it = tid; it < cvalid * nall; it += kGatherThreads) {
+      const int i = it / cvalid, cb = it - i * cvalid;
+      const float* pw = X + cb * pl + s_off[i];
+      float sum = 0.f;
+      for (int dy = 0; dy < fh; ++dy)
+        for (int dx = 0; dx < fw; ++dx) sum += pw[dy * W + dx];
+      win_mean[(static_cast<size_t>(b) * k + i) * C + c0 + cb] = sum / farea;
+    }
+  }
+  const int Kin = C * area;
+  const int KinP = (Kin + 7) & ~7;
+  const float fn = static_cast<float>(nsel);
+  const int e_begin = c0 * area;
+  // the last CTA of an image also writes the zero padding [Kin, KinP)
+  const int e_end = (c0 + cvalid >= C) ? KinP : (c0 + cvalid) * area;
+  uint16_t* uh = U_hi + static_cast<size_t>(b) * ldu;
+  uint16_t* ul = (U_lo != nullptr) ? U_lo + static_cast<size_t>(b) * ldu : nullptr;
+  for (int e = e_begin + 2 * tid; e < e_end; e += 2 * kGatherThreads) {   // e_begin is even (CBg % 2 == 0)
+    uint16_t hi[2], lo[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int ee = e + t;
+      float u = 0.f;
+      if (ee < Kin) {
+        const int c = ee / area, r = ee - c * area;
+        const int dy = r / fw, dx = r - dy * fw;
+        const float* plane = X + (c - c0) * pl + dy * W + dx;
+        for (int i = 0; i < nsel; ++i) u = fmaf(plane[s_off[i]], s_norm[i], u);
+        u += fn * __ldg(shift + ee);
+      }
+      hi[t] = bf16_rn(u);
+      lo[t] = bf16_rn(u - bf16_f(hi[t]));
+    }
+    *reinterpret_cast<uint32_t*>(uh + e) = hi[0] | (static_cast<uint32_t>(hi[1]) << 16);
+    if (ul != nullptr) *reinterpret_cast<uint32_t*>(ul + e) = lo[0] | (static_cast<uint32_t>(lo[1]) << 16);
+  }
+}
+
+// ------------------------------------------------------------------ 5b. exact logits of the selected windows
+// cls_out[b, :, i] = Wc . mean_i + bc in fp32 from the exact window means
+// (model/siamese.py:188,216), one CTA per image: the k means sit in shared memory,
+// every warp takes classes j, j + 8, ... and forms the k dot products of one
+// weight row together.  The k windows are then put in their exact order (class-max
+// desc, window asc, :191-194) and checked against the best window that was NOT
+// selected: runner_up[b] (its fp32-grade class-max) must stay below the exact k-th
+// value by 8 sigma, sigma = rms(fp32-grade - exact) over the k selected.
+constexpr int kLogThreads = 256;
+constexpr int kLogMaxK = 8;   // windows per pass over the classifier
+
+__global__ void __launch_bounds__(kLogThreads)
+region_logits_kernel(const float* __restrict__ win_mean, const float* __restrict__ cls_w,
+                     const float* __restrict__ cls_b, int C, int ncls, int ke, int k,
+                     const int* __restrict__ nsel_in, const float* __restrict__ approx_max,
+                     const float* __restrict__ runner_up, const int64_t* __restrict__ idx_in,
+                     const float* __restrict__ norm_in, int64_t* __restrict__ idx_out,
+                     float* __restrict__ norm_out, int* __restrict__ nsel_out,
+                     float* __restrict__ cls_out, int* __restrict__ changed_list,
+                     int* __restrict__ n_changed, int* __restrict__ n_uncertified) {
+  extern __shared__ __align__(16) uint8_t log_smem_raw[];
+  float* ms = reinterpret_cast<float*>(log_smem_raw);          // [ke][C]
+  float* lg = ms + static_cast<size_t>(ke) * C;                 // [ke][ncls]
+  __shared__ float wmax[kSelMaxCand];
+  __shared__ int order[kSelMaxCand];
+  __shared__ int64_t widx[kSelMaxCand];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nall = nsel_in[b];
+  const int nsel = min(nall, k);
+  for (int i = tid; i < nall * C; i += kLogThreads) ms[i] = win_mean[static_cast<size_t>(b) * ke * C + i];
+  if (tid < ke) widx[tid] = idx_in[static_cast<size_t>(b) * ke + tid];
+  __syncthreads();
+  const bool vec = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(cls_w) & 15) == 0;
+  for (int i0 = 0; i0 < nall; i0 += kLogMaxK) {
+    const int ni = min(kLogMaxK, nall - i0);
+    for (int j = warp; j < ncls; j += kLogThreads / 32) {
+      const float* wr = cls_w + static_cast<size_t>(j) * C;
+      float acc[kLogMaxK];
+#pragma unroll
+      for (int t = 0; t < kLogMaxK; ++t) acc[t] = 0.f;
+      if (vec) {
+        const float4* w4 = reinterpret_cast<const float4*>(wr);
+#pragma unroll 4
+        for (int c4 = lane; c4 < C / 4; c4 += 32) {
+          const float4 wv = __ldg(w4 + c4);
+#pragma unroll
+          for (int t = 0; t < kLogMaxK; ++t) {
+            if (t < ni) {
+              const float4 m = reinterpret_cast<const float4*>(ms + (i0 + t) * C)[c4];
+              acc[t] = fmaf(wv.x, m.x, acc[t]);
+              acc[t] = fmaf(wv.y, m.y, acc[t]);
+              acc[t] = fmaf(wv.z, m.z, acc[t]);
+              acc[t] = fmaf(wv.w, m.w, acc[t]);
+            }
+          }
+        }
+      } else {
+        for (int c = lane; c < C; c += 32) {
+          const float wv = __ldg(wr + c);
+#pragma unroll
+          for (int t = 0; t < kLogMaxK; ++t)
+            if (t < ni) acc[t] = fmaf(wv, ms[(i0 + t) * C + c], acc[t]);
+        }
+      }
+      const float bj = __ldg(cls_b + j);
+#pragma unroll
+      for (int t = 0; t < kLogMaxK; ++t) {
+        float a = acc[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0 && t < ni) lg[(i0 + t) * ncls + j] = a + bj;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = warp; i < nall; i += kLogThreads / 32) {
+    float m = -INFINITY;
+    for (int j = lane; j < ncls; j += 32) m = fmaxf(m, lg[i * ncls + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) wmax[i] = m;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < nall; ++i) order[i] = i;
+    for (int i = 1; i < nall; ++i) {
+      const int o = order[i];
+      int j = i - 1;
+      while (j >= 0 && (wmax[order[j]] < wmax[o] || (wmax[order[j]] == wmax[o] && widx[order[j]] > widx[o]))) {
+        order[j + 1] = order[j];
+        --j;
+      }
+      order[j + 1] = o;
+    }
+    nsel_out[b] = nsel;
+    // did a runner-up displace one of the k windows the operand was summed over?
+    bool changed = false;
+    for (int i = 0; i < nsel; ++i) changed = changed || (order[i] >= nsel);
+    if (changed && changed_list != nullptr) changed_list[atomicAdd(n_changed, 1)] = b;
+    if (n_uncertified != nullptr && nsel > 0) {
+      float s2 = 0.f;
+      for (int i = 0; i < nall; ++i) {
+        const float d = approx_max[static_cast<size_t>(b) * ke + i] - wmax[i];
+        s2 += d * d;
+      }
+      const float sigma = sqrtf(s2 / static_cast<float>(nall));
+      const float kth = wmax[order[nsel - 1]];
+      const float ru = runner_up[b];   // best fp32-grade class-max among the windows NOT scored here
+      if (!(kth - ru > 8.f * sigma + 4e-7f * fabsf(kth))) atomicAdd(n_uncertified, 1);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < k; i += kLogThreads) {
+    idx_out[static_cast<size_t>(b) * k + i] = (i < nsel) ? widx[order[i]] : -1;
+    norm_out[static_cast<size_t>(b) * k + i] = (i < nsel) ? norm_in[static_cast<size_t>(b) * ke + order[i]] : 1.f;
+  }
+  for (int t = tid; t < ncls * k; t += kLogThreads) {
+    const int j = t / k, i = t - j * k;
+    cls_out[(static_cast<size_t>(b) * ncls + j) * k + i] = (i < nsel) ? lg[order[i] * ncls + j] : 0.f;
+  }
 }
 
 // ------------------------------------------------------------------ 6. finalize
@@ -413,31 +1123,82 @@ descriptor_finalize_kernel(const float* __restrict__ y, const float* __restrict_
 }
 
 struct RegionPlan {
-  int Ho, Wo, nwin, CB, nblk, ncand;
+  int Ho, Wo, nwin, CB, G, nblk, ngroups, ncand, ncand_max, ldl;
+  bool fast;       // region_pool_fast_kernel applies
+  FastGeom geom;
   int64_t ldp;
-  size_t off_P, off_epart, off_screen, total;
-  size_t pool_smem, sel_smem;
+  size_t off_Phi, off_Plo, off_epart, off_screen, off_cand, off_cscreen, off_Ahi, off_Alo, off_logits, total;
+  size_t pool_smem, cand_smem;
 };
 
-static RegionPlan make_region_plan(int64_t B, int C, int H, int W, int ncls, int fh, int fw, int k,
-                                   int margin) {
-  RegionPlan p;
+static size_t pool_smem_bytes(int CB, int HW, int nwin) {
+  size_t words = static_cast<size_t>(nwin) * (CB + 1);
+  words += words & 1;
+  return static_cast<size_t>(2) * CB * HW * 4 + static_cast<size_t>(kEParts) * HW * 4 + words * 4 + 16;
+}
+
+static bool make_region_plan(RegionPlan& p, int64_t B, int C, int H, int W, int ncls, int fh, int fw, int k,
+                             int margin) {
   p.Ho = H - fh + 1; p.Wo = W - fw + 1; p.nwin = p.Ho * p.Wo;
-  p.CB = (H * W <= 400) ? 32 : 16;
+  const int HW = H * W;
+  p.CB = 0;
+  p.fast = false;
+  if (fh == 7 && fw == 7 && H <= 32 && W <= 32 && C % 2 == 0) {
+    // fast path: needs CB * W <= 1024 threads for the column pass, CB >= 16 (32-byte
+    // sectors on the stores), the skewed transposed planes to fit in place, and enough
+    // warps for the row pass
+    const int Hop = p.Ho | 1;
+    for (int cb : {64, 32, 16}) {
+      const size_t smem = static_cast<size_t>(2) * cb * HW * 4 + static_cast<size_t>(kEParts) * HW * 4 + 64;
+      if (cb * W > kFastThreads || smem > 200 * 1024 || 31 + W * Hop > HW) continue;
+      const int Q = 32 / (cb < 32 ? cb : 32);
+      const int cgroups = (cb + (32 / Q) - 1) / (32 / Q);
+      const int hoblks = (p.Ho + Q - 1) / Q;
+      const int warps_per_seg = cgroups * hoblks;
+      if (warps_per_seg > kFastThreads / 32) continue;
+      int nseg = (kFastThreads / 32) / warps_per_seg;
+      if (nseg > (p.Wo + 1) / 2) nseg = (p.Wo + 1) / 2;
+      if (nseg < 1) nseg = 1;
+      p.CB = cb;
+      p.fast = true;
+      p.geom.Hop = Hop; p.geom.Q = Q; p.geom.nseg = nseg; p.geom.segw = (p.Wo + nseg - 1) / nseg;
+      p.pool_smem = smem;
+      break;
+    }
+  }
+  if (!p.fast) {
+    for (int cb : {64, 32, 16, 8, 4}) {
+      if (pool_smem_bytes(cb, HW, p.nwin) <= 200 * 1024) { p.CB = cb; break; }
+    }
+    if (p.CB == 0) return false;
+    p.pool_smem = pool_smem_bytes(p.CB, HW, p.nwin);
+  }
   p.nblk = (C + p.CB - 1) / p.CB;
-  p.ncand = k + margin;
-  if (p.ncand > kSelMaxCand) p.ncand = kSelMaxCand;
-  if (p.ncand > p.nwin) p.ncand = p.nwin;
+  // channel blocks per CTA: enough CTAs to fill the machine a few times over, few
+  // enough energy partials (one plane of H*W floats per CTA)
+  p.G = 1;
+  while (p.G < 8 && static_cast<int64_t>(B) * ((p.nblk + 2 * p.G - 1) / (2 * p.G)) >= 148 * 4) p.G *= 2;
+  p.ngroups = (p.nblk + p.G - 1) / p.G;
+  p.ncand_max = k + margin;
+  if (p.ncand_max > kSelMaxCand) p.ncand_max = kSelMaxCand;
+  p.ncand = p.ncand_max < p.nwin ? p.ncand_max : p.nwin;
   p.ldp = static_cast<int64_t>(align_up(static_cast<size_t>(C), 8));
+  p.ldl = static_cast<int>(align_up(static_cast<size_t>(ncls), 4));
   size_t off = 0;
-  p.off_P = off;      off = align_up(off + static_cast<size_t>(B) * p.nwin * p.ldp * 2, 1024);
-  p.off_epart = off;  off = align_up(off + static_cast<size_t>(B) * p.nblk * H * W * 4, 1024);
-  p.off_screen = off; off = align_up(off + static_cast<size_t>(B) * p.nwin * 4, 1024);
+  const size_t Pbytes = static_cast<size_t>(B) * p.nwin * p.ldp * 2;
+  const size_t Abytes = static_cast<size_t>(B) * p.ncand_max * p.ldp * 2;
+  p.off_Phi = off;     off = align_up(off + Pbytes, 1024);
+  p.off_Plo = off;     off = align_up(off + Pbytes, 1024);
+  p.off_epart = off;   off = align_up(off + static_cast<size_t>(B) * p.ngroups * HW * 4, 1024);
+  p.off_screen = off;  off = align_up(off + static_cast<size_t>(B) * p.nwin * 4, 1024);
+  p.off_cand = off;    off = align_up(off + static_cast<size_t>(B) * p.ncand_max * 4, 1024);
+  p.off_cscreen = off; off = align_up(off + static_cast<size_t>(B) * p.ncand_max * 4, 1024);
+  p.off_Ahi = off;     off = align_up(off + Abytes, 1024);
+  p.off_Alo = off;     off = align_up(off + Abytes, 1024);
+  p.off_logits = off;  off = align_up(off + static_cast<size_t>(B) * p.ncand_max * p.ldl * 4, 1024);
   p.total = off;
-  p.pool_smem = static_cast<size_t>(p.CB) * (((H * W) | 1) + ((H * p.Wo) | 1)) * 4;
-  p.sel_smem = (static_cast<size_t>((p.nwin + 3) & ~3) + static_cast<size_t>(kSelChunk) * C +
-                static_cast<size_t>(p.ncand) * ncls) * 4;
-  return p;
+  p.cand_smem = static_cast<size_t>((p.nwin + 3) & ~3) * 4;
+  return true;
 }
 
 }  // namespace isb
@@ -446,56 +1207,85 @@ using namespace isb;
 
 extern "C" size_t isb_region_select_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W,
                                                     int64_t ncls, int fh, int fw, int k, int margin) {
-  if (B <= 0 || C <= 0 || H < fh || W < fw || fh <= 0 || fw <= 0) return 0;
-  return make_region_plan(B, (int)C, (int)H, (int)W, (int)ncls, fh, fw, k, margin).total + 1024;
+  if (B <= 0 || C <= 0 || H < fh || W < fw || fh <= 0 || fw <= 0 || k <= 0) return 0;
+  RegionPlan p;
+  if (!make_region_plan(p, B, (int)C, (int)H, (int)W, (int)ncls, fh, fw, k, margin)) return 0;
+  return p.total + 1024;
 }
 
 extern "C" int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H, int64_t W,
-                                 const float* cls_w, const uint16_t* cls_w_bf16, int64_t ld_w,
-                                 const float* cls_b, int64_t ncls, int fh, int fw, int k, int margin,
-                                 int64_t* idx, int32_t* nsel, float* cls_out, float* win_norm,
-                                 void* workspace, size_t workspace_bytes, void* stream) {
-  ISB_CHECK_ARG(x && cls_w && cls_w_bf16 && cls_b && idx && nsel && cls_out && win_norm,
+                                 const float* cls_w, const uint16_t* cls_w_hi, const uint16_t* cls_w_lo,
+                                 int64_t ld_w, const float* cls_b, int64_t ncls, int fh, int fw, int k,
+                                 int margin, int exact_mode, int64_t* idx, int32_t* nsel, float* cls_out,
+                                 float* win_norm, float* approx_max, float* runner_up,
+                                 int32_t* n_uncertified, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  ISB_CHECK_ARG(x && cls_w && cls_w_hi && cls_w_lo && cls_b && idx && nsel && cls_out && win_norm,
                 "isb_region_select: null pointer");
+  ISB_CHECK_ARG((approx_max == nullptr) == (runner_up == nullptr),
+                "isb_region_select: approx_max and runner_up go together");
   ISB_CHECK_ARG(B > 0 && C > 0 && ncls > 0 && fh > 0 && fw > 0 && H >= fh && W >= fw,
                 "isb_region_select: bad shape (B=%lld C=%lld H=%lld W=%lld window %dx%d)", (long long)B,
                 (long long)C, (long long)H, (long long)W, fh, fw);
   ISB_CHECK_ARG(k >= 1 && k <= kSelMaxCand && margin >= 0, "isb_region_select: need 1 <= k <= %d", kSelMaxCand);
   ISB_CHECK_ARG(ld_w >= C && ld_w % 8 == 0, "isb_region_select: bad ld_w");
-  ISB_CHECK_ARG(B * (H - fh + 1) * (W - fw + 1) < (1ll << 31), "isb_region_select: too many windows");
+  ISB_CHECK_ARG(B * (H - fh + 1) * (W - fw + 1) < (1ll << 31) && B * C * H * W < (1ll << 40),
+                "isb_region_select: too many windows");
+  ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 3) == 0, "isb_region_select: x must be 4-byte aligned");
   int rc = isb_check_device();
   if (rc) return rc;
-  const RegionPlan p = make_region_plan(B, (int)C, (int)H, (int)W, (int)ncls, fh, fw, k, margin);
+  RegionPlan p;
+  ISB_CHECK_ARG(make_region_plan(p, B, (int)C, (int)H, (int)W, (int)ncls, fh, fw, k, margin),
+                "isb_region_select: feature map too large for the shared-memory tiles (H*W=%lld)",
+                (long long)(H * W));
   uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
   if (workspace == nullptr || ws + p.total > static_cast<uint8_t*>(workspace) + workspace_bytes) {
     set_error("isb_region_select: workspace too small (need %zu bytes, got %zu)", p.total + 1024, workspace_bytes);
     return ISB_ERR_WORKSPACE;
   }
-  ISB_CHECK_ARG(p.pool_smem <= 200 * 1024 && p.sel_smem <= 200 * 1024,
-                "isb_region_select: feature map too large for the shared-memory tiles (H*W=%lld)",
-                (long long)(H * W));
+  ISB_CHECK_ARG(p.cand_smem <= 200 * 1024, "isb_region_select: too many windows per image (%d)", p.nwin);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  uint16_t* P = reinterpret_cast<uint16_t*>(ws + p.off_P);
+  uint16_t* P_hi = reinterpret_cast<uint16_t*>(ws + p.off_Phi);
+  uint16_t* P_lo = reinterpret_cast<uint16_t*>(ws + p.off_Plo);
   float* e_part = reinterpret_cast<float*>(ws + p.off_epart);
   float* screen = reinterpret_cast<float*>(ws + p.off_screen);
+  int* cand = reinterpret_cast<int*>(ws + p.off_cand);
+  float* cscreen = reinterpret_cast<float*>(ws + p.off_cscreen);
+  uint16_t* A_hi = reinterpret_cast<uint16_t*>(ws + p.off_Ahi);
+  uint16_t* A_lo = reinterpret_cast<uint16_t*>(ws + p.off_Alo);
+  float* logits = reinterpret_cast<float*>(ws + p.off_logits);
   const int64_t M = B * p.nwin;
+  if (n_uncertified != nullptr) ISB_CUDA(cudaMemsetAsync(n_uncertified, 0, 4, st));
 
-  if (p.ldp != C) ISB_CUDA(cudaMemsetAsync(P, 0, static_cast<size_t>(M) * p.ldp * 2, st));
-  dim3 pgrid(p.nblk, static_cast<unsigned>(B));
-  if (p.CB == 32) {
-    ISB_CUDA(cudaFuncSetAttribute(region_pool_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
-    region_pool_kernel<32><<<pgrid, 256, p.pool_smem, st>>>(x, (int)C, (int)H, (int)W, fh, fw, P, (int)p.ldp, e_part);
+  // 1. window means (bf16 hi / lo, window-major) + per-pixel energy partials
+  PoolParams pp;
+  pp.x = x; pp.C = (int)C; pp.H = (int)H; pp.W = (int)W; pp.fh = fh; pp.fw = fw;
+  pp.CB = p.CB; pp.G = p.G; pp.nblk = p.nblk; pp.ngroups = p.ngroups;
+  pp.P_hi = P_hi; pp.P_lo = P_lo; pp.ldp = (int)p.ldp; pp.e_part = e_part;
+  dim3 pgrid(p.ngroups, static_cast<unsigned>(B));
+  ISB_CHECK_ARG(p.nwin <= kMaxWinPerThread * kPoolThreads, "isb_region_select: too many windows per image (%d)", p.nwin);
+  if (p.fast) {
+    if (H <= 16) {
+      ISB_CUDA(cudaFuncSetAttribute(region_pool_fast_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
+      region_pool_fast_kernel<16><<<pgrid, kFastThreads, p.pool_smem, st>>>(pp, p.geom);
+    } else {
+      ISB_CUDA(cudaFuncSetAttribute(region_pool_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
+      region_pool_fast_kernel<32><<<pgrid, kFastThreads, p.pool_smem, st>>>(pp, p.geom);
+    }
+  } else if (fh == 7 && fw == 7) {
+    ISB_CUDA(cudaFuncSetAttribute(region_pool_generic_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
+    region_pool_generic_kernel<7><<<pgrid, kPoolThreads, p.pool_smem, st>>>(pp);
   } else {
-    ISB_CUDA(cudaFuncSetAttribute(region_pool_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
-    region_pool_kernel<16><<<pgrid, 256, p.pool_smem, st>>>(x, (int)C, (int)H, (int)W, fh, fw, P, (int)p.ldp, e_part);
+    ISB_CUDA(cudaFuncSetAttribute(region_pool_generic_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
+    region_pool_generic_kernel<0><<<pgrid, kPoolThreads, p.pool_smem, st>>>(pp);
   }
   ISB_CUDA(cudaGetLastError());
 
-  // window classifier + class-max:  screen[m] = max_j (P[m,:] . Wc[j,:] + bc[j])
+  // 2. window classifier screen + class-max:  screen[m] = max_j (P_hi[m,:] . Wc_hi[j,:] + bc[j])
   CUtensorMap ta, tb;
-  rc = make_tmap_bf16_k64(&ta, P, M, C, p.ldp, kBM);
+  rc = make_tmap_bf16_k64(&ta, P_hi, M, C, p.ldp, kBM);
   if (rc) return rc;
-  rc = make_tmap_bf16_k64(&tb, cls_w_bf16, ncls, C, ld_w, kBN);
+  rc = make_tmap_bf16_k64(&tb, cls_w_hi, ncls, C, ld_w, kBN);
   if (rc) return rc;
   RowSched sched{static_cast<int>((M + kBM - 1) / kBM), static_cast<int>((ncls + kBN - 1) / kBN),
                  static_cast<int>((C + kBK - 1) / kBK)};
@@ -506,18 +1296,46 @@ extern "C" int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H
   kern<<<sched.m_blocks < sms ? sched.m_blocks : sms, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, ta, tb, kSingleTerm, sched, ep);
   ISB_CUDA(cudaGetLastError());
 
-  ISB_CUDA(cudaFuncSetAttribute(region_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.sel_smem));
-  region_select_kernel<<<static_cast<unsigned>(B), kSelThreads, p.sel_smem, st>>>(
-      x, (int)C, (int)H, (int)W, fh, fw, cls_w, cls_b, (int)ncls, screen, e_part, p.nblk, k, p.ncand,
-      1e-10f, idx, nsel, cls_out, win_norm);
+  if (exact_mode) {
+    // second line: fp64-exact re-score of the candidates straight from the fp32 inputs
+    const size_t sel_smem = (static_cast<size_t>((p.nwin + 3) & ~3) + static_cast<size_t>(kSelChunk) * C +
+                             static_cast<size_t>(p.ncand) * ncls) * 4;
+    ISB_CHECK_ARG(sel_smem <= 200 * 1024, "isb_region_select: exact mode needs %zu bytes of shared memory", sel_smem);
+    ISB_CUDA(cudaFuncSetAttribute(region_select_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+    region_select_exact_kernel<<<static_cast<unsigned>(B), kSelThreads, sel_smem, st>>>(
+        x, (int)C, (int)H, (int)W, fh, fw, cls_w, cls_b, (int)ncls, screen, e_part, p.ngroups, k, p.ncand,
+        1e-10f, idx, nsel, cls_out, win_norm, n_uncertified);
+    ISB_CUDA(cudaGetLastError());
+    return ISB_OK;
+  }
+
+  // 3. candidates of every image + their pooled rows as split operands
+  if (p.cand_smem > 48 * 1024)
+    ISB_CUDA(cudaFuncSetAttribute(region_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.cand_smem));
+  region_candidates_kernel<<<static_cast<unsigned>(B), kSelThreads, p.cand_smem, st>>>(
+      screen, p.nwin, p.ncand, p.ncand_max, P_hi, P_lo, (int)p.ldp, cand, cscreen, A_hi, A_lo);
+  ISB_CUDA(cudaGetLastError());
+
+  // 4. fp32-grade logits of the candidates: (A_hi, A_lo) . (Wc_hi, Wc_lo)^T + bc
+  rc = isb_gemm_nt_split(A_hi, A_lo, p.ldp, cls_w_hi, cls_w_lo, ld_w, B * p.ncand_max, ncls, C, cls_b, logits,
+                         p.ldl, 1, nullptr, 0, stream);
+  if (rc) return rc;
+
+  // 5. final order, outputs, crop norms, certificate
+  region_finalize_select_kernel<<<static_cast<unsigned>(B), kSelThreads, 0, st>>>(
+      logits, p.ldl, (int)ncls, cand, cscreen, p.nwin, p.ncand, p.ncand_max, e_part, p.ngroups, (int)H, (int)W,
+      fh, fw, k, 1e-10f, idx, nsel, cls_out, win_norm, approx_max, runner_up, n_uncertified);
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;
 }
 
 extern "C" int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int fh,
-                                 int fw, int k, const int64_t* idx, const int32_t* nsel,
+                                 int fw, int k, int k_sum, const int32_t* image_list,
+                                 const int32_t* n_list, const int64_t* idx, const int32_t* nsel,
                                  const float* win_norm, const float* shift, uint16_t* U_hi,
-                                 uint16_t* U_lo, int64_t ldu, void* stream) {
+                                 uint16_t* U_lo, int64_t ldu, float* win_mean, void* stream) {
+  ISB_CHECK_ARG(k_sum >= 1 && k_sum <= k, "isb_region_gather: need 1 <= k_sum <= k");
+  ISB_CHECK_ARG((image_list == nullptr) == (n_list == nullptr), "isb_region_gather: image_list and n_list go together");
   ISB_CHECK_ARG(x && idx && nsel && win_norm && shift && U_hi, "isb_region_gather: null pointer");
   ISB_CHECK_ARG(B > 0 && C > 0 && fh > 0 && fw > 0 && H >= fh && W >= fw, "isb_region_gather: bad shape");
   ISB_CHECK_ARG(k >= 1 && k <= kSelMaxCand, "isb_region_gather: need 1 <= k <= %d", kSelMaxCand);
@@ -526,9 +1344,52 @@ extern "C" int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H
   ISB_CHECK_ARG(Kin < (1ll << 30), "isb_region_gather: C*fh*fw too large");
   ISB_CHECK_ARG(ldu >= KinP && ldu % 8 == 0 && (reinterpret_cast<uintptr_t>(U_hi) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(U_lo) & 15) == 0, "isb_region_gather: bad ldu / alignment");
-  dim3 grid(static_cast<unsigned>((KinP / 8 + 255) / 256), static_cast<unsigned>(B));
-  region_gather_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, (int)C, (int)H, (int)W, fh, fw, k, idx, nsel, win_norm, shift, U_hi, U_lo, ldu);
+  const int64_t HW = H * W;
+  int CBg = 0;
+  for (int cb : {64, 32, 16, 8, 4, 2}) {
+    if (static_cast<size_t>(cb) * HW * 4 <= 96 * 1024) { CBg = cb; break; }
+  }
+  ISB_CHECK_ARG(CBg > 0, "isb_region_gather: feature map too large (H*W=%lld)", (long long)HW);
+  const int row_align = (W % 4 == 0) ? 1 : ((W % 2 == 0) ? 2 : 4);
+  const size_t smem = static_cast<size_t>(CBg) * HW * 4;
+  dim3 grid(static_cast<unsigned>((C + CBg - 1) / CBg), static_cast<unsigned>(B));
+  if (fh == 7 && fw == 7) {
+    if (smem > 48 * 1024)
+      ISB_CUDA(cudaFuncSetAttribute(region_gather_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    region_gather_kernel<7><<<grid, kGatherThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        x, (int)C, (int)H, (int)W, fh, fw, k, k_sum, CBg, row_align, image_list, n_list, idx, nsel, win_norm, shift, U_hi, U_lo, ldu, win_mean);
+  } else {
+    if (smem > 48 * 1024)
+      ISB_CUDA(cudaFuncSetAttribute(region_gather_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    region_gather_kernel<0><<<grid, kGatherThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        x, (int)C, (int)H, (int)W, fh, fw, k, k_sum, CBg, row_align, image_list, n_list, idx, nsel, win_norm, shift, U_hi, U_lo, ldu, win_mean);
+  }
+  ISB_CUDA(cudaGetLastError());
+  return ISB_OK;
+}
+
+extern "C" int isb_region_logits(const float* win_mean, const float* cls_w, const float* cls_b, int64_t B,
+                                 int64_t C, int64_t ncls, int ke, int k, const int32_t* nsel_in,
+                                 const float* approx_max, const float* runner_up, const int64_t* idx_in,
+                                 const float* norm_in, int64_t* idx_out, float* norm_out, int32_t* nsel_out,
+                                 float* cls_out, int32_t* changed_list, int32_t* n_changed,
+                                 int32_t* n_uncertified, void* stream) {
+  ISB_CHECK_ARG(win_mean && cls_w && cls_b && nsel_in && idx_in && norm_in && idx_out && norm_out && nsel_out &&
+                cls_out, "isb_region_logits: null pointer");
+  ISB_CHECK_ARG(B > 0 && C > 0 && ncls > 0 && k >= 1 && ke >= k && ke <= kSelMaxCand, "isb_region_logits: bad shape");
+  ISB_CHECK_ARG((changed_list == nullptr) == (n_changed == nullptr), "isb_region_logits: changed_list and n_changed go together");
+  ISB_CHECK_ARG(n_uncertified == nullptr || (approx_max != nullptr && runner_up != nullptr),
+                "isb_region_logits: the certificate needs approx_max and runner_up");
+  const size_t smem = (static_cast<size_t>(ke) * C + static_cast<size_t>(ke) * ncls) * 4;
+  ISB_CHECK_ARG(smem <= 200 * 1024, "isb_region_logits: ke * (C + ncls) too large for shared memory");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_uncertified != nullptr) ISB_CUDA(cudaMemsetAsync(n_uncertified, 0, 4, st));
+  if (n_changed != nullptr) ISB_CUDA(cudaMemsetAsync(n_changed, 0, 4, st));
+  if (smem > 48 * 1024)
+    ISB_CUDA(cudaFuncSetAttribute(region_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  region_logits_kernel<<<static_cast<unsigned>(B), kLogThreads, smem, st>>>(
+      win_mean, cls_w, cls_b, (int)C, (int)ncls, ke, k, nsel_in, approx_max, runner_up, idx_in, norm_in, idx_out,
+      norm_out, nsel_out, cls_out, changed_list, n_changed, n_uncertified);
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;
 }

@@ -32,7 +32,8 @@ class HeadWeights(object):
         self.terms = terms
         self.cls_w = None if cls_w is None else ops._f32c(cls_w.reshape(cls_w.size(0), -1))
         self.cls_b = None if cls_b is None else ops._f32c(cls_b)
-        self.cls_w_bf16 = None if cls_w is None else ops.to_bf16(self.cls_w)
+        self.cls_w_hi = None if cls_w is None else ops.to_bf16(self.cls_w, 0)
+        self.cls_w_lo = None if cls_w is None else ops.to_bf16(self.cls_w, 1)
         self.shift = ops._f32c(shift)
         self.lin_b = None if lin_b is None else ops._f32c(lin_b)
         lin_w = ops._f32c(lin_w)
@@ -57,58 +58,133 @@ def _project(U_hi, U_lo, hw, B):
     return ops.gemm_nt_split(U_hi, U_lo, hw.lin_w_hi, hw.lin_w_lo, splits=splits)
 
 
-def region_select(x, hw, k, fsize, margin=WINDOW_MARGIN):
-    """a3: (idx [B,k] int64, nsel [B] int32, cls_out [B,ncls,k], win_norm [B,k])."""
+def region_select(x, hw, k, fsize, margin=WINDOW_MARGIN, exact_mode=False):
+    """a3, first stage: (idx [B,k] int64, nsel [B] int32, cls_out [B,ncls,k], win_norm [B,k],
+    approx_max [B,k], runner_up [B], n_uncertified [1] int32).  exact_mode: the slow
+    fp64 second line (candidates = 32), cls_out / order final."""
     ops._need_cuda(x)
     x = ops._f32c(x)
     B, C, H, W = x.shape
     fh, fw = fsize
     ncls = hw.cls_w.size(0)
-    margin = max(0, min(margin, 32 - k))
+    margin = 32 - k if exact_mode else max(0, min(margin, 32 - k))
     dev = x.device
     idx = torch.empty((B, k), dtype=torch.int64, device=dev)
     nsel = torch.empty((B,), dtype=torch.int32, device=dev)
     cls_out = torch.empty((B, ncls, k), dtype=torch.float32, device=dev)
     win_norm = torch.empty((B, k), dtype=torch.float32, device=dev)
+    approx_max = torch.empty((B, k), dtype=torch.float32, device=dev)
+    runner_up = torch.empty((B,), dtype=torch.float32, device=dev)
+    n_unc = torch.zeros(1, dtype=torch.int32, device=dev)
     L = _lib.lib()
     nbytes = L.isb_region_select_workspace_bytes(B, C, H, W, ncls, fh, fw, k, margin)
     ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
-    _lib.check(L.isb_region_select(x.data_ptr(), B, C, H, W, hw.cls_w.data_ptr(),
-                                   hw.cls_w_bf16.data_ptr(), hw.cls_w_bf16.size(1),
-                                   hw.cls_b.data_ptr(), ncls, fh, fw, k, margin, idx.data_ptr(),
-                                   nsel.data_ptr(), cls_out.data_ptr(), win_norm.data_ptr(),
-                                   ws.data_ptr(), nbytes, ops._stream()), "isb_region_select")
-    return idx, nsel, cls_out, win_norm
+    _lib.check(L.isb_region_select(x.data_ptr(), B, C, H, W, hw.cls_w.data_ptr(), hw.cls_w_hi.data_ptr(),
+                                   hw.cls_w_lo.data_ptr(), hw.cls_w_hi.size(1), hw.cls_b.data_ptr(), ncls,
+                                   fh, fw, k, margin, 1 if exact_mode else 0, idx.data_ptr(), nsel.data_ptr(),
+                                   cls_out.data_ptr(), win_norm.data_ptr(), approx_max.data_ptr(),
+                                   runner_up.data_ptr(), n_unc.data_ptr(), ws.data_ptr(), nbytes,
+                                   ops._stream()), "isb_region_select")
+    return idx, nsel, cls_out, win_norm, approx_max, runner_up, n_unc
 
 
-def region_aggregate(x, hw, k, fsize, idx, nsel, win_norm):
-    """a4 + a5: descriptors [B, D] of the selected windows."""
+RUNNER_UPS = 2   # windows beyond k whose logits are also recomputed in true fp32
+
+
+def region_gather(x, hw, k, fsize, idx, nsel, win_norm, k_sum=None, want_means=True, out=None,
+                  image_list=None, n_list=None):
+    """a4 operand: (U_hi, U_lo or None, win_mean [B,k,C] or None).  idx / win_norm are
+    [B, k]; the first min(nsel, k_sum) windows of every image are summed.  image_list /
+    n_list (device int32): fix-up pass over the listed images only, into ``out``."""
     x = ops._f32c(x)
     B, C, H, W = x.shape
     fh, fw = fsize
     if C * fh * fw != hw.Kin:
         raise IsbError("feature map channels x window (%d) != projection in_features (%d)" %
                        (C * fh * fw, hw.Kin))
-    L = _lib.lib()
-    U_hi = torch.empty((B, hw.KinP), dtype=torch.bfloat16, device=x.device)
-    U_lo = torch.empty_like(U_hi) if hw.terms == 3 else None
-    _lib.check(L.isb_region_gather(x.data_ptr(), B, C, H, W, fh, fw, k, idx.data_ptr(),
-                                   nsel.data_ptr(), win_norm.data_ptr(), hw.shift.data_ptr(),
-                                   U_hi.data_ptr(), ops._ptr(U_lo), hw.KinP, ops._stream()),
-               "isb_region_gather")
+    if out is None:
+        U_hi = torch.empty((B, hw.KinP), dtype=torch.bfloat16, device=x.device)
+        U_lo = torch.empty_like(U_hi) if hw.terms == 3 else None
+    else:
+        U_hi, U_lo = out
+    win_mean = torch.empty((B, k, C), dtype=torch.float32, device=x.device) if want_means else None
+    _lib.check(_lib.lib().isb_region_gather(x.data_ptr(), B, C, H, W, fh, fw, k, k if k_sum is None else k_sum,
+                                            ops._ptr(image_list), ops._ptr(n_list), idx.data_ptr(),
+                                            nsel.data_ptr(), win_norm.data_ptr(), hw.shift.data_ptr(),
+                                            U_hi.data_ptr(), ops._ptr(U_lo), hw.KinP, ops._ptr(win_mean),
+                                            ops._stream()), "isb_region_gather")
+    return U_hi, U_lo, win_mean
+
+
+def region_logits(win_mean, hw, k, nsel_in, idx_in, norm_in, approx_max, runner_up):
+    """Exact fp32 logits of the ke = win_mean.size(1) scored windows -> the final k.
+    Returns (idx [B,k], win_norm [B,k], nsel [B], cls_out [B,ncls,k], changed_list [B] int32,
+    n_changed [1], n_uncertified [1])."""
+    B, ke, C = win_mean.shape
+    ncls = hw.cls_w.size(0)
+    dev = win_mean.device
+    idx = torch.empty((B, k), dtype=torch.int64, device=dev)
+    norm = torch.empty((B, k), dtype=torch.float32, device=dev)
+    nsel = torch.empty((B,), dtype=torch.int32, device=dev)
+    cls_out = torch.empty((B, ncls, k), dtype=torch.float32, device=dev)
+    changed = torch.empty((B,), dtype=torch.int32, device=dev)
+    n_changed = torch.zeros(1, dtype=torch.int32, device=dev)
+    n_unc = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().isb_region_logits(win_mean.data_ptr(), hw.cls_w.data_ptr(), hw.cls_b.data_ptr(), B, C,
+                                            ncls, ke, k, nsel_in.data_ptr(), approx_max.data_ptr(),
+                                            runner_up.data_ptr(), idx_in.data_ptr(), norm_in.data_ptr(),
+                                            idx.data_ptr(), norm.data_ptr(), nsel.data_ptr(), cls_out.data_ptr(),
+                                            changed.data_ptr(), n_changed.data_ptr(), n_unc.data_ptr(),
+                                            ops._stream()), "isb_region_logits")
+    return idx, norm, nsel, cls_out, changed, n_changed, n_unc
+
+
+def region_project(U_hi, U_lo, hw, nsel):
+    """a4 projection + a5: desc = l2norm(u . W^T + nsel * bias)."""
+    B = U_hi.size(0)
     y = _project(U_hi, U_lo, hw, B)
-    desc = torch.empty((B, hw.D), dtype=torch.float32, device=x.device)
-    _lib.check(L.isb_descriptor_finalize(y.data_ptr(), B, hw.D, ops._ptr(hw.lin_b), nsel.data_ptr(),
-                                         1e-10, desc.data_ptr(), ops._stream()),
+    desc = torch.empty((B, hw.D), dtype=torch.float32, device=U_hi.device)
+    _lib.check(_lib.lib().isb_descriptor_finalize(y.data_ptr(), B, hw.D, ops._ptr(hw.lin_b), nsel.data_ptr(),
+                                                  1e-10, desc.data_ptr(), ops._stream()),
                "isb_descriptor_finalize")
     return desc
 
 
-def region_descriptors(x, hw, k, fsize, margin=WINDOW_MARGIN):
+def region_head(x, hw, k, fsize, margin=WINDOW_MARGIN):
+    """The certified fast path, all asynchronous: returns (U_hi, U_lo, idx, nsel, cls_out,
+    n_uncertified [1] device int32)."""
+    ke = min(32, k + RUNNER_UPS)
+    # 1. screen all windows, fp32-grade scores of the candidates, the best ke of them
+    idx_e, nsel_e, _, norm_e, approx_e, runner_up, n1 = region_select(x, hw, ke, fsize, margin)
+    # 2. operand from the first k, exact means of all ke
+    U_hi, U_lo, win_mean = region_gather(x, hw, ke, fsize, idx_e, nsel_e, norm_e, k_sum=k)
+    # 3. true-fp32 logits -> final k, exact order; images whose k changed are listed
+    idx, norm, nsel, cls_out, changed, n_changed, n2 = region_logits(win_mean, hw, k, nsel_e, idx_e, norm_e,
+                                                                      approx_e, runner_up)
+    # 4. fix-up: re-gather the (rare) images where a runner-up entered the top k
+    region_gather(x, hw, k, fsize, idx, nsel, norm, want_means=False, out=(U_hi, U_lo), image_list=changed,
+                  n_list=n_changed)
+    return U_hi, U_lo, idx, nsel, cls_out, n1 + n2
+
+
+def region_descriptors(x, hw, k, fsize, margin=WINDOW_MARGIN, exact=True, stats=None):
     """x [B, C, H, W] trunk feature maps -> (desc [B, D], cls_out [B, ncls, k],
-    idx [B, k], nsel [B]).  reference: model/siamese.py:187-223 per image."""
-    idx, nsel, cls_out, win_norm = region_select(x, hw, k, fsize, margin)
-    desc = region_aggregate(x, hw, k, fsize, idx, nsel, win_norm)
+    idx [B, k], nsel [B]).  reference: model/siamese.py:187-223 per image.
+
+    exact=True: the certificates of the fast path (screen completeness, selection
+    against the unscored runner-ups) are read back (ONE 4-byte D2H read); a batch with
+    an uncertified image is redone with the fp64-exact second line.  exact=False skips
+    the read-back (no host sync)."""
+    U_hi, U_lo, idx, nsel, cls_out, n_unc = region_head(x, hw, k, fsize, margin)
+    if exact:
+        n_bad = int(n_unc.item())
+        if stats is not None:
+            stats["batches"] = stats.get("batches", 0) + 1
+            stats["batches_resolved_exactly"] = stats.get("batches_resolved_exactly", 0) + (1 if n_bad else 0)
+        if n_bad:
+            idx, nsel, cls_out, win_norm, _, _, _ = region_select(x, hw, k, fsize, exact_mode=True)
+            U_hi, U_lo, _ = region_gather(x, hw, k, fsize, idx, nsel, win_norm, want_means=False)
+    desc = region_project(U_hi, U_lo, hw, nsel)
     return desc, cls_out, idx, nsel
 
 

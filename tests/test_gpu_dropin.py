@@ -158,7 +158,7 @@ def test_region_descriptor_net_eval_matches_oracle_and_reloads():
     assert desc.shape == (5, 16) and cls_out.shape == (5, 5, 6)
     assert torch.equal(desc, d2)
     assert torch.allclose(desc.cpu(), od, rtol=0, atol=3e-5)
-    assert torch.allclose(cls_out.cpu(), oc, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(cls_out.cpu(), oc, rtol=1e-5, atol=2e-6)
     # parameters change in place (optimizer step / load_state_dict) -> cached operands rebuilt
     sd = {k: v.clone() for k, v in net.state_dict().items()}
     other = _toy_region_net(1)
@@ -177,6 +177,8 @@ def test_region_descriptor_net_train_mode_composed_path():
     for p in net.feature_reduc1.parameters():
         p.requires_grad = True
     x = _randn(2, 3, 32, 32, seed=12).cuda()
+    torch.backends.cudnn.allow_tf32 = False          # the composed path's conv / linear in true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
     with torch.no_grad():
         fused_desc, fused_cls = net.forward_single(x)
     from instance_search_b200.model.nn_utils import set_net_train

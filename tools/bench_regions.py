@@ -12,7 +12,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from instance_search_b200 import _lib, ops, regions  # noqa: E402
+from instance_search_b200 import regions  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--B", type=int, default=256)
@@ -51,31 +51,32 @@ def ev():
 for hw_size in [int(s) for s in a.sizes.split(",")]:
     H = W = hw_size
     x = torch.relu(torch.randn(a.B, a.C, H, W, device=dev, generator=g))
-    stages = {"select": [], "gather": [], "project": [], "finalize": [], "total": []}
+    stages = {"select": [], "gather": [], "logits_fixup": [], "project": [], "total": []}
+    changed_total = 0
+    uncert = 0
     for it in range(a.warmup + a.iters):
         flush.zero_()   # L2 flush between iterations (x at 14x14 is 411 MB, at 32x32 2.1 GB)
         e = [ev() for _ in range(5)]
+        ke = a.k + regions.RUNNER_UPS
         e[0].record()
-        idx, nsel, cls_out, win_norm = regions.region_select(x, hw, a.k, (7, 7))
+        idx_e, nsel_e, _, norm_e, approx_e, runner_up, n1 = regions.region_select(x, hw, ke, (7, 7))
         e[1].record()
-        L = _lib.lib()
-        U_hi = torch.empty((a.B, hw.KinP), dtype=torch.bfloat16, device=dev)
-        U_lo = torch.empty_like(U_hi) if hw.terms == 3 else None
-        _lib.check(L.isb_region_gather(x.data_ptr(), a.B, a.C, H, W, 7, 7, a.k, idx.data_ptr(), nsel.data_ptr(),
-                                       win_norm.data_ptr(), hw.shift.data_ptr(), U_hi.data_ptr(),
-                                       ops._ptr(U_lo), hw.KinP, ops._stream()), "gather")
+        U_hi, U_lo, win_mean = regions.region_gather(x, hw, ke, (7, 7), idx_e, nsel_e, norm_e, k_sum=a.k)
         e[2].record()
-        y = regions._project(U_hi, U_lo, hw, a.B)
+        idx, norm, nsel, cls_out, changed, n_changed, n2 = regions.region_logits(
+            win_mean, hw, a.k, nsel_e, idx_e, norm_e, approx_e, runner_up)
+        regions.region_gather(x, hw, a.k, (7, 7), idx, nsel, norm, want_means=False, out=(U_hi, U_lo),
+                              image_list=changed, n_list=n_changed)
         e[3].record()
-        desc = torch.empty((a.B, hw.D), dtype=torch.float32, device=dev)
-        _lib.check(L.isb_descriptor_finalize(y.data_ptr(), a.B, hw.D, ops._ptr(hw.lin_b), nsel.data_ptr(), 1e-10,
-                                             desc.data_ptr(), ops._stream()), "finalize")
+        desc = regions.region_project(U_hi, U_lo, hw, nsel)
         e[4].record()
         torch.cuda.synchronize()
         if it >= a.warmup:
-            for n, (s, t) in zip(["select", "gather", "project", "finalize"], zip(e[:-1], e[1:])):
+            for n, (s, t) in zip(["select", "gather", "logits_fixup", "project"], zip(e[:-1], e[1:])):
                 stages[n].append(s.elapsed_time(t))
             stages["total"].append(e[0].elapsed_time(e[4]))
+            uncert += int((n1 + n2).item())
+            changed_total += int(n_changed.item())
     med = {n: sorted(v)[len(v) // 2] for n, v in stages.items()}
     nwin = (H - 6) * (W - 6)
     kk = min(nwin, a.k)
@@ -90,7 +91,7 @@ for hw_size in [int(s) for s in a.sizes.split(",")]:
     print(json.dumps({
         "workload": "region descriptors, B=%d C=%d %dx%d map, ncls=%d, D=%d, k=%d, terms=%d" %
                     (a.B, a.C, H, W, a.ncls, a.D, a.k, a.terms),
-        "ms": med, "region_desc_per_s": units / (med["total"] * 1e-3),
+        "ms": med, "uncertified_images": uncert, "regathered_images": changed_total, "region_desc_per_s": units / (med["total"] * 1e-3),
         "images_per_s": a.B / (med["total"] * 1e-3),
         "pool_select_gather": {"algorithmic_bytes": bw_bytes, "ms": bw_ms,
                                "achieved_gbs": bw_bytes / (bw_ms * 1e-3) / 1e9,
