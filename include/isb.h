@@ -215,13 +215,18 @@ int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H, int64_t W
  * re-gathered (isb_region_gather with image_list).  Certificate: the k-th exact
  * class-max must clear runner_up[b] -- the best fp32-grade value among the windows
  * NOT scored here -- by 8 sigma, sigma = rms(approx_max - exact) over the ke windows;
- * failures are counted in *n_uncertified (NULL: no certificate). */
+ * failures are counted in *n_uncertified (NULL: no certificate).
+ * cls_out == NULL (eval: the reference's forward returns only the descriptor,
+ * model/siamese.py:231): only the class-max is needed, so only the classes whose
+ * fp32-grade logit (approx_cls [B, ncls, ke] = isb_region_select's cls_out) lies
+ * within twice the worst-case error of the split, 2 * 3 * 2^-18 * sum|mean| * max|cls_w|
+ * (wabs_max = max|cls_w|), of the window's best are evaluated in fp32. */
 int isb_region_logits(const float* win_mean, const float* cls_w, const float* cls_b, int64_t B,
                       int64_t C, int64_t ncls, int ke, int k, const int32_t* nsel_in,
                       const float* approx_max, const float* runner_up, const int64_t* idx_in,
                       const float* norm_in, int64_t* idx_out, float* norm_out, int32_t* nsel_out,
-                      float* cls_out, int32_t* changed_list, int32_t* n_changed,
-                      int32_t* n_uncertified, void* stream);
+                      float* cls_out, const float* approx_cls, float wabs_max, int32_t* changed_list,
+                      int32_t* n_changed, int32_t* n_uncertified, void* stream);
 
 /* ---------------------------------------------------------------- a4 (operand)
  * u[b, :] = sum_{i < nsel[b]} crop_i / win_norm[b, i]  +  nsel[b] * shift

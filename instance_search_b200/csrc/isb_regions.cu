@@ -980,6 +980,7 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, 
 // value by 8 sigma, sigma = rms(fp32-grade - exact) over the k selected.
 constexpr int kLogThreads = 256;
 constexpr int kLogMaxK = 8;   // windows per pass over the classifier
+constexpr int kLogMaxPairs = 256;   // (window, class) contenders evaluated exactly in class-max-only mode
 
 __global__ void __launch_bounds__(kLogThreads)
 region_logits_kernel(const float* __restrict__ win_mean, const float* __restrict__ cls_w,
@@ -988,12 +989,16 @@ region_logits_kernel(const float* __restrict__ win_mean, const float* __restrict
                      const float* __restrict__ runner_up, const int64_t* __restrict__ idx_in,
                      const float* __restrict__ norm_in, int64_t* __restrict__ idx_out,
                      float* __restrict__ norm_out, int* __restrict__ nsel_out,
-                     float* __restrict__ cls_out, int* __restrict__ changed_list,
-                     int* __restrict__ n_changed, int* __restrict__ n_uncertified) {
+                     float* __restrict__ cls_out, const float* __restrict__ approx_cls, float wabs_max,
+                     int* __restrict__ changed_list, int* __restrict__ n_changed,
+                     int* __restrict__ n_uncertified) {
   extern __shared__ __align__(16) uint8_t log_smem_raw[];
   float* ms = reinterpret_cast<float*>(log_smem_raw);          // [ke][C]
   float* lg = ms + static_cast<size_t>(ke) * C;                 // [ke][ncls]
   __shared__ float wmax[kSelMaxCand];
+  __shared__ float tau[kSelMaxCand];
+  __shared__ int pair_list[kLogMaxPairs];
+  __shared__ int n_pairs;
   __shared__ int order[kSelMaxCand];
   __shared__ int64_t widx[kSelMaxCand];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1003,6 +1008,73 @@ region_logits_kernel(const float* __restrict__ win_mean, const float* __restrict
   if (tid < ke) widx[tid] = idx_in[static_cast<size_t>(b) * ke + tid];
   __syncthreads();
   const bool vec = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(cls_w) & 15) == 0;
+  // ---- class-max only (eval: the logits themselves are not an output).  A class can
+  // hold the exact maximum of window i only if its fp32-grade logit is within tau_i of
+  // the fp32-grade maximum, tau_i = twice the worst-case error of the three-product
+  // split, 3 * 2^-18 * sum_c |mean_c| * max|w|.  Only those (window, class) pairs are
+  // evaluated in true fp32.
+  bool pruned = (cls_out == nullptr) && (approx_cls != nullptr);
+  if (pruned) {
+    if (tid == 0) n_pairs = 0;
+    for (int i = warp; i < nall; i += kLogThreads / 32) {
+      float sabs = 0.f, am = -INFINITY;
+      for (int c = lane; c < C; c += 32) sabs += fabsf(ms[i * C + c]);
+      for (int j = lane; j < ncls; j += 32)
+        am = fmaxf(am, approx_cls[(static_cast<size_t>(b) * ncls + j) * ke + i]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sabs += __shfl_xor_sync(0xffffffffu, sabs, o);
+        am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+      }
+      if (lane == 0) { wmax[i] = am; tau[i] = 2.4e-5f * sabs * wabs_max + 1e-6f; }
+    }
+    __syncthreads();
+    for (int t = tid; t < nall * ncls; t += kLogThreads) {
+      const int i = t / ncls, j = t - i * ncls;
+      if (approx_cls[(static_cast<size_t>(b) * ncls + j) * ke + i] >= wmax[i] - tau[i]) {
+        const int pos = atomicAdd(&n_pairs, 1);
+        if (pos < kLogMaxPairs) pair_list[pos] = t;
+      }
+    }
+    __syncthreads();
+    if (n_pairs > kLogMaxPairs) pruned = false;   // too many contenders: score every class (block-uniform)
+  }
+  if (pruned) {
+    const int np = n_pairs;
+    for (int q = tid; q < nall; q += kLogThreads) wmax[q] = -INFINITY;
+    __syncthreads();
+    for (int q = warp; q < np; q += kLogThreads / 32) {
+      const int t = pair_list[q];
+      const int i = t / ncls, j = t - i * ncls;
+      const float* wr = cls_w + static_cast<size_t>(j) * C;
+      float acc = 0.f;
+      if (vec) {
+        const float4* w4 = reinterpret_cast<const float4*>(wr);
+#pragma unroll 4
+        for (int c4 = lane; c4 < C / 4; c4 += 32) {
+          const float4 wv = __ldg(w4 + c4);
+          const float4 m = reinterpret_cast<const float4*>(ms + i * C)[c4];
+          acc = fmaf(wv.x, m.x, acc);
+          acc = fmaf(wv.y, m.y, acc);
+          acc = fmaf(wv.z, m.z, acc);
+          acc = fmaf(wv.w, m.w, acc);
+        }
+      } else {
+        for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(wr + c), ms[i * C + c], acc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) lg[q] = acc + __ldg(cls_b + j);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int q = 0; q < np; ++q) {
+        const int i = pair_list[q] / ncls;
+        wmax[i] = fmaxf(wmax[i], lg[q]);
+      }
+    }
+    __syncthreads();
+  } else {
   for (int i0 = 0; i0 < nall; i0 += kLogMaxK) {
     const int ni = min(kLogMaxK, nall - i0);
     for (int j = warp; j < ncls; j += kLogThreads / 32) {
@@ -1053,6 +1125,7 @@ region_logits_kernel(const float* __restrict__ win_mean, const float* __restrict
     if (lane == 0) wmax[i] = m;
   }
   __syncthreads();
+  }
   if (tid == 0) {
     for (int i = 0; i < nall; ++i) order[i] = i;
     for (int i = 1; i < nall; ++i) {
@@ -1086,9 +1159,11 @@ region_logits_kernel(const float* __restrict__ win_mean, const float* __restrict
     idx_out[static_cast<size_t>(b) * k + i] = (i < nsel) ? widx[order[i]] : -1;
     norm_out[static_cast<size_t>(b) * k + i] = (i < nsel) ? norm_in[static_cast<size_t>(b) * ke + order[i]] : 1.f;
   }
-  for (int t = tid; t < ncls * k; t += kLogThreads) {
-    const int j = t / k, i = t - j * k;
-    cls_out[(static_cast<size_t>(b) * ncls + j) * k + i] = (i < nsel) ? lg[order[i] * ncls + j] : 0.f;
+  if (cls_out != nullptr) {
+    for (int t = tid; t < ncls * k; t += kLogThreads) {
+      const int j = t / k, i = t - j * k;
+      cls_out[(static_cast<size_t>(b) * ncls + j) * k + i] = (i < nsel) ? lg[order[i] * ncls + j] : 0.f;
+    }
   }
 }
 
@@ -1372,10 +1447,13 @@ extern "C" int isb_region_logits(const float* win_mean, const float* cls_w, cons
                                  int64_t C, int64_t ncls, int ke, int k, const int32_t* nsel_in,
                                  const float* approx_max, const float* runner_up, const int64_t* idx_in,
                                  const float* norm_in, int64_t* idx_out, float* norm_out, int32_t* nsel_out,
-                                 float* cls_out, int32_t* changed_list, int32_t* n_changed,
-                                 int32_t* n_uncertified, void* stream) {
-  ISB_CHECK_ARG(win_mean && cls_w && cls_b && nsel_in && idx_in && norm_in && idx_out && norm_out && nsel_out &&
-                cls_out, "isb_region_logits: null pointer");
+                                 float* cls_out, const float* approx_cls, float wabs_max,
+                                 int32_t* changed_list, int32_t* n_changed, int32_t* n_uncertified,
+                                 void* stream) {
+  ISB_CHECK_ARG(win_mean && cls_w && cls_b && nsel_in && idx_in && norm_in && idx_out && norm_out && nsel_out,
+                "isb_region_logits: null pointer");
+  ISB_CHECK_ARG(cls_out != nullptr || (approx_cls != nullptr && wabs_max > 0.f),
+                "isb_region_logits: without cls_out, approx_cls and max|cls_w| are needed to prune the classes");
   ISB_CHECK_ARG(B > 0 && C > 0 && ncls > 0 && k >= 1 && ke >= k && ke <= kSelMaxCand, "isb_region_logits: bad shape");
   ISB_CHECK_ARG((changed_list == nullptr) == (n_changed == nullptr), "isb_region_logits: changed_list and n_changed go together");
   ISB_CHECK_ARG(n_uncertified == nullptr || (approx_max != nullptr && runner_up != nullptr),
@@ -1389,7 +1467,7 @@ extern "C" int isb_region_logits(const float* win_mean, const float* cls_w, cons
     ISB_CUDA(cudaFuncSetAttribute(region_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   region_logits_kernel<<<static_cast<unsigned>(B), kLogThreads, smem, st>>>(
       win_mean, cls_w, cls_b, (int)C, (int)ncls, ke, k, nsel_in, approx_max, runner_up, idx_in, norm_in, idx_out,
-      norm_out, nsel_out, cls_out, changed_list, n_changed, n_uncertified);
+      norm_out, nsel_out, cls_out, approx_cls, wabs_max, changed_list, n_changed, n_uncertified);
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;
 }

@@ -169,14 +169,16 @@ class RegionDescriptorNet(nn.Module):
             cls_out = torch.cat([cls_out, cls_out.new_zeros(c.size(0), c.size(1), self.k - k)], 2)
         return self.feature_reduc2(acc), cls_out
 
-    def forward_single(self, x):
+    def forward_single(self, x, want_cls_out=True):
         """x: [B, 3, h, w] images -> (desc [B, D], cls_out [B, ncls, k]); every image is
-        treated as the reference's batch-1 call (model/siamese.py:184)."""
+        treated as the reference's batch-1 call (model/siamese.py:184).  want_cls_out=False
+        (what the eval-mode forward needs, :231) skips the logits output: cls_out is None."""
         x = self.features(x)
         if self._needs_grad(x) or not self._fusable():
             outs = [self._forward_single_composed(x[b:b + 1]) for b in range(x.size(0))]
             return torch.cat([d for d, _ in outs], 0), torch.cat([c for _, c in outs], 0)
-        desc, cls_out, _, _ = regions.region_descriptors(x.detach(), self._head(), self.k, self.feature_size2d)
+        desc, cls_out, _, _ = regions.region_descriptors(x.detach(), self._head(), self.k, self.feature_size2d,
+                                                          want_cls_out=want_cls_out)
         return desc, cls_out
 
     def forward(self, x1, x2=None, x3=None):
@@ -185,4 +187,4 @@ class RegionDescriptorNet(nn.Module):
         elif self.training:
             return self.forward_single(x1), self.forward_single(x2)
         else:
-            return self.forward_single(x1)[0]
+            return self.forward_single(x1, want_cls_out=False)[0]

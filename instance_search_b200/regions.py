@@ -34,6 +34,7 @@ class HeadWeights(object):
         self.cls_b = None if cls_b is None else ops._f32c(cls_b)
         self.cls_w_hi = None if cls_w is None else ops.to_bf16(self.cls_w, 0)
         self.cls_w_lo = None if cls_w is None else ops.to_bf16(self.cls_w, 1)
+        self.cls_w_absmax = 0.0 if cls_w is None else float(self.cls_w.abs().max())
         self.shift = ops._f32c(shift)
         self.lin_b = None if lin_b is None else ops._f32c(lin_b)
         lin_w = ops._f32c(lin_w)
@@ -116,24 +117,26 @@ def region_gather(x, hw, k, fsize, idx, nsel, win_norm, k_sum=None, want_means=T
     return U_hi, U_lo, win_mean
 
 
-def region_logits(win_mean, hw, k, nsel_in, idx_in, norm_in, approx_max, runner_up):
+def region_logits(win_mean, hw, k, nsel_in, idx_in, norm_in, approx_max, runner_up, approx_cls=None):
     """Exact fp32 logits of the ke = win_mean.size(1) scored windows -> the final k.
     Returns (idx [B,k], win_norm [B,k], nsel [B], cls_out [B,ncls,k], changed_list [B] int32,
-    n_changed [1], n_uncertified [1])."""
+    n_changed [1], n_uncertified [1]).  approx_cls (region_select's cls_out): class-max
+    only -- cls_out is not computed and returned as None."""
     B, ke, C = win_mean.shape
     ncls = hw.cls_w.size(0)
     dev = win_mean.device
     idx = torch.empty((B, k), dtype=torch.int64, device=dev)
     norm = torch.empty((B, k), dtype=torch.float32, device=dev)
     nsel = torch.empty((B,), dtype=torch.int32, device=dev)
-    cls_out = torch.empty((B, ncls, k), dtype=torch.float32, device=dev)
+    cls_out = torch.empty((B, ncls, k), dtype=torch.float32, device=dev) if approx_cls is None else None
     changed = torch.empty((B,), dtype=torch.int32, device=dev)
     n_changed = torch.zeros(1, dtype=torch.int32, device=dev)
     n_unc = torch.zeros(1, dtype=torch.int32, device=dev)
     _lib.check(_lib.lib().isb_region_logits(win_mean.data_ptr(), hw.cls_w.data_ptr(), hw.cls_b.data_ptr(), B, C,
                                             ncls, ke, k, nsel_in.data_ptr(), approx_max.data_ptr(),
                                             runner_up.data_ptr(), idx_in.data_ptr(), norm_in.data_ptr(),
-                                            idx.data_ptr(), norm.data_ptr(), nsel.data_ptr(), cls_out.data_ptr(),
+                                            idx.data_ptr(), norm.data_ptr(), nsel.data_ptr(), ops._ptr(cls_out),
+                                            ops._ptr(approx_cls), hw.cls_w_absmax,
                                             changed.data_ptr(), n_changed.data_ptr(), n_unc.data_ptr(),
                                             ops._stream()), "isb_region_logits")
     return idx, norm, nsel, cls_out, changed, n_changed, n_unc
@@ -150,24 +153,25 @@ def region_project(U_hi, U_lo, hw, nsel):
     return desc
 
 
-def region_head(x, hw, k, fsize, margin=WINDOW_MARGIN):
+def region_head(x, hw, k, fsize, margin=WINDOW_MARGIN, want_cls_out=True):
     """The certified fast path, all asynchronous: returns (U_hi, U_lo, idx, nsel, cls_out,
-    n_uncertified [1] device int32)."""
+    n_uncertified [1] device int32).  want_cls_out=False (eval): cls_out is None and only
+    the contending classes of every window are scored in fp32."""
     ke = min(32, k + RUNNER_UPS)
     # 1. screen all windows, fp32-grade scores of the candidates, the best ke of them
-    idx_e, nsel_e, _, norm_e, approx_e, runner_up, n1 = region_select(x, hw, ke, fsize, margin)
+    idx_e, nsel_e, approx_cls, norm_e, approx_e, runner_up, n1 = region_select(x, hw, ke, fsize, margin)
     # 2. operand from the first k, exact means of all ke
     U_hi, U_lo, win_mean = region_gather(x, hw, ke, fsize, idx_e, nsel_e, norm_e, k_sum=k)
     # 3. true-fp32 logits -> final k, exact order; images whose k changed are listed
-    idx, norm, nsel, cls_out, changed, n_changed, n2 = region_logits(win_mean, hw, k, nsel_e, idx_e, norm_e,
-                                                                      approx_e, runner_up)
+    idx, norm, nsel, cls_out, changed, n_changed, n2 = region_logits(
+        win_mean, hw, k, nsel_e, idx_e, norm_e, approx_e, runner_up, None if want_cls_out else approx_cls)
     # 4. fix-up: re-gather the (rare) images where a runner-up entered the top k
     region_gather(x, hw, k, fsize, idx, nsel, norm, want_means=False, out=(U_hi, U_lo), image_list=changed,
                   n_list=n_changed)
     return U_hi, U_lo, idx, nsel, cls_out, n1 + n2
 
 
-def region_descriptors(x, hw, k, fsize, margin=WINDOW_MARGIN, exact=True, stats=None):
+def region_descriptors(x, hw, k, fsize, margin=WINDOW_MARGIN, exact=True, stats=None, want_cls_out=True):
     """x [B, C, H, W] trunk feature maps -> (desc [B, D], cls_out [B, ncls, k],
     idx [B, k], nsel [B]).  reference: model/siamese.py:187-223 per image.
 
@@ -175,7 +179,7 @@ def region_descriptors(x, hw, k, fsize, margin=WINDOW_MARGIN, exact=True, stats=
     against the unscored runner-ups) are read back (ONE 4-byte D2H read); a batch with
     an uncertified image is redone with the fp64-exact second line.  exact=False skips
     the read-back (no host sync)."""
-    U_hi, U_lo, idx, nsel, cls_out, n_unc = region_head(x, hw, k, fsize, margin)
+    U_hi, U_lo, idx, nsel, cls_out, n_unc = region_head(x, hw, k, fsize, margin, want_cls_out)
     if exact:
         n_bad = int(n_unc.item())
         if stats is not None:

@@ -133,3 +133,14 @@ def test_region_near_tied_windows_fall_to_the_exact_line(R):
                                                     s["lin_b"], 6, (7, 7))
     assert torch.allclose(d.cpu(), od, rtol=0, atol=DESC_ATOL)      # identical crops: same descriptor
     assert torch.allclose(c.cpu(), oc, rtol=CLS_RTOL, atol=CLS_ATOL)
+
+
+@pytest.mark.parametrize("B,C,H,W,ncls,D", [(6, 64, 14, 14, 20, 32), (3, 256, 20, 24, 464, 32)])
+def test_region_eval_path_without_cls_out(R, B, C, H, W, ncls, D):
+    # eval (descriptor only): class-max from the contending classes only -- same windows, same descriptor
+    s = _synthetic(B, C, H, W, ncls, D, seed=31)
+    hw = _hw(R, s)
+    x = s["x"].cuda()
+    d0, c0, i0, n0 = R.region_descriptors(x, hw, 6, (7, 7))
+    d1, c1, i1, n1 = R.region_descriptors(x, hw, 6, (7, 7), want_cls_out=False)
+    assert c1 is None and torch.equal(i1, i0) and torch.equal(n1, n0) and torch.equal(d1, d0)

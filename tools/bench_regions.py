@@ -24,6 +24,7 @@ ap.add_argument("--k", type=int, default=6)
 ap.add_argument("--terms", type=int, default=3)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--cls-out", type=int, default=0, help="1: also produce cls_out (training); 0: eval, class-max only")
 a = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -59,12 +60,12 @@ for hw_size in [int(s) for s in a.sizes.split(",")]:
         e = [ev() for _ in range(5)]
         ke = a.k + regions.RUNNER_UPS
         e[0].record()
-        idx_e, nsel_e, _, norm_e, approx_e, runner_up, n1 = regions.region_select(x, hw, ke, (7, 7))
+        idx_e, nsel_e, approx_cls, norm_e, approx_e, runner_up, n1 = regions.region_select(x, hw, ke, (7, 7))
         e[1].record()
         U_hi, U_lo, win_mean = regions.region_gather(x, hw, ke, (7, 7), idx_e, nsel_e, norm_e, k_sum=a.k)
         e[2].record()
         idx, norm, nsel, cls_out, changed, n_changed, n2 = regions.region_logits(
-            win_mean, hw, a.k, nsel_e, idx_e, norm_e, approx_e, runner_up)
+            win_mean, hw, a.k, nsel_e, idx_e, norm_e, approx_e, runner_up, None if a.cls_out else approx_cls)
         regions.region_gather(x, hw, a.k, (7, 7), idx, nsel, norm, want_means=False, out=(U_hi, U_lo),
                               image_list=changed, n_list=n_changed)
         e[3].record()
@@ -89,8 +90,8 @@ for hw_size in [int(s) for s in a.sizes.split(",")]:
     proj_flops = 2.0 * a.B * Kin * a.D * a.terms     # tensor-pipe flops actually issued
     alg_flops = 2.0 * a.B * Kin * a.D                # one fp32-grade product
     print(json.dumps({
-        "workload": "region descriptors, B=%d C=%d %dx%d map, ncls=%d, D=%d, k=%d, terms=%d" %
-                    (a.B, a.C, H, W, a.ncls, a.D, a.k, a.terms),
+        "workload": "region descriptors, B=%d C=%d %dx%d map, ncls=%d, D=%d, k=%d, terms=%d, cls_out=%d" %
+                    (a.B, a.C, H, W, a.ncls, a.D, a.k, a.terms, a.cls_out),
         "ms": med, "uncertified_images": uncert, "regathered_images": changed_total, "region_desc_per_s": units / (med["total"] * 1e-3),
         "images_per_s": a.B / (med["total"] * 1e-3),
         "pool_select_gather": {"algorithmic_bytes": bw_bytes, "ms": bw_ms,
