@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--k", type=int, default=K_DEFAULT)
     ap.add_argument("--cpu-sample-queries", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the region-descriptor / mining side measurements (N=1 only)")
     return ap.parse_args()
 
 
@@ -264,7 +266,11 @@ def run_b200(a, rank, world, local_rank):
     achieved = flops / (screen_ms * 1e-3) / 1e12
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])  # timed inside a long step
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak,
+                "traffic": (NCU_SCREEN_TRAFFIC_BYTES if (world == 1 and a.queries == Q_DEFAULT and
+                                                         a.db_rows == N_DEFAULT and a.dim == D_DEFAULT) else None),
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_search_screen_1M.txt",
+                "algorithmic_bytes": 2.0 * rows_local * a.dim + 2.0 * a.queries * a.dim + 8.0 * a.queries * a.k,
                 "kernel": "gemm_tc_kernel<TopkSched,TopkEpilogue> (tcgen05 screen + streaming top-k)",
                 "kernel_ms": screen_ms, "peak_source": pk_src + " bf16_tflops_sustained",
                 "frac_of_burst_peak": achieved / pk["bf16_tflops"]}
@@ -294,12 +300,95 @@ def run_b200(a, rank, world, local_rank):
                     "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": launches_per_step * a.steps * 2,  # resident + e2e timed regions
             "clocks": clocks,
+            "exactness": dict(index.local.stats),   # rows searched / re-screened fp32-grade / searched exhaustively
         }
+        if world == 1 and not a.no_secondary:
+            del index
+            torch.cuda.empty_cache()
+            line["secondary"] = {"region_descriptors": side_regions(dev, pk), "mining": side_mining(dev, pk)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ side measurements (N = 1)
+# BASELINE.json's metric also names "region descriptors/s" (configs[1]) and the path includes
+# the mining of configs[2]; they are measured here after the headline, on rank 0, a few ms each.
+NCU_SCREEN_TRAFFIC_BYTES = 14.2e9   # dram read + write of the screen kernel at the headline size,
+                                    # profiles/r01_ncu_search_screen_1M.txt (ncu --set full)
+
+
+def _median_ms(fn, iters=10, warmup=3, flush=None):
+    ts = []
+    for it in range(warmup + iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= warmup:
+            ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+def side_regions(dev, pk):
+    """configs[1]: 256 x 2048 x {14x14, 32x32} fp32 maps -> descriptors (eval path, D=2048, k=6)."""
+    from instance_search_b200 import regions
+    g = torch.Generator(device=dev).manual_seed(1234 + 2)
+    B, C, ncls, D, k = 256, 2048, 464, 2048, 6
+    Kin = C * 49
+    hw = regions.HeadWeights(torch.randn(ncls, C, device=dev, generator=g) / C ** 0.5,
+                             0.01 * torch.randn(ncls, device=dev, generator=g),
+                             0.01 * torch.randn(Kin, device=dev, generator=g),
+                             torch.randn(D, Kin, device=dev, generator=g) / Kin ** 0.5,
+                             0.01 * torch.randn(D, device=dev, generator=g))
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB > L2
+    out = {}
+    for hwsize in (14, 32):
+        x = torch.relu(torch.randn(B, C, hwsize, hwsize, device=dev, generator=g))
+        stats = {}
+        ms = _median_ms(lambda: regions.region_descriptors(x, hw, k, (7, 7), want_cls_out=False, stats=stats),
+                        flush=flush)
+        ms_head = _median_ms(lambda: regions.region_head(x, hw, k, (7, 7), want_cls_out=False), flush=flush)
+        # SURVEY 8d bytes of the bandwidth-bound part: x once + classifier + the bf16 hi+lo operand
+        nbytes = 4 * B * C * hwsize * hwsize + 4 * ncls * C + 2 * 2 * B * Kin
+        units = B * min((hwsize - 6) ** 2, k)
+        out["%dx%d" % (hwsize, hwsize)] = {
+            "region_descriptors_per_s": units / (ms * 1e-3), "images_per_s": B / (ms * 1e-3), "ms_per_batch": ms,
+            "pool_select_gather": {"bound": "hbm", "ms": ms_head, "algorithmic_bytes": nbytes,
+                                   "achieved": nbytes / (ms_head * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                                   "unit": "GB/s", "frac": nbytes / (ms_head * 1e-3) / 1e9 / pk["hbm_gbs"]},
+            "projection_ms": ms - ms_head,
+            "batches_resolved_exactly": stats.get("batches_resolved_exactly", 0), "batches": stats.get("batches", 0)}
+        del x
+    return {"workload": "region descriptors (eval), 256 x 2048 x HxW fp32 maps, ncls=464, k=6, D=2048 "
+                        "(BASELINE configs[1]); L2 flushed between batches", **out}
+
+
+def side_mining(dev, pk):
+    """configs[2]: all-pairs similarities + (semi-)hard negative of every anchor, 16384 x 2048."""
+    from instance_search_b200 import mining
+    g = torch.Generator(device=dev).manual_seed(1234 + 3)
+    N, D, per = 16384, 2048, 16
+    lab = torch.arange(N, device=dev) // per
+    E = torch.randn(N // per, D, device=dev, generator=g)[lab] + 0.5 * torch.randn(N, D, device=dev, generator=g)
+    E = E / E.norm(dim=1, keepdim=True)
+    anchors = torch.arange(N, device=dev)
+    positives = (anchors // per) * per + (anchors % per + 1) % per
+    idx = mining.MiningIndex(E, lab.int())
+    out = {"workload": "negative mining, 16384 x 2048-d descriptors, 16 per label, one couple per anchor "
+                       "(BASELINE configs[2])"}
+    flops = 2.0 * N * N * D
+    for semi in (True, False):
+        ms = _median_ms(lambda: idx.select_negatives(anchors, positives, semi))
+        out["semi_hard" if semi else "hard"] = {
+            "ms": ms, "anchors_per_s": N / (ms * 1e-3), "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+            "issued_tflops": 3 * flops / (ms * 1e-3) / 1e12, "bruteforce_rows": int(idx.last_bruteforce)}
+    return out
 
 
 def make_rows_slice(n, d, seed, device, lo, hi, chunk=131072):
