@@ -35,7 +35,7 @@ extern "C" {
 #define ISB_ERR_WORKSPACE 3
 #define ISB_ERR_UNSUPPORTED_DEVICE 4
 
-#define ISB_ABI_VERSION 2
+#define ISB_ABI_VERSION 3
 
 /* Largest k (after the screening margin is added) one search call supports. */
 #define ISB_MAX_CANDIDATES 128
@@ -142,6 +142,42 @@ int isb_topk_exhaustive(const float* q, const float* db_f32, int64_t N, int64_t 
  * exchange step of the row-sharded search. */
 int isb_topk_merge(const float* cand_scores, const int64_t* cand_idx, int R, int64_t Q, int k,
                    float* out_scores, int64_t* out_idx, void* stream);
+
+/* Row-sharded search with candidate exchange (one process per GPU, R shards).  Running
+ * isb_topk_rerank on every shard costs R times the gathers of the single-GPU search
+ * although only k + margin of the R * (k + margin) candidates can reach the result.
+ * Instead, after isb_topk_screen on its shard, every rank
+ *   1. isb_topk_candidates        lists its kc_out = k + margin best screen entries per query:
+ *                                 cand_screen [Q, kc_out] fp32 (-inf = none), cand_col [Q, kc_out]
+ *                                 int32 local row (-1 = none); `k`, `margin` as passed to the screen
+ *      -- all-gather of cand_screen (4 bytes per candidate) --
+ *   2. isb_topk_global_threshold  thr [Q] = the kc-th best screen score over all shards
+ *                                 (all_screen [R, Q, kc]); -inf when fewer than kc exist
+ *   3. isb_topk_rerank_owned      exact fp64-accumulated scores of ITS candidates >= thr, sorted
+ *                                 into out_scores / out_idx [Q, k] (-inf / -1 padded, global indices
+ *                                 = local row + idx_offset); stat [Q, 2] fp32 = (sum (screen -
+ *                                 exact)^2, candidates scored)
+ *      -- all-gather of out_scores, out_idx, stat --
+ *   4. isb_topk_merge_certified   isb_topk_merge of cand_scores / cand_idx [R, Q, k] plus the
+ *                                 completeness certificate of isb_topk_search evaluated globally:
+ *                                 every row not re-ranked anywhere has a screen score <= thr, the
+ *                                 noise is the rms over stat [R, Q, 2]; rows that fail are listed
+ *                                 (resolve them with isb_topk_resolve on every shard + isb_topk_merge).
+ * In total k + margin database rows are gathered per query, independent of R.
+ * Replaces the same reference lines as isb_topk_search; the reference is single-device. */
+int isb_topk_candidates(int64_t Q, int64_t N, int64_t D, int k, int margin, int kc_out,
+                        float* cand_screen, int32_t* cand_col, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int isb_topk_global_threshold(const float* all_screen, int R, int64_t Q, int kc, float* thr,
+                              void* stream);
+int isb_topk_rerank_owned(const float* q, int64_t Q, const float* db_f32, int64_t N, int64_t D,
+                          int k, int kc, int64_t idx_offset, const float* cand_screen,
+                          const int32_t* cand_col, const float* thr, float* out_scores,
+                          int64_t* out_idx, float* stat, void* stream);
+int isb_topk_merge_certified(const float* cand_scores, const int64_t* cand_idx, const float* stat,
+                             const float* thr, int R, int64_t Q, int k, float* out_scores,
+                             int64_t* out_idx, int32_t* uncertified_rows, int32_t* n_uncertified,
+                             void* stream);
 
 /* ---------------------------------------------------------------- dense contraction
  * C[M, N] (fp32, leading dimension ldc) = A[M, K] . B[N, K]^T  (+ bias[N])

@@ -216,6 +216,32 @@ __device__ __forceinline__ bool row_certified(const SelectSmem& sm, int kc, doub
   return kth_exact - t_min > static_cast<double>(cert_z) * sigma + floor_;
 }
 
+// Bitonic sort of sm.sel_score / sm.sel_col [kMaxCand], best first (score desc, column
+// asc); called by every thread of the CTA after a __syncthreads().
+__device__ __forceinline__ void sort_selected(SelectSmem& sm) {
+  const int tid = threadIdx.x;
+  double* sel_score = sm.sel_score;
+  int* sel_col = sm.sel_col;
+  for (int size = 2; size <= kMaxCand; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (tid < kMaxCand) {
+        const int partner = tid ^ stride;
+        if (partner > tid) {
+          const bool up = (tid & size) == 0;  // "up" blocks sort best-first
+          const double sa = sel_score[tid], sb = sel_score[partner];
+          const int ia = sel_col[tid], ib = sel_col[partner];
+          const bool a_first = entry_before(sa, ia, sb, ib);
+          if (a_first != up) {
+            sel_score[tid] = sb; sel_score[partner] = sa;
+            sel_col[tid] = ib; sel_col[partner] = ia;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // One CTA per listed row.  row_map == nullptr: CTA p handles query row p and pool
 // row p.  Otherwise (resolve pass) pool row p belongs to query row row_map[p].
 __global__ void __launch_bounds__(kRerankThreads)
@@ -255,24 +281,7 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, 
   __syncthreads();
 
   // ---- 3. bitonic sort of 128 entries (first 128 threads)
-  for (int size = 2; size <= kMaxCand; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (tid < kMaxCand) {
-        const int partner = tid ^ stride;
-        if (partner > tid) {
-          const bool up = (tid & size) == 0;  // "up" blocks sort best-first
-          const double sa = sel_score[tid], sb = sel_score[partner];
-          const int ia = sel_col[tid], ib = sel_col[partner];
-          const bool a_first = entry_before(sa, ia, sb, ib);
-          if (a_first != up) {
-            sel_score[tid] = sb; sel_score[partner] = sa;
-            sel_col[tid] = ib; sel_col[partner] = ia;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
+  sort_selected(sm);
   for (int j = tid; j < k; j += kRerankThreads) {
     const bool ok = j < n_sel;
     out_scores[static_cast<size_t>(row) * k + j] = ok ? static_cast<float>(sel_score[j]) : -INFINITY;
@@ -282,6 +291,193 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, 
     const bool ok = (k <= n_sel) && row_certified(sm, kc, s_sig2, n_sel, sel_score[k - 1], cert_z);
     if (!ok) unc_rows[atomicAdd(unc_count, 1)] = row;
   }
+}
+
+// ------------------------------------------------------------------ sharded search: candidate exchange
+// Row-sharded database: re-ranking k + margin candidates on EVERY shard
+// would cost R times the gathers of the single-GPU search although only k + margin of
+// the R * (k + margin) candidates can matter.  Instead the shards exchange the screen
+// scores of their candidates (4 bytes each), every rank derives the same global
+// threshold -- the kc-th best screen score over all shards -- and re-ranks only its own
+// candidates at or above it: kc gathers per query in total instead of R * kc.
+//
+// The selections below are warp-cooperative: one warp owns one query row, its entries sit
+// in shared memory and the k-th largest key is found by a 32-step bitwise binary search
+// (count of keys >= candidate per step) -- no block barriers, four rows per CTA.
+constexpr int kSelWarps = 4;   // rows per CTA (launches may use fewer when a row needs much shared memory)
+
+__host__ __device__ __forceinline__ size_t align_up_dev(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t* keys, int n, int kth) {
+  // precondition: n >= kth >= 1; all 32 lanes call it with the same arguments
+  const int lane = threadIdx.x & 31;
+  uint32_t T = 0u;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+    for (int e = lane; e < n; e += 32) c += (keys[e] >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= kth) T = cand;
+  }
+  return T;
+}
+
+// (1) the kc best screen entries of every row of the local pool, unsorted (entries above
+// the kc-th key in slot order, then as many ties with it as fit: deterministic)
+__global__ void __launch_bounds__(32 * kSelWarps)
+pool_candidates_kernel(int64_t Q, int n_groups, const uint2* __restrict__ pool,
+                       const int* __restrict__ pool_cnt, int kc, int kc_out,
+                       float* __restrict__ cand_screen, int* __restrict__ cand_col) {
+  extern __shared__ __align__(16) uint8_t pc_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  if (row >= Q) return;
+  const int slots = n_groups * kMaxCand;
+  uint32_t* keys = reinterpret_cast<uint32_t*>(pc_smem) + static_cast<size_t>(warp) * 2 * slots;
+  uint32_t* cols = keys + slots;
+  const uint2* rpool = pool + static_cast<size_t>(row) * slots;
+  const int* rcnt = pool_cnt + static_cast<size_t>(row) * n_groups;
+  // compact the valid entries of every group (group g holds rcnt[g] leading entries)
+  int total = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    const int c = rcnt[g];
+    for (int e = lane; e < c; e += 32) {
+      const uint2 ent = rpool[g * kMaxCand + e];
+      keys[total + e] = f2key(ent.x);
+      cols[total + e] = ent.y;
+    }
+    total += c;
+  }
+  __syncwarp();
+  const int want = min(total, kc);
+  uint32_t T = 0u;
+  int n_gt = total;
+  if (total > kc) {
+    T = warp_kth_largest(keys, total, kc);
+    int c = 0;
+    for (int e = lane; e < total; e += 32) c += (keys[e] > T) ? 1 : 0;
+    n_gt = __reduce_add_sync(0xffffffffu, c);
+  }
+  float* os = cand_screen + static_cast<size_t>(row) * kc_out;
+  int* oc = cand_col + static_cast<size_t>(row) * kc_out;
+  int pos_gt = 0, pos_eq = n_gt;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (int base = 0; base < total; base += 32) {
+    const int e = base + lane;
+    const uint32_t key = (e < total) ? keys[e] : 0u;
+    const bool gt = (e < total) && (total <= kc || key > T);
+    const bool eq = (e < total) && !gt && key == T;
+    const uint32_t bgt = __ballot_sync(0xffffffffu, gt), beq = __ballot_sync(0xffffffffu, eq);
+    if (gt) {
+      const int p = pos_gt + __popc(bgt & lt_mask);
+      os[p] = __uint_as_float(key2f(key));
+      oc[p] = static_cast<int>(cols[e]);
+    } else if (eq) {
+      const int p = pos_eq + __popc(beq & lt_mask);
+      if (p < want) {
+        os[p] = __uint_as_float(key2f(key));
+        oc[p] = static_cast<int>(cols[e]);
+      }
+    }
+    pos_gt += __popc(bgt);
+    pos_eq += __popc(beq);
+  }
+  for (int j = want + lane; j < kc_out; j += 32) {
+    os[j] = -INFINITY;
+    oc[j] = -1;
+  }
+}
+
+// Same contract, one CTA per row (4 x 8-bit radix select): used when a row's pool does not
+// fit one warp's share of shared memory (very few query rows => very many n-groups).
+__global__ void __launch_bounds__(kRerankThreads)
+pool_candidates_cta_kernel(int n_groups, const uint2* __restrict__ pool, const int* __restrict__ pool_cnt,
+                           int kc, int kc_out, float* __restrict__ cand_screen, int* __restrict__ cand_col) {
+  __shared__ SelectSmem sm;
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int n_sel = select_pool_candidates(sm, pool + static_cast<size_t>(row) * n_groups * kMaxCand,
+                                           pool_cnt + static_cast<size_t>(row) * n_groups, n_groups, kc);
+  for (int j = tid; j < kc_out; j += kRerankThreads) {
+    const bool ok = j < n_sel;
+    cand_screen[static_cast<size_t>(row) * kc_out + j] = ok ? sm.sel_screen[j] : -INFINITY;
+    cand_col[static_cast<size_t>(row) * kc_out + j] = ok ? sm.sel_col[j] : -1;
+  }
+}
+
+// (2) thr[row] = the kc-th largest of the row's R * kc gathered screen scores
+// (all_screen [R, Q, kc], -inf = no entry); -inf when fewer than kc entries exist, i.e.
+// when no shard dropped anything that could matter.
+__global__ void __launch_bounds__(32 * kSelWarps)
+global_threshold_kernel(const float* __restrict__ all_screen, int R, int64_t Q, int kc,
+                        float* __restrict__ thr) {
+  extern __shared__ __align__(16) uint8_t gt_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kSelWarps + warp;
+  if (row >= Q) return;
+  const int n = R * kc;
+  uint32_t* keys = reinterpret_cast<uint32_t*>(gt_smem) + static_cast<size_t>(warp) * n;
+  int valid = 0;
+  for (int e = lane; e < n; e += 32) {
+    const int r = e / kc, j = e - r * kc;
+    const uint32_t key = f2key(__float_as_uint(all_screen[(static_cast<size_t>(r) * Q + row) * kc + j]));
+    keys[e] = key;
+    valid += (key > kKeyNegInf) ? 1 : 0;
+  }
+  valid = __reduce_add_sync(0xffffffffu, valid);
+  __syncwarp();
+  float t = -INFINITY;
+  if (valid >= kc) t = __uint_as_float(key2f(warp_kth_largest(keys, n, kc)));
+  if (lane == 0) thr[row] = t;
+}
+
+// (3) exact scores of the row's OWN candidates at or above the global threshold, sorted
+// best first into out_scores / out_idx [Q, k] (-inf / -1 beyond), plus the row's share of
+// the screen-noise measurement: stat[row] = (sum (screen - exact)^2, candidates scored).
+__global__ void __launch_bounds__(kRerankThreads)
+rerank_owned_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, int kc, int k,
+                    int64_t idx_offset, const float* __restrict__ cand_screen,
+                    const int* __restrict__ cand_col, const float* __restrict__ thr,
+                    float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
+                    float2* __restrict__ stat) {
+  extern __shared__ __align__(16) uint8_t rr_smem[];
+  float* qs = reinterpret_cast<float*>(rr_smem);  // [D]
+  __shared__ SelectSmem sm;
+  __shared__ double s_sig2;
+  const int row = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) { s_sig2 = 0.0; sm.sel = 0; }
+  for (int i = tid; i < D / 4; i += kRerankThreads)
+    reinterpret_cast<float4*>(qs)[i] = __ldg(reinterpret_cast<const float4*>(q + static_cast<size_t>(row) * D) + i);
+  __syncthreads();
+  const float t = thr[row];
+  for (int j = tid; j < kc; j += kRerankThreads) {
+    const float s = cand_screen[static_cast<size_t>(row) * kc + j];
+    const int c = cand_col[static_cast<size_t>(row) * kc + j];
+    if (c >= 0 && s >= t) {
+      const int pos = atomicAdd(&sm.sel, 1);
+      sm.sel_col[pos] = c;
+      sm.sel_screen[pos] = s;
+    }
+  }
+  __syncthreads();
+  const int n_sel = sm.sel;
+  exact_scores(sm, qs, db, D, n_sel);
+  double d2 = 0.0;
+  if (tid < n_sel) {
+    const double d = static_cast<double>(sm.sel_screen[tid]) - sm.sel_score[tid];
+    d2 = d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+  if ((tid & 31) == 0 && tid < kMaxCand) atomicAdd(&s_sig2, d2);
+  __syncthreads();
+  sort_selected(sm);
+  for (int j = tid; j < k; j += kRerankThreads) {
+    const bool ok = j < n_sel;
+    out_scores[static_cast<size_t>(row) * k + j] = ok ? static_cast<float>(sm.sel_score[j]) : -INFINITY;
+    out_idx[static_cast<size_t>(row) * k + j] = ok ? static_cast<int64_t>(sm.sel_col[j]) + idx_offset : -1;
+  }
+  if (tid == 0) stat[row] = make_float2(static_cast<float>(s_sig2), static_cast<float>(n_sel));
 }
 
 // ------------------------------------------------------------------ resolve pass operands
@@ -577,7 +773,9 @@ constexpr int kMergeMax = 4096;
 
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const float* __restrict__ cs, const int64_t* __restrict__ ci, int R, int64_t Q,
-                  int k, int n_pow2, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+                  int k, int n_pow2, float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
+                  const float2* __restrict__ stat, const float* __restrict__ thr, float cert_z,
+                  int* __restrict__ unc_rows, int* __restrict__ unc_count) {
   extern __shared__ __align__(16) uint8_t mg_smem[];
   int64_t* sidx = reinterpret_cast<int64_t*>(mg_smem);           // [n_pow2]
   float* sscore = reinterpret_cast<float*>(sidx + n_pow2);        // [n_pow2]
@@ -619,6 +817,168 @@ topk_merge_kernel(const float* __restrict__ cs, const int64_t* __restrict__ ci, 
     const bool ok = j < n && sidx[j] != INT64_MAX;
     out_scores[row * k + j] = ok ? sscore[j] : -INFINITY;
     out_idx[row * k + j] = ok ? sidx[j] : -1;
+  }
+  // Completeness certificate of the sharded search (see row_certified): every database row
+  // that was not re-ranked on its shard has a screen score <= thr[row]; the screen noise is
+  // the rms over ALL shards' re-ranked candidates of the row (stat [R, Q]).
+  if (unc_count != nullptr && threadIdx.x == 0) {
+    const float t_min = thr[row];
+    bool ok = true;
+    if (t_min > -INFINITY) {
+      double s2 = 0.0, cnt = 0.0;
+      for (int r = 0; r < R; ++r) {
+        const float2 st = stat[static_cast<size_t>(r) * Q + row];
+        s2 += static_cast<double>(st.x);
+        cnt += static_cast<double>(st.y);
+      }
+      const bool have_k = (k - 1 < n) && sidx[k - 1] != INT64_MAX && sidx[k - 1] >= 0;
+      const double kth = static_cast<double>(sscore[k - 1]);
+      const double sigma = sqrt(s2 / (cnt > 0.0 ? cnt : 1.0));
+      const double floor_ = 4e-7 * fmax(fabs(kth), fabs(static_cast<double>(t_min))) + 1e-30;
+      ok = have_k && (kth - static_cast<double>(t_min) > static_cast<double>(cert_z) * sigma + floor_);
+    }
+    if (!ok) unc_rows[atomicAdd(unc_count, 1)] = static_cast<int>(row);
+  }
+}
+
+// Fast path for k <= kMaxCand: one warp per query.  The k-th best (score, index) entry is
+// found by the bitwise search on the score key and, only when more entries tie with it
+// than there is room for, a second search on the index; the k survivors are sorted by a
+// warp-synchronous bitonic network (4 entries per lane).
+__device__ __forceinline__ bool merge_before(float sa, int64_t ia, float sb, int64_t ib) {
+  // invalid (index < 0 or the INT64_MAX padding) entries sort last
+  const bool va = ia >= 0 && ia != INT64_MAX, vb = ib >= 0 && ib != INT64_MAX;
+  if (va != vb) return va;
+  return (sa > sb) || (sa == sb && ia < ib);
+}
+
+__global__ void __launch_bounds__(32 * kSelWarps)
+topk_merge_warp_kernel(const float* __restrict__ cs, const int64_t* __restrict__ ci, int R, int64_t Q,
+                       int k, float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
+                       const float2* __restrict__ stat, const float* __restrict__ thr, float cert_z,
+                       int* __restrict__ unc_rows, int* __restrict__ unc_count) {
+  extern __shared__ __align__(16) uint8_t mw_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kSelWarps + warp;
+  if (row >= Q) return;
+  const int n = R * k;
+  // per warp: keys [n] u32 | sel_idx [kMaxCand] i64 | sel_score [kMaxCand] f32
+  const size_t per_warp = align_up_dev(static_cast<size_t>(n) * 4, 8) + kMaxCand * 12;
+  uint8_t* base = mw_smem + warp * per_warp;
+  uint32_t* keys = reinterpret_cast<uint32_t*>(base);
+  int64_t* sidx = reinterpret_cast<int64_t*>(base + align_up_dev(static_cast<size_t>(n) * 4, 8));
+  float* sscore = reinterpret_cast<float*>(sidx + kMaxCand);
+
+  auto entry_off = [&](int e) -> size_t {
+    const int r = e / k, j = e - r * k;
+    return (static_cast<size_t>(r) * Q + row) * k + j;
+  };
+  // keys: invalid entries (index < 0) get key 0 (below every real score incl. -inf)
+  int valid = 0;
+  for (int e = lane; e < n; e += 32) {
+    const size_t off = entry_off(e);
+    const bool ok = ci[off] >= 0;
+    keys[e] = ok ? f2key(__float_as_uint(cs[off])) : 0u;
+    valid += ok ? 1 : 0;
+  }
+  valid = __reduce_add_sync(0xffffffffu, valid);
+  __syncwarp();
+  const int want = min(valid, k);
+  uint32_t T = 1u;            // every valid key is >= kKeyNegInf > 1
+  int n_gt = 0;
+  int64_t I = INT64_MAX;      // ties with T are taken while index <= I
+  if (valid > k) {
+    T = warp_kth_largest(keys, n, k);
+    int c = 0, ceq = 0;
+    for (int e = lane; e < n; e += 32) {
+      c += (keys[e] > T) ? 1 : 0;
+      ceq += (keys[e] == T) ? 1 : 0;
+    }
+    n_gt = __reduce_add_sync(0xffffffffu, c);
+    const int n_eq = __reduce_add_sync(0xffffffffu, ceq);
+    const int room = k - n_gt;
+    if (n_eq > room) {
+      // the `room` lowest indices among the ties: smallest I with count(idx <= I) >= room
+      uint64_t lo = 0;   // bitwise search for the room-th smallest index (indices are >= 0)
+      for (int bit = 62; bit >= 0; --bit) {
+        const uint64_t cand = lo | (1ull << bit);
+        int cc = 0;   // ties with index < cand
+        for (int e = lane; e < n; e += 32)
+          if (keys[e] == T && static_cast<uint64_t>(ci[entry_off(e)]) < cand) ++cc;
+        cc = __reduce_add_sync(0xffffffffu, cc);
+        if (cc < room) lo = cand;     // fewer than room ties lie below cand: the answer is >= cand
+      }
+      I = static_cast<int64_t>(lo);
+    }
+  } else {
+    T = 1u;
+  }
+  // collect the survivors
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  int pos = 0;
+  for (int b0 = 0; b0 < n; b0 += 32) {
+    const int e = b0 + lane;
+    bool take = false;
+    size_t off = 0;
+    if (e < n) {
+      off = entry_off(e);
+      const uint32_t key = keys[e];
+      take = (valid <= k) ? (key != 0u) : (key > T || (key == T && ci[off] <= I));
+    }
+    const uint32_t bt = __ballot_sync(0xffffffffu, take);
+    if (take) {
+      const int p = pos + __popc(bt & lt_mask);
+      if (p < kMaxCand) {
+        sscore[p] = cs[off];
+        sidx[p] = ci[off];
+      }
+    }
+    pos += __popc(bt);
+  }
+  for (int j = min(pos, kMaxCand) + lane; j < kMaxCand; j += 32) {
+    sscore[j] = -INFINITY;
+    sidx[j] = INT64_MAX;
+  }
+  __syncwarp();
+  // warp-synchronous bitonic sort of kMaxCand = 128 entries (64 compare-exchanges per stage)
+  for (int size = 2; size <= kMaxCand; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = lane; t < kMaxCand / 2; t += 32) {
+        const int lo_i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+        const int hi_i = lo_i | stride;
+        const bool up = (lo_i & size) == 0;
+        const float sa = sscore[lo_i], sb = sscore[hi_i];
+        const int64_t ia = sidx[lo_i], ib = sidx[hi_i];
+        if (merge_before(sa, ia, sb, ib) != up) {
+          sscore[lo_i] = sb; sscore[hi_i] = sa;
+          sidx[lo_i] = ib; sidx[hi_i] = ia;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int j = lane; j < k; j += 32) {
+    const bool ok = j < want;
+    out_scores[row * k + j] = ok ? sscore[j] : -INFINITY;
+    out_idx[row * k + j] = ok ? sidx[j] : -1;
+  }
+  if (unc_count != nullptr && lane == 0) {
+    const float t_min = thr[row];
+    bool ok = true;
+    if (t_min > -INFINITY) {
+      double s2 = 0.0, cnt = 0.0;
+      for (int r = 0; r < R; ++r) {
+        const float2 st = stat[static_cast<size_t>(r) * Q + row];
+        s2 += static_cast<double>(st.x);
+        cnt += static_cast<double>(st.y);
+      }
+      const bool have_k = want >= k;
+      const double kth = static_cast<double>(sscore[k - 1]);
+      const double sigma = sqrt(s2 / (cnt > 0.0 ? cnt : 1.0));
+      const double floor_ = 4e-7 * fmax(fabs(kth), fabs(static_cast<double>(t_min))) + 1e-30;
+      ok = have_k && (kth - static_cast<double>(t_min) > static_cast<double>(cert_z) * sigma + floor_);
+    }
+    if (!ok) unc_rows[atomicAdd(unc_count, 1)] = static_cast<int>(row);
   }
 }
 
@@ -929,6 +1289,29 @@ extern "C" int isb_topk_exhaustive(const float* q, const float* db_f32, int64_t 
   return ISB_OK;
 }
 
+static int launch_merge(const float* cand_scores, const int64_t* cand_idx, int R, int64_t Q, int k,
+                        float* out_scores, int64_t* out_idx, const float2* stat, const float* thr,
+                        int32_t* unc_rows, int32_t* unc_count, cudaStream_t st) {
+  if (k <= kMaxCand) {
+    const size_t smem = kSelWarps * (align_up_dev(static_cast<size_t>(R) * k * 4, 8) + kMaxCand * 12);
+    if (smem > 48 * 1024)
+      ISB_CUDA(cudaFuncSetAttribute(topk_merge_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_merge_warp_kernel<<<static_cast<unsigned>((Q + kSelWarps - 1) / kSelWarps), 32 * kSelWarps, smem, st>>>(
+        cand_scores, cand_idx, R, Q, k, out_scores, out_idx, stat, thr, kCertZ, unc_rows, unc_count);
+  } else {
+    int n_pow2 = 2;
+    while (n_pow2 < R * k) n_pow2 <<= 1;
+    const size_t smem = static_cast<size_t>(n_pow2) * 12;
+    if (smem > 48 * 1024)
+      ISB_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_merge_kernel<<<static_cast<unsigned>(Q), 256, smem, st>>>(cand_scores, cand_idx, R, Q, k, n_pow2,
+                                                                  out_scores, out_idx, stat, thr, kCertZ,
+                                                                  unc_rows, unc_count);
+  }
+  ISB_CUDA(cudaGetLastError());
+  return ISB_OK;
+}
+
 extern "C" int isb_topk_merge(const float* cand_scores, const int64_t* cand_idx, int R, int64_t Q, int k,
                               float* out_scores, int64_t* out_idx, void* stream) {
   ISB_CHECK_ARG(cand_scores && cand_idx && out_scores && out_idx, "isb_topk_merge: null pointer");
@@ -936,15 +1319,97 @@ extern "C" int isb_topk_merge(const float* cand_scores, const int64_t* cand_idx,
   ISB_CHECK_ARG(static_cast<int64_t>(R) * k <= kMergeMax, "isb_topk_merge: R*k (%lld) > %d",
                 (long long)R * k, kMergeMax);
   if (Q == 0) return ISB_OK;
-  int n_pow2 = 2;
-  while (n_pow2 < R * k) n_pow2 <<= 1;
-  const size_t smem = static_cast<size_t>(n_pow2) * 12;
-  if (smem > 48 * 1024)
-    ISB_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  topk_merge_kernel<<<static_cast<unsigned>(Q), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      cand_scores, cand_idx, R, Q, k, n_pow2, out_scores, out_idx);
+  return launch_merge(cand_scores, cand_idx, R, Q, k, out_scores, out_idx, nullptr, nullptr, nullptr, nullptr,
+                      static_cast<cudaStream_t>(stream));
+}
+
+// ---- sharded search with candidate exchange (three local stages around two all-gathers)
+extern "C" int isb_topk_candidates(int64_t Q, int64_t N, int64_t D, int k, int margin, int kc_out,
+                                   float* cand_screen, int32_t* cand_col, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  ISB_CHECK_ARG(cand_screen && cand_col, "isb_topk_candidates: null pointer");
+  int rc = check_search_args("isb_topk_candidates", Q, N, D, k, margin);
+  if (rc) return rc;
+  const SearchPlan plan = make_search_plan(Q, N, D);
+  uint8_t* ws;
+  rc = carve_workspace("isb_topk_candidates", plan, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  int kc = k + margin;   // what isb_topk_screen kept per row (a shard shorter than that keeps all its rows)
+  if (kc > N) kc = static_cast<int>(N);
+  ISB_CHECK_ARG(kc_out >= kc && kc_out <= ISB_MAX_CANDIDATES, "isb_topk_candidates: need %d <= kc_out <= %d", kc,
+                ISB_MAX_CANDIDATES);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint2* pool = reinterpret_cast<const uint2*>(ws + plan.off_pool);
+  const int* pool_cnt = reinterpret_cast<const int*>(ws + plan.off_pool_cnt);
+  const size_t per_warp = static_cast<size_t>(plan.n_groups) * kMaxCand * 8;
+  int wpc = kSelWarps;
+  while (wpc > 1 && per_warp * wpc > 96 * 1024) wpc >>= 1;
+  if (per_warp * wpc <= 200 * 1024) {
+    const size_t smem = per_warp * wpc;
+    if (smem > 48 * 1024)
+      ISB_CUDA(cudaFuncSetAttribute(pool_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pool_candidates_kernel<<<static_cast<unsigned>((Q + wpc - 1) / wpc), 32 * wpc, smem, st>>>(
+        Q, plan.n_groups, pool, pool_cnt, kc, kc_out, cand_screen, cand_col);
+  } else {
+    pool_candidates_cta_kernel<<<static_cast<unsigned>(Q), kRerankThreads, 0, st>>>(
+        plan.n_groups, pool, pool_cnt, kc, kc_out, cand_screen, cand_col);
+  }
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;
+}
+
+extern "C" int isb_topk_global_threshold(const float* all_screen, int R, int64_t Q, int kc, float* thr,
+                                         void* stream) {
+  ISB_CHECK_ARG(all_screen && thr, "isb_topk_global_threshold: null pointer");
+  ISB_CHECK_ARG(R >= 1 && Q >= 0 && kc >= 1 && kc <= ISB_MAX_CANDIDATES, "isb_topk_global_threshold: bad shape");
+  if (Q == 0) return ISB_OK;
+  const size_t smem = static_cast<size_t>(kSelWarps) * R * kc * 4;
+  ISB_CHECK_ARG(smem <= 200 * 1024, "isb_topk_global_threshold: R * kc (%d) too large", R * kc);
+  if (smem > 48 * 1024)
+    ISB_CUDA(cudaFuncSetAttribute(global_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  global_threshold_kernel<<<static_cast<unsigned>((Q + kSelWarps - 1) / kSelWarps), 32 * kSelWarps, smem,
+                            static_cast<cudaStream_t>(stream)>>>(all_screen, R, Q, kc, thr);
+  ISB_CUDA(cudaGetLastError());
+  return ISB_OK;
+}
+
+extern "C" int isb_topk_rerank_owned(const float* q, int64_t Q, const float* db_f32, int64_t N, int64_t D,
+                                     int k, int kc, int64_t idx_offset, const float* cand_screen,
+                                     const int32_t* cand_col, const float* thr, float* out_scores,
+                                     int64_t* out_idx, float* stat, void* stream) {
+  ISB_CHECK_ARG(q && db_f32 && cand_screen && cand_col && thr && out_scores && out_idx && stat,
+                "isb_topk_rerank_owned: null pointer");
+  ISB_CHECK_ARG(Q >= 0 && N > 0 && D > 0 && D % 8 == 0, "isb_topk_rerank_owned: bad shape");
+  ISB_CHECK_ARG(k >= 1 && kc >= k && kc <= ISB_MAX_CANDIDATES, "isb_topk_rerank_owned: need 1 <= k <= kc <= %d",
+                ISB_MAX_CANDIDATES);
+  ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(db_f32) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(stat) & 7) == 0, "isb_topk_rerank_owned: misaligned input");
+  if (Q == 0) return ISB_OK;
+  const size_t smem = static_cast<size_t>(D) * 4;
+  ISB_CHECK_ARG(smem <= 160 * 1024, "isb_topk_rerank_owned: D too large for the re-rank kernel");
+  if (smem > 48 * 1024)
+    ISB_CUDA(cudaFuncSetAttribute(rerank_owned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rerank_owned_kernel<<<static_cast<unsigned>(Q), kRerankThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      q, db_f32, static_cast<int>(D), kc, k, idx_offset, cand_screen, cand_col, thr, out_scores, out_idx,
+      reinterpret_cast<float2*>(stat));
+  ISB_CUDA(cudaGetLastError());
+  return ISB_OK;
+}
+
+extern "C" int isb_topk_merge_certified(const float* cand_scores, const int64_t* cand_idx, const float* stat,
+                                        const float* thr, int R, int64_t Q, int k, float* out_scores,
+                                        int64_t* out_idx, int32_t* uncertified_rows, int32_t* n_uncertified,
+                                        void* stream) {
+  ISB_CHECK_ARG(cand_scores && cand_idx && stat && thr && out_scores && out_idx && uncertified_rows &&
+                n_uncertified, "isb_topk_merge_certified: null pointer");
+  ISB_CHECK_ARG(R >= 1 && Q >= 0 && k >= 1, "isb_topk_merge_certified: bad shape");
+  ISB_CHECK_ARG(static_cast<int64_t>(R) * k <= kMergeMax, "isb_topk_merge_certified: R*k (%lld) > %d",
+                (long long)R * k, kMergeMax);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ISB_CUDA(cudaMemsetAsync(n_uncertified, 0, 4, st));
+  if (Q == 0) return ISB_OK;
+  return launch_merge(cand_scores, cand_idx, R, Q, k, out_scores, out_idx, reinterpret_cast<const float2*>(stat),
+                      thr, uncertified_rows, n_uncertified, st);
 }
 
 // ------------------------------------------------------------------ a13 entry point

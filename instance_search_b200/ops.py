@@ -221,6 +221,42 @@ def topk_merge(cand_scores, cand_idx):
     return scores, idx
 
 
+def topk_global_threshold(all_screen):
+    """all_screen [R, Q, kc] fp32 (the all-gathered screen scores of every shard's
+    candidates, -inf = none) -> thr [Q]: the kc-th best per query, -inf when fewer exist."""
+    _need_cuda(all_screen)
+    all_screen = _f32c(all_screen)
+    R, Q, kc = all_screen.shape
+    thr = torch.empty((Q,), dtype=torch.float32, device=all_screen.device)
+    _lib.check(_lib.lib().isb_topk_global_threshold(all_screen.data_ptr(), R, Q, kc, thr.data_ptr(), _stream()),
+               "isb_topk_global_threshold")
+    return thr
+
+
+def topk_merge_certified(cand_scores, cand_idx, stat, thr):
+    """topk_merge of the shards' re-ranked lists [R, Q, k] + the global completeness
+    certificate (stat [R, Q, 2], thr [Q]; include/isb.h).  Returns (scores [Q, k],
+    idx [Q, k], uncertified_rows [Q] int32, n_uncertified [1] int32)."""
+    _need_cuda(cand_scores, cand_idx, stat, thr)
+    cand_scores, stat, thr = _f32c(cand_scores), _f32c(stat), _f32c(thr)
+    cand_idx = cand_idx.contiguous()
+    if cand_idx.dtype != torch.int64 or cand_scores.shape != cand_idx.shape or cand_idx.dim() != 3:
+        raise IsbError("topk_merge_certified: expected [R, Q, k] fp32 scores and int64 indices")
+    R, Q, k = cand_scores.shape
+    if tuple(stat.shape) != (R, Q, 2) or tuple(thr.shape) != (Q,):
+        raise IsbError("topk_merge_certified: expected stat [R, Q, 2] and thr [Q]")
+    dev = cand_scores.device
+    scores = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    unc_rows = torch.empty((max(Q, 1),), dtype=torch.int32, device=dev)
+    n_unc = torch.empty((1,), dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().isb_topk_merge_certified(cand_scores.data_ptr(), cand_idx.data_ptr(), stat.data_ptr(),
+                                                   thr.data_ptr(), R, Q, k, scores.data_ptr(), idx.data_ptr(),
+                                                   unc_rows.data_ptr(), n_unc.data_ptr(), _stream()),
+               "isb_topk_merge_certified")
+    return scores, idx, unc_rows, n_unc
+
+
 # --------------------------------------------------------------------- metrics
 def row_kth_largest(sim, kth=1):
     """(val [Q], idx [Q] int64): the kth largest entry of every row of sim and its

@@ -75,6 +75,59 @@ class DescriptorIndex(object):
             self._db_lo = ops.to_bf16(self.db_f32, 1, ld=self.db_bf16.size(1))
         return self._db_lo
 
+    def _screen(self, q, k_eff, margin, events=None):
+        """Stage 1 (isb_topk_screen): bf16 tcgen05 GEMM + streaming top-(k+margin) into the
+        candidate pool of the workspace, which is returned.  q: padded fp32 queries."""
+        Q = q.size(0)
+        ws = self._workspace(Q, k_eff, margin)
+        L = ops._lib.lib()
+        st = torch.cuda.current_stream().cuda_stream
+        N, D = self.db_f32.shape
+        if events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        ops._lib.check(L.isb_topk_screen(q.data_ptr(), Q, self.db_bf16.data_ptr(), N, D,
+                                         self.db_bf16.size(1), k_eff, margin, ws.data_ptr(),
+                                         ws.numel(), st), "isb_topk_screen")
+        if events is not None:
+            e1.record()
+            events.append((e0, e1))
+        return ws
+
+    def candidates(self, q, k, kc, events=None):
+        """Sharded search, local stage 1: screen this shard and list its kc best screen
+        entries per query: (cand_screen [Q, kc] fp32, cand_col [Q, kc] int32 local row;
+        -inf / -1 where the shard has fewer than kc rows)."""
+        q = self._queries(q)
+        Q, N = q.size(0), len(self)
+        k_eff = min(k, N)
+        margin = min(kc, N) - k_eff
+        cand_screen = torch.empty((Q, kc), dtype=torch.float32, device=q.device)
+        cand_col = torch.empty((Q, kc), dtype=torch.int32, device=q.device)
+        if Q == 0:
+            return cand_screen, cand_col
+        ws = self._screen(q, k_eff, margin, events)
+        ops._lib.check(ops._lib.lib().isb_topk_candidates(
+            Q, N, self.db_f32.size(1), k_eff, margin, kc, cand_screen.data_ptr(), cand_col.data_ptr(),
+            ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "isb_topk_candidates")
+        return cand_screen, cand_col
+
+    def rerank_owned(self, q, k, cand_screen, cand_col, thr):
+        """Sharded search, local stage 2: exact scores of this shard's candidates at or above
+        the global threshold -> (scores [Q, k] (-inf padded), idx [Q, k] global (-1 padded),
+        stat [Q, 2] = (sum (screen - exact)^2, candidates scored))."""
+        q = self._queries(q)
+        Q, kc = cand_screen.shape
+        scores = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+        idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+        stat = torch.empty((Q, 2), dtype=torch.float32, device=q.device)
+        N, D = self.db_f32.shape
+        ops._lib.check(ops._lib.lib().isb_topk_rerank_owned(
+            q.data_ptr(), Q, self.db_f32.data_ptr(), N, D, k, kc, self.row_offset, cand_screen.data_ptr(),
+            cand_col.data_ptr(), thr.data_ptr(), scores.data_ptr(), idx.data_ptr(), stat.data_ptr(),
+            torch.cuda.current_stream().cuda_stream), "isb_topk_rerank_owned")
+        return scores, idx, stat
+
     def search(self, q, k, margin=None, events=None, exact=True):
         """(scores [Q, k] fp32, idx [Q, k] int64 global), best first.
 
@@ -97,19 +150,10 @@ class DescriptorIndex(object):
         idx = torch.empty((Q, k_eff), dtype=torch.int64, device=q.device)
         if Q == 0:
             return scores, idx
-        ws = self._workspace(Q, k_eff, margin)
+        ws = self._screen(q, k_eff, margin, events)
         L = ops._lib.lib()
         st = torch.cuda.current_stream().cuda_stream
         N, D = self.db_f32.shape
-        if events is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        ops._lib.check(L.isb_topk_screen(q.data_ptr(), Q, self.db_bf16.data_ptr(), N, D,
-                                         self.db_bf16.size(1), k_eff, margin, ws.data_ptr(),
-                                         ws.numel(), st), "isb_topk_screen")
-        if events is not None:
-            e1.record()
-            events.append((e0, e1))
         unc_rows = torch.empty(Q, dtype=torch.int32, device=q.device) if exact else None
         n_unc = torch.zeros(1, dtype=torch.int32, device=q.device) if exact else None
         ops._lib.check(L.isb_topk_rerank(q.data_ptr(), Q, self.db_f32.data_ptr(), N, D, k_eff, margin,
@@ -137,6 +181,8 @@ class ShardedIndex(object):
         if local_db.size(0) != self.hi - self.lo:
             raise IsbError("rank %d: shard has %d rows, expected %d" %
                            (rank, local_db.size(0), self.hi - self.lo))
+        self.device = local_db.device
+        self.stats = {}
         self.local = self._make_local(local_db, self.lo)
 
     # hooks (the gloo CPU tests replace them to exercise the plumbing)
@@ -149,23 +195,90 @@ class ShardedIndex(object):
     def _merge(self, cand_scores, cand_idx):
         return ops.topk_merge(cand_scores, cand_idx)
 
-    def search(self, q, k, events=None):
+    def _local_candidates(self, q, k, kc, events=None):
+        return self.local.candidates(q, k, kc, events)
+
+    def _global_threshold(self, all_screen):
+        return ops.topk_global_threshold(all_screen)
+
+    def _rerank_owned(self, q, k, cand_screen, cand_col, thr):
+        return self.local.rerank_owned(q, k, cand_screen, cand_col, thr)
+
+    def _merge_certified(self, cand_scores, cand_idx, stat, thr):
+        return ops.topk_merge_certified(cand_scores, cand_idx, stat, thr)
+
+    def _gather(self, t):
+        """all-gather of a [Q, c] tensor -> [R, Q, c] (the [R*Q, c] view is the layout both
+        the NCCL and the gloo backend accept)."""
         import torch.distributed as dist
+        out = torch.empty((self.world_size,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out.view(-1, t.size(-1)), t.contiguous(), group=self.group)
+        return out
+
+    def upload_queries(self, q_host):
+        """Pinned host queries -> device on every rank: each rank copies 1/R of the rows over
+        its own PCIe link and the slices are all-gathered over NVLink (instead of R full
+        host->device copies)."""
+        if self.world_size == 1 or q_host.size(0) < self.world_size:
+            return q_host.to(self.device, non_blocking=True)
+        import torch.distributed as dist
+        Q = q_host.size(0)
+        bounds = shard_bounds(Q, self.world_size)
+        per = bounds[0][1] - bounds[0][0]            # the largest slice
+        lo, hi = bounds[self.rank]
+        part = torch.zeros((per, q_host.size(1)), dtype=q_host.dtype, device=self.device)
+        part[:hi - lo].copy_(q_host[lo:hi], non_blocking=True)
+        full = torch.empty((self.world_size * per, q_host.size(1)), dtype=q_host.dtype, device=self.device)
+        dist.all_gather_into_tensor(full, part, group=self.group)
+        if per * self.world_size == Q:
+            return full
+        keep = torch.cat([torch.arange(r * per, r * per + (b[1] - b[0]), device=self.device)
+                          for r, b in enumerate(bounds)])
+        return full.index_select(0, keep)
+
+    def search(self, q, k, events=None, exchange=True):
+        """(scores [Q, kk] fp32, idx [Q, kk] int64 global), kk = min(k, n_total), best first,
+        identical on every rank.  q: the same queries on every rank (CUDA tensor, or a pinned
+        host tensor -> upload_queries).
+
+        exchange=True (default): candidate exchange -- the shards all-gather the screen scores
+        of their candidates, agree on the global (k + margin)-th best and re-rank only their
+        own candidates above it, so the exact re-rank costs k + margin gathers per query in
+        total instead of per shard; then ONE all-gather of the per-shard [Q, k] lists and the
+        merge with the global completeness certificate.  exchange=False: every shard runs the
+        full single-GPU search (screen + re-rank of k + margin) before the all-gather."""
+        if not q.is_cuda and self.device.type == "cuda":
+            q = self.upload_queries(q)
+        if self.world_size == 1:
+            return self._local_search(q, min(k, self.hi - self.lo), events)
+        if not exchange:
+            return self._search_replicated_rerank(q, k, events)
+        kk = min(k, self.n_total)
+        kc = min(kk + ops.DEFAULT_MARGIN, ops.MAX_CANDIDATES)
+        cand_screen, cand_col = self._local_candidates(q, kk, kc, events)
+        thr = self._global_threshold(self._gather(cand_screen))
+        s, i, stat = self._rerank_owned(q, kk, cand_screen, cand_col, thr)
+        ms, mi, unc_rows, n_unc = self._merge_certified(self._gather(s), self._gather(i), self._gather(stat), thr)
+        n_bad = int(n_unc.item())           # the one 4-byte D2H read of the exactness guarantee
+        self.stats["rows"] = self.stats.get("rows", 0) + q.size(0)
+        self.stats["resolved_locally_exact"] = self.stats.get("resolved_locally_exact", 0) + n_bad
+        if n_bad:
+            # rows the global certificate rejects: every shard answers them with its own
+            # certified search (fp32-grade re-screen / exhaustive as needed), plain merge
+            rows = unc_rows[:n_bad].long().sort().values   # same order on every rank
+            rs, ri = self._search_replicated_rerank(q.index_select(0, rows), k, None)
+            ms.index_copy_(0, rows, rs)
+            mi.index_copy_(0, rows, ri)
+        return ms, mi
+
+    def _search_replicated_rerank(self, q, k, events=None):
         k_local = min(k, self.hi - self.lo)
         s, i = self._local_search(q, k_local, events)
-        if self.world_size == 1:
-            return s, i
         if k_local < k:  # a shard smaller than k: pad with invalid entries
             pad = k - k_local
             s = torch.cat([s, s.new_full((s.size(0), pad), float("-inf"))], 1)
             i = torch.cat([i, i.new_full((i.size(0), pad), -1)], 1)
-        Q = s.size(0)
-        gs = torch.empty((self.world_size, Q, k), dtype=s.dtype, device=s.device)
-        gi = torch.empty((self.world_size, Q, k), dtype=i.dtype, device=i.device)
-        # the one exchange step of the path: k candidates per query per shard
-        # (concatenated [R*Q, k] view: the layout both the NCCL and the gloo backend accept)
-        dist.all_gather_into_tensor(gs.view(-1, k), s.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(gi.view(-1, k), i.contiguous(), group=self.group)
-        ms, mi = self._merge(gs, gi)
+        # the one exchange step of this variant: k results per query per shard
+        ms, mi = self._merge(self._gather(s), self._gather(i))
         kk = min(k, self.n_total)
         return ms[:, :kk], mi[:, :kk]

@@ -1,0 +1,165 @@
+"""GPU parity tests of the row-sharded search with candidate exchange
+(include/isb.h: isb_topk_candidates -> isb_topk_global_threshold ->
+isb_topk_rerank_owned -> isb_topk_merge_certified), SURVEY.md section 8e.
+
+The R shards live on ONE device here and are stepped in lock-step, the two
+all-gathers being torch.stack; the stages, their order and their arguments are
+those of ShardedIndex.search (tests/test_sharded_gloo.py covers that plumbing
+with real processes).  Results must equal the single-index search and the
+oracle, whatever the number of shards."""
+
+import pytest
+import torch
+
+import oracle
+from parity import check_topk_against_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _rows(n, d, seed):
+    g = torch.Generator().manual_seed(seed)
+    return oracle.normalize_l2(torch.randn(n, d, generator=g))
+
+
+def _lockstep_search(q, db, k, R, kc=None):
+    """What R ranks compute, on one device.  Returns (scores, idx, n_uncertified, stats)."""
+    from instance_search_b200 import ops
+    from instance_search_b200.search import DescriptorIndex, shard_bounds
+    dev = torch.device("cuda:0")
+    qd = q.to(dev)
+    kk = min(k, db.size(0))
+    if kc is None:
+        kc = min(kk + ops.DEFAULT_MARGIN, ops.MAX_CANDIDATES)
+    shards = [DescriptorIndex(db[lo:hi].to(dev), lo) for lo, hi in shard_bounds(db.size(0), R)]
+    cands = [sh.candidates(qd, kk, kc) for sh in shards]
+    all_screen = torch.stack([c[0] for c in cands])                 # all-gather 1
+    thr = ops.topk_global_threshold(all_screen)
+    parts = [sh.rerank_owned(qd, kk, c[0], c[1], thr) for sh, c in zip(shards, cands)]
+    gs, gi, gstat = (torch.stack([p[j] for p in parts]) for j in range(3))   # all-gather 2
+    s, i, unc_rows, n_unc = ops.topk_merge_certified(gs, gi, gstat, thr)
+    torch.cuda.synchronize()
+    scored = gstat[:, :, 1].sum(0)       # candidates re-ranked per query over all shards
+    return s, i, int(n_unc.item()), {"scored": scored.cpu(), "thr": thr.cpu(), "unc_rows": unc_rows.cpu(),
+                                     "all_screen": all_screen.cpu()}
+
+
+@pytest.mark.parametrize("R,Q,N,D,k", [
+    (2, 33, 5000, 128, 10),
+    (3, 70, 20011, 256, 100),     # uneven shards, k + margin = 128
+    (8, 17, 4096, 64, 25),
+    (4, 5, 300, 32, 100),         # shards (75 rows) shorter than k: padded candidate lists
+    (1, 20, 3000, 128, 10),       # R = 1 degenerates to the single-GPU result
+])
+def test_candidate_exchange_equals_oracle(R, Q, N, D, k):
+    q, db = _rows(Q, D, 11), _rows(N, D, 12)
+    s, i, n_unc, st = _lockstep_search(q, db, k, R)
+    assert n_unc == 0
+    check_topk_against_oracle(q, db, k, s, i)
+    # the point of the exchange: k + margin exact scores per query IN TOTAL (ties at the
+    # threshold may add a few), not per shard
+    kc = min(k + 28, 128)
+    assert int(st["scored"].min()) >= min(kc, N)
+    assert int(st["scored"].max()) <= min(kc, N) + 4
+
+
+def test_candidate_exchange_matches_single_index():
+    from instance_search_b200.search import DescriptorIndex
+    q, db = _rows(64, 512, 21), _rows(30000, 512, 22)
+    one_s, one_i = DescriptorIndex(db.cuda()).search(q.cuda(), 100)
+    for R in (2, 5):
+        s, i, n_unc, _ = _lockstep_search(q, db, 100, R)
+        assert n_unc == 0
+        assert torch.equal(i.cpu(), one_i.cpu())
+        assert torch.equal(s.cpu(), one_s.cpu())
+
+
+def test_global_threshold_kernel_is_the_kc_th_best():
+    from instance_search_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    R, Q, kc = 5, 40, 37
+    x = torch.randn(R, Q, kc, generator=g)
+    x[:, 3, :] = float("-inf")                    # a row with no candidates at all
+    x[1:, 4, :] = float("-inf")                   # exactly kc candidates
+    x[:, 5, 10:] = float("-inf")                  # 50 candidates, some shards short
+    x[:, 6, :] = 0.25                             # all tied
+    x[2, 7, :] = x[3, 7, :]                       # duplicated values across shards
+    thr = ops.topk_global_threshold(x.cuda()).cpu()
+    flat = x.permute(1, 0, 2).reshape(Q, R * kc)
+    want = flat.sort(dim=1, descending=True).values[:, kc - 1]
+    assert torch.equal(thr, want)
+    assert thr[3] == float("-inf") and thr[4] == x[0, 4].min()
+    y = x.clone()
+    y[:, 8, 5:] = float("-inf")                   # 25 < kc candidates -> nothing dropped -> -inf
+    assert ops.topk_global_threshold(y.cuda()).cpu()[8] == float("-inf")
+
+
+def test_duplicate_dense_rows_are_flagged_and_resolvable():
+    """300 exact duplicates of the best match: more rows tie with the k-th score than the
+    margin holds, the global certificate must reject those queries (ShardedIndex.search then
+    answers them with every shard's own certified search + isb_topk_merge)."""
+    from instance_search_b200 import ops
+    from instance_search_b200.search import DescriptorIndex, shard_bounds
+    q, db = _rows(12, 128, 31), _rows(6000, 128, 32)
+    db[1000:1300] = q[2]          # 300 duplicates, spread over shards 0 and 1 of 4
+    k, R = 100, 4
+    s, i, n_unc, st = _lockstep_search(q, db, k, R)
+    assert n_unc >= 1 and 2 in st["unc_rows"][:n_unc].tolist()
+    # the resolve path of ShardedIndex.search, in lock-step
+    rows = st["unc_rows"][:n_unc].long().sort().values
+    dev = torch.device("cuda:0")
+    ls, li = [], []
+    for lo, hi in shard_bounds(db.size(0), R):
+        a, b = DescriptorIndex(db[lo:hi].to(dev), lo).search(q[rows].to(dev), k)
+        ls.append(a), li.append(b)
+    rs, ri = ops.topk_merge(torch.stack(ls), torch.stack(li))
+    s.index_copy_(0, rows.to(dev), rs)
+    i.index_copy_(0, rows.to(dev), ri)
+    want_s, want_i = oracle.topk_search_f64(q, db, k)
+    # duplicates tie exactly: the k best are the k lowest-indexed duplicates
+    assert torch.equal(i.cpu()[2], torch.arange(1000, 1100))
+    others = [r for r in range(12) if r != 2]
+    assert torch.equal(i.cpu()[others], want_i[others])
+    assert torch.allclose(s.cpu().double(), want_s, rtol=2e-7, atol=1e-9)
+
+
+def _merge_reference(cs, ci, k):
+    """contract of isb_topk_merge: best first, ties -> lower index, index < 0 last / dropped"""
+    R, Q, kk = cs.shape
+    s = cs.permute(1, 0, 2).reshape(Q, R * kk).clone()
+    i = ci.permute(1, 0, 2).reshape(Q, R * kk)
+    s[i < 0] = float("-inf")
+    key = i.clone()
+    key[i < 0] = torch.iinfo(torch.int64).max
+    o1 = key.argsort(dim=1, stable=True)
+    s1, i1 = s.gather(1, o1), i.gather(1, o1)
+    o2 = s1.argsort(dim=1, descending=True, stable=True)
+    s2, i2 = s1.gather(1, o2)[:, :k], i1.gather(1, o2)[:, :k]
+    s2 = torch.where(i2 < 0, torch.full_like(s2, float("-inf")), s2)
+    return s2, i2
+
+
+@pytest.mark.parametrize("R,Q,k,levels,n_invalid", [
+    (2, 50, 10, 0, 0),        # continuous scores
+    (8, 37, 100, 0, 3),       # the 8-GPU headline shape, a few padded entries
+    (8, 33, 100, 7, 0),       # 7 distinct score values: hundreds of ties at the cut -> index search
+    (4, 9, 128, 3, 40),       # k = 128, heavy ties, many invalid
+    (3, 5, 100, 0, 295),      # fewer valid entries (5) than k
+    (2, 6, 300, 5, 10),       # k > 128: the block-wide bitonic kernel
+])
+def test_topk_merge_kernels(R, Q, k, levels, n_invalid):
+    from instance_search_b200 import ops
+    g = torch.Generator().manual_seed(R * 1000 + k)
+    cs = torch.randn(R, Q, k, generator=g)
+    if levels:
+        cs = (cs * 1.5).round().clamp(-(levels // 2), levels // 2) / 4
+    ci = torch.stack([torch.randperm(1 << 20, generator=g)[:R * k].reshape(R, k) for _ in range(Q)], 1)
+    ci[0, 0, 0] = (1 << 40) + 5           # a global index beyond 32 bits
+    for q in range(Q):
+        bad = torch.randperm(R * k, generator=g)[:n_invalid]
+        ci[bad // k, q, bad % k] = -1
+        cs[bad // k, q, bad % k] = float("-inf")
+    s, i = ops.topk_merge(cs.cuda(), ci.cuda())
+    want_s, want_i = _merge_reference(cs, ci, k)
+    assert torch.equal(i.cpu(), want_i)
+    assert torch.equal(s.cpu(), want_s)

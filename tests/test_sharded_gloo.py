@@ -1,9 +1,12 @@
 """CPU, world_size 2 and 3 over gloo: the host-side plumbing of the row-sharded
-search (shard bounds, global index offsets, padding of short shards, the ONE
-all-gather, merge order) -- SURVEY.md section 8e.  The GPU kernels are replaced
-through ShardedIndex's hooks by the oracle (local search) and a torch sort
-(merge), so what is exercised is exactly the code bench.py runs at N > 1 minus
-the kernels, which tests/test_gpu_core.py covers on the device."""
+search (shard bounds, global index offsets, padding of short shards, the
+candidate exchange -- all-gather of screen scores, global threshold, re-rank of
+the owned candidates, all-gather of the per-shard lists, certified merge, the
+resolve path of uncertified rows -- and the replicated-re-rank variant) --
+SURVEY.md section 8e.  The GPU kernels are replaced through ShardedIndex's hooks
+by torch restatements of their contracts (include/isb.h) on top of the oracle,
+so what is exercised is exactly the code bench.py runs at N > 1 minus the
+kernels, which tests/test_gpu_core.py / test_gpu_sharded.py cover on the device."""
 
 import os
 import socket
@@ -64,11 +67,70 @@ def _worker(rank, world, port, n_total, k, out_dir):
             o2 = s1.argsort(dim=1, descending=True, stable=True)
             return s1.gather(1, o2)[:, :kk], i1.gather(1, o2)[:, :kk]
 
+        # ---- candidate exchange hooks (contracts of isb_topk_candidates / _global_threshold /
+        # _rerank_owned / _merge_certified)
+        def _local_candidates(self, q, k, kc, events=None):
+            sim = oracle.similarity(q, self.local.rows)
+            screen = sim.bfloat16().float()          # a noisy screen, like the bf16 GEMM
+            n = min(kc, sim.size(1))
+            v, c = screen.topk(n, dim=1)
+            cs = torch.full((q.size(0), kc), float("-inf"))
+            cc = torch.full((q.size(0), kc), -1, dtype=torch.int32)
+            cs[:, :n], cc[:, :n] = v, c.int()
+            return cs, cc
+
+        def _global_threshold(self, all_screen):
+            R, Q, kc = all_screen.shape
+            flat = all_screen.permute(1, 0, 2).reshape(Q, R * kc)
+            kth = flat.sort(dim=1, descending=True).values[:, kc - 1]
+            return torch.where((flat > float("-inf")).sum(1) >= kc, kth, torch.full_like(kth, float("-inf")))
+
+        def _rerank_owned(self, q, k, cand_screen, cand_col, thr):
+            sim = oracle.similarity(q, self.local.rows)
+            Q, kc = cand_screen.shape
+            own = (cand_col >= 0) & (cand_screen >= thr[:, None])
+            exact = sim.gather(1, cand_col.clamp(min=0).long())
+            exact = torch.where(own, exact, torch.full_like(exact, float("-inf")))
+            gidx = torch.where(own, cand_col.long() + self.local.off, torch.full_like(cand_col.long(), -1))
+            key = torch.where(own, gidx, torch.full_like(gidx, torch.iinfo(torch.int64).max))
+            o1 = key.argsort(dim=1, stable=True)
+            e1, g1 = exact.gather(1, o1), gidx.gather(1, o1)
+            o2 = e1.argsort(dim=1, descending=True, stable=True)
+            e2, g2 = e1.gather(1, o2), g1.gather(1, o2)
+            s = torch.full((Q, k), float("-inf"))
+            i = torch.full((Q, k), -1, dtype=torch.int64)
+            n = min(k, kc)
+            s[:, :n], i[:, :n] = e2[:, :n], g2[:, :n]
+            d = torch.where(own, cand_screen - sim.gather(1, cand_col.clamp(min=0).long()), torch.zeros_like(exact))
+            stat = torch.stack([(d * d).sum(1), own.sum(1).float()], 1)
+            return s, i, stat
+
+        def _merge_certified(self, cs, ci, stat, thr):
+            assert stat.shape == (cs.size(0), cs.size(1), 2) and thr.shape == (cs.size(1),)
+            # every candidate >= thr was re-ranked by exactly one shard
+            total = stat[:, :, 1].sum(0)
+            kc = min(cs.size(2) + 28, 128)
+            assert bool(((total >= min(kc, n_total)) | (thr == float("-inf"))).all())
+            s, i = self._merge(cs, ci)
+            # pretend the certificate rejects every 5th row (listed in a rank-dependent order,
+            # like the device's atomicAdd): the resolve path must reproduce them exactly
+            rows = torch.arange(3, cs.size(1), 5, dtype=torch.int32)
+            if self.rank % 2:
+                rows = rows.flip(0)
+            unc = torch.zeros(cs.size(1), dtype=torch.int32)
+            unc[:rows.numel()] = rows
+            s[rows.long()] = 123.0           # garbage the resolve path has to overwrite
+            i[rows.long()] = -7
+            return s, i, unc, torch.tensor([rows.numel()], dtype=torch.int32)
+
     lo, hi = shard_bounds(n_total, world)[rank]
     index = CpuSharded(db[lo:hi], n_total, rank, world)
-    s, i = index.search(q, k)
     want_s, want_i = oracle.topk_search(q, db, k)
-    ok = torch.equal(i, want_i) and torch.equal(s, want_s)
+    ok = True
+    for exchange in (True, False):
+        s, i = index.search(q, k, exchange=exchange)
+        ok = ok and torch.equal(i, want_i) and torch.equal(s, want_s)
+    ok = ok and index.stats["resolved_locally_exact"] == len(range(3, 17, 5))
     # every rank holds the full merged answer
     flags = [torch.zeros(1) for _ in range(world)]
     dist.all_gather(flags, torch.tensor([1.0 if ok else 0.0]))
