@@ -154,15 +154,17 @@ int isb_topk_merge(const float* cand_scores, const int64_t* cand_idx, int R, int
  *   2. isb_topk_global_threshold  thr [Q] = the kc-th best screen score over all shards
  *                                 (all_screen [R, Q, kc]); -inf when fewer than kc exist
  *   3. isb_topk_rerank_owned      exact fp64-accumulated scores of ITS candidates >= thr, sorted
- *                                 into out_scores / out_idx [Q, k] (-inf / -1 padded, global indices
- *                                 = local row + idx_offset); stat [Q, 2] fp32 = (sum (screen -
- *                                 exact)^2, candidates scored)
- *      -- all-gather of out_scores, out_idx, stat --
- *   4. isb_topk_merge_certified   isb_topk_merge of cand_scores / cand_idx [R, Q, k] plus the
- *                                 completeness certificate of isb_topk_search evaluated globally:
- *                                 every row not re-ranked anywhere has a screen score <= thr, the
- *                                 noise is the rms over stat [R, Q, 2]; rows that fail are listed
- *                                 (resolve them with isb_topk_resolve on every shard + isb_topk_merge).
+ *                                 best first into ONE packed row of 2k + 2 32-bit words per query:
+ *                                 k scores (fp32, -inf padded) | k local rows (int32, -1 padded) |
+ *                                 sum (screen - exact)^2 | candidates scored   (both fp32)
+ *      -- ONE all-gather of the packed rows (8k + 8 bytes per query and shard) --
+ *   4. isb_topk_merge_certified   the k best of packed_all [R, Q, 2k + 2] (global index = local row +
+ *                                 row_offsets[shard], int64 [R] device), best first, ties -> lower
+ *                                 index, plus the completeness certificate of isb_topk_search
+ *                                 evaluated globally: every row not re-ranked anywhere has a screen
+ *                                 score <= thr, the noise is the rms over all shards' stat words;
+ *                                 rows that fail are listed (resolve them with isb_topk_search on
+ *                                 every shard + isb_topk_merge).
  * In total k + margin database rows are gathered per query, independent of R.
  * Replaces the same reference lines as isb_topk_search; the reference is single-device. */
 int isb_topk_candidates(int64_t Q, int64_t N, int64_t D, int k, int margin, int kc_out,
@@ -171,13 +173,11 @@ int isb_topk_candidates(int64_t Q, int64_t N, int64_t D, int k, int margin, int 
 int isb_topk_global_threshold(const float* all_screen, int R, int64_t Q, int kc, float* thr,
                               void* stream);
 int isb_topk_rerank_owned(const float* q, int64_t Q, const float* db_f32, int64_t N, int64_t D,
-                          int k, int kc, int64_t idx_offset, const float* cand_screen,
-                          const int32_t* cand_col, const float* thr, float* out_scores,
-                          int64_t* out_idx, float* stat, void* stream);
-int isb_topk_merge_certified(const float* cand_scores, const int64_t* cand_idx, const float* stat,
-                             const float* thr, int R, int64_t Q, int k, float* out_scores,
-                             int64_t* out_idx, int32_t* uncertified_rows, int32_t* n_uncertified,
-                             void* stream);
+                          int k, int kc, const float* cand_screen, const int32_t* cand_col,
+                          const float* thr, uint32_t* packed, void* stream);
+int isb_topk_merge_certified(const uint32_t* packed_all, const int64_t* row_offsets, const float* thr,
+                             int R, int64_t Q, int k, float* out_scores, int64_t* out_idx,
+                             int32_t* uncertified_rows, int32_t* n_uncertified, void* stream);
 
 /* ---------------------------------------------------------------- dense contraction
  * C[M, N] (fp32, leading dimension ldc) = A[M, K] . B[N, K]^T  (+ bias[N])

@@ -43,10 +43,10 @@ SIGNATURES = {
     "isb_topk_candidates": (c_int, [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_size,
                                     c_ptr]),
     "isb_topk_global_threshold": (c_int, [c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr]),
-    "isb_topk_rerank_owned": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_ptr, c_ptr,
-                                      c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "isb_topk_merge_certified": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr,
-                                         c_ptr, c_ptr, c_ptr]),
+    "isb_topk_rerank_owned": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr,
+                                      c_ptr, c_ptr]),
+    "isb_topk_merge_certified": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+                                         c_ptr]),
     "isb_region_select_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int,
                                                   c_int, c_int]),
     "isb_region_select": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr,

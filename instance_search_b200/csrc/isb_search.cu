@@ -308,19 +308,61 @@ constexpr int kSelWarps = 4;   // rows per CTA (launches may use fewer when a ro
 
 __host__ __device__ __forceinline__ size_t align_up_dev(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t* keys, int n, int kth) {
-  // precondition: n >= kth >= 1; all 32 lanes call it with the same arguments
+// k-th largest of n keys in shared memory by a 4 x 8-bit radix select; hist: 256 ints of
+// the warp's own scratch.  Precondition n >= kth >= 1; all 32 lanes call it together.
+__device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t* keys, int n, int kth, int* hist) {
   const int lane = threadIdx.x & 31;
-  uint32_t T = 0u;
+  uint32_t prefix = 0u;
+  int remaining = kth;
 #pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t cand = T | (1u << bit);
-    int c = 0;
-    for (int e = lane; e < n; e += 32) c += (keys[e] >= cand) ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= kth) T = cand;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    const uint32_t pmask = (pass == 0) ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int b = lane; b < 256; b += 32) hist[b] = 0;
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) {
+      const uint32_t key = keys[e];
+      if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+    }
+    __syncwarp();
+    // lane L owns bins 255 - 8L ... 248 - 8L; running count from the top bin downwards
+    int c[8], local = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      c[j] = hist[255 - 8 * lane - j];
+      local += c[j];
+    }
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int excl = incl - local;
+    const bool mine = excl < remaining && remaining <= incl;
+    const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+    if (bal == 0u) return 0u;   // n < kth (precondition violated): everything qualifies
+    const int src = __ffs(bal) - 1;
+    int d = 0, above = 0;
+    if (mine) {
+      int run = excl;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (run + c[j] >= remaining) {
+          d = 255 - 8 * lane - j;
+          above = run;
+          break;
+        }
+        run += c[j];
+      }
+    }
+    d = __shfl_sync(0xffffffffu, d, src);
+    above = __shfl_sync(0xffffffffu, above, src);
+    prefix |= static_cast<uint32_t>(d) << shift;
+    remaining -= above;
+    __syncwarp();
   }
-  return T;
+  return prefix;
 }
 
 // (1) the kc best screen entries of every row of the local pool, unsorted (entries above
@@ -334,27 +376,63 @@ pool_candidates_kernel(int64_t Q, int n_groups, const uint2* __restrict__ pool,
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
   if (row >= Q) return;
   const int slots = n_groups * kMaxCand;
-  uint32_t* keys = reinterpret_cast<uint32_t*>(pc_smem) + static_cast<size_t>(warp) * 2 * slots;
+  // per warp: keys [slots] | cols [slots] | hist [256] | pref [n_groups + 1]
+  const size_t per_warp = static_cast<size_t>(2 * slots + 256 + n_groups + 1);
+  uint32_t* keys = reinterpret_cast<uint32_t*>(pc_smem) + static_cast<size_t>(warp) * per_warp;
   uint32_t* cols = keys + slots;
+  int* hist = reinterpret_cast<int*>(cols + slots);
+  int* pref = hist + 256;
   const uint2* rpool = pool + static_cast<size_t>(row) * slots;
   const int* rcnt = pool_cnt + static_cast<size_t>(row) * n_groups;
-  // compact the valid entries of every group (group g holds rcnt[g] leading entries)
+  // group g holds rcnt[g] leading entries: exclusive prefix of the counts, then ONE flat pass
+  // over all slots (independent loads) compacts the valid entries
   int total = 0;
-  for (int g = 0; g < n_groups; ++g) {
-    const int c = rcnt[g];
-    for (int e = lane; e < c; e += 32) {
-      const uint2 ent = rpool[g * kMaxCand + e];
-      keys[total + e] = f2key(ent.x);
-      cols[total + e] = ent.y;
+  for (int g0 = 0; g0 < n_groups; g0 += 32) {
+    const int g = g0 + lane;
+    const int c = (g < n_groups) ? rcnt[g] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    total += c;
+    if (g < n_groups) pref[g] = total + incl - c;
+    total += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) pref[n_groups] = total;
+  __syncwarp();
+  constexpr int kBatch = 8;   // loads in flight per lane (the smem stores below would otherwise
+                              // serialise against the next iteration's reads of pref)
+  for (int base = 0; base < slots; base += 32 * kBatch) {
+    uint2 ent[kBatch];
+    int dst[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int e = base + u * 32 + lane;
+      dst[u] = -1;
+      if (e < slots) {
+        const int g = e / kMaxCand, j = e - g * kMaxCand;
+        const int p0 = pref[g];
+        if (j < pref[g + 1] - p0) {
+          dst[u] = p0 + j;
+          ent[u] = __ldg(rpool + e);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      if (dst[u] >= 0) {
+        keys[dst[u]] = f2key(ent[u].x);
+        cols[dst[u]] = ent[u].y;
+      }
+    }
   }
   __syncwarp();
   const int want = min(total, kc);
   uint32_t T = 0u;
   int n_gt = total;
   if (total > kc) {
-    T = warp_kth_largest(keys, total, kc);
+    T = warp_kth_largest(keys, total, kc, hist);
     int c = 0;
     for (int e = lane; e < total; e += 32) c += (keys[e] > T) ? 1 : 0;
     n_gt = __reduce_add_sync(0xffffffffu, c);
@@ -416,7 +494,8 @@ global_threshold_kernel(const float* __restrict__ all_screen, int R, int64_t Q, 
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kSelWarps + warp;
   if (row >= Q) return;
   const int n = R * kc;
-  uint32_t* keys = reinterpret_cast<uint32_t*>(gt_smem) + static_cast<size_t>(warp) * n;
+  uint32_t* keys = reinterpret_cast<uint32_t*>(gt_smem) + static_cast<size_t>(warp) * (n + 256);
+  int* hist = reinterpret_cast<int*>(keys + n);
   int valid = 0;
   for (int e = lane; e < n; e += 32) {
     const int r = e / kc, j = e - r * kc;
@@ -427,19 +506,17 @@ global_threshold_kernel(const float* __restrict__ all_screen, int R, int64_t Q, 
   valid = __reduce_add_sync(0xffffffffu, valid);
   __syncwarp();
   float t = -INFINITY;
-  if (valid >= kc) t = __uint_as_float(key2f(warp_kth_largest(keys, n, kc)));
+  if (valid >= kc) t = __uint_as_float(key2f(warp_kth_largest(keys, n, kc, hist)));
   if (lane == 0) thr[row] = t;
 }
 
 // (3) exact scores of the row's OWN candidates at or above the global threshold, sorted
-// best first into out_scores / out_idx [Q, k] (-inf / -1 beyond), plus the row's share of
-// the screen-noise measurement: stat[row] = (sum (screen - exact)^2, candidates scored).
+// best first, plus the row's share of the screen-noise measurement, written as ONE packed
+// row of 2k + 2 32-bit words (what the second all-gather exchanges).
 __global__ void __launch_bounds__(kRerankThreads)
 rerank_owned_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, int kc, int k,
-                    int64_t idx_offset, const float* __restrict__ cand_screen,
-                    const int* __restrict__ cand_col, const float* __restrict__ thr,
-                    float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
-                    float2* __restrict__ stat) {
+                    const float* __restrict__ cand_screen, const int* __restrict__ cand_col,
+                    const float* __restrict__ thr, uint32_t* __restrict__ packed) {
   extern __shared__ __align__(16) uint8_t rr_smem[];
   float* qs = reinterpret_cast<float*>(rr_smem);  // [D]
   __shared__ SelectSmem sm;
@@ -472,12 +549,17 @@ rerank_owned_kernel(const float* __restrict__ q, const float* __restrict__ db, i
   if ((tid & 31) == 0 && tid < kMaxCand) atomicAdd(&s_sig2, d2);
   __syncthreads();
   sort_selected(sm);
+  // packed row: k scores | k local rows (-1 = none) | sum (screen - exact)^2 | candidates scored
+  uint32_t* out = packed + static_cast<size_t>(row) * (2 * k + 2);
   for (int j = tid; j < k; j += kRerankThreads) {
     const bool ok = j < n_sel;
-    out_scores[static_cast<size_t>(row) * k + j] = ok ? static_cast<float>(sm.sel_score[j]) : -INFINITY;
-    out_idx[static_cast<size_t>(row) * k + j] = ok ? static_cast<int64_t>(sm.sel_col[j]) + idx_offset : -1;
+    out[j] = __float_as_uint(ok ? static_cast<float>(sm.sel_score[j]) : -INFINITY);
+    out[k + j] = static_cast<uint32_t>(ok ? sm.sel_col[j] : -1);
   }
-  if (tid == 0) stat[row] = make_float2(static_cast<float>(s_sig2), static_cast<float>(n_sel));
+  if (tid == 0) {
+    out[2 * k] = __float_as_uint(static_cast<float>(s_sig2));
+    out[2 * k + 1] = __float_as_uint(static_cast<float>(n_sel));
+  }
 }
 
 // ------------------------------------------------------------------ resolve pass operands
@@ -852,9 +934,14 @@ __device__ __forceinline__ bool merge_before(float sa, int64_t ia, float sb, int
   return (sa > sb) || (sa == sb && ia < ib);
 }
 
+// PACKED: the shards' lists arrive as ONE all-gathered buffer, packed [R, Q, 2k + 2] 32-bit
+// words per (shard, query): k scores (fp32) | k local rows (int32, -1 = none) | the two
+// stat words; global index = local row + row_offset[shard].  cs / ci / stat are unused.
+template <bool PACKED>
 __global__ void __launch_bounds__(32 * kSelWarps)
-topk_merge_warp_kernel(const float* __restrict__ cs, const int64_t* __restrict__ ci, int R, int64_t Q,
-                       int k, float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
+topk_merge_warp_kernel(const float* __restrict__ cs, const int64_t* __restrict__ ci,
+                       const uint32_t* __restrict__ packed, const int64_t* __restrict__ row_offset, int R,
+                       int64_t Q, int k, float* __restrict__ out_scores, int64_t* __restrict__ out_idx,
                        const float2* __restrict__ stat, const float* __restrict__ thr, float cert_z,
                        int* __restrict__ unc_rows, int* __restrict__ unc_count) {
   extern __shared__ __align__(16) uint8_t mw_smem[];
@@ -862,23 +949,33 @@ topk_merge_warp_kernel(const float* __restrict__ cs, const int64_t* __restrict__
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kSelWarps + warp;
   if (row >= Q) return;
   const int n = R * k;
-  // per warp: keys [n] u32 | sel_idx [kMaxCand] i64 | sel_score [kMaxCand] f32
-  const size_t per_warp = align_up_dev(static_cast<size_t>(n) * 4, 8) + kMaxCand * 12;
+  // per warp: keys [n] u32 | sel_idx [kMaxCand] i64 | sel_score [kMaxCand] f32 | hist [256]
+  const size_t per_warp = align_up_dev(static_cast<size_t>(n) * 4, 8) + kMaxCand * 12 + 1024;
   uint8_t* base = mw_smem + warp * per_warp;
   uint32_t* keys = reinterpret_cast<uint32_t*>(base);
   int64_t* sidx = reinterpret_cast<int64_t*>(base + align_up_dev(static_cast<size_t>(n) * 4, 8));
   float* sscore = reinterpret_cast<float*>(sidx + kMaxCand);
+  int* hist = reinterpret_cast<int*>(sscore + kMaxCand);
+  const int pw = 2 * k + 2;   // packed words per (shard, query)
 
-  auto entry_off = [&](int e) -> size_t {
+  auto entry_score = [&](int e) -> float {
     const int r = e / k, j = e - r * k;
-    return (static_cast<size_t>(r) * Q + row) * k + j;
+    if (PACKED) return __uint_as_float(packed[(static_cast<size_t>(r) * Q + row) * pw + j]);
+    return cs[(static_cast<size_t>(r) * Q + row) * k + j];
+  };
+  auto entry_idx = [&](int e) -> int64_t {
+    const int r = e / k, j = e - r * k;
+    if (PACKED) {
+      const int col = static_cast<int>(packed[(static_cast<size_t>(r) * Q + row) * pw + k + j]);
+      return col >= 0 ? static_cast<int64_t>(col) + row_offset[r] : -1;
+    }
+    return ci[(static_cast<size_t>(r) * Q + row) * k + j];
   };
   // keys: invalid entries (index < 0) get key 0 (below every real score incl. -inf)
   int valid = 0;
   for (int e = lane; e < n; e += 32) {
-    const size_t off = entry_off(e);
-    const bool ok = ci[off] >= 0;
-    keys[e] = ok ? f2key(__float_as_uint(cs[off])) : 0u;
+    const bool ok = entry_idx(e) >= 0;
+    keys[e] = ok ? f2key(__float_as_uint(entry_score(e))) : 0u;
     valid += ok ? 1 : 0;
   }
   valid = __reduce_add_sync(0xffffffffu, valid);
@@ -887,8 +984,12 @@ topk_merge_warp_kernel(const float* __restrict__ cs, const int64_t* __restrict__
   uint32_t T = 1u;            // every valid key is >= kKeyNegInf > 1
   int n_gt = 0;
   int64_t I = INT64_MAX;      // ties with T are taken while index <= I
-  if (valid > k) {
-    T = warp_kth_largest(keys, n, k);
+  // up to kMaxCand valid entries (the usual case after a candidate exchange: only the
+  // k + margin candidates above the global threshold were re-ranked at all) go straight to
+  // the sort; otherwise the k best are selected first
+  const bool need_select = valid > kMaxCand;
+  if (need_select) {
+    T = warp_kth_largest(keys, n, k, hist);
     int c = 0, ceq = 0;
     for (int e = lane; e < n; e += 32) {
       c += (keys[e] > T) ? 1 : 0;
@@ -904,7 +1005,7 @@ topk_merge_warp_kernel(const float* __restrict__ cs, const int64_t* __restrict__
         const uint64_t cand = lo | (1ull << bit);
         int cc = 0;   // ties with index < cand
         for (int e = lane; e < n; e += 32)
-          if (keys[e] == T && static_cast<uint64_t>(ci[entry_off(e)]) < cand) ++cc;
+          if (keys[e] == T && static_cast<uint64_t>(entry_idx(e)) < cand) ++cc;
         cc = __reduce_add_sync(0xffffffffu, cc);
         if (cc < room) lo = cand;     // fewer than room ties lie below cand: the answer is >= cand
       }
@@ -919,18 +1020,16 @@ topk_merge_warp_kernel(const float* __restrict__ cs, const int64_t* __restrict__
   for (int b0 = 0; b0 < n; b0 += 32) {
     const int e = b0 + lane;
     bool take = false;
-    size_t off = 0;
     if (e < n) {
-      off = entry_off(e);
       const uint32_t key = keys[e];
-      take = (valid <= k) ? (key != 0u) : (key > T || (key == T && ci[off] <= I));
+      take = !need_select ? (key != 0u) : (key > T || (key == T && (I == INT64_MAX || entry_idx(e) <= I)));
     }
     const uint32_t bt = __ballot_sync(0xffffffffu, take);
     if (take) {
       const int p = pos + __popc(bt & lt_mask);
       if (p < kMaxCand) {
-        sscore[p] = cs[off];
-        sidx[p] = ci[off];
+        sscore[p] = entry_score(e);
+        sidx[p] = entry_idx(e);
       }
     }
     pos += __popc(bt);
@@ -968,7 +1067,13 @@ topk_merge_warp_kernel(const float* __restrict__ cs, const int64_t* __restrict__
     if (t_min > -INFINITY) {
       double s2 = 0.0, cnt = 0.0;
       for (int r = 0; r < R; ++r) {
-        const float2 st = stat[static_cast<size_t>(r) * Q + row];
+        float2 st;
+        if (PACKED) {
+          const uint32_t* w = packed + (static_cast<size_t>(r) * Q + row) * pw + 2 * k;
+          st = make_float2(__uint_as_float(w[0]), __uint_as_float(w[1]));
+        } else {
+          st = stat[static_cast<size_t>(r) * Q + row];
+        }
         s2 += static_cast<double>(st.x);
         cnt += static_cast<double>(st.y);
       }
@@ -1289,16 +1394,28 @@ extern "C" int isb_topk_exhaustive(const float* q, const float* db_f32, int64_t 
   return ISB_OK;
 }
 
-static int launch_merge(const float* cand_scores, const int64_t* cand_idx, int R, int64_t Q, int k,
-                        float* out_scores, int64_t* out_idx, const float2* stat, const float* thr,
-                        int32_t* unc_rows, int32_t* unc_count, cudaStream_t st) {
+static int launch_merge(const float* cand_scores, const int64_t* cand_idx, const uint32_t* packed,
+                        const int64_t* row_offset, int R, int64_t Q, int k, float* out_scores,
+                        int64_t* out_idx, const float2* stat, const float* thr, int32_t* unc_rows,
+                        int32_t* unc_count, cudaStream_t st) {
   if (k <= kMaxCand) {
-    const size_t smem = kSelWarps * (align_up_dev(static_cast<size_t>(R) * k * 4, 8) + kMaxCand * 12);
-    if (smem > 48 * 1024)
-      ISB_CUDA(cudaFuncSetAttribute(topk_merge_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_merge_warp_kernel<<<static_cast<unsigned>((Q + kSelWarps - 1) / kSelWarps), 32 * kSelWarps, smem, st>>>(
-        cand_scores, cand_idx, R, Q, k, out_scores, out_idx, stat, thr, kCertZ, unc_rows, unc_count);
+    const size_t smem = kSelWarps * (align_up_dev(static_cast<size_t>(R) * k * 4, 8) + kMaxCand * 12 + 1024);
+    const unsigned grid = static_cast<unsigned>((Q + kSelWarps - 1) / kSelWarps);
+    if (packed != nullptr) {
+      auto kern = topk_merge_warp_kernel<true>;
+      if (smem > 48 * 1024)
+        ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, 32 * kSelWarps, smem, st>>>(nullptr, nullptr, packed, row_offset, R, Q, k, out_scores, out_idx,
+                                               nullptr, thr, kCertZ, unc_rows, unc_count);
+    } else {
+      auto kern = topk_merge_warp_kernel<false>;
+      if (smem > 48 * 1024)
+        ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, 32 * kSelWarps, smem, st>>>(cand_scores, cand_idx, nullptr, nullptr, R, Q, k, out_scores,
+                                               out_idx, stat, thr, kCertZ, unc_rows, unc_count);
+    }
   } else {
+    ISB_CHECK_ARG(packed == nullptr, "isb_topk_merge: k > %d is not supported with packed lists", kMaxCand);
     int n_pow2 = 2;
     while (n_pow2 < R * k) n_pow2 <<= 1;
     const size_t smem = static_cast<size_t>(n_pow2) * 12;
@@ -1319,8 +1436,8 @@ extern "C" int isb_topk_merge(const float* cand_scores, const int64_t* cand_idx,
   ISB_CHECK_ARG(static_cast<int64_t>(R) * k <= kMergeMax, "isb_topk_merge: R*k (%lld) > %d",
                 (long long)R * k, kMergeMax);
   if (Q == 0) return ISB_OK;
-  return launch_merge(cand_scores, cand_idx, R, Q, k, out_scores, out_idx, nullptr, nullptr, nullptr, nullptr,
-                      static_cast<cudaStream_t>(stream));
+  return launch_merge(cand_scores, cand_idx, nullptr, nullptr, R, Q, k, out_scores, out_idx, nullptr, nullptr,
+                      nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 // ---- sharded search with candidate exchange (three local stages around two all-gathers)
@@ -1341,7 +1458,7 @@ extern "C" int isb_topk_candidates(int64_t Q, int64_t N, int64_t D, int k, int m
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint2* pool = reinterpret_cast<const uint2*>(ws + plan.off_pool);
   const int* pool_cnt = reinterpret_cast<const int*>(ws + plan.off_pool_cnt);
-  const size_t per_warp = static_cast<size_t>(plan.n_groups) * kMaxCand * 8;
+  const size_t per_warp = (static_cast<size_t>(plan.n_groups) * kMaxCand * 2 + 256 + plan.n_groups + 1) * 4;
   int wpc = kSelWarps;
   while (wpc > 1 && per_warp * wpc > 96 * 1024) wpc >>= 1;
   if (per_warp * wpc <= 200 * 1024) {
@@ -1363,7 +1480,7 @@ extern "C" int isb_topk_global_threshold(const float* all_screen, int R, int64_t
   ISB_CHECK_ARG(all_screen && thr, "isb_topk_global_threshold: null pointer");
   ISB_CHECK_ARG(R >= 1 && Q >= 0 && kc >= 1 && kc <= ISB_MAX_CANDIDATES, "isb_topk_global_threshold: bad shape");
   if (Q == 0) return ISB_OK;
-  const size_t smem = static_cast<size_t>(kSelWarps) * R * kc * 4;
+  const size_t smem = static_cast<size_t>(kSelWarps) * (static_cast<size_t>(R) * kc + 256) * 4;
   ISB_CHECK_ARG(smem <= 200 * 1024, "isb_topk_global_threshold: R * kc (%d) too large", R * kc);
   if (smem > 48 * 1024)
     ISB_CUDA(cudaFuncSetAttribute(global_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1374,42 +1491,39 @@ extern "C" int isb_topk_global_threshold(const float* all_screen, int R, int64_t
 }
 
 extern "C" int isb_topk_rerank_owned(const float* q, int64_t Q, const float* db_f32, int64_t N, int64_t D,
-                                     int k, int kc, int64_t idx_offset, const float* cand_screen,
-                                     const int32_t* cand_col, const float* thr, float* out_scores,
-                                     int64_t* out_idx, float* stat, void* stream) {
-  ISB_CHECK_ARG(q && db_f32 && cand_screen && cand_col && thr && out_scores && out_idx && stat,
-                "isb_topk_rerank_owned: null pointer");
+                                     int k, int kc, const float* cand_screen, const int32_t* cand_col,
+                                     const float* thr, uint32_t* packed, void* stream) {
+  ISB_CHECK_ARG(q && db_f32 && cand_screen && cand_col && thr && packed, "isb_topk_rerank_owned: null pointer");
   ISB_CHECK_ARG(Q >= 0 && N > 0 && D > 0 && D % 8 == 0, "isb_topk_rerank_owned: bad shape");
   ISB_CHECK_ARG(k >= 1 && kc >= k && kc <= ISB_MAX_CANDIDATES, "isb_topk_rerank_owned: need 1 <= k <= kc <= %d",
                 ISB_MAX_CANDIDATES);
   ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(db_f32) & 15) == 0 &&
-                (reinterpret_cast<uintptr_t>(stat) & 7) == 0, "isb_topk_rerank_owned: misaligned input");
+                (reinterpret_cast<uintptr_t>(packed) & 3) == 0, "isb_topk_rerank_owned: misaligned input");
   if (Q == 0) return ISB_OK;
   const size_t smem = static_cast<size_t>(D) * 4;
   ISB_CHECK_ARG(smem <= 160 * 1024, "isb_topk_rerank_owned: D too large for the re-rank kernel");
   if (smem > 48 * 1024)
     ISB_CUDA(cudaFuncSetAttribute(rerank_owned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rerank_owned_kernel<<<static_cast<unsigned>(Q), kRerankThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      q, db_f32, static_cast<int>(D), kc, k, idx_offset, cand_screen, cand_col, thr, out_scores, out_idx,
-      reinterpret_cast<float2*>(stat));
+      q, db_f32, static_cast<int>(D), kc, k, cand_screen, cand_col, thr, packed);
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;
 }
 
-extern "C" int isb_topk_merge_certified(const float* cand_scores, const int64_t* cand_idx, const float* stat,
+extern "C" int isb_topk_merge_certified(const uint32_t* packed_all, const int64_t* row_offsets,
                                         const float* thr, int R, int64_t Q, int k, float* out_scores,
                                         int64_t* out_idx, int32_t* uncertified_rows, int32_t* n_uncertified,
                                         void* stream) {
-  ISB_CHECK_ARG(cand_scores && cand_idx && stat && thr && out_scores && out_idx && uncertified_rows &&
-                n_uncertified, "isb_topk_merge_certified: null pointer");
-  ISB_CHECK_ARG(R >= 1 && Q >= 0 && k >= 1, "isb_topk_merge_certified: bad shape");
+  ISB_CHECK_ARG(packed_all && row_offsets && thr && out_scores && out_idx && uncertified_rows && n_uncertified,
+                "isb_topk_merge_certified: null pointer");
+  ISB_CHECK_ARG(R >= 1 && Q >= 0 && k >= 1 && k <= ISB_MAX_CANDIDATES, "isb_topk_merge_certified: bad shape");
   ISB_CHECK_ARG(static_cast<int64_t>(R) * k <= kMergeMax, "isb_topk_merge_certified: R*k (%lld) > %d",
                 (long long)R * k, kMergeMax);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ISB_CUDA(cudaMemsetAsync(n_uncertified, 0, 4, st));
   if (Q == 0) return ISB_OK;
-  return launch_merge(cand_scores, cand_idx, R, Q, k, out_scores, out_idx, reinterpret_cast<const float2*>(stat),
-                      thr, uncertified_rows, n_uncertified, st);
+  return launch_merge(nullptr, nullptr, packed_all, row_offsets, R, Q, k, out_scores, out_idx, nullptr, thr,
+                      uncertified_rows, n_uncertified, st);
 }
 
 // ------------------------------------------------------------------ a13 entry point

@@ -233,27 +233,28 @@ def topk_global_threshold(all_screen):
     return thr
 
 
-def topk_merge_certified(cand_scores, cand_idx, stat, thr):
-    """topk_merge of the shards' re-ranked lists [R, Q, k] + the global completeness
-    certificate (stat [R, Q, 2], thr [Q]; include/isb.h).  Returns (scores [Q, k],
-    idx [Q, k], uncertified_rows [Q] int32, n_uncertified [1] int32)."""
-    _need_cuda(cand_scores, cand_idx, stat, thr)
-    cand_scores, stat, thr = _f32c(cand_scores), _f32c(stat), _f32c(thr)
-    cand_idx = cand_idx.contiguous()
-    if cand_idx.dtype != torch.int64 or cand_scores.shape != cand_idx.shape or cand_idx.dim() != 3:
-        raise IsbError("topk_merge_certified: expected [R, Q, k] fp32 scores and int64 indices")
-    R, Q, k = cand_scores.shape
-    if tuple(stat.shape) != (R, Q, 2) or tuple(thr.shape) != (Q,):
-        raise IsbError("topk_merge_certified: expected stat [R, Q, 2] and thr [Q]")
-    dev = cand_scores.device
+def topk_merge_certified(packed_all, row_offsets, thr, k):
+    """The k best of the shards' packed re-ranked lists + the global completeness
+    certificate (include/isb.h).  packed_all [R, Q, 2k + 2] (32-bit words, any 4-byte
+    dtype), row_offsets [R] int64 (first global row of every shard), thr [Q].  Returns
+    (scores [Q, k], idx [Q, k] int64 global, uncertified_rows [Q] int32, n_uncertified [1])."""
+    _need_cuda(packed_all, row_offsets, thr)
+    packed_all = packed_all.contiguous()
+    R, Q, pw = packed_all.shape
+    if packed_all.element_size() != 4 or pw != 2 * k + 2:
+        raise IsbError("topk_merge_certified: expected packed_all [R, Q, 2k + 2] of 32-bit words")
+    if row_offsets.dtype != torch.int64 or row_offsets.numel() != R or tuple(thr.shape) != (Q,):
+        raise IsbError("topk_merge_certified: expected row_offsets [R] int64 and thr [Q]")
+    thr = _f32c(thr)
+    dev = packed_all.device
     scores = torch.empty((Q, k), dtype=torch.float32, device=dev)
     idx = torch.empty((Q, k), dtype=torch.int64, device=dev)
     unc_rows = torch.empty((max(Q, 1),), dtype=torch.int32, device=dev)
     n_unc = torch.empty((1,), dtype=torch.int32, device=dev)
-    _lib.check(_lib.lib().isb_topk_merge_certified(cand_scores.data_ptr(), cand_idx.data_ptr(), stat.data_ptr(),
-                                                   thr.data_ptr(), R, Q, k, scores.data_ptr(), idx.data_ptr(),
-                                                   unc_rows.data_ptr(), n_unc.data_ptr(), _stream()),
-               "isb_topk_merge_certified")
+    _lib.check(_lib.lib().isb_topk_merge_certified(packed_all.data_ptr(), row_offsets.contiguous().data_ptr(),
+                                                   thr.data_ptr(), R, Q, int(k), scores.data_ptr(),
+                                                   idx.data_ptr(), unc_rows.data_ptr(), n_unc.data_ptr(),
+                                                   _stream()), "isb_topk_merge_certified")
     return scores, idx, unc_rows, n_unc
 
 

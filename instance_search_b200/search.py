@@ -7,10 +7,12 @@ host (utils/metrics.py).  Here the reference set lives in HBM as a
 tensor-core screen) and is searched without materialising the Q x N matrix.
 
 Multi-GPU: the database is split row-wise across the
-ranks of a ``torch.distributed`` group, one process per GPU; every rank
-searches its shard for the full (replicated) query batch, the per-shard
-``[Q, k]`` (score, global index) lists are exchanged with ONE all-gather over
-NCCL/NVLink, and every rank merges them (``isb_topk_merge``).
+ranks of a ``torch.distributed`` group, one process per GPU; every rank screens
+its shard for the full (replicated) query batch.  Candidate exchange: the
+shards all-gather the screen scores of their k + margin candidates (NCCL over
+NVLink), derive the same global threshold, re-rank exactly only their own
+candidates above it, all-gather the packed per-shard lists and merge them with
+the global completeness certificate (``isb_topk_merge_certified``).
 """
 
 import torch
@@ -114,19 +116,18 @@ class DescriptorIndex(object):
 
     def rerank_owned(self, q, k, cand_screen, cand_col, thr):
         """Sharded search, local stage 2: exact scores of this shard's candidates at or above
-        the global threshold -> (scores [Q, k] (-inf padded), idx [Q, k] global (-1 padded),
-        stat [Q, 2] = (sum (screen - exact)^2, candidates scored))."""
+        the global threshold, best first, as packed rows [Q, 2k + 2] int32 words: k scores
+        (fp32 bits, -inf padded) | k local rows (-1 padded) | sum (screen - exact)^2 |
+        candidates scored (fp32 bits) -- what the second all-gather exchanges."""
         q = self._queries(q)
         Q, kc = cand_screen.shape
-        scores = torch.empty((Q, k), dtype=torch.float32, device=q.device)
-        idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
-        stat = torch.empty((Q, 2), dtype=torch.float32, device=q.device)
+        packed = torch.empty((Q, 2 * k + 2), dtype=torch.int32, device=q.device)
         N, D = self.db_f32.shape
         ops._lib.check(ops._lib.lib().isb_topk_rerank_owned(
-            q.data_ptr(), Q, self.db_f32.data_ptr(), N, D, k, kc, self.row_offset, cand_screen.data_ptr(),
-            cand_col.data_ptr(), thr.data_ptr(), scores.data_ptr(), idx.data_ptr(), stat.data_ptr(),
+            q.data_ptr(), Q, self.db_f32.data_ptr(), N, D, k, kc, cand_screen.data_ptr(),
+            cand_col.data_ptr(), thr.data_ptr(), packed.data_ptr(),
             torch.cuda.current_stream().cuda_stream), "isb_topk_rerank_owned")
-        return scores, idx, stat
+        return packed
 
     def search(self, q, k, margin=None, events=None, exact=True):
         """(scores [Q, k] fp32, idx [Q, k] int64 global), best first.
@@ -183,6 +184,7 @@ class ShardedIndex(object):
                            (rank, local_db.size(0), self.hi - self.lo))
         self.device = local_db.device
         self.stats = {}
+        self._row_offsets = None
         self.local = self._make_local(local_db, self.lo)
 
     # hooks (the gloo CPU tests replace them to exercise the plumbing)
@@ -204,8 +206,11 @@ class ShardedIndex(object):
     def _rerank_owned(self, q, k, cand_screen, cand_col, thr):
         return self.local.rerank_owned(q, k, cand_screen, cand_col, thr)
 
-    def _merge_certified(self, cand_scores, cand_idx, stat, thr):
-        return ops.topk_merge_certified(cand_scores, cand_idx, stat, thr)
+    def _merge_certified(self, packed_all, thr, k):
+        if self._row_offsets is None:
+            self._row_offsets = torch.tensor([lo for lo, _ in shard_bounds(self.n_total, self.world_size)],
+                                             dtype=torch.int64, device=packed_all.device)
+        return ops.topk_merge_certified(packed_all, self._row_offsets, thr, k)
 
     def _gather(self, t):
         """all-gather of a [Q, c] tensor -> [R, Q, c] (the [R*Q, c] view is the layout both
@@ -244,8 +249,8 @@ class ShardedIndex(object):
         exchange=True (default): candidate exchange -- the shards all-gather the screen scores
         of their candidates, agree on the global (k + margin)-th best and re-rank only their
         own candidates above it, so the exact re-rank costs k + margin gathers per query in
-        total instead of per shard; then ONE all-gather of the per-shard [Q, k] lists and the
-        merge with the global completeness certificate.  exchange=False: every shard runs the
+        total instead of per shard; then ONE all-gather of the per-shard lists (packed: scores,
+        local rows, noise statistics) and the merge with the global completeness certificate.  exchange=False: every shard runs the
         full single-GPU search (screen + re-rank of k + margin) before the all-gather."""
         if not q.is_cuda and self.device.type == "cuda":
             q = self.upload_queries(q)
@@ -257,8 +262,8 @@ class ShardedIndex(object):
         kc = min(kk + ops.DEFAULT_MARGIN, ops.MAX_CANDIDATES)
         cand_screen, cand_col = self._local_candidates(q, kk, kc, events)
         thr = self._global_threshold(self._gather(cand_screen))
-        s, i, stat = self._rerank_owned(q, kk, cand_screen, cand_col, thr)
-        ms, mi, unc_rows, n_unc = self._merge_certified(self._gather(s), self._gather(i), self._gather(stat), thr)
+        packed = self._rerank_owned(q, kk, cand_screen, cand_col, thr)
+        ms, mi, unc_rows, n_unc = self._merge_certified(self._gather(packed), thr, kk)
         n_bad = int(n_unc.item())           # the one 4-byte D2H read of the exactness guarantee
         self.stats["rows"] = self.stats.get("rows", 0) + q.size(0)
         self.stats["resolved_locally_exact"] = self.stats.get("resolved_locally_exact", 0) + n_bad

@@ -35,9 +35,10 @@ def _lockstep_search(q, db, k, R, kc=None):
     cands = [sh.candidates(qd, kk, kc) for sh in shards]
     all_screen = torch.stack([c[0] for c in cands])                 # all-gather 1
     thr = ops.topk_global_threshold(all_screen)
-    parts = [sh.rerank_owned(qd, kk, c[0], c[1], thr) for sh, c in zip(shards, cands)]
-    gs, gi, gstat = (torch.stack([p[j] for p in parts]) for j in range(3))   # all-gather 2
-    s, i, unc_rows, n_unc = ops.topk_merge_certified(gs, gi, gstat, thr)
+    packed_all = torch.stack([sh.rerank_owned(qd, kk, c[0], c[1], thr) for sh, c in zip(shards, cands)])  # all-gather 2
+    offs = torch.tensor([lo for lo, _ in shard_bounds(db.size(0), R)], dtype=torch.int64, device=dev)
+    s, i, unc_rows, n_unc = ops.topk_merge_certified(packed_all, offs, thr, kk)
+    gstat = packed_all[:, :, 2 * kk:].contiguous().view(torch.float32)
     torch.cuda.synchronize()
     scored = gstat[:, :, 1].sum(0)       # candidates re-ranked per query over all shards
     return s, i, int(n_unc.item()), {"scored": scored.cpu(), "thr": thr.cpu(), "unc_rows": unc_rows.cpu(),

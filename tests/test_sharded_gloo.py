@@ -103,13 +103,21 @@ def _worker(rank, world, port, n_total, k, out_dir):
             s[:, :n], i[:, :n] = e2[:, :n], g2[:, :n]
             d = torch.where(own, cand_screen - sim.gather(1, cand_col.clamp(min=0).long()), torch.zeros_like(exact))
             stat = torch.stack([(d * d).sum(1), own.sum(1).float()], 1)
-            return s, i, stat
+            # packed row (include/isb.h): k scores | k LOCAL rows | 2 stat words, 32 bits each
+            col = torch.where(i >= 0, i - self.local.off, i).int()
+            return torch.cat([s.view(torch.int32), col, stat.view(torch.int32)], 1)
 
-        def _merge_certified(self, cs, ci, stat, thr):
-            assert stat.shape == (cs.size(0), cs.size(1), 2) and thr.shape == (cs.size(1),)
+        def _merge_certified(self, packed_all, thr, k):
+            R, Q, pw = packed_all.shape
+            assert pw == 2 * k + 2 and thr.shape == (Q,) and packed_all.dtype == torch.int32
+            cs = packed_all[:, :, :k].contiguous().view(torch.float32)
+            col = packed_all[:, :, k:2 * k].long()
+            offs = torch.tensor([lo for lo, _ in shard_bounds(self.n_total, self.world_size)])
+            ci = torch.where(col >= 0, col + offs[:, None, None], col)
+            stat = packed_all[:, :, 2 * k:].contiguous().view(torch.float32)
             # every candidate >= thr was re-ranked by exactly one shard
             total = stat[:, :, 1].sum(0)
-            kc = min(cs.size(2) + 28, 128)
+            kc = min(k + 28, 128)
             assert bool(((total >= min(kc, n_total)) | (thr == float("-inf"))).all())
             s, i = self._merge(cs, ci)
             # pretend the certificate rejects every 5th row (listed in a rank-dependent order,
