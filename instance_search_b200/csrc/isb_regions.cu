@@ -16,6 +16,7 @@
 //                               projection -- the Linear is linear) -> bf16 hi (+ lo)
 //   5. isb_gemm_nt[_split]      u . W^T   (nn.Linear(100352, D), :180)
 //   6. descriptor_finalize      desc = l2norm(y + nsel * bias)   (:220-222)
+#include <cstdlib>
 #include "isb_host.cuh"
 #include "isb_gemm_core.cuh"
 
@@ -274,7 +275,8 @@ region_pool_generic_kernel(const PoolParams p) {
 //      sums out of VT, mean -> bf16 hi / lo (cvt.rn.bf16.f32), stored straight to
 //      P_hi / P_lo with the 32 lanes of a warp on 32 consecutive channels (full
 //      32-byte sectors; no staging tile, no fourth pass)
-constexpr int kFastThreads = 1024;
+constexpr int kFastThreads = 1024;   // maps up to 32 x 32
+constexpr int kFastThreadsSmall = 256;   // maps up to 16 x 16: two or three CTAs per SM overlap their passes
 
 __device__ __forceinline__ uint16_t cvt_bf16(float f) {
   uint16_t h;
@@ -294,8 +296,8 @@ __device__ __forceinline__ int vt_base(int cb, int HW, int Q) {
   return cb * HW + ((target - cb * HW) & 31);
 }
 
-template <int HMAX>
-__global__ void __launch_bounds__(kFastThreads, 1)
+template <int HMAX, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 region_pool_fast_kernel(const PoolParams p, const FastGeom g) {
   extern __shared__ __align__(128) uint8_t pool_smem_raw[];
   constexpr int FH = 7;
@@ -312,7 +314,7 @@ region_pool_fast_kernel(const PoolParams p, const FastGeom g) {
   const int blk1 = min(blk0 + p.G, p.nblk);
   const float* xb = p.x + static_cast<size_t>(b) * p.C * HW;
 
-  for (int i = tid; i < kEParts * HW; i += kFastThreads) E[i] = 0.f;
+  for (int i = tid; i < kEParts * HW; i += NT) E[i] = 0.f;
   if (tid == 0) {
     ptx::mbar_init(&bars[0], 1);
     ptx::mbar_init(&bars[1], 1);
@@ -341,7 +343,7 @@ region_pool_fast_kernel(const PoolParams p, const FastGeom g) {
   const bool rowv = seg < g.nseg && cb_c < CB && ho_c < Ho && wo0 < wo1;
   const int row_in = vt_base(cb_c < CB ? cb_c : 0, HW, g.Q) + ho_c;
   const float inv_area = 1.f / 49.f;
-  const int eparts = min(kEParts, max(1, kFastThreads / HW));
+  const int eparts = min(kEParts, max(1, NT / HW));
 
   int cv;
   auto block_src = [&](int blk, int& cvalid) -> const float* {
@@ -378,7 +380,7 @@ region_pool_fast_kernel(const PoolParams p, const FastGeom g) {
     // ---- A: per-pixel energy
     {
       const int cb_per = (cvalid + eparts - 1) / eparts;
-      for (int i = tid; i < eparts * HW; i += kFastThreads) {
+      for (int i = tid; i < eparts * HW; i += NT) {
         const int part = i / HW, px = i - part * HW;
         const int cb_lo = part * cb_per, cb_hi = min(cvalid, cb_lo + cb_per);
         const float* xp = X + px;
@@ -461,10 +463,303 @@ region_pool_fast_kernel(const PoolParams p, const FastGeom g) {
     __syncthreads();
   }
   float* eo = p.e_part + (static_cast<size_t>(b) * p.ngroups + grp) * HW;
-  for (int px = tid; px < HW; px += kFastThreads) {
+  for (int px = tid; px < HW; px += NT) {
     float t = 0.f;
     for (int part = 0; part < eparts; ++part) t += E[part * HW + px];
     eo[px] = t;
+  }
+}
+
+// ------------------------------------------------------------------ 1c. pooling on the tensor cores
+// Maps of up to 256 pixels (14 x 14 at the reference's 448-px input): the window sums are
+// one small matrix product per block of 64 channels,
+//     S[win, c] = sum_px Box[win, px] * x[c, px],      Box[win, px] = 1 inside the window,
+// so the feature map goes HBM -> smem (one bulk copy per 64 channel planes) -> tensor cores
+// and no CUDA-core pass ever slides a window.  fp32 inputs are split into bf16 hi + lo
+// (x = hi + lo to 2^-16) and both terms accumulate in ONE fp32 TMEM tile; Box is exact in
+// bf16.  Persistent CTAs, warp-specialised, three 64 KB buffers that each hold first the raw
+// planes and then, converted IN PLACE, the two operand tiles:
+//   warp 0       producer    cp.async.bulk of 64 planes into a free buffer
+//   warps 6..21  converter   planes -> registers -> K-major 128B-swizzled bf16 hi / lo tiles
+//                            (pixels along K); per-pixel channel energy sum_c x^2 on the way
+//   warp 1       MMA issuer  tcgen05.mma 128 x 64 x 16: A = Box, B = operand tile, 13 k-steps
+//                            per term at 14 x 14, ring of four 64-column accumulators
+//   warps 2..5   epilogue    tcgen05.ld (lane = window, 64 channels), mean -> bf16 hi / lo ->
+//                            P_hi / P_lo rows (128 contiguous bytes per window and term)
+// Box has round8(nwin) real rows; the MMA is issued with M = 128 and the rows beyond read
+// whatever follows in shared memory -- their accumulator lanes are never loaded.
+constexpr int kTcThreads = 704;
+constexpr int kTcCB = 64;       // channels per block = rows of an operand tile = N of the MMA
+constexpr int kTcConv = 512;    // converter threads: the conversion is ALU work and needs the issue slots of 16 warps
+constexpr int kTcConvWarp0 = 6;
+constexpr int kTcBufs = 3;
+constexpr int kTcAccBufs = 4;   // accumulator ring
+constexpr int kTcMaxItems = 8;  // float4 items a converter thread holds in registers (7 at 14 x 14)
+constexpr uint32_t kTcTmemCols = 256;
+constexpr uint32_t kTcSlabBytes = kTcCB * 128;   // one 64-pixel slab of an operand tile: 8 KB
+constexpr uint32_t kTcBufBytes = 65536;          // raw planes (<= 64 KB), then hi [0,32K) + lo [32K,64K)
+
+struct TcGeom {
+  int nslab;     // ceil(H*W / 64)
+  int R8;        // rows of Box: nwin rounded up to 8
+  int lanes_c;   // converter channel lanes: kTcConv / (H*W/4); energy partial planes per unit
+  int n_units;   // B * ngroups
+  uint32_t off_buf, off_bars, raw_bytes;
+  int dbg;   // development ablation switches (ISB_TC_DEBUG): 1 no MMA, 2 no conversion, 4 no epilogue stores
+};
+
+struct TcBars {
+  uint64_t raw_full[kTcBufs], op_full[kTcBufs], buf_free[kTcBufs];
+  uint64_t acc_full[kTcAccBufs], acc_empty[kTcAccBufs];
+  uint32_t tmem_base;
+};
+
+// fp32 -> bf16 round-to-nearest (ties away from zero) with integer arithmetic: the bf16 is
+// the upper half of the result.  One IADD instead of cvt.rn.bf16x2.f32 (F2FP issues on the
+// quarter-rate XU pipe); the tie rule is immaterial here because x - hi is carried by the lo
+// term, and |x - hi| <= half an ulp either way.  Finite inputs.
+__device__ __forceinline__ uint32_t rn_bf16_hi16(float f) { return __float_as_uint(f) + 0x8000u; }
+// two rounded values -> {bf16(b) : bf16(a)}, a at the lower address
+__device__ __forceinline__ uint32_t pack_hi16(uint32_t ra, uint32_t rb) { return __byte_perm(ra, rb, 0x7632); }
+
+__device__ __forceinline__ void stg256(void* ptr, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__global__ void __maxnreg__(88)
+region_pool_tc_kernel(const PoolParams p, const TcGeom g) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int HW = p.H * p.W, Wo = p.W - p.fw + 1, Ho = p.H - p.fh + 1, nwin = Ho * Wo;
+  const int Q4 = HW >> 2;
+  uint8_t* box = smem;
+  uint8_t* bufs = smem + g.off_buf;
+  TcBars* bars = reinterpret_cast<TcBars*>(smem + g.off_bars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+
+  // ---- one-time setup: barriers, TMEM, Box (zero elsewhere)
+  if (tid == 0) {
+    for (int i = 0; i < kTcBufs; ++i) {
+      ptx::mbar_init(&bars->raw_full[i], 1);
+      ptx::mbar_init(&bars->op_full[i], kTcConv);
+      ptx::mbar_init(&bars->buf_free[i], 1);
+    }
+    for (int i = 0; i < kTcAccBufs; ++i) {
+      ptx::mbar_init(&bars->acc_full[i], 1);
+      ptx::mbar_init(&bars->acc_empty[i], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<kTcTmemCols>(&bars->tmem_base);
+  for (uint32_t i = tid * 16u; i < g.off_bars; i += kTcThreads * 16u)
+    *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  for (int i = tid; i < nwin * p.fh * p.fw; i += kTcThreads) {
+    const int win = i / (p.fh * p.fw), r = i - win * (p.fh * p.fw);
+    const int dy = r / p.fw, dx = r - dy * p.fw;
+    const int px = (win / Wo + dy) * p.W + (win % Wo) + dx;
+    const int slab = px >> 6, col = px & 63;
+    uint8_t* a = box + static_cast<size_t>(slab) * g.R8 * 128 + win * 128 + (((col >> 3) ^ (win & 7)) << 4) +
+                 ((col & 7) << 1);
+    *reinterpret_cast<uint16_t*>(a) = 0x3F80u;   // bf16 1.0
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int nb_unit = p.G;   // blocks per unit (the last unit of an image may hold fewer)
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
+        const int b = u / p.ngroups, grp = u - b * p.ngroups;
+        const int blk0 = grp * nb_unit, blk1 = min(blk0 + nb_unit, p.nblk);
+        for (int blk = blk0; blk < blk1; ++blk, ++it) {
+          const uint32_t q = it % kTcBufs;
+          ptx::mbar_wait(&bars->buf_free[q], ((it / kTcBufs) & 1u) ^ 1u);
+          const float* src = p.x + (static_cast<size_t>(b) * p.C + static_cast<size_t>(blk) * kTcCB) * HW;
+          ptx::mbar_arrive_expect_tx(&bars->raw_full[q], g.raw_bytes);
+          uint8_t* dst = bufs + static_cast<size_t>(q) * kTcBufBytes;
+          const uint32_t chunk = (g.dbg & 32) ? 65536u : ((g.dbg & 64) ? 4096u : 16384u);
+          for (uint32_t off = 0; off < g.raw_bytes; off += chunk) {
+            const uint32_t n = min(chunk, g.raw_bytes - off);
+            ptx::bulk_load_1d(dst + off, reinterpret_cast<const uint8_t*>(src) + off, n, &bars->raw_full[q]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, kTcCB);
+      const uint32_t box_addr = ptx::smem_u32(box), buf_addr = ptx::smem_u32(bufs);
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
+        const int b = u / p.ngroups, grp = u - b * p.ngroups;
+        const int blk0 = grp * nb_unit, blk1 = min(blk0 + nb_unit, p.nblk);
+        for (int blk = blk0; blk < blk1; ++blk, ++it) {
+          const uint32_t q = it % kTcBufs, d = it % kTcAccBufs;
+          ptx::mbar_wait(&bars->op_full[q], (it / kTcBufs) & 1u);
+          ptx::mbar_wait(&bars->acc_empty[d], ((it / kTcAccBufs) & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t tmem_acc = tmem_base + d * kTcCB;
+          uint32_t accumulate = 0u;
+          for (int term = 0; term < 2; ++term) {
+            for (int slab = 0; slab < g.nslab; ++slab) {
+              const int px_left = HW - slab * 64;
+              const int ks = px_left >= 64 ? 4 : (px_left + 15) >> 4;
+              const uint64_t da = ptx::make_smem_desc_k_sw128(box_addr + static_cast<uint32_t>(slab) * g.R8 * 128u);
+              const uint64_t db = ptx::make_smem_desc_k_sw128(buf_addr + q * kTcBufBytes + term * (kTcBufBytes / 2) +
+                                                              slab * kTcSlabBytes);
+              for (int k = 0; k < ks; ++k) {
+                if (!(g.dbg & 1)) ptx::umma_bf16(tmem_acc, da + 2 * k, db + 2 * k, idesc, accumulate);
+                accumulate = 1u;
+              }
+            }
+          }
+          ptx::umma_commit(&bars->buf_free[q]);
+          ptx::umma_commit(&bars->acc_full[d]);
+        }
+      }
+    }
+  } else if (warp < kTcConvWarp0) {
+    // ------------------------------------------------------------ epilogue
+    const int lg = warp & 3;
+    const int win = lg * 32 + lane;
+    const float inv_area = 1.f / static_cast<float>(p.fh * p.fw);
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
+      const int b = u / p.ngroups, grp = u - b * p.ngroups;
+      const int blk0 = grp * nb_unit, blk1 = min(blk0 + nb_unit, p.nblk);
+      for (int blk = blk0; blk < blk1; ++blk, ++it) {
+        const uint32_t d = it % kTcAccBufs;
+        ptx::mbar_wait(&bars->acc_full[d], (it / kTcAccBufs) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + d * kTcCB + (static_cast<uint32_t>(lg * 32) << 16);
+        const size_t o = (static_cast<size_t>(b) * nwin + win) * p.ldp + static_cast<size_t>(blk) * kTcCB;
+#pragma unroll 1
+        for (int hv = 0; hv < 2; ++hv) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(taddr + 32 * hv, v);
+          ptx::tmem_ld_wait();
+          if (hv == 1) {
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&bars->acc_empty[d]);
+          }
+          if (win < nwin && !(g.dbg & 4)) {
+            // 32 channels = 64 bytes per term: two 256-bit stores (whole 32-byte sectors)
+            uint16_t* ohi = p.P_hi + o + 32 * hv;
+            uint16_t* olo = p.P_lo + o + 32 * hv;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              uint32_t hw_[8], lw_[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float m0 = __uint_as_float(v[16 * q + 2 * j]) * inv_area;
+                const float m1 = __uint_as_float(v[16 * q + 2 * j + 1]) * inv_area;
+                const uint32_t r0 = rn_bf16_hi16(m0), r1 = rn_bf16_hi16(m1);
+                hw_[j] = pack_hi16(r0, r1);
+                lw_[j] = pack_hi16(rn_bf16_hi16(m0 - __uint_as_float(r0 & 0xFFFF0000u)),
+                                   rn_bf16_hi16(m1 - __uint_as_float(r1 & 0xFFFF0000u)));
+              }
+              stg256(ohi + 16 * q, hw_);
+              stg256(olo + 16 * q, lw_);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ converter
+    // thread (cl, t): pixel quad t of channels cl, cl + lanes_c, ... of every block
+    const int tc = tid - kTcConvWarp0 * 32;
+    const int cl = tc / Q4, t = tc - cl * Q4;
+    const bool active = cl < g.lanes_c;
+    const int n_items = active ? (kTcCB - cl + g.lanes_c - 1) / g.lanes_c : 0;
+    // pixel quad t -> slab t / 16, 16-byte chunk (t % 16) / 2, 8-byte half t % 2; the 
+    const uint32_t t_off = static_cast<uint32_t>(t >> 4) * kTcSlabBytes + ((t & 1) << 3);
+    const uint32_t t_chunk = (t & 15) >> 1;
+    const bool tail = active && (t == Q4 - 1) && (HW & 63) != 0;   // this thread also zeroes the K tail
+    const uint32_t bufs_addr = ptx::smem_u32(bufs);
+    const uint32_t ld_off = (static_cast<uint32_t>(cl) * Q4 + t) * 16u;
+    const uint32_t ld_step = static_cast<uint32_t>(g.lanes_c) * Q4 * 16u;
+    float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
+      const int b = u / p.ngroups, grp = u - b * p.ngroups;
+      const int blk0 = grp * nb_unit, blk1 = min(blk0 + nb_unit, p.nblk);
+      for (int blk = blk0; blk < blk1; ++blk, ++it) {
+        const uint32_t q = it % kTcBufs;
+        const uint32_t base = bufs_addr + q * kTcBufBytes;
+        ptx::mbar_wait(&bars->raw_full[q], (it / kTcBufs) & 1u);
+        float4 x4[kTcMaxItems];
+#pragma unroll
+        for (int j = 0; j < kTcMaxItems; ++j)
+          if (j < n_items && !(g.dbg & 16)) x4[j] = lds128(base + ld_off + j * ld_step);
+        ptx::named_bar_sync(1, kTcConv);   // every plane is in registers: the tiles may overwrite them
+#pragma unroll
+        for (int j = 0; j < kTcMaxItems; ++j) {
+          if (j < n_items && !(g.dbg & 2)) {
+            const float4 x = x4[j];
+            e0 = fmaf(x.x, x.x, e0); e1 = fmaf(x.y, x.y, e1);
+            e2 = fmaf(x.z, x.z, e2); e3 = fmaf(x.w, x.w, e3);
+            // hi = the upper 16 bits (truncation), lo = bf16(x - hi): x = hi + lo to 2^-16
+            const uint32_t u0 = __float_as_uint(x.x), u1 = __float_as_uint(x.y);
+            const uint32_t u2 = __float_as_uint(x.z), u3 = __float_as_uint(x.w);
+            const uint32_t l0 = rn_bf16_hi16(x.x - __uint_as_float(u0 & 0xFFFF0000u));
+            const uint32_t l1 = rn_bf16_hi16(x.y - __uint_as_float(u1 & 0xFFFF0000u));
+            const uint32_t l2 = rn_bf16_hi16(x.z - __uint_as_float(u2 & 0xFFFF0000u));
+            const uint32_t l3 = rn_bf16_hi16(x.w - __uint_as_float(u3 & 0xFFFF0000u));
+            const uint32_t ch = static_cast<uint32_t>(cl + j * g.lanes_c);
+            const uint32_t o = base + t_off + ch * 128u + ((t_chunk ^ (ch & 7u)) << 4);
+            sts64(o, pack_hi16(u0, u1), pack_hi16(u2, u3));
+            sts64(o + kTcBufBytes / 2, pack_hi16(l0, l1), pack_hi16(l2, l3));
+            if (tail) {
+              // pixels [HW, next multiple of 16) of the last slab are read by the MMA: zero them
+              // (the raw planes were lying there)
+              const uint32_t rowb = base + static_cast<uint32_t>(t >> 4) * kTcSlabBytes + ch * 128u;
+              const int col_end = (((HW & 63) + 15) >> 4) << 4;       // columns the MMA reads in this slab
+              for (int col = (HW & 63); col < col_end; col += 4) {  // HW % 4 == 0: whole 8-byte halves
+                const uint32_t oz = rowb + ((static_cast<uint32_t>(col >> 3) ^ (ch & 7u)) << 4) + ((col & 4) << 1);
+                sts64(oz, 0u, 0u);
+                sts64(oz + kTcBufBytes / 2, 0u, 0u);
+              }
+            }
+          }
+        }
+        ptx::fence_proxy_async();    // generic-proxy tile writes -> visible to the tensor core
+        ptx::mbar_arrive(&bars->op_full[q]);
+      }
+      // unit done: this lane's share of the per-pixel energy (the consumer sums the planes)
+      if (active) {
+        float* eo = p.e_part + ((static_cast<size_t>(b) * p.ngroups + grp) * g.lanes_c + cl) * HW + 4 * t;
+        *reinterpret_cast<float4*>(eo) = make_float4(e0, e1, e2, e3);
+        e0 = e1 = e2 = e3 = 0.f;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTcTmemCols>(tmem_base);
   }
 }
 
@@ -1204,6 +1499,10 @@ struct RegionPlan {
   int64_t ldp;
   size_t off_Phi, off_Plo, off_epart, off_screen, off_cand, off_cscreen, off_Ahi, off_Alo, off_logits, total;
   size_t pool_smem, cand_smem;
+  int fast_threads;   // block size of region_pool_fast_kernel
+  bool tc;        // tensor-core pooling (region_pool_tc_kernel)
+  int eplanes;    // energy partial planes per (image, channel group): 1, or the converter lanes of the tc kernel
+  TcGeom tcg;
 };
 
 static size_t pool_smem_bytes(int CB, int HW, int nwin) {
@@ -1223,15 +1522,16 @@ static bool make_region_plan(RegionPlan& p, int64_t B, int C, int H, int W, int 
     // sectors on the stores), the skewed transposed planes to fit in place, and enough
     // warps for the row pass
     const int Hop = p.Ho | 1;
+    p.fast_threads = (H <= 16 && W <= 16) ? kFastThreadsSmall : kFastThreads;
     for (int cb : {64, 32, 16}) {
       const size_t smem = static_cast<size_t>(2) * cb * HW * 4 + static_cast<size_t>(kEParts) * HW * 4 + 64;
-      if (cb * W > kFastThreads || smem > 200 * 1024 || 31 + W * Hop > HW) continue;
+      if (cb * W > p.fast_threads || smem > 200 * 1024 || 31 + W * Hop > HW) continue;
       const int Q = 32 / (cb < 32 ? cb : 32);
       const int cgroups = (cb + (32 / Q) - 1) / (32 / Q);
       const int hoblks = (p.Ho + Q - 1) / Q;
       const int warps_per_seg = cgroups * hoblks;
-      if (warps_per_seg > kFastThreads / 32) continue;
-      int nseg = (kFastThreads / 32) / warps_per_seg;
+      if (warps_per_seg > p.fast_threads / 32) continue;
+      int nseg = (p.fast_threads / 32) / warps_per_seg;
       if (nseg > (p.Wo + 1) / 2) nseg = (p.Wo + 1) / 2;
       if (nseg < 1) nseg = 1;
       p.CB = cb;
@@ -1248,12 +1548,42 @@ static bool make_region_plan(RegionPlan& p, int64_t B, int C, int H, int W, int 
     if (p.CB == 0) return false;
     p.pool_smem = pool_smem_bytes(p.CB, HW, p.nwin);
   }
+  // tensor-core pooling: maps of <= 256 pixels in whole float4 quads, <= 128 windows, whole
+  // 64-channel blocks (any window size: Box is built from fh x fw)
+  p.tc = false;
+  p.eplanes = 1;
+  // Opt-in (ISB_REGION_POOL=tc) while it is slower than the CUDA-core kernel: 229 us vs 202 us
+  // per 256 x 2048 x 14 x 14 batch (profiles/r01_ncu_pool_tc.txt: latency-bound hand-offs
+  // between the roles, 29% of DRAM bandwidth); results are identical either way.
+  const char* pool_mode = getenv("ISB_REGION_POOL");
+  const bool want_tc = pool_mode != nullptr && pool_mode[0] == 't' && pool_mode[1] == 'c';
+  if (want_tc && HW <= 256 && HW % 4 == 0 && p.nwin <= 128 && C % kTcCB == 0) {
+    TcGeom& t = p.tcg;
+    t.nslab = (HW + 63) / 64;
+    t.R8 = (p.nwin + 7) & ~7;
+    t.lanes_c = kTcConv / (HW / 4);
+    if (t.lanes_c > kTcCB) t.lanes_c = kTcCB;
+    t.raw_bytes = static_cast<uint32_t>(kTcCB) * HW * 4;
+    t.off_buf = static_cast<uint32_t>(t.nslab) * t.R8 * 128;             // Box, then the buffers
+    t.off_bars = t.off_buf + kTcBufs * kTcBufBytes;
+    const size_t smem = t.off_bars + sizeof(TcBars) + 1024;
+    const bool items_ok = (kTcCB + t.lanes_c - 1) / t.lanes_c <= kTcMaxItems;
+    if (smem <= 227 * 1024 && items_ok) {
+      p.tc = true;
+      const char* dbg = getenv("ISB_TC_DEBUG");
+      t.dbg = dbg ? atoi(dbg) : 0;
+      p.CB = kTcCB;
+      p.pool_smem = smem;
+      p.eplanes = t.lanes_c;
+    }
+  }
   p.nblk = (C + p.CB - 1) / p.CB;
   // channel blocks per CTA: enough CTAs to fill the machine a few times over, few
   // enough energy partials (one plane of H*W floats per CTA)
   p.G = 1;
   while (p.G < 8 && static_cast<int64_t>(B) * ((p.nblk + 2 * p.G - 1) / (2 * p.G)) >= 148 * 4) p.G *= 2;
   p.ngroups = (p.nblk + p.G - 1) / p.G;
+  if (p.tc) p.tcg.n_units = static_cast<int>(B) * p.ngroups;
   p.ncand_max = k + margin;
   if (p.ncand_max > kSelMaxCand) p.ncand_max = kSelMaxCand;
   p.ncand = p.ncand_max < p.nwin ? p.ncand_max : p.nwin;
@@ -1264,7 +1594,7 @@ static bool make_region_plan(RegionPlan& p, int64_t B, int C, int H, int W, int 
   const size_t Abytes = static_cast<size_t>(B) * p.ncand_max * p.ldp * 2;
   p.off_Phi = off;     off = align_up(off + Pbytes, 1024);
   p.off_Plo = off;     off = align_up(off + Pbytes, 1024);
-  p.off_epart = off;   off = align_up(off + static_cast<size_t>(B) * p.ngroups * HW * 4, 1024);
+  p.off_epart = off;   off = align_up(off + static_cast<size_t>(B) * p.ngroups * p.eplanes * HW * 4, 1024);
   p.off_screen = off;  off = align_up(off + static_cast<size_t>(B) * p.nwin * 4, 1024);
   p.off_cand = off;    off = align_up(off + static_cast<size_t>(B) * p.ncand_max * 4, 1024);
   p.off_cscreen = off; off = align_up(off + static_cast<size_t>(B) * p.ncand_max * 4, 1024);
@@ -1339,13 +1669,23 @@ extern "C" int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H
   pp.P_hi = P_hi; pp.P_lo = P_lo; pp.ldp = (int)p.ldp; pp.e_part = e_part;
   dim3 pgrid(p.ngroups, static_cast<unsigned>(B));
   ISB_CHECK_ARG(p.nwin <= kMaxWinPerThread * kPoolThreads, "isb_region_select: too many windows per image (%d)", p.nwin);
-  if (p.fast) {
-    if (H <= 16) {
-      ISB_CUDA(cudaFuncSetAttribute(region_pool_fast_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
-      region_pool_fast_kernel<16><<<pgrid, kFastThreads, p.pool_smem, st>>>(pp, p.geom);
+  if (p.tc && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    ISB_CUDA(cudaFuncSetAttribute(region_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
+    const int sms = device_sm_count();
+    region_pool_tc_kernel<<<p.tcg.n_units < sms ? p.tcg.n_units : sms, kTcThreads, p.pool_smem, st>>>(pp, p.tcg);
+    if (p.tcg.dbg & 8) return ISB_OK;   // timing of the pool kernel alone (outputs undefined)
+  } else if (p.tc) {
+    set_error("isb_region_select: x must be 16-byte aligned for maps of this size");
+    return ISB_ERR_INVALID_ARGUMENT;
+  } else if (p.fast) {
+    if (p.fast_threads == kFastThreadsSmall) {
+      auto kern = region_pool_fast_kernel<16, kFastThreadsSmall, 4>;
+      ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
+      kern<<<pgrid, kFastThreadsSmall, p.pool_smem, st>>>(pp, p.geom);
     } else {
-      ISB_CUDA(cudaFuncSetAttribute(region_pool_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
-      region_pool_fast_kernel<32><<<pgrid, kFastThreads, p.pool_smem, st>>>(pp, p.geom);
+      auto kern = region_pool_fast_kernel<32, kFastThreads, 1>;
+      ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
+      kern<<<pgrid, kFastThreads, p.pool_smem, st>>>(pp, p.geom);
     }
   } else if (fh == 7 && fw == 7) {
     ISB_CUDA(cudaFuncSetAttribute(region_pool_generic_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
@@ -1378,7 +1718,7 @@ extern "C" int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H
     ISB_CHECK_ARG(sel_smem <= 200 * 1024, "isb_region_select: exact mode needs %zu bytes of shared memory", sel_smem);
     ISB_CUDA(cudaFuncSetAttribute(region_select_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     region_select_exact_kernel<<<static_cast<unsigned>(B), kSelThreads, sel_smem, st>>>(
-        x, (int)C, (int)H, (int)W, fh, fw, cls_w, cls_b, (int)ncls, screen, e_part, p.ngroups, k, p.ncand,
+        x, (int)C, (int)H, (int)W, fh, fw, cls_w, cls_b, (int)ncls, screen, e_part, p.ngroups * p.eplanes, k, p.ncand,
         1e-10f, idx, nsel, cls_out, win_norm, n_uncertified);
     ISB_CUDA(cudaGetLastError());
     return ISB_OK;
@@ -1398,7 +1738,7 @@ extern "C" int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H
 
   // 5. final order, outputs, crop norms, certificate
   region_finalize_select_kernel<<<static_cast<unsigned>(B), kSelThreads, 0, st>>>(
-      logits, p.ldl, (int)ncls, cand, cscreen, p.nwin, p.ncand, p.ncand_max, e_part, p.ngroups, (int)H, (int)W,
+      logits, p.ldl, (int)ncls, cand, cscreen, p.nwin, p.ncand, p.ncand_max, e_part, p.ngroups * p.eplanes, (int)H, (int)W,
       fh, fw, k, 1e-10f, idx, nsel, cls_out, win_norm, approx_max, runner_up, n_uncertified);
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;
