@@ -1210,10 +1210,18 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, 
   const bool bulk = ((reinterpret_cast<uintptr_t>(src0) & 15) == 0) && ((HW & 3) == 0) && ((pl & 3) == 0) && pl > 0;
   if (bulk) {
     if (tid < 32) {
-      if (tid == 0) ptx::mbar_arrive_expect_tx(&bar, static_cast<uint32_t>(cvalid) * pl * 4u);
+      const uint32_t total = static_cast<uint32_t>(cvalid) * pl * 4u;
+      if (tid == 0) ptx::mbar_arrive_expect_tx(&bar, total);
       __syncwarp();
-      for (int cb = tid; cb < cvalid; cb += 32)
-        ptx::bulk_load_1d(X + cb * pl, src0 + static_cast<size_t>(cb) * HW, static_cast<uint32_t>(pl) * 4u, &bar);
+      if (pl == HW) {
+        // whole planes: the channel block is ONE contiguous range -> a few large copies
+        for (uint32_t off = tid * 8192u; off < total; off += 32u * 8192u)
+          ptx::bulk_load_1d(reinterpret_cast<uint8_t*>(X) + off, reinterpret_cast<const uint8_t*>(src0) + off,
+                            min(8192u, total - off), &bar);
+      } else {
+        for (int cb = tid; cb < cvalid; cb += 32)
+          ptx::bulk_load_1d(X + cb * pl, src0 + static_cast<size_t>(cb) * HW, static_cast<uint32_t>(pl) * 4u, &bar);
+      }
     }
     ptx::mbar_wait(&bar, 0);
   } else {
@@ -1227,8 +1235,12 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, 
   // AvgPool2d's own arithmetic, model/siamese.py:187), input of isb_region_logits
   if (win_mean != nullptr) {
     const float farea = static_cast<float>(area);
-    for (int it = tid; it < cvalid * nall; it += kGatherThreads) {
-      const int i = it / cvalid, cb = it - i * cvalid;
+    // lanes: 8 consecutive channels (their planes are pl floats apart: 8 distinct banks when
+    // pl % 32 == 4, as at 14 x 14) x 4 windows, instead of 32 channels (4-way conflicts)
+    const int cgroups8 = (cvalid + 7) >> 3;
+    for (int it = tid; it < cgroups8 * 8 * nall; it += kGatherThreads) {
+      const int cb = ((it / (8 * nall)) << 3) | (it & 7), i = (it >> 3) % nall;
+      if (cb >= cvalid) continue;
       const float* pw = X + cb * pl + s_off[i];
       float sum = 0.f;
       for (int dy = 0; dy < fh; ++dy)
@@ -1244,6 +1256,15 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, 
   const int e_end = (c0 + cvalid >= C) ? KinP : (c0 + cvalid) * area;
   uint16_t* uh = U_hi + static_cast<size_t>(b) * ldu;
   uint16_t* ul = (U_lo != nullptr) ? U_lo + static_cast<size_t>(b) * ldu : nullptr;
+  // the (at most kGatherRegWin) summed windows live in registers; more fall back to smem
+  constexpr int kGatherRegWin = 8;
+  int r_off[kGatherRegWin];
+  float r_norm[kGatherRegWin];
+#pragma unroll
+  for (int i = 0; i < kGatherRegWin; ++i) {
+    r_off[i] = (i < nsel) ? s_off[i] : 0;
+    r_norm[i] = (i < nsel) ? s_norm[i] : 0.f;
+  }
   for (int e = e_begin + 2 * tid; e < e_end; e += 2 * kGatherThreads) {   // e_begin is even (CBg % 2 == 0)
     uint16_t hi[2], lo[2];
 #pragma unroll
@@ -1254,7 +1275,13 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, 
         const int c = ee / area, r = ee - c * area;
         const int dy = r / fw, dx = r - dy * fw;
         const float* plane = X + (c - c0) * pl + dy * W + dx;
-        for (int i = 0; i < nsel; ++i) u = fmaf(plane[s_off[i]], s_norm[i], u);
+        if (nsel <= kGatherRegWin) {
+#pragma unroll
+          for (int i = 0; i < kGatherRegWin; ++i)
+            if (i < nsel) u = fmaf(plane[r_off[i]], r_norm[i], u);   // block-uniform predicate
+        } else {
+          for (int i = 0; i < nsel; ++i) u = fmaf(plane[s_off[i]], s_norm[i], u);
+        }
         u += fn * __ldg(shift + ee);
       }
       hi[t] = bf16_rn(u);
