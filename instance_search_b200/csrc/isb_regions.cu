@@ -1788,8 +1788,16 @@ extern "C" int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H
                 (reinterpret_cast<uintptr_t>(U_lo) & 15) == 0, "isb_region_gather: bad ldu / alignment");
   const int64_t HW = H * W;
   int CBg = 0;
-  for (int cb : {64, 32, 16, 8, 4, 2}) {
-    if (static_cast<size_t>(cb) * HW * 4 <= 96 * 1024) { CBg = cb; break; }
+  // <= 28 KB of planes per CTA when that still leaves >= 16 channels: more CTAs per SM, so that
+  // the load phase of one overlaps the arithmetic of the others (a CTA is load -> wait -> compute
+  // -> store, nothing pipelined inside); larger maps take what fits in 96 KB
+  for (int cb : {64, 32, 16}) {
+    if (static_cast<size_t>(cb) * HW * 4 <= 28 * 1024) { CBg = cb; break; }
+  }
+  if (CBg == 0) {
+    for (int cb : {64, 32, 16, 8, 4, 2}) {
+      if (static_cast<size_t>(cb) * HW * 4 <= 96 * 1024) { CBg = cb; break; }
+    }
   }
   ISB_CHECK_ARG(CBg > 0, "isb_region_gather: feature map too large (H*W=%lld)", (long long)HW);
   const int row_align = (W % 4 == 0) ? 1 : ((W % 2 == 0) ? 2 : 4);
