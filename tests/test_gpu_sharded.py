@@ -164,3 +164,19 @@ def test_topk_merge_kernels(R, Q, k, levels, n_invalid):
     want_s, want_i = _merge_reference(cs, ci, k)
     assert torch.equal(i.cpu(), want_i)
     assert torch.equal(s.cpu(), want_s)
+
+
+def test_persisted_database_loads_into_an_index(tmp_path):
+    """store.py: descriptors written once, every shard loads its rows straight to the GPU."""
+    from instance_search_b200 import ops, store
+    from instance_search_b200.search import DescriptorIndex, shard_bounds
+    q, db = _rows(40, 96, 51), _rows(9001, 96, 52)
+    path = str(tmp_path / "db.isbd")
+    store.write_descriptors(path, db.cuda(), chunk_rows=1000)       # from device memory, in chunks
+    index = store.load_index(path)
+    assert len(index) == 9001 and torch.equal(index.db_f32.cpu(), db)
+    s, i = index.search(q.cuda(), 20)
+    check_topk_against_oracle(q, db, 20, s, i)
+    f = store.DescriptorFile(path)
+    for lo, hi in shard_bounds(9001, 4):
+        assert torch.equal(f.load_rows(lo, hi, "cuda:0", chunk_rows=700).cpu(), db[lo:hi])
