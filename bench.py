@@ -74,16 +74,66 @@ def make_rows(n, d, seed, device, chunk=131072):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock / power / throttle reasons DURING the timed region: NVML polled every
+    2 ms from a thread (a timed region of a few tens of ms still gets samples);
+    nvidia-smi -lms 100 when NVML cannot be opened."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bits
+    REASON_BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20),
+                   ("hw_thermal_slowdown", 0x40), ("hw_power_brake_slowdown", 0x80))
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.handle, self.stop_flag, self.t = None, None, threading.Event(), None
+        self.samples, self.mask, self.sm_max = [], 0, None
+
+    def _open_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        handle = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            handle = None
+        if handle is None:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if vis:
+                ent = vis.split(",")[self.index].strip()
+                if ent.isdigit():
+                    phys = int(ent)
+            handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)   # fails here rather than in the thread
+        self.nvml, self.handle = pynvml, handle
+
+    def _poll_nvml(self):
+        nv, h = self.nvml, self.handle
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append((sm, pw))
+                if reasons is not None:
+                    self.mask |= int(reasons(h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            self._open_nvml()
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -98,9 +148,23 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    @staticmethod
+    def _summary(sm, pw, sm_max, reasons, source):
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": sm_max, "reasons": ["no samples"], "source": source}
+        busy = [c for c, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": sm_max, "samples": len(sm),
+                "power_w_max": max(pw), "reasons": sorted(reasons), "source": source}
+
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=2)
+            reasons = [name for name, bit in self.REASON_BITS if self.mask & bit]
+            return self._summary([s for s, _ in self.samples], [p for _, p in self.samples], self.sm_max,
+                                 reasons, "nvml, 2 ms poll")
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -116,11 +180,7 @@ class ClockSampler(object):
                                 "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = [c for c, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "samples": len(sm),
-                "power_w_max": max(pw), "reasons": sorted(reasons)}
+        return self._summary(sm, pw, max(mx) if mx else None, reasons, "nvidia-smi -lms 100")
 
 
 # ------------------------------------------------------------------ reference arm

@@ -40,12 +40,15 @@ __device__ __forceinline__ float bf16_f(uint16_t h) { return __uint_as_float(sta
 constexpr int kPoolThreads = 512;
 constexpr int kMaxWinPerThread = 6;   // windows per thread in the horizontal pass (nwin <= 6 * 512)
 constexpr int kEParts = 4;   // energy partial planes per CTA (summed in a fixed order)
+constexpr int kPoolMaxStages = 6;
+constexpr int kPoolDefaultStages = 3;
 
 struct PoolParams {
   const float* x;
   int C, H, W, fh, fw;
   int CB;        // channels per block (multiple of 4)
   int G;         // channel blocks per CTA (one energy partial per CTA)
+  int stages;    // plane buffers of the fast kernel's prefetch ring
   int nblk;      // ceil(C / CB)
   int ngroups;   // ceil(nblk / G)
   uint16_t* P_hi;   // [B * nwin, ldp]  bf16(mean)
@@ -291,22 +294,42 @@ struct FastGeom {
   int segw;   // outputs per segment
 };
 
+// thread geometry of the row pass for a (H x W map, CB channels, NT threads) block; nseg == 0: does not fit
+__host__ __device__ constexpr FastGeom make_fast_geom(int H, int W, int cb, int nt) {
+  const int Ho = H - 6, Wo = W - 6;
+  const int Q = 32 / (cb < 32 ? cb : 32);
+  const int cpw = 32 / Q;
+  const int cgroups = (cb + cpw - 1) / cpw;
+  const int hoblks = (Ho + Q - 1) / Q;
+  const int warps_per_seg = cgroups * hoblks;
+  int nseg = warps_per_seg > nt / 32 ? 0 : (nt / 32) / warps_per_seg;
+  if (nseg > (Wo + 1) / 2) nseg = (Wo + 1) / 2;
+  return FastGeom{Ho | 1, Q, nseg, nseg > 0 ? (Wo + nseg - 1) / nseg : 0};
+}
+
 __device__ __forceinline__ int vt_base(int cb, int HW, int Q) {
   const int target = (cb % (32 / Q)) * Q;                // bank of VT[cb][0][0]
   return cb * HW + ((target - cb * HW) & 31);
 }
 
-template <int HMAX, int NT, int MINB>
+// HC, WC, CBC != 0: map size and channel block known at compile time (the reference's 14 x 14
+// and 32 x 32 maps) -- every index, pitch and loop bound below folds to a constant, which cuts
+// the instruction count per plane ~3x (the kernel is issue-bound otherwise: ncu, 83 % issue
+// slots busy at 3.1 TB/s).  0: taken from the launch parameters.
+template <int HMAX, int NT, int MINB, int HC, int WC, int CBC>
 __global__ void __launch_bounds__(NT, MINB)
-region_pool_fast_kernel(const PoolParams p, const FastGeom g) {
+region_pool_fast_kernel(const PoolParams p, const FastGeom g_rt) {
   extern __shared__ __align__(128) uint8_t pool_smem_raw[];
   constexpr int FH = 7;
-  const int HW = p.H * p.W, Wo = p.W - 6, Ho = p.H - 6, nwin = Ho * Wo;
-  const int CB = p.CB;
+  constexpr bool kStatic = HC != 0;
+  const int H = kStatic ? HC : p.H, W = kStatic ? WC : p.W;
+  const int CB = kStatic ? CBC : p.CB;
+  const FastGeom g = kStatic ? make_fast_geom(HC ? HC : 7, WC ? WC : 7, CBC ? CBC : 16, NT) : g_rt;
+  const int HW = H * W, Wo = W - 6, Ho = H - 6, nwin = Ho * Wo;
   const int plane_floats = CB * HW;
+  const int NST = p.stages;                                       // ring of NST plane buffers (2 .. kPoolMaxStages)
   float* X0 = reinterpret_cast<float*>(pool_smem_raw);
-  float* X1 = X0 + plane_floats;
-  float* E = X1 + plane_floats;                                   // [kEParts][HW]
+  float* E = X0 + static_cast<size_t>(NST) * plane_floats;        // [kEParts][HW]
   uint64_t* bars = reinterpret_cast<uint64_t*>(E + kEParts * HW + ((kEParts * HW) & 1));
 
   const int b = blockIdx.y, grp = blockIdx.x, tid = threadIdx.x;
@@ -316,16 +339,20 @@ region_pool_fast_kernel(const PoolParams p, const FastGeom g) {
 
   for (int i = tid; i < kEParts * HW; i += NT) E[i] = 0.f;
   if (tid == 0) {
-    ptx::mbar_init(&bars[0], 1);
-    ptx::mbar_init(&bars[1], 1);
+    for (int s = 0; s < NST; ++s) ptx::mbar_init(&bars[s], 1);
     ptx::fence_barrier_init();
   }
   __syncthreads();
 
   // ---- fixed thread roles
+  // pass A: four pixels (one float4) x a quarter of the channels per thread when H*W % 4 == 0
+  const bool quadA = (HW & 3) == 0 && NT >= (HW >> 2);
+  const int HW4 = HW >> 2;
+  const int eparts4 = min(kEParts, NT / max(HW4, 1));
+  const int partA = tid / max(HW4, 1), qA = tid - partA * HW4;
   // pass B: column (cb_b, w_b)
-  const bool colv = tid < CB * p.W;
-  const int cb_b = tid / p.W, w_b = tid - cb_b * p.W;
+  const bool colv = tid < CB * W;
+  const int cb_b = tid / W, w_b = tid - cb_b * W;
   const int col_in = cb_b * HW + w_b;
   const int col_out = vt_base(colv ? cb_b : 0, HW, g.Q) + w_b * g.Hop;
   // pass C: lane -> (channel, q), warp -> (channel group, ho block, segment)
@@ -344,41 +371,84 @@ region_pool_fast_kernel(const PoolParams p, const FastGeom g) {
   const int row_in = vt_base(cb_c < CB ? cb_c : 0, HW, g.Q) + ho_c;
   const float inv_area = 1.f / 49.f;
   const int eparts = min(kEParts, max(1, NT / HW));
+  // rows of P this thread writes: window (ho_c, wo) of image b, channel c0 + cb_c
+  const size_t prow = (static_cast<size_t>(b) * nwin + ho_c * Wo) * p.ldp + cb_c;
+  const ptrdiff_t lo_delta = p.P_lo - p.P_hi;     // same offsets into both planes
 
-  int cv;
   auto block_src = [&](int blk, int& cvalid) -> const float* {
     const int c0 = blk * CB;
     cvalid = min(CB, p.C - c0);
     return xb + static_cast<size_t>(c0) * HW;
   };
-  auto can_bulk = [&](const float* src, int n) -> bool {
-    return ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((n & 3) == 0);
-  };
-  const float* src = block_src(blk0, cv);
-  bool bulk_cur = can_bulk(src, cv * HW);
-  stage_planes(X0, src, cv * HW, &bars[0], bulk_cur);
-  uint32_t ph0 = 0u, ph1 = 0u;
+  // Bulk copies need 16-byte aligned, 16-byte sized ranges.  Every block of this CTA starts a
+  // whole number of CB-plane blocks after the first, so one test covers them all; otherwise
+  // (odd H*W with an unlucky channel count) the CTA takes the plain-load path, unpipelined.
+  int cv_last;
+  block_src(blk1 - 1, cv_last);
+  const bool bulk_all = ((reinterpret_cast<uintptr_t>(xb + static_cast<size_t>(blk0) * plane_floats) & 15) == 0) &&
+                        ((plane_floats & 3) == 0) && (((cv_last * HW) & 3) == 0);
+  const int nloc = blk1 - blk0;
+  if (bulk_all) {
+    // prologue: NST - 1 blocks in flight before the first wait
+    for (int j = 0; j < NST - 1 && j < nloc; ++j) {
+      int cvn;
+      const float* nsrc = block_src(blk0 + j, cvn);
+      stage_planes(X0 + static_cast<size_t>(j) * plane_floats, nsrc, cvn * HW, &bars[j], true);
+    }
+  }
 
-  for (int blk = blk0; blk < blk1; ++blk) {
-    const int s = (blk - blk0) & 1;
-    float* X = s ? X1 : X0;
+  int s = 0;            // ring slot of the block being consumed
+  uint32_t par = 0u;    // its mbarrier phase parity
+  for (int it = 0; it < nloc; ++it) {
+    const int blk = blk0 + it;
+    float* X = X0 + static_cast<size_t>(s) * plane_floats;
     const int c0 = blk * CB;
     const int cvalid = min(CB, p.C - c0);
-    bool bulk_next = false;
-    if (blk + 1 < blk1) {
-      int cvn;
-      const float* nsrc = block_src(blk + 1, cvn);
-      bulk_next = can_bulk(nsrc, cvn * HW);
-      if (bulk_next) stage_planes(s ? X0 : X1, nsrc, cvn * HW, &bars[s ^ 1], true);
-    }
-    if (bulk_cur) {
-      ptx::mbar_wait(&bars[s], s ? ph1 : ph0);
-      if (s) ph1 ^= 1u; else ph0 ^= 1u;
+    if (bulk_all) {
+      // refill the buffer the previous iteration finished with (every thread passed its last
+      // __syncthreads), NST - 1 blocks ahead of the one consumed now
+      const int ahead = it + NST - 1;
+      if (ahead < nloc) {
+        int cvn;
+        const float* nsrc = block_src(blk0 + ahead, cvn);
+        const int sn = (s == 0) ? NST - 1 : s - 1;
+        stage_planes(X0 + static_cast<size_t>(sn) * plane_floats, nsrc, cvn * HW, &bars[sn], true);
+      }
+      ptx::mbar_wait(&bars[s], par);
     } else {
+      int cvn;
+      const float* nsrc = block_src(blk, cvn);
+      stage_planes(X, nsrc, cvn * HW, &bars[s], false);
       __syncthreads();
     }
     // ---- A: per-pixel energy
-    {
+    if (quadA) {
+      if (partA < eparts4) {
+        const int cb_per = (cvalid + eparts4 - 1) / eparts4;
+        const int cb_lo = partA * cb_per, cb_hi = min(cvalid, cb_lo + cb_per);
+        const float4* xp = reinterpret_cast<const float4*>(X) + qA;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kStatic && cvalid == CB && eparts4 == kEParts) {
+          constexpr int kPer = kStatic ? (CBC + kEParts - 1) / kEParts : 1;   // eparts4 == kEParts for the static shapes
+#pragma unroll
+          for (int j = 0; j < kPer; ++j) {
+            const float4 v = xp[(cb_lo + j) * HW4];
+            a.x = fmaf(v.x, v.x, a.x); a.y = fmaf(v.y, v.y, a.y);
+            a.z = fmaf(v.z, v.z, a.z); a.w = fmaf(v.w, v.w, a.w);
+          }
+        } else {
+          for (int cb = cb_lo; cb < cb_hi; ++cb) {
+            const float4 v = xp[cb * HW4];
+            a.x = fmaf(v.x, v.x, a.x); a.y = fmaf(v.y, v.y, a.y);
+            a.z = fmaf(v.z, v.z, a.z); a.w = fmaf(v.w, v.w, a.w);
+          }
+        }
+        float4* ep = reinterpret_cast<float4*>(E) + partA * HW4 + qA;
+        float4 e = *ep;
+        e.x += a.x; e.y += a.y; e.z += a.z; e.w += a.w;
+        *ep = e;
+      }
+    } else {
       const int cb_per = (cvalid + eparts - 1) / eparts;
       for (int i = tid; i < eparts * HW; i += NT) {
         const int part = i / HW, px = i - part * HW;
@@ -401,13 +471,13 @@ region_pool_fast_kernel(const PoolParams p, const FastGeom g) {
       const float* col = X + col_in;
       float r[7];
 #pragma unroll
-      for (int j = 0; j < 7; ++j) r[j] = col[j * p.W];
+      for (int j = 0; j < 7; ++j) r[j] = col[j * W];
       float sum = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + r[6]);
       o[0] = sum;
 #pragma unroll
       for (int ho = 1; ho < HMAX - FH + 1; ++ho) {
         if (ho < Ho) {
-          const float nv = col[(ho + FH - 1) * p.W];
+          const float nv = col[(ho + FH - 1) * W];
           sum += nv - r[(ho - 1) % 7];      // row ho - 1 leaves the window, row ho + 6 enters
           r[(ho - 1) % 7] = nv;
           o[ho] = sum;
@@ -423,49 +493,63 @@ region_pool_fast_kernel(const PoolParams p, const FastGeom g) {
     __syncthreads();
     // ---- C: horizontal sliding sums -> mean -> bf16 hi / lo -> global
     if (rowv && cb_c < cvalid) {
-      const float* r = X + row_in;
+      const float* r = X + row_in + wo0 * g.Hop;
       const int pitch = g.Hop;
-      uint16_t* ohi = p.P_hi + (static_cast<size_t>(b) * nwin + ho_c * Wo) * p.ldp + c0 + cb_c;
-      uint16_t* olo = p.P_lo + (static_cast<size_t>(b) * nwin + ho_c * Wo) * p.ldp + c0 + cb_c;
+      uint16_t* ohi = p.P_hi + prow + c0 + static_cast<size_t>(wo0) * p.ldp;
       float q[7];
 #pragma unroll
-      for (int j = 0; j < 7; ++j) q[j] = r[(wo0 + j) * pitch];
+      for (int j = 0; j < 7; ++j) q[j] = r[j * pitch];
       float sum = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + q[6]);
       {
         const float mean = sum * inv_area;
         const uint16_t hi = cvt_bf16(mean);
-        ohi[static_cast<size_t>(wo0) * p.ldp] = hi;
-        olo[static_cast<size_t>(wo0) * p.ldp] = cvt_bf16(mean - __uint_as_float(static_cast<uint32_t>(hi) << 16));
+        ohi[0] = hi;
+        ohi[lo_delta] = cvt_bf16(mean - __uint_as_float(static_cast<uint32_t>(hi) << 16));
       }
-      for (int base = wo0 + 1; base < wo1; base += 7) {
+      if (kStatic) {
+        // segw is a compile-time constant: fully unrolled, offsets are immediates
+        constexpr int kSegw = kStatic ? make_fast_geom(HC ? HC : 7, WC ? WC : 7, CBC ? CBC : 16, NT).segw : 1;
+        const int nout = wo1 - wo0;
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          const int wo = base + j;            // (wo - wo0 - 1) % 7 == j: slot j leaves, column wo + 6 enters
-          if (wo < wo1) {
-            const float nv = r[(wo + 6) * pitch];
-            sum += nv - q[j];
-            q[j] = nv;
+        for (int d = 1; d < kSegw; ++d) {
+          if (d < nout) {
+            const float nv = r[(d + 6) * pitch];
+            sum += nv - q[(d - 1) % 7];
+            q[(d - 1) % 7] = nv;
             const float mean = sum * inv_area;
             const uint16_t hi = cvt_bf16(mean);
-            ohi[static_cast<size_t>(wo) * p.ldp] = hi;
-            olo[static_cast<size_t>(wo) * p.ldp] = cvt_bf16(mean - __uint_as_float(static_cast<uint32_t>(hi) << 16));
+            uint16_t* o2 = ohi + static_cast<size_t>(d) * p.ldp;
+            o2[0] = hi;
+            o2[lo_delta] = cvt_bf16(mean - __uint_as_float(static_cast<uint32_t>(hi) << 16));
+          }
+        }
+      } else {
+        for (int base = wo0 + 1; base < wo1; base += 7) {
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {
+            const int wo = base + j;            // (wo - wo0 - 1) % 7 == j: slot j leaves, column wo + 6 enters
+            if (wo < wo1) {
+              const float nv = r[(wo - wo0 + 6) * pitch];
+              sum += nv - q[j];
+              q[j] = nv;
+              const float mean = sum * inv_area;
+              const uint16_t hi = cvt_bf16(mean);
+              uint16_t* o2 = ohi + static_cast<size_t>(wo - wo0) * p.ldp;
+              o2[0] = hi;
+              o2[lo_delta] = cvt_bf16(mean - __uint_as_float(static_cast<uint32_t>(hi) << 16));
+            }
           }
         }
       }
     }
-    if (blk + 1 < blk1 && !bulk_next) {
-      __syncthreads();
-      int cvn;
-      const float* nsrc = block_src(blk + 1, cvn);
-      stage_planes(s ? X0 : X1, nsrc, cvn * HW, &bars[s ^ 1], false);
-    }
-    bulk_cur = bulk_next;
     __syncthreads();
+    if (++s == NST) { s = 0; par ^= 1u; }
   }
   float* eo = p.e_part + (static_cast<size_t>(b) * p.ngroups + grp) * HW;
+  const int epsum = quadA ? eparts4 : eparts;
   for (int px = tid; px < HW; px += NT) {
     float t = 0.f;
-    for (int part = 0; part < eparts; ++part) t += E[part * HW + px];
+    for (int part = 0; part < epsum; ++part) t += E[part * HW + px];
     eo[px] = t;
   }
 }
@@ -1149,55 +1233,165 @@ region_select_exact_kernel(const float* __restrict__ x, int C, int H, int W, int
 
 
 // ------------------------------------------------------------------ 5. gather
-// One CTA = one image x CBg channels.  Only the rows [r0, r1) of each plane that the
-// image's selected windows touch are staged in shared memory (one bulk copy per
-// plane when aligned); every thread then produces two consecutive elements of
+// One CTA = one image x GG blocks of CBg channels.  Only the rows [r0, r1) of each plane that
+// the image's selected windows touch are staged in shared memory (bulk copies when aligned:
+// one per block when the windows span the whole map, else one per plane), through a ring of
+// NST buffers filled NST - 1 blocks ahead of the arithmetic -- the per-image set-up (window
+// offsets, norms) is paid once per CTA and the loads of the next blocks are in flight while
+// the current one is reduced.  Every thread then produces two consecutive elements of
 //   u[e] = sum_i x[b, c, h_i + dy, w_i + dx] / norm_i + nsel * shift[e],  e = (c, dy, dx)
-// -- the CBg * fh * fw outputs of a CTA are one contiguous run of the operand row.
+// -- the CBg * fh * fw outputs of a block are one contiguous run of the operand row.
 constexpr int kGatherThreads = 256;
+constexpr int kGatherMaxStages = 6;
+constexpr int kGatherDefaultStages = 3;
+constexpr int kGatherDefaultG = 4;      // channel blocks per CTA
+
+constexpr int kGatherRegWin = 8;
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// The outputs [e_begin, e_end) of one staged channel block.  A warp takes 64 consecutive
+// outputs per pass, lane l the elements base + l and base + 32 + l: consecutive lanes read
+// consecutive pixels of a window row (at most 2-way bank conflicts) and store 64 contiguous
+// bytes per instruction.  NW >= 0: the number of summed windows as a compile-time constant --
+// one address add, one ld.shared and one FMA per window, offsets and reciprocal norms in
+// registers, explicit 32-bit shared addresses (the generic-pointer form cost ten instructions
+// per window: ncu source view, profiles/r01_ncu_gather_*).  NW < 0: any count, out of smem.
+template <int NW>
+__device__ __forceinline__ void gather_block(const float* X, int c0, int pl, int W, int area, int fw, int Kin,
+                                             int e_begin, int e_end, const uint32_t (&r_off4)[kGatherRegWin],
+                                             const float (&r_norm)[kGatherRegWin], const int* s_off,
+                                             const float* s_norm, int nsel, float fn,
+                                             const float* __restrict__ shift, uint16_t* uh, uint16_t* ul) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t xs = ptx::smem_u32(X);
+  for (int base = e_begin + warp * 64 + lane; base < e_end; base += 2 * kGatherThreads) {
+    float u[2], sh[2];
+    uint32_t a[2];
+    bool live[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int ee = base + 32 * t;
+      live[t] = ee < Kin && ee < e_end;      // beyond: zero padding, or the next block's element (not stored)
+      const int el = live[t] ? ee : e_begin;
+      sh[t] = __ldg(shift + el);             // issued ahead of the shared-memory loads
+      const int c = el / area, r = el - c * area;
+      const int dy = r / fw, dx = r - dy * fw;
+      a[t] = xs + static_cast<uint32_t>((c - c0) * pl + dy * W + dx) * 4u;
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      float acc = 0.f;
+      if (NW >= 0) {
+#pragma unroll
+        for (int i = 0; i < (NW > 0 ? NW : 0); ++i) acc = fmaf(lds_f32(a[t] + r_off4[i]), r_norm[i], acc);
+      } else {
+        for (int i = 0; i < nsel; ++i) acc = fmaf(lds_f32(a[t] + static_cast<uint32_t>(s_off[i]) * 4u), s_norm[i], acc);
+      }
+      u[t] = live[t] ? fmaf(fn, sh[t], acc) : 0.f;
+    }
+    // bf16 hi / lo of both values: one packed convert each (round to nearest even)
+    uint32_t hi2, lo2;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(u[1]), "f"(u[0]));
+    const float r0f = u[0] - __uint_as_float(hi2 << 16);
+    const float r1f = u[1] - __uint_as_float(hi2 & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(r1f), "f"(r0f));
+    uh[base] = static_cast<uint16_t>(hi2 & 0xFFFFu);
+    if (ul != nullptr) ul[base] = static_cast<uint16_t>(lo2 & 0xFFFFu);
+    if (base + 32 < e_end) {
+      uh[base + 32] = static_cast<uint16_t>(hi2 >> 16);
+      if (ul != nullptr) ul[base + 32] = static_cast<uint16_t>(lo2 >> 16);
+    }
+  }
+}
 
 template <int FHW>   // FHW = 7: 7 x 7 window with compile-time index arithmetic; 0: generic
 __global__ void __launch_bounds__(kGatherThreads)
 region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, int fw_, int k, int k_sum,
-                     int CBg, int row_align, const int* __restrict__ image_list,
+                     int CBg, int GG, int NST, int row_align, const int* __restrict__ image_list,
                      const int* __restrict__ n_list, const int64_t* __restrict__ idx,
                      const int* __restrict__ nsel_in,
                      const float* __restrict__ win_norm, const float* __restrict__ shift,
                      uint16_t* __restrict__ U_hi, uint16_t* __restrict__ U_lo, int64_t ldu,
                      float* __restrict__ win_mean) {
   extern __shared__ __align__(128) uint8_t gat_smem_raw[];
-  float* X = reinterpret_cast<float*>(gat_smem_raw);
+  float* X0 = reinterpret_cast<float*>(gat_smem_raw);
   __shared__ int s_off[kSelMaxCand];
   __shared__ float s_norm[kSelMaxCand];
   __shared__ int s_r0, s_r1;
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bars[kGatherMaxStages];
   const int fh = FHW ? FHW : fh_, fw = FHW ? FHW : fw_;
   // optional image list (fix-up pass): grid.y covers the whole batch, rows beyond *n_list exit
   if (image_list != nullptr && static_cast<int>(blockIdx.y) >= *n_list) return;
   const int b = (image_list != nullptr) ? image_list[blockIdx.y] : blockIdx.y;
-  const int c0 = blockIdx.x * CBg, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const int Wo = W - fw + 1, HW = H * W, area = fh * fw;
-  const int cvalid = min(CBg, C - c0);
+  const int nblk = (C + CBg - 1) / CBg;
+  const int blk0 = blockIdx.x * GG;
+  const int nloc = min(GG, nblk - blk0);
   const int nall = nsel_in[b];                 // windows listed for this image (means are taken of all)
   const int nsel = min(nall, k_sum);           // leading windows summed into the operand
-  if (tid == 0) {
+  // window rows of this image: every lane of warp 0 reads one index, the range is a warp reduction
+  if (tid < 32) {
     int r0 = H, r1 = 0;
-    for (int i = 0; i < nall; ++i) {
+    for (int i = tid; i < nall; i += 32) {
       const int win = static_cast<int>(idx[static_cast<size_t>(b) * k + i]);
       const int h = win / Wo;
       r0 = min(r0, h);
       r1 = max(r1, h + fh);
     }
-    if (nall == 0) { r0 = 0; r1 = 0; }
-    r0 = (r0 / row_align) * row_align;                       // keep every plane's range 16-byte aligned
-    r1 = min(H, ((r1 + row_align - 1) / row_align) * row_align);
-    s_r0 = r0; s_r1 = r1;
-    ptx::mbar_init(&bar, 1);
-    ptx::fence_barrier_init();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      r0 = min(r0, __shfl_xor_sync(0xffffffffu, r0, o));
+      r1 = max(r1, __shfl_xor_sync(0xffffffffu, r1, o));
+    }
+    if (tid == 0) {
+      if (nall == 0) { r0 = 0; r1 = 0; }
+      r0 = (r0 / row_align) * row_align;                       // keep every plane's range 16-byte aligned
+      r1 = min(H, ((r1 + row_align - 1) / row_align) * row_align);
+      s_r0 = r0; s_r1 = r1;
+      for (int s = 0; s < NST; ++s) ptx::mbar_init(&bars[s], 1);
+      ptx::fence_barrier_init();
+    }
   }
   __syncthreads();
   const int r0 = s_r0, nrows = s_r1 - s_r0;
   const int pl = nrows * W;                                  // floats staged per plane
+  const size_t stage_floats = static_cast<size_t>(CBg) * HW;
+  const float* xsrc = x + static_cast<size_t>(b) * C * HW + r0 * W;    // + channel * HW
+  const bool bulk = ((reinterpret_cast<uintptr_t>(xsrc + static_cast<size_t>(blk0) * CBg * HW) & 15) == 0) &&
+                    ((HW & 3) == 0) && ((pl & 3) == 0) && pl > 0;
+  // warp 0 issues the copies of local block j into ring slot j % NST
+  auto issue = [&](int j) {
+    if (tid < 32) {
+      const int c0 = (blk0 + j) * CBg;
+      const int cvalid = min(CBg, C - c0);
+      float* dst = X0 + static_cast<size_t>(j % NST) * stage_floats;
+      uint64_t* bar = &bars[j % NST];
+      const float* src0 = xsrc + static_cast<size_t>(c0) * HW;
+      const uint32_t total = static_cast<uint32_t>(cvalid) * pl * 4u;
+      if (tid == 0) {
+        ptx::fence_proxy_async();   // the slot's previous contents were read through the generic proxy
+        ptx::mbar_arrive_expect_tx(bar, total);
+      }
+      __syncwarp();
+      if (pl == HW) {
+        // whole planes: the channel block is ONE contiguous range -> a few large copies
+        for (uint32_t off = tid * 8192u; off < total; off += 32u * 8192u)
+          ptx::bulk_load_1d(reinterpret_cast<uint8_t*>(dst) + off, reinterpret_cast<const uint8_t*>(src0) + off,
+                            min(8192u, total - off), bar);
+      } else {
+        for (int cb = tid; cb < cvalid; cb += 32)
+          ptx::bulk_load_1d(dst + cb * pl, src0 + static_cast<size_t>(cb) * HW, static_cast<uint32_t>(pl) * 4u, bar);
+      }
+    }
+  };
+  if (bulk)
+    for (int j = 0; j < NST - 1 && j < nloc; ++j) issue(j);
   if (tid < nall) {
     const int win = static_cast<int>(idx[static_cast<size_t>(b) * k + tid]);
     const int h = win / Wo, w = win - h * Wo;
@@ -1206,89 +1400,69 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, 
     // reference's division (model/custom_modules.py:56) changes nothing that survives that rounding
     s_norm[tid] = 1.f / win_norm[static_cast<size_t>(b) * k + tid];
   }
-  const float* src0 = x + (static_cast<size_t>(b) * C + c0) * HW + r0 * W;
-  const bool bulk = ((reinterpret_cast<uintptr_t>(src0) & 15) == 0) && ((HW & 3) == 0) && ((pl & 3) == 0) && pl > 0;
-  if (bulk) {
-    if (tid < 32) {
-      const uint32_t total = static_cast<uint32_t>(cvalid) * pl * 4u;
-      if (tid == 0) ptx::mbar_arrive_expect_tx(&bar, total);
-      __syncwarp();
-      if (pl == HW) {
-        // whole planes: the channel block is ONE contiguous range -> a few large copies
-        for (uint32_t off = tid * 8192u; off < total; off += 32u * 8192u)
-          ptx::bulk_load_1d(reinterpret_cast<uint8_t*>(X) + off, reinterpret_cast<const uint8_t*>(src0) + off,
-                            min(8192u, total - off), &bar);
-      } else {
-        for (int cb = tid; cb < cvalid; cb += 32)
-          ptx::bulk_load_1d(X + cb * pl, src0 + static_cast<size_t>(cb) * HW, static_cast<uint32_t>(pl) * 4u, &bar);
-      }
-    }
-    ptx::mbar_wait(&bar, 0);
-  } else {
-    for (int i = tid; i < cvalid * pl; i += kGatherThreads) {
-      const int cb = i / pl, o = i - cb * pl;
-      X[i] = __ldg(src0 + static_cast<size_t>(cb) * HW + o);
-    }
-  }
   __syncthreads();
-  // by-product: the exact fp32 mean of every selected window (row-major sum, then / area --
-  // AvgPool2d's own arithmetic, model/siamese.py:187), input of isb_region_logits
-  if (win_mean != nullptr) {
-    const float farea = static_cast<float>(area);
-    // lanes: 8 consecutive channels (their planes are pl floats apart: 8 distinct banks when
-    // pl % 32 == 4, as at 14 x 14) x 4 windows, instead of 32 channels (4-way conflicts)
-    const int cgroups8 = (cvalid + 7) >> 3;
-    for (int it = tid; it < cgroups8 * 8 * nall; it += kGatherThreads) {
-      const int cb = ((it / (8 * nall)) << 3) | (it & 7), i = (it >> 3) % nall;
-      if (cb >= cvalid) continue;
-      const float* pw = X + cb * pl + s_off[i];
-      float sum = 0.f;
-      for (int dy = 0; dy < fh; ++dy)
-        for (int dx = 0; dx < fw; ++dx) sum += pw[dy * W + dx];
-      win_mean[(static_cast<size_t>(b) * k + i) * C + c0 + cb] = sum / farea;
-    }
-  }
   const int Kin = C * area;
   const int KinP = (Kin + 7) & ~7;
   const float fn = static_cast<float>(nsel);
-  const int e_begin = c0 * area;
-  // the last CTA of an image also writes the zero padding [Kin, KinP)
-  const int e_end = (c0 + cvalid >= C) ? KinP : (c0 + cvalid) * area;
   uint16_t* uh = U_hi + static_cast<size_t>(b) * ldu;
   uint16_t* ul = (U_lo != nullptr) ? U_lo + static_cast<size_t>(b) * ldu : nullptr;
   // the (at most kGatherRegWin) summed windows live in registers; more fall back to smem
-  constexpr int kGatherRegWin = 8;
-  int r_off[kGatherRegWin];
+  uint32_t r_off4[kGatherRegWin];   // byte offsets of the summed windows inside a staged plane
   float r_norm[kGatherRegWin];
 #pragma unroll
   for (int i = 0; i < kGatherRegWin; ++i) {
-    r_off[i] = (i < nsel) ? s_off[i] : 0;
+    r_off4[i] = (i < nsel) ? static_cast<uint32_t>(s_off[i]) * 4u : 0u;
     r_norm[i] = (i < nsel) ? s_norm[i] : 0.f;
   }
-  for (int e = e_begin + 2 * tid; e < e_end; e += 2 * kGatherThreads) {   // e_begin is even (CBg % 2 == 0)
-    uint16_t hi[2], lo[2];
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int ee = e + t;
-      float u = 0.f;
-      if (ee < Kin) {
-        const int c = ee / area, r = ee - c * area;
-        const int dy = r / fw, dx = r - dy * fw;
-        const float* plane = X + (c - c0) * pl + dy * W + dx;
-        if (nsel <= kGatherRegWin) {
-#pragma unroll
-          for (int i = 0; i < kGatherRegWin; ++i)
-            if (i < nsel) u = fmaf(plane[r_off[i]], r_norm[i], u);   // block-uniform predicate
-        } else {
-          for (int i = 0; i < nsel; ++i) u = fmaf(plane[s_off[i]], s_norm[i], u);
-        }
-        u += fn * __ldg(shift + ee);
+
+  for (int it = 0; it < nloc; ++it) {
+    const int c0 = (blk0 + it) * CBg;
+    const int cvalid = min(CBg, C - c0);
+    float* X = X0 + static_cast<size_t>(it % NST) * stage_floats;
+    if (bulk) {
+      if (it + NST - 1 < nloc) issue(it + NST - 1);   // into the slot iteration it - 1 has released
+      ptx::mbar_wait(&bars[it % NST], static_cast<uint32_t>((it / NST) & 1));
+    } else {
+      const float* src0 = xsrc + static_cast<size_t>(c0) * HW;
+      for (int i = tid; i < cvalid * pl; i += kGatherThreads) {
+        const int cb = i / pl, o = i - cb * pl;
+        X[i] = __ldg(src0 + static_cast<size_t>(cb) * HW + o);
       }
-      hi[t] = bf16_rn(u);
-      lo[t] = bf16_rn(u - bf16_f(hi[t]));
+      __syncthreads();
     }
-    *reinterpret_cast<uint32_t*>(uh + e) = hi[0] | (static_cast<uint32_t>(hi[1]) << 16);
-    if (ul != nullptr) *reinterpret_cast<uint32_t*>(ul + e) = lo[0] | (static_cast<uint32_t>(lo[1]) << 16);
+    // by-product: the exact fp32 mean of every selected window (row-major sum, then / area --
+    // AvgPool2d's own arithmetic, model/siamese.py:187), input of isb_region_logits
+    if (win_mean != nullptr) {
+      const float farea = static_cast<float>(area);
+      // lanes: 8 consecutive channels (their planes are pl floats apart: 8 distinct banks when
+      // pl % 32 == 4, as at 14 x 14) x 4 windows, instead of 32 channels (4-way conflicts)
+      const int cgroups8 = (cvalid + 7) >> 3;
+      for (int t = tid; t < cgroups8 * 8 * nall; t += kGatherThreads) {
+        const int cb = ((t / (8 * nall)) << 3) | (t & 7), i = (t >> 3) % nall;
+        if (cb >= cvalid) continue;
+        const float* pw = X + cb * pl + s_off[i];
+        float sum = 0.f;
+        for (int dy = 0; dy < fh; ++dy)
+          for (int dx = 0; dx < fw; ++dx) sum += pw[dy * W + dx];
+        win_mean[(static_cast<size_t>(b) * k + i) * C + c0 + cb] = sum / farea;
+      }
+    }
+    const int e_begin = c0 * area;
+    // the last block of an image also writes the zero padding [Kin, KinP)
+    const int e_end = (c0 + cvalid >= C) ? KinP : (c0 + cvalid) * area;
+    switch (nsel <= kGatherRegWin ? nsel : -1) {
+      case 0: gather_block<0>(X, c0, pl, W, area, fw, Kin, e_begin, e_end, r_off4, r_norm, s_off, s_norm, nsel, fn, shift, uh, ul); break;
+      case 1: gather_block<1>(X, c0, pl, W, area, fw, Kin, e_begin, e_end, r_off4, r_norm, s_off, s_norm, nsel, fn, shift, uh, ul); break;
+      case 2: gather_block<2>(X, c0, pl, W, area, fw, Kin, e_begin, e_end, r_off4, r_norm, s_off, s_norm, nsel, fn, shift, uh, ul); break;
+      case 3: gather_block<3>(X, c0, pl, W, area, fw, Kin, e_begin, e_end, r_off4, r_norm, s_off, s_norm, nsel, fn, shift, uh, ul); break;
+      case 4: gather_block<4>(X, c0, pl, W, area, fw, Kin, e_begin, e_end, r_off4, r_norm, s_off, s_norm, nsel, fn, shift, uh, ul); break;
+      case 5: gather_block<5>(X, c0, pl, W, area, fw, Kin, e_begin, e_end, r_off4, r_norm, s_off, s_norm, nsel, fn, shift, uh, ul); break;
+      case 6: gather_block<6>(X, c0, pl, W, area, fw, Kin, e_begin, e_end, r_off4, r_norm, s_off, s_norm, nsel, fn, shift, uh, ul); break;
+      case 7: gather_block<7>(X, c0, pl, W, area, fw, Kin, e_begin, e_end, r_off4, r_norm, s_off, s_norm, nsel, fn, shift, uh, ul); break;
+      case 8: gather_block<8>(X, c0, pl, W, area, fw, Kin, e_begin, e_end, r_off4, r_norm, s_off, s_norm, nsel, fn, shift, uh, ul); break;
+      default: gather_block<-1>(X, c0, pl, W, area, fw, Kin, e_begin, e_end, r_off4, r_norm, s_off, s_norm, nsel, fn, shift, uh, ul); break;
+    }
+    __syncthreads();   // slot it % NST is free for the copy issued at the top of iteration it + 1
   }
 }
 
@@ -1527,6 +1701,7 @@ struct RegionPlan {
   size_t off_Phi, off_Plo, off_epart, off_screen, off_cand, off_cscreen, off_Ahi, off_Alo, off_logits, total;
   size_t pool_smem, cand_smem;
   int fast_threads;   // block size of region_pool_fast_kernel
+  int stages;     // plane buffers of the fast pooling kernel's prefetch ring
   bool tc;        // tensor-core pooling (region_pool_tc_kernel)
   int eplanes;    // energy partial planes per (image, channel group): 1, or the converter lanes of the tc kernel
   TcGeom tcg;
@@ -1544,27 +1719,34 @@ static bool make_region_plan(RegionPlan& p, int64_t B, int C, int H, int W, int 
   const int HW = H * W;
   p.CB = 0;
   p.fast = false;
+  p.stages = 2;
   if (fh == 7 && fw == 7 && H <= 32 && W <= 32 && C % 2 == 0) {
     // fast path: needs CB * W <= 1024 threads for the column pass, CB >= 16 (32-byte
     // sectors on the stores), the skewed transposed planes to fit in place, and enough
     // warps for the row pass
     const int Hop = p.Ho | 1;
     p.fast_threads = (H <= 16 && W <= 16) ? kFastThreadsSmall : kFastThreads;
+    // prefetch ring: as many plane buffers (<= want) as leave room for 4 CTAs per SM on small
+    // maps (their passes overlap) / fit one SM on large ones
+    const char* st_env = getenv("ISB_POOL_STAGES");
+    int want = st_env ? atoi(st_env) : kPoolDefaultStages;
+    if (want < 2) want = 2;
+    if (want > kPoolMaxStages) want = kPoolMaxStages;
+    const size_t budget = (p.fast_threads == kFastThreadsSmall) ? 55 * 1024 : 224 * 1024;
     for (int cb : {64, 32, 16}) {
-      const size_t smem = static_cast<size_t>(2) * cb * HW * 4 + static_cast<size_t>(kEParts) * HW * 4 + 64;
-      if (cb * W > p.fast_threads || smem > 200 * 1024 || 31 + W * Hop > HW) continue;
-      const int Q = 32 / (cb < 32 ? cb : 32);
-      const int cgroups = (cb + (32 / Q) - 1) / (32 / Q);
-      const int hoblks = (p.Ho + Q - 1) / Q;
-      const int warps_per_seg = cgroups * hoblks;
-      if (warps_per_seg > p.fast_threads / 32) continue;
-      int nseg = (p.fast_threads / 32) / warps_per_seg;
-      if (nseg > (p.Wo + 1) / 2) nseg = (p.Wo + 1) / 2;
-      if (nseg < 1) nseg = 1;
+      const size_t fixed = static_cast<size_t>(kEParts) * HW * 4 + 64;
+      const size_t stage = static_cast<size_t>(cb) * HW * 4;
+      int nst = want;
+      while (nst > 2 && nst * stage + fixed > budget) --nst;
+      const size_t smem = nst * stage + fixed;
+      if (cb * W > p.fast_threads || smem > 224 * 1024 || 31 + W * Hop > HW) continue;
+      const FastGeom fg = make_fast_geom(H, W, cb, p.fast_threads);
+      if (fg.nseg < 1) continue;
+      p.stages = nst;
+      p.geom = fg;
+      p.pool_smem = smem;
       p.CB = cb;
       p.fast = true;
-      p.geom.Hop = Hop; p.geom.Q = Q; p.geom.nseg = nseg; p.geom.segw = (p.Wo + nseg - 1) / nseg;
-      p.pool_smem = smem;
       break;
     }
   }
@@ -1692,7 +1874,7 @@ extern "C" int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H
   // 1. window means (bf16 hi / lo, window-major) + per-pixel energy partials
   PoolParams pp;
   pp.x = x; pp.C = (int)C; pp.H = (int)H; pp.W = (int)W; pp.fh = fh; pp.fw = fw;
-  pp.CB = p.CB; pp.G = p.G; pp.nblk = p.nblk; pp.ngroups = p.ngroups;
+  pp.CB = p.CB; pp.G = p.G; pp.stages = p.stages; pp.nblk = p.nblk; pp.ngroups = p.ngroups;
   pp.P_hi = P_hi; pp.P_lo = P_lo; pp.ldp = (int)p.ldp; pp.e_part = e_part;
   dim3 pgrid(p.ngroups, static_cast<unsigned>(B));
   ISB_CHECK_ARG(p.nwin <= kMaxWinPerThread * kPoolThreads, "isb_region_select: too many windows per image (%d)", p.nwin);
@@ -1705,15 +1887,17 @@ extern "C" int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H
     set_error("isb_region_select: x must be 16-byte aligned for maps of this size");
     return ISB_ERR_INVALID_ARGUMENT;
   } else if (p.fast) {
-    if (p.fast_threads == kFastThreadsSmall) {
-      auto kern = region_pool_fast_kernel<16, kFastThreadsSmall, 4>;
-      ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
-      kern<<<pgrid, kFastThreadsSmall, p.pool_smem, st>>>(pp, p.geom);
-    } else {
-      auto kern = region_pool_fast_kernel<32, kFastThreads, 1>;
-      ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
-      kern<<<pgrid, kFastThreads, p.pool_smem, st>>>(pp, p.geom);
-    }
+    // compile-time geometry for the reference's two map sizes, launch-parameter geometry otherwise
+    void (*kern)(const PoolParams, const FastGeom);
+    if (H == 14 && W == 14 && p.CB == 16) kern = region_pool_fast_kernel<16, kFastThreadsSmall, 4, 14, 14, 16>;
+    else if (H == 32 && W == 32 && p.CB == 16) kern = region_pool_fast_kernel<32, kFastThreads, 1, 32, 32, 16>;
+    else if (p.fast_threads == kFastThreadsSmall) kern = region_pool_fast_kernel<16, kFastThreadsSmall, 4, 0, 0, 0>;
+    else kern = region_pool_fast_kernel<32, kFastThreads, 1, 0, 0, 0>;
+    if (getenv("ISB_POOL_GENERIC_GEOM") != nullptr)   // A/B switch: same kernel without the folded constants
+      kern = (p.fast_threads == kFastThreadsSmall) ? region_pool_fast_kernel<16, kFastThreadsSmall, 4, 0, 0, 0>
+                                                   : region_pool_fast_kernel<32, kFastThreads, 1, 0, 0, 0>;
+    ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
+    kern<<<pgrid, p.fast_threads, p.pool_smem, st>>>(pp, p.geom);
   } else if (fh == 7 && fw == 7) {
     ISB_CUDA(cudaFuncSetAttribute(region_pool_generic_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
     region_pool_generic_kernel<7><<<pgrid, kPoolThreads, p.pool_smem, st>>>(pp);
@@ -1788,31 +1972,49 @@ extern "C" int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H
                 (reinterpret_cast<uintptr_t>(U_lo) & 15) == 0, "isb_region_gather: bad ldu / alignment");
   const int64_t HW = H * W;
   int CBg = 0;
-  // <= 28 KB of planes per CTA when that still leaves >= 16 channels: more CTAs per SM, so that
-  // the load phase of one overlaps the arithmetic of the others (a CTA is load -> wait -> compute
-  // -> store, nothing pipelined inside); larger maps take what fits in 96 KB
+  // ring slots of <= 28 KB when that still leaves >= 16 channels (several CTAs per SM on top of
+  // the ring inside each); larger maps take what fits in 64 KB
   for (int cb : {64, 32, 16}) {
     if (static_cast<size_t>(cb) * HW * 4 <= 28 * 1024) { CBg = cb; break; }
   }
   if (CBg == 0) {
     for (int cb : {64, 32, 16, 8, 4, 2}) {
-      if (static_cast<size_t>(cb) * HW * 4 <= 96 * 1024) { CBg = cb; break; }
+      if (static_cast<size_t>(cb) * HW * 4 <= 64 * 1024) { CBg = cb; break; }
     }
+  }
+  if (const char* e = getenv("ISB_GATHER_CB")) {
+    const int cb = atoi(e);
+    if (cb >= 2 && cb % 2 == 0 && static_cast<size_t>(cb) * HW * 4 <= 96 * 1024) CBg = cb;
   }
   ISB_CHECK_ARG(CBg > 0, "isb_region_gather: feature map too large (H*W=%lld)", (long long)HW);
   const int row_align = (W % 4 == 0) ? 1 : ((W % 2 == 0) ? 2 : 4);
-  const size_t smem = static_cast<size_t>(CBg) * HW * 4;
-  dim3 grid(static_cast<unsigned>((C + CBg - 1) / CBg), static_cast<unsigned>(B));
+  const size_t stage = static_cast<size_t>(CBg) * HW * 4;
+  const int nblk_g = static_cast<int>((C + CBg - 1) / CBg);
+  // blocks per CTA: the ring needs a few blocks to run ahead of; keep >= 8 waves of CTAs
+  int GG = kGatherDefaultG;
+  if (const char* e = getenv("ISB_GATHER_G")) GG = atoi(e);
+  if (GG < 1) GG = 1;
+  while (GG > 1 && B * ((nblk_g + GG - 1) / GG) < 148 * 8) GG >>= 1;
+  if (GG > nblk_g) GG = nblk_g;
+  int NST = kGatherDefaultStages;
+  if (const char* e = getenv("ISB_GATHER_STAGES")) NST = atoi(e);
+  if (NST < 1) NST = 1;
+  if (NST > kGatherMaxStages) NST = kGatherMaxStages;
+  if (NST > GG + 1) NST = GG + 1;                  // no point in more slots than blocks + 1
+  while (NST > 2 && NST * stage > 200 * 1024) --NST;
+  if (NST * stage > 200 * 1024) NST = 1;           // a single 96 KB+ slot: no ring (ISB_GATHER_CB only)
+  const size_t smem = NST * stage;
+  dim3 grid(static_cast<unsigned>((nblk_g + GG - 1) / GG), static_cast<unsigned>(B));
   if (fh == 7 && fw == 7) {
     if (smem > 48 * 1024)
       ISB_CUDA(cudaFuncSetAttribute(region_gather_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     region_gather_kernel<7><<<grid, kGatherThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        x, (int)C, (int)H, (int)W, fh, fw, k, k_sum, CBg, row_align, image_list, n_list, idx, nsel, win_norm, shift, U_hi, U_lo, ldu, win_mean);
+        x, (int)C, (int)H, (int)W, fh, fw, k, k_sum, CBg, GG, NST, row_align, image_list, n_list, idx, nsel, win_norm, shift, U_hi, U_lo, ldu, win_mean);
   } else {
     if (smem > 48 * 1024)
       ISB_CUDA(cudaFuncSetAttribute(region_gather_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     region_gather_kernel<0><<<grid, kGatherThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        x, (int)C, (int)H, (int)W, fh, fw, k, k_sum, CBg, row_align, image_list, n_list, idx, nsel, win_norm, shift, U_hi, U_lo, ldu, win_mean);
+        x, (int)C, (int)H, (int)W, fh, fw, k, k_sum, CBg, GG, NST, row_align, image_list, n_list, idx, nsel, win_norm, shift, U_hi, U_lo, ldu, win_mean);
   }
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;

@@ -25,6 +25,8 @@ ap.add_argument("--terms", type=int, default=3)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--cls-out", type=int, default=0, help="1: also produce cls_out (training); 0: eval, class-max only")
+ap.add_argument("--variants", default="", help="';'-separated tuning variants, each 'ENV=val,ENV=val' (ISB_POOL_STAGES, "
+                "ISB_GATHER_CB / _G / _STAGES); one JSON line per variant and map size")
 a = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -49,9 +51,16 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 
-for hw_size in [int(s) for s in a.sizes.split(",")]:
+TUNABLES = ("ISB_POOL_STAGES", "ISB_GATHER_CB", "ISB_GATHER_G", "ISB_GATHER_STAGES")
+variants = [v for v in a.variants.split(";")] if a.variants else [""]
+for hw_size, variant in [(int(s), v) for s in a.sizes.split(",") for v in variants]:
     H = W = hw_size
-    x = torch.relu(torch.randn(a.B, a.C, H, W, device=dev, generator=g))
+    for name in (TUNABLES if a.variants else ()):
+        os.environ.pop(name, None)
+    for kv in [t for t in variant.split(",") if t]:
+        name, val = kv.split("=")
+        os.environ[name] = val            # read by libisb's launch plans at every call
+    x = torch.relu(torch.randn(a.B, a.C, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(77 + hw_size)))
     stages = {"select": [], "gather": [], "logits_fixup": [], "project": [], "total": []}
     changed_total = 0
     uncert = 0
@@ -92,6 +101,7 @@ for hw_size in [int(s) for s in a.sizes.split(",")]:
     print(json.dumps({
         "workload": "region descriptors, B=%d C=%d %dx%d map, ncls=%d, D=%d, k=%d, terms=%d, cls_out=%d" %
                     (a.B, a.C, H, W, a.ncls, a.D, a.k, a.terms, a.cls_out),
+        "variant": variant,
         "ms": med, "uncertified_images": uncert, "regathered_images": changed_total, "region_desc_per_s": units / (med["total"] * 1e-3),
         "images_per_s": a.B / (med["total"] * 1e-3),
         "pool_select_gather": {"algorithmic_bytes": bw_bytes, "ms": bw_ms,
