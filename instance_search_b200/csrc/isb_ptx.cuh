@@ -70,12 +70,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // of this library finishes in well under one.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  // try_wait itself suspends the thread for a while; the clock is read only every 256 failed
+  // polls so that a waiting warp costs the working ones as few issue slots as possible
+  uint32_t polls = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("isb: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
-             (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
-      __trap();
+    if ((++polls & 255u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > 4000000000LL) {
+        printf("isb: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+               (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }

@@ -1243,14 +1243,20 @@ region_select_exact_kernel(const float* __restrict__ x, int C, int H, int W, int
 // -- the CBg * fh * fw outputs of a block are one contiguous run of the operand row.
 constexpr int kGatherThreads = 256;
 constexpr int kGatherMaxStages = 6;
-constexpr int kGatherDefaultStages = 3;
-constexpr int kGatherDefaultG = 4;      // channel blocks per CTA
+constexpr int kGatherDefaultStages = 2;
+constexpr int kGatherDefaultG = 2;      // channel blocks per CTA on maps of <= 256 pixels, twice that beyond
 
 constexpr int kGatherRegWin = 8;
 
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float lds_f32_off(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
   return v;
 }
 
@@ -1421,7 +1427,10 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, 
     float* X = X0 + static_cast<size_t>(it % NST) * stage_floats;
     if (bulk) {
       if (it + NST - 1 < nloc) issue(it + NST - 1);   // into the slot iteration it - 1 has released
-      ptx::mbar_wait(&bars[it % NST], static_cast<uint32_t>((it / NST) & 1));
+      // one warp polls the mbarrier, the others sleep in the CTA barrier (eight polling warps
+      // took 18 % of the issue slots: ncu source view)
+      if (tid < 32) ptx::mbar_wait(&bars[it % NST], static_cast<uint32_t>((it / NST) & 1));
+      __syncthreads();
     } else {
       const float* src0 = xsrc + static_cast<size_t>(c0) * HW;
       for (int i = tid; i < cvalid * pl; i += kGatherThreads) {
@@ -1437,13 +1446,26 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, 
       // lanes: 8 consecutive channels (their planes are pl floats apart: 8 distinct banks when
       // pl % 32 == 4, as at 14 x 14) x 4 windows, instead of 32 channels (4-way conflicts)
       const int cgroups8 = (cvalid + 7) >> 3;
+      const uint32_t xs = ptx::smem_u32(X);
       for (int t = tid; t < cgroups8 * 8 * nall; t += kGatherThreads) {
         const int cb = ((t / (8 * nall)) << 3) | (t & 7), i = (t >> 3) % nall;
         if (cb >= cvalid) continue;
-        const float* pw = X + cb * pl + s_off[i];
         float sum = 0.f;
-        for (int dy = 0; dy < fh; ++dy)
-          for (int dx = 0; dx < fw; ++dx) sum += pw[dy * W + dx];
+        if (FHW == 7) {
+          // explicit shared addresses, the seven taps of a row as immediates
+          uint32_t ra = xs + static_cast<uint32_t>(cb * pl + s_off[i]) * 4u;
+#pragma unroll
+          for (int dy = 0; dy < 7; ++dy) {
+            sum += lds_f32_off<0>(ra);  sum += lds_f32_off<4>(ra);  sum += lds_f32_off<8>(ra);
+            sum += lds_f32_off<12>(ra); sum += lds_f32_off<16>(ra); sum += lds_f32_off<20>(ra);
+            sum += lds_f32_off<24>(ra);
+            ra += static_cast<uint32_t>(W) * 4u;
+          }
+        } else {
+          const float* pw = X + cb * pl + s_off[i];
+          for (int dy = 0; dy < fh; ++dy)
+            for (int dx = 0; dx < fw; ++dx) sum += pw[dy * W + dx];
+        }
         win_mean[(static_cast<size_t>(b) * k + i) * C + c0 + cb] = sum / farea;
       }
     }
@@ -1972,14 +1994,14 @@ extern "C" int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H
                 (reinterpret_cast<uintptr_t>(U_lo) & 15) == 0, "isb_region_gather: bad ldu / alignment");
   const int64_t HW = H * W;
   int CBg = 0;
-  // ring slots of <= 28 KB when that still leaves >= 16 channels (several CTAs per SM on top of
-  // the ring inside each); larger maps take what fits in 64 KB
-  for (int cb : {64, 32, 16}) {
-    if (static_cast<size_t>(cb) * HW * 4 <= 28 * 1024) { CBg = cb; break; }
+  // ring slots of <= 32 KB: several CTAs per SM on top of the short ring inside each (measured:
+  // 14 x 14 -> 32 channels, 32 x 32 -> 8 channels per slot)
+  for (int cb : {64, 32, 16, 8, 4, 2}) {
+    if (static_cast<size_t>(cb) * HW * 4 <= 32 * 1024) { CBg = cb; break; }
   }
   if (CBg == 0) {
-    for (int cb : {64, 32, 16, 8, 4, 2}) {
-      if (static_cast<size_t>(cb) * HW * 4 <= 64 * 1024) { CBg = cb; break; }
+    for (int cb : {8, 4, 2}) {
+      if (static_cast<size_t>(cb) * HW * 4 <= 96 * 1024) { CBg = cb; break; }
     }
   }
   if (const char* e = getenv("ISB_GATHER_CB")) {
@@ -1991,7 +2013,7 @@ extern "C" int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H
   const size_t stage = static_cast<size_t>(CBg) * HW * 4;
   const int nblk_g = static_cast<int>((C + CBg - 1) / CBg);
   // blocks per CTA: the ring needs a few blocks to run ahead of; keep >= 8 waves of CTAs
-  int GG = kGatherDefaultG;
+  int GG = (HW <= 256) ? kGatherDefaultG : 2 * kGatherDefaultG;
   if (const char* e = getenv("ISB_GATHER_G")) GG = atoi(e);
   if (GG < 1) GG = 1;
   while (GG > 1 && B * ((nblk_g + GG - 1) / GG) < 148 * 8) GG >>= 1;

@@ -5,6 +5,7 @@
 // replaces  sim = torch.mm(Q, DB.t())  (test/siamese_regions_test.py:76,
 // utils/train_siamese.py:70) + the descending sort / max / kthvalue that consume
 // it (utils/metrics.py:11,13,33) of the reference.
+#include <cstdlib>
 #include "isb_host.cuh"
 #include "isb_topk.cuh"
 
@@ -1544,6 +1545,8 @@ static MiningPlan make_mining_plan(int64_t P, int64_t N, int64_t D, int split) {
   return m;
 }
 
+constexpr int kMiningCand = 32;   // candidates re-checked exactly per couple (<= kMaxCand)
+
 extern "C" size_t isb_select_negatives_workspace_bytes(int64_t P, int64_t N, int64_t D, int split) {
   if (P <= 0 || N <= 0 || D <= 0) return 0;
   return make_mining_plan(P, N, D, split).total + 1024;
@@ -1590,7 +1593,15 @@ extern "C" int isb_select_negatives(const float* emb, const uint16_t* emb_hi, co
   ISB_CUDA(cudaMemcpyAsync(pos_sim, pos32, static_cast<size_t>(P) * 4, cudaMemcpyDeviceToDevice, st));
   if (n_bruteforce != nullptr) ISB_CUDA(cudaMemsetAsync(n_bruteforce, 0, 4, st));
 
-  int kc = kMaxCand;
+  // One negative per couple is wanted: a short candidate list is enough -- the certificate
+  // (worst candidate's screen score + screen_eps < the exact winner) sends the rows it is not
+  // enough for to the brute-force pass.  The exact re-check gathers kc rows of D floats per
+  // couple: 128 candidates were 17 GB of random 8 KB reads at the 16k x 2048 configuration.
+  int kc = kMiningCand;
+  if (const char* e = getenv("ISB_MINING_KC")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= kMaxCand) kc = v;
+  }
   if (kc > N) kc = static_cast<int>(N);
   // semi-hard: columns scoring >= sim_pos (+ the screen's error bound) are masked in the epilogue
   rc = launch_topk_screen(a_hi, a_lo, ld, P, emb_hi, emb_lo, ld, N, D, kc, mp.sp, ws, label, row_label,

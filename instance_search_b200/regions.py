@@ -171,24 +171,41 @@ def region_head(x, hw, k, fsize, margin=WINDOW_MARGIN, want_cls_out=True):
     return U_hi, U_lo, idx, nsel, cls_out, n1 + n2
 
 
+def region_descriptors_async(x, hw, k, fsize, margin=WINDOW_MARGIN, want_cls_out=True):
+    """The certified fast path with nothing read back: (desc, cls_out, idx, nsel,
+    n_uncertified [1] device int32).  The caller checks n_uncertified whenever it likes
+    (e.g. after queueing the next batch) and, if it is non-zero, replaces the result with
+    region_descriptors_exact(x, ...)."""
+    U_hi, U_lo, idx, nsel, cls_out, n_unc = region_head(x, hw, k, fsize, margin, want_cls_out)
+    desc = region_project(U_hi, U_lo, hw, nsel)
+    return desc, cls_out, idx, nsel, n_unc
+
+
+def region_descriptors_exact(x, hw, k, fsize):
+    """The fp64-exact second line (candidates = 32 windows, everything re-scored from the
+    fp32 inputs): what a batch with an uncertified image is redone with."""
+    idx, nsel, cls_out, win_norm, _, _, _ = region_select(x, hw, k, fsize, exact_mode=True)
+    U_hi, U_lo, _ = region_gather(x, hw, k, fsize, idx, nsel, win_norm, want_means=False)
+    return region_project(U_hi, U_lo, hw, nsel), cls_out, idx, nsel
+
+
 def region_descriptors(x, hw, k, fsize, margin=WINDOW_MARGIN, exact=True, stats=None, want_cls_out=True):
     """x [B, C, H, W] trunk feature maps -> (desc [B, D], cls_out [B, ncls, k],
     idx [B, k], nsel [B]).  reference: model/siamese.py:187-223 per image.
 
     exact=True: the certificates of the fast path (screen completeness, selection
-    against the unscored runner-ups) are read back (ONE 4-byte D2H read); a batch with
-    an uncertified image is redone with the fp64-exact second line.  exact=False skips
-    the read-back (no host sync)."""
-    U_hi, U_lo, idx, nsel, cls_out, n_unc = region_head(x, hw, k, fsize, margin, want_cls_out)
+    against the unscored runner-ups) are read back (ONE 4-byte D2H read, issued after
+    the projection has been queued so the GPU does not idle during the round trip); a
+    batch with an uncertified image is redone with the fp64-exact second line.
+    exact=False skips the read-back (no host sync)."""
+    desc, cls_out, idx, nsel, n_unc = region_descriptors_async(x, hw, k, fsize, margin, want_cls_out)
     if exact:
         n_bad = int(n_unc.item())
         if stats is not None:
             stats["batches"] = stats.get("batches", 0) + 1
             stats["batches_resolved_exactly"] = stats.get("batches_resolved_exactly", 0) + (1 if n_bad else 0)
         if n_bad:
-            idx, nsel, cls_out, win_norm, _, _, _ = region_select(x, hw, k, fsize, exact_mode=True)
-            U_hi, U_lo, _ = region_gather(x, hw, k, fsize, idx, nsel, win_norm, want_means=False)
-    desc = region_project(U_hi, U_lo, hw, nsel)
+            desc, cls_out, idx, nsel = region_descriptors_exact(x, hw, k, fsize)
     return desc, cls_out, idx, nsel
 
 

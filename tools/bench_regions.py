@@ -88,6 +88,21 @@ for hw_size, variant in [(int(s), v) for s in a.sizes.split(",") for v in varian
             uncert += int((n1 + n2).item())
             changed_total += int(n_changed.item())
     med = {n: sorted(v)[len(v) // 2] for n, v in stages.items()}
+    # streamed: 8 batches back to back over two alternating inputs, certificates read at the end
+    x2 = torch.relu(torch.randn(a.B, a.C, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(78 + hw_size)))
+    st = []
+    for it in range(2 + 5):
+        e0, e1 = ev(), ev()
+        torch.cuda.synchronize()
+        e0.record()
+        flags = [regions.region_descriptors_async((x, x2)[i & 1], hw, a.k, (7, 7), want_cls_out=not not a.cls_out)[4]
+                 for i in range(8)]
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            st.append(e0.elapsed_time(e1) / 8)
+    med["streamed_per_batch"] = sorted(st)[len(st) // 2]
+    del x2
     nwin = (H - 6) * (W - 6)
     kk = min(nwin, a.k)
     units = a.B * kk                                  # region descriptors per batch (SURVEY 8d unit)
