@@ -429,7 +429,7 @@ def side_regions(dev, pk):
             pending.clear()
             for i in range(nstream):
                 pending.append(regions.region_descriptors_async((x, x2)[i & 1], hw, k, (7, 7),
-                                                                want_cls_out=False)[4])
+                                                                want_cls_out=False)[4][:, 0])
         ms_stream = _median_ms(stream, iters=5, warmup=2) / nstream
         n_unc_stream = int(torch.stack(pending).sum().item())
         del x2
@@ -444,7 +444,8 @@ def side_regions(dev, pk):
             "projection_ms": ms - ms_head,
             "streamed": {"ms_per_batch": ms_stream, "region_descriptors_per_s": units / (ms_stream * 1e-3),
                          "batches_in_flight": nstream, "uncertified_images_last_pass": n_unc_stream},
-            "batches_resolved_exactly": stats.get("batches_resolved_exactly", 0), "batches": stats.get("batches", 0)}
+            "batches_resolved_exactly": stats.get("batches_resolved_exactly", 0),
+            "images_resolved_exactly": stats.get("images_resolved_exactly", 0), "batches": stats.get("batches", 0)}
         del x
     return {"workload": "region descriptors (eval), 256 x 2048 x HxW fp32 maps, ncls=464, k=6, D=2048 "
                         "(BASELINE configs[1]); L2 flushed between batches", **out}

@@ -35,7 +35,7 @@ extern "C" {
 #define ISB_ERR_WORKSPACE 3
 #define ISB_ERR_UNSUPPORTED_DEVICE 4
 
-#define ISB_ABI_VERSION 3
+#define ISB_ABI_VERSION 4
 
 /* Largest k (after the screening margin is added) one search call supports. */
 #define ISB_MAX_CANDIDATES 128
@@ -214,9 +214,10 @@ int isb_gemm_nt_split(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda, c
  * tcgen05 products, ~1e-6) and the final order / logits come from that pass.
  * Completeness certificate as for the search: every non-candidate window has a
  * screen value <= t_min; an image whose k-th exact class-max does not clear t_min
- * by 8 sigma (sigma = rms(screen - exact) over its candidates) is counted in
- * *n_uncertified (device int32, may be NULL); the caller re-runs such a batch
- * with a larger margin (margin = 32 - k scores up to 32 windows exactly).
+ * by 8 sigma (sigma = rms(screen - exact) over its candidates) is reported in
+ * n_uncertified (device int32 [1 + B], may be NULL): [0] = how many images, [1 + j] =
+ * the j-th of them (order unspecified); the caller re-runs those images with the
+ * exact second line (exact_mode, margin = 32 - k scores up to 32 windows exactly).
  * The logits of this pass are fp32-GRADE, not fp32: cls_out here is a preview
  * (abs. error ~1e-5 x logit scale); isb_region_logits recomputes the selected
  * windows' logits in true fp32, fixes their order and closes the certificate.
@@ -251,7 +252,8 @@ int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H, int64_t W
  * re-gathered (isb_region_gather with image_list).  Certificate: the k-th exact
  * class-max must clear runner_up[b] -- the best fp32-grade value among the windows
  * NOT scored here -- by 8 sigma, sigma = rms(approx_max - exact) over the ke windows;
- * failures are counted in *n_uncertified (NULL: no certificate).
+ * failures are reported in n_uncertified [1 + B] (count, then the images; NULL: no
+ * certificate).
  * cls_out == NULL (eval: the reference's forward returns only the descriptor,
  * model/siamese.py:231): only the class-max is needed, so only the classes whose
  * fp32-grade logit (approx_cls [B, ncls, ke] = isb_region_select's cls_out) lies

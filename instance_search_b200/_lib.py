@@ -16,7 +16,7 @@ c_f32 = ctypes.c_float
 c_ptr = ctypes.c_void_p
 c_size = ctypes.c_size_t
 
-ABI_VERSION = 3   # == ISB_ABI_VERSION in include/isb.h
+ABI_VERSION = 4   # == ISB_ABI_VERSION in include/isb.h
 
 # name -> (restype, argtypes); mirrors include/isb.h one to one
 SIGNATURES = {

@@ -77,6 +77,8 @@ struct StoreEpilogue {
 // concurrently share a B tile; then the k-split, then the n-tile.
 struct PlainSched {
   int m_blocks, n_tiles, k_blocks, splits;
+  __device__ __forceinline__ void gate(const Segment&, int, int, int) const {}
+  __device__ __forceinline__ void leave(const Segment&) const {}
   __device__ __forceinline__ int num_segments() const { return m_blocks * n_tiles * splits; }
   __device__ __forceinline__ Segment segment(int s) const {
     Segment seg;

@@ -108,12 +108,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int s = blockIdx.x; s < num_segments; s += gridDim.x) {
-        const Segment seg = sched.segment(s);
-        for (int nt = seg.nt_begin; nt < seg.nt_end; ++nt) {
+    // (lane 0 issues; the whole warp takes part in the scheduler's gate)
+    int stage = 0;
+    uint32_t phase = 0;
+    int wave = 0;
+    for (int s = blockIdx.x; s < num_segments; s += gridDim.x, ++wave) {
+      const Segment seg = sched.segment(s);
+      for (int nt = seg.nt_begin; nt < seg.nt_end; ++nt) {
+        sched.gate(seg, nt, wave, gridDim.x);
+        if (lane == 0) {
           for (int kb = seg.kb_begin; kb < seg.kb_end; ++kb) {
             ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* sa = ring + stage * kStageBytes;
@@ -131,7 +134,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
+        __syncwarp();
       }
+      if (lane == 0) sched.leave(seg);
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
@@ -195,6 +200,191 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ CTA-pair variant
+// Same roles, one tile of 256 x 256 per CTA PAIR (cluster of 2 = the two SMs of a TPC):
+//   * each CTA loads ITS 128 rows of A and ITS half (128 rows) of the B tile -- 32 KB per
+//     stage instead of 48 KB, so the ring is 6 deep, and the tensor core reads every B row
+//     from shared memory once per 256 accumulator rows instead of once per 128 (the single-CTA
+//     kernel moves 192 B/clk through shared memory, TMA writes + operand reads, against a
+//     128 B/clk port: 74 % tensor-pipe utilisation, profiles/r01_ncu_search_screen_1M_v2.txt)
+//   * the leader (cluster rank 0) issues tcgen05.mma.cta_group::2 with M = 256; both CTAs'
+//     TMA loads complete on the LEADER's full barrier (cp.async.bulk.tensor.cta_group::2),
+//     the leader's commits are multicast to both CTAs' empty / tmem_full barriers
+//   * every CTA's epilogue warps drain their own 128 TMEM lanes (rows 128 * rank + lane of
+//     the pair tile); the peer's warp 1, which has no MMAs to issue, relays "my accumulator
+//     is drained" to the leader (one remote arrive per tile), so the Epilogue policies are the
+//     single-CTA ones unchanged.
+// The scheduler enumerates segments in units of PAIR row blocks: seg.m_block counts 256-row
+// blocks; CTA `rank` works on the 128-row block 2 * seg.m_block + rank.
+constexpr int kPairStages = 6;
+constexpr int kPairBRows = kBN / 2;                                       // B rows loaded per CTA
+constexpr uint32_t kPairBBytes = kPairBRows * kBK * 2;                    // 16 KB
+constexpr uint32_t kPairStageBytes = kABytes + kPairBBytes;               // 32 KB
+constexpr uint32_t kPairRingBytes = kPairStages * kPairStageBytes;        // 192 KB
+constexpr uint32_t kPairSmemBytes = kPairRingBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct PairSmem {
+  uint64_t full[kPairStages];    // leader's: TMA bytes of BOTH CTAs for the stage have landed
+  uint64_t empty[kPairStages];   // each CTA's: the MMAs reading the stage retired (multicast commit)
+  uint64_t tmem_full[2];         // each CTA's: accumulator complete (multicast commit)
+  uint64_t tmem_empty[2];        // each CTA's: its 128 epilogue threads drained the accumulator
+  uint64_t peer_empty[2];        // leader's: the peer drained ITS accumulator (relayed)
+  uint32_t tmem_base;
+};
+
+template <class Sched, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_a_lo,
+                    const __grid_constant__ CUtensorMap tmap_b_lo, const int kb_per_term,
+                    const Sched sched, const typename Epi::Params ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  PairSmem* bars = reinterpret_cast<PairSmem*>(ring + kPairRingBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_b);
+    if (kb_per_term != kSingleTerm) {
+      ptx::prefetch_tensormap(&tmap_a_lo);
+      ptx::prefetch_tensormap(&tmap_b_lo);
+    }
+    for (int s = 0; s < kPairStages; ++s) {
+      ptx::mbar_init(&bars->full[s], 1);
+      ptx::mbar_init(&bars->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&bars->tmem_full[b], 1);
+      ptx::mbar_init(&bars->tmem_empty[b], 128);
+      ptx::mbar_init(&bars->peer_empty[b], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc_pair<kTmemCols>(&bars->tmem_base);
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();   // both CTAs' barriers are initialised before any remote signal
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  const int num_segments = sched.num_segments();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    // (lane 0 issues; the leader's whole warp takes part in the scheduler's gate, the peer
+    // follows through the shared empty barriers)
+    int stage = 0;
+    uint32_t phase = 0;
+    int wave = 0;
+    for (int s = pair_id; s < num_segments; s += n_pairs, ++wave) {
+      const Segment seg = sched.segment(s);
+      const int my_m_block = 2 * seg.m_block + static_cast<int>(rank);
+      for (int nt = seg.nt_begin; nt < seg.nt_end; ++nt) {
+        if (leader) sched.gate(seg, nt, wave, n_pairs);
+        if (lane == 0) {
+          for (int kb = seg.kb_begin; kb < seg.kb_end; ++kb) {
+            ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+            uint8_t* sa = ring + stage * kPairStageBytes;
+            uint8_t* sb = sa + kABytes;
+            if (leader) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * kPairStageBytes);
+            const uint32_t full_leader = ptx::mapa_u32(ptx::smem_u32(&bars->full[stage]), 0);
+            const int term = kb / kb_per_term;          // 0 unless split operands
+            const int kk = kb - term * kb_per_term;
+            const CUtensorMap* ma = (term == 1) ? &tmap_a_lo : &tmap_a;
+            const CUtensorMap* mb = (term == 2) ? &tmap_b_lo : &tmap_b;
+            ptx::tma_load_2d_pair(sa, ma, full_leader, kk * kBK, my_m_block * kBM, ptx::kEvictLast);
+            ptx::tma_load_2d_pair(sb, mb, full_leader, kk * kBK, nt * kBN + static_cast<int>(rank) * kPairBRows,
+                                  ptx::kEvictNormal);
+            if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        __syncwarp();
+      }
+      if (leader && lane == 0) sched.leave(seg);
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ------------------------------------------------------------ MMA issuer (leader)
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(2 * kBM, kBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t acc_iter = 0;
+      for (int s = pair_id; s < num_segments; s += n_pairs) {
+        const Segment seg = sched.segment(s);
+        for (int nt = seg.nt_begin; nt < seg.nt_end; ++nt, ++acc_iter) {
+          const uint32_t buf = acc_iter & 1;
+          const uint32_t acc_phase = (acc_iter >> 1) & 1;
+          ptx::mbar_wait(&bars->tmem_empty[buf], acc_phase ^ 1);
+          ptx::mbar_wait(&bars->peer_empty[buf], acc_phase ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t tmem_acc = tmem_base + buf * kBN;
+          for (int kb = seg.kb_begin; kb < seg.kb_end; ++kb) {
+            ptx::mbar_wait(&bars->full[stage], phase);
+            ptx::tc_fence_after();
+            const uint32_t sa = ptx::smem_u32(ring + stage * kPairStageBytes);
+            const uint64_t da = ptx::make_smem_desc_k_sw128(sa);
+            const uint64_t db = ptx::make_smem_desc_k_sw128(sa + kABytes);
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              ptx::umma_bf16_pair(tmem_acc, da + 2 * k, db + 2 * k, idesc,
+                                  (kb > seg.kb_begin || k > 0) ? 1u : 0u);
+            }
+            ptx::umma_commit_pair(&bars->empty[stage], 3);   // both CTAs' slots are free
+            if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+          }
+          ptx::umma_commit_pair(&bars->tmem_full[buf], 3);   // both CTAs' accumulators complete
+        }
+      }
+    } else if (lane == 0) {
+      // ------------------------------------------------------------ drain relay (peer)
+      uint32_t acc_iter = 0;
+      for (int s = pair_id; s < num_segments; s += n_pairs) {
+        const Segment seg = sched.segment(s);
+        for (int nt = seg.nt_begin; nt < seg.nt_end; ++nt, ++acc_iter) {
+          const uint32_t buf = acc_iter & 1;
+          const uint32_t acc_phase = (acc_iter >> 1) & 1;
+          ptx::mbar_wait(&bars->tmem_empty[buf], acc_phase);
+          ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&bars->peer_empty[buf]), 0));
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (both CTAs)
+    const int lane_group = warp & 3;
+    const int row_in_tile = lane_group * 32 + lane;
+    Epi epi(ep, row_in_tile);
+    uint32_t acc_iter = 0;
+    for (int s = pair_id; s < num_segments; s += n_pairs) {
+      Segment seg = sched.segment(s);
+      seg.m_block = 2 * seg.m_block + static_cast<int>(rank);
+      epi.begin_segment(seg);
+      for (int nt = seg.nt_begin; nt < seg.nt_end; ++nt, ++acc_iter) {
+        const uint32_t buf = acc_iter & 1;
+        const uint32_t acc_phase = (acc_iter >> 1) & 1;
+        ptx::mbar_wait(&bars->tmem_full[buf], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + buf * kBN + (static_cast<uint32_t>(lane_group * 32) << 16);
+        epi.tile(seg, nt, tmem_acc, &bars->tmem_empty[buf]);
+      }
+      epi.end_segment(seg);
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal it
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair<kTmemCols>(tmem_base);
   }
 }
 

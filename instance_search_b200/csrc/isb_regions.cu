@@ -899,6 +899,8 @@ struct RowMaxEpilogue {
 // one segment = one m-block x ALL n-tiles (the max runs over every class)
 struct RowSched {
   int m_blocks, n_tiles, k_blocks;
+  __device__ __forceinline__ void gate(const Segment&, int, int, int) const {}
+  __device__ __forceinline__ void leave(const Segment&) const {}
   __device__ __forceinline__ int num_segments() const { return m_blocks; }
   __device__ __forceinline__ Segment segment(int s) const {
     Segment seg;
@@ -1053,7 +1055,8 @@ region_finalize_select_kernel(const float* __restrict__ logits, int ldl, int ncl
       }
       const float sigma = sqrtf(s2 / static_cast<float>(ncand));
       const float kth = cand_max[order[nsel - 1]];
-      if (!(kth - t_min > 8.f * sigma + 4e-7f * fmaxf(fabsf(kth), fabsf(t_min)))) atomicAdd(n_uncertified, 1);
+      if (!(kth - t_min > 8.f * sigma + 4e-7f * fmaxf(fabsf(kth), fabsf(t_min))))
+        n_uncertified[1 + atomicAdd(n_uncertified, 1)] = b;   // count, then the list of images
     }
   }
   __syncthreads();
@@ -1200,7 +1203,8 @@ region_select_exact_kernel(const float* __restrict__ x, int C, int H, int W, int
       }
       const float sigma = sqrtf(s2 / static_cast<float>(ncand));
       const float kth = cand_max[order[nsel - 1]];
-      if (!(kth - t_min > 8.f * sigma + 4e-7f * fmaxf(fabsf(kth), fabsf(t_min)))) atomicAdd(n_uncertified, 1);
+      if (!(kth - t_min > 8.f * sigma + 4e-7f * fmaxf(fabsf(kth), fabsf(t_min))))
+        n_uncertified[1 + atomicAdd(n_uncertified, 1)] = b;   // count, then the list of images
     }
   }
   __syncthreads();
@@ -1669,7 +1673,7 @@ region_logits_kernel(const float* __restrict__ win_mean, const float* __restrict
       const float sigma = sqrtf(s2 / static_cast<float>(nall));
       const float kth = wmax[order[nsel - 1]];
       const float ru = runner_up[b];   // best fp32-grade class-max among the windows NOT scored here
-      if (!(kth - ru > 8.f * sigma + 4e-7f * fabsf(kth))) atomicAdd(n_uncertified, 1);
+      if (!(kth - ru > 8.f * sigma + 4e-7f * fabsf(kth))) n_uncertified[1 + atomicAdd(n_uncertified, 1)] = b;
     }
   }
   __syncthreads();

@@ -1091,8 +1091,9 @@ topk_merge_warp_kernel(const float* __restrict__ cs, const int64_t* __restrict__
 // ------------------------------------------------------------------ host side
 struct SearchPlan {
   int m_blocks, n_tiles, k_blocks, n_groups, grid;
+  bool pair;   // CTA-pair screen kernel (256 x 256 tiles): m-blocks are scheduled two at a time
   int64_t ldq;
-  size_t off_qbf16, off_cta_buf, off_gthr, off_pool, off_pool_cnt, total;
+  size_t off_qbf16, off_cta_buf, off_gthr, off_pool, off_pool_cnt, off_progress, total;
 };
 
 // Pick the number of n-groups so that m_blocks * n_groups segments fill whole
@@ -1117,7 +1118,14 @@ static int pick_n_groups(int m_blocks, int n_tiles, int grid) {
   return best;
 }
 
-static SearchPlan make_search_plan(int64_t Q, int64_t N, int64_t D, int terms = 1) {
+// ISB_SCREEN_PAIR=0 keeps the single-CTA 128 x 256 kernel (A/B switch; the workspace layout
+// follows the plan, so the variable must not change between the size query and the call)
+static bool screen_pair_enabled() {
+  const char* e = getenv("ISB_SCREEN_PAIR");
+  return e == nullptr || e[0] != '0';
+}
+
+static SearchPlan make_search_plan(int64_t Q, int64_t N, int64_t D, int terms = 1, bool allow_pair = true) {
   SearchPlan p;
   p.m_blocks = static_cast<int>((Q + kBM - 1) / kBM);
   p.n_tiles = static_cast<int>((N + kBN - 1) / kBN);
@@ -1125,14 +1133,24 @@ static SearchPlan make_search_plan(int64_t Q, int64_t N, int64_t D, int terms = 
   const int sms = device_sm_count();
   const long long tiles = static_cast<long long>(p.m_blocks) * p.n_tiles;
   p.grid = static_cast<int>(tiles < sms ? tiles : sms);
-  p.n_groups = pick_n_groups(p.m_blocks, p.n_tiles, p.grid);
+  // pairs pay off once the whole machine is busy with >= 2 row blocks per n-tile
+  const int pair_m = (p.m_blocks + 1) / 2;
+  p.pair = allow_pair && screen_pair_enabled() && p.m_blocks >= 2 &&
+           static_cast<long long>(pair_m) * p.n_tiles >= sms / 2 && sms >= 2;
+  if (p.pair) {
+    p.grid = (sms / 2) * 2;
+    p.n_groups = pick_n_groups(pair_m, p.n_tiles, p.grid / 2);
+  } else {
+    p.n_groups = pick_n_groups(p.m_blocks, p.n_tiles, p.grid);
+  }
   p.ldq = static_cast<int64_t>(align_up(static_cast<size_t>(D), 8));
   size_t off = 0;
   p.off_qbf16 = off;    off = align_up(off + static_cast<size_t>(Q) * p.ldq * 2 * (terms == 3 ? 2 : 1), 1024);
   p.off_cta_buf = off;  off = align_up(off + static_cast<size_t>(p.grid) * kBM * kCap * sizeof(uint2), 1024);
-  p.off_gthr = off;     off = align_up(off + static_cast<size_t>(p.m_blocks) * kBM * 4, 1024);
+  p.off_gthr = off;     off = align_up(off + static_cast<size_t>(p.m_blocks + 1) * kBM * 4, 1024);
   p.off_pool = off;     off = align_up(off + static_cast<size_t>(Q) * p.n_groups * kMaxCand * sizeof(uint2), 1024);
   p.off_pool_cnt = off; off = align_up(off + static_cast<size_t>(Q) * p.n_groups * 4, 1024);
+  p.off_progress = off; off = align_up(off + static_cast<size_t>(kMaxWaves) * 4, 1024);
   p.total = off;
   return p;
 }
@@ -1162,10 +1180,18 @@ int launch_topk_screen(const uint16_t* a_bf16, const uint16_t* a_lo, int64_t lda
   }
 
   uint32_t* gthr = reinterpret_cast<uint32_t*>(ws + plan.off_gthr);
-  const size_t n_thr = static_cast<size_t>(plan.m_blocks) * kBM;
+  const size_t n_thr = static_cast<size_t>(plan.m_blocks + 1) * kBM;
   fill_u32_kernel<<<static_cast<int>((n_thr + 255) / 256), 256, 0, st>>>(gthr, n_thr, kKeyNegInf);
 
-  TopkSched sched{plan.m_blocks, plan.n_tiles, plan.n_groups, plan.k_blocks};
+  // wave barrier of the scheduler: ISB_SCREEN_WAVESYNC=0 switches it off
+  int* progress = nullptr;
+  int window = 0;
+  const char* wsync = getenv("ISB_SCREEN_WAVESYNC");
+  if ((wsync == nullptr || wsync[0] != '0') && plan.grid >= device_sm_count() / 2) {
+    progress = reinterpret_cast<int*>(ws + plan.off_progress);
+    ISB_CUDA(cudaMemsetAsync(progress, 0, static_cast<size_t>(kMaxWaves) * 4, st));
+  }
+  TopkSched sched{plan.m_blocks, plan.n_tiles, plan.n_groups, plan.k_blocks, progress, window};
   TopkEpiParams ep;
   ep.Q = static_cast<int>(Q);
   ep.N = static_cast<int>(N);
@@ -1180,7 +1206,26 @@ int launch_topk_screen(const uint16_t* a_bf16, const uint16_t* a_lo, int64_t lda
   ep.row_ub = row_ub;
   ep.ub_slack = ub_slack;
 
-  if (col_label != nullptr) {
+  if (plan.pair) {
+    // pair kernel: every CTA loads its own half (128 rows) of a 256-row B tile
+    rc = make_tmap_bf16_k64(&tb, b_bf16, N, D, ldb, kPairBRows);
+    if (rc) return rc;
+    tb_lo = tb;
+    if (kb_per_term != kSingleTerm) {
+      rc = make_tmap_bf16_k64(&tb_lo, b_lo, N, D, ldb, kPairBRows);
+      if (rc) return rc;
+    }
+    sched.m_blocks = (plan.m_blocks + 1) / 2;   // 256-row blocks
+    if (col_label != nullptr) {
+      auto kern = gemm_tc_pair_kernel<TopkSched, TopkEpilogue<true>>;
+      ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+      kern<<<plan.grid, kGemmThreads, kPairSmemBytes, st>>>(ta, tb, ta_lo, tb_lo, kb_per_term, sched, ep);
+    } else {
+      auto kern = gemm_tc_pair_kernel<TopkSched, TopkEpilogue<false>>;
+      ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+      kern<<<plan.grid, kGemmThreads, kPairSmemBytes, st>>>(ta, tb, ta_lo, tb_lo, kb_per_term, sched, ep);
+    }
+  } else if (col_label != nullptr) {
     auto kern = gemm_tc_kernel<TopkSched, TopkEpilogue<true>>;
     ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     kern<<<plan.grid, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, ta_lo, tb_lo, kb_per_term, sched, ep);

@@ -20,6 +20,7 @@ namespace isb {
 constexpr int kCap = 512;        // private buffer entries per row
 constexpr int kTrig = 256;       // compact when a row holds more than this after a tile
 constexpr int kMaxCand = 128;    // == ISB_MAX_CANDIDATES
+constexpr int kMaxWaves = 1024;  // wave-barrier counters of the screen scheduler
 
 // order-preserving float <-> uint32 key (larger float <=> larger key)
 __host__ __device__ __forceinline__ uint32_t f2key(uint32_t bits) {
@@ -291,6 +292,14 @@ struct TopkEpilogue {
 // rest L2 hits) while the whole query matrix stays L2-resident.
 struct TopkSched {
   int m_blocks, n_tiles, n_groups, k_blocks;
+  // Wave barrier.  Segments are handed out round-robin, so the workers (CTAs or CTA pairs) go
+  // through them in waves; the row blocks of one n-group stream the same database tiles and
+  // share them through L2 only while they run in step.  Their start times drift apart from
+  // wave to wave (ncu: 84 GB of DRAM reads for a 4.1 GB database in the CTA-pair kernel), so
+  // every worker checks in at the start of each segment and waits -- for a bounded time, the
+  // barrier is advisory -- until the whole wave has arrived.  wave_sync[w] counts arrivals.
+  int* wave_sync;   // [kMaxWaves] zeroed before the launch; null: no barrier
+  int window;       // unused (0) unless the barrier is on
   __device__ __forceinline__ int num_segments() const { return m_blocks * n_groups; }
   __device__ __forceinline__ Segment segment(int s) const {
     Segment seg;
@@ -303,6 +312,20 @@ struct TopkSched {
     seg.aux = g;
     return seg;
   }
+  // called by ALL 32 lanes of the producer warp before n-tile nt of the segment is loaded;
+  // wave = how many segments this worker has finished, workers = CTAs (pairs) in the grid
+  __device__ __forceinline__ void gate(const Segment& seg, int nt, int wave, int workers) const {
+    if (wave_sync == nullptr || nt != seg.nt_begin || wave >= kMaxWaves) return;   // warp-uniform
+    if ((threadIdx.x & 31) == 0) {
+      const int total = num_segments();
+      const int expected = min(workers, total - wave * workers);
+      volatile int* cnt = wave_sync + wave;
+      atomicAdd(wave_sync + wave, 1);
+      for (int polls = 0; polls < 8192 && *cnt < expected; ++polls) __nanosleep(100);
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void leave(const Segment&) const {}
 };
 
 }  // namespace isb

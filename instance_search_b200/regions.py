@@ -12,6 +12,7 @@ from . import _lib, ops
 from ._lib import IsbError
 
 WINDOW_MARGIN = 10   # windows re-scored exactly beyond k (k + margin <= 32)
+LARGE_MAP_WINDOWS = 128   # maps with more windows than this always use the full 32 candidates
 
 
 class HeadWeights(object):
@@ -68,6 +69,9 @@ def region_select(x, hw, k, fsize, margin=WINDOW_MARGIN, exact_mode=False):
     B, C, H, W = x.shape
     fh, fw = fsize
     ncls = hw.cls_w.size(0)
+    nwin = (H - fh + 1) * (W - fw + 1)
+    if nwin > LARGE_MAP_WINDOWS:
+        margin = 32 - k   # dense maps: the screen's candidate list must reach further down
     margin = 32 - k if exact_mode else max(0, min(margin, 32 - k))
     dev = x.device
     idx = torch.empty((B, k), dtype=torch.int64, device=dev)
@@ -76,7 +80,7 @@ def region_select(x, hw, k, fsize, margin=WINDOW_MARGIN, exact_mode=False):
     win_norm = torch.empty((B, k), dtype=torch.float32, device=dev)
     approx_max = torch.empty((B, k), dtype=torch.float32, device=dev)
     runner_up = torch.empty((B,), dtype=torch.float32, device=dev)
-    n_unc = torch.zeros(1, dtype=torch.int32, device=dev)
+    n_unc = torch.zeros(1 + B, dtype=torch.int32, device=dev)   # count, then the uncertified images
     L = _lib.lib()
     nbytes = L.isb_region_select_workspace_bytes(B, C, H, W, ncls, fh, fw, k, margin)
     ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
@@ -131,7 +135,7 @@ def region_logits(win_mean, hw, k, nsel_in, idx_in, norm_in, approx_max, runner_
     cls_out = torch.empty((B, ncls, k), dtype=torch.float32, device=dev) if approx_cls is None else None
     changed = torch.empty((B,), dtype=torch.int32, device=dev)
     n_changed = torch.zeros(1, dtype=torch.int32, device=dev)
-    n_unc = torch.zeros(1, dtype=torch.int32, device=dev)
+    n_unc = torch.zeros(1 + B, dtype=torch.int32, device=dev)   # count, then the uncertified images
     _lib.check(_lib.lib().isb_region_logits(win_mean.data_ptr(), hw.cls_w.data_ptr(), hw.cls_b.data_ptr(), B, C,
                                             ncls, ke, k, nsel_in.data_ptr(), approx_max.data_ptr(),
                                             runner_up.data_ptr(), idx_in.data_ptr(), norm_in.data_ptr(),
@@ -155,8 +159,9 @@ def region_project(U_hi, U_lo, hw, nsel):
 
 def region_head(x, hw, k, fsize, margin=WINDOW_MARGIN, want_cls_out=True):
     """The certified fast path, all asynchronous: returns (U_hi, U_lo, idx, nsel, cls_out,
-    n_uncertified [1] device int32).  want_cls_out=False (eval): cls_out is None and only
-    the contending classes of every window are scored in fp32."""
+    n_uncertified [2, 1 + B] device int32: per certificate, the count and then the images it
+    rejected).  want_cls_out=False (eval): cls_out is None and only the contending classes of
+    every window are scored in fp32."""
     ke = min(32, k + RUNNER_UPS)
     # 1. screen all windows, fp32-grade scores of the candidates, the best ke of them
     idx_e, nsel_e, approx_cls, norm_e, approx_e, runner_up, n1 = region_select(x, hw, ke, fsize, margin)
@@ -168,25 +173,46 @@ def region_head(x, hw, k, fsize, margin=WINDOW_MARGIN, want_cls_out=True):
     # 4. fix-up: re-gather the (rare) images where a runner-up entered the top k
     region_gather(x, hw, k, fsize, idx, nsel, norm, want_means=False, out=(U_hi, U_lo), image_list=changed,
                   n_list=n_changed)
-    return U_hi, U_lo, idx, nsel, cls_out, n1 + n2
+    return U_hi, U_lo, idx, nsel, cls_out, torch.stack([n1, n2])
 
 
 def region_descriptors_async(x, hw, k, fsize, margin=WINDOW_MARGIN, want_cls_out=True):
     """The certified fast path with nothing read back: (desc, cls_out, idx, nsel,
-    n_uncertified [1] device int32).  The caller checks n_uncertified whenever it likes
-    (e.g. after queueing the next batch) and, if it is non-zero, replaces the result with
-    region_descriptors_exact(x, ...)."""
+    n_uncertified [2, 1 + B] device int32).  The caller checks n_uncertified[:, 0] whenever
+    it likes (e.g. after queueing the next batch) and, if it is non-zero, patches the
+    listed images with region_descriptors_fix."""
     U_hi, U_lo, idx, nsel, cls_out, n_unc = region_head(x, hw, k, fsize, margin, want_cls_out)
     desc = region_project(U_hi, U_lo, hw, nsel)
     return desc, cls_out, idx, nsel, n_unc
 
 
+def uncertified_images(n_unc):
+    """Sorted image indices listed by the certificates (host sync).  n_unc: [2, 1 + B]."""
+    host = n_unc.cpu()
+    bad = set()
+    for row in host:
+        bad.update(int(v) for v in row[1:1 + int(row[0])])
+    return sorted(bad)
+
+
 def region_descriptors_exact(x, hw, k, fsize):
     """The fp64-exact second line (candidates = 32 windows, everything re-scored from the
-    fp32 inputs): what a batch with an uncertified image is redone with."""
+    fp32 inputs): what uncertified images are redone with."""
     idx, nsel, cls_out, win_norm, _, _, _ = region_select(x, hw, k, fsize, exact_mode=True)
     U_hi, U_lo, _ = region_gather(x, hw, k, fsize, idx, nsel, win_norm, want_means=False)
     return region_project(U_hi, U_lo, hw, nsel), cls_out, idx, nsel
+
+
+def region_descriptors_fix(x, hw, k, fsize, bad, desc, cls_out, idx, nsel):
+    """Redo the images ``bad`` (list of batch indices) with the exact second line and patch
+    the fast path's outputs in place."""
+    sel = torch.tensor(bad, dtype=torch.int64, device=x.device)
+    d2, c2, i2, n2 = region_descriptors_exact(x.index_select(0, sel).contiguous(), hw, k, fsize)
+    desc.index_copy_(0, sel, d2)
+    idx.index_copy_(0, sel, i2)
+    nsel.index_copy_(0, sel, n2)
+    if cls_out is not None:
+        cls_out.index_copy_(0, sel, c2)
 
 
 def region_descriptors(x, hw, k, fsize, margin=WINDOW_MARGIN, exact=True, stats=None, want_cls_out=True):
@@ -194,18 +220,22 @@ def region_descriptors(x, hw, k, fsize, margin=WINDOW_MARGIN, exact=True, stats=
     idx [B, k], nsel [B]).  reference: model/siamese.py:187-223 per image.
 
     exact=True: the certificates of the fast path (screen completeness, selection
-    against the unscored runner-ups) are read back (ONE 4-byte D2H read, issued after
-    the projection has been queued so the GPU does not idle during the round trip); a
-    batch with an uncertified image is redone with the fp64-exact second line.
-    exact=False skips the read-back (no host sync)."""
+    against the unscored runner-ups) are read back (ONE small D2H read, issued after
+    the projection has been queued so the GPU does not idle during the round trip);
+    the images they reject -- and only those -- are redone with the fp64-exact second
+    line.  exact=False skips the read-back (no host sync)."""
     desc, cls_out, idx, nsel, n_unc = region_descriptors_async(x, hw, k, fsize, margin, want_cls_out)
     if exact:
-        n_bad = int(n_unc.item())
+        n_bad = int(n_unc[:, 0].sum().item())
         if stats is not None:
             stats["batches"] = stats.get("batches", 0) + 1
             stats["batches_resolved_exactly"] = stats.get("batches_resolved_exactly", 0) + (1 if n_bad else 0)
+            stats["images_resolved_exactly"] = stats.get("images_resolved_exactly", 0)
         if n_bad:
-            desc, cls_out, idx, nsel = region_descriptors_exact(x, hw, k, fsize)
+            bad = uncertified_images(n_unc)
+            if stats is not None:
+                stats["images_resolved_exactly"] += len(bad)
+            region_descriptors_fix(x, hw, k, fsize, bad, desc, cls_out, idx, nsel)
     return desc, cls_out, idx, nsel
 
 

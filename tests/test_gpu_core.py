@@ -151,6 +151,8 @@ def test_topk_search_golden(ops):
     (300, 20000, 256, 100),
     (64, 70000, 128, 100),   # many n-tiles per segment
     (1000, 5000, 64, 20),    # several m-blocks
+    (641, 40001, 200, 100),  # CTA-pair kernel: 6 row blocks (3 pairs, the last one ragged), ragged N and D
+    (385, 25000, 96, 10),    # CTA-pair kernel: odd number of row blocks (the last pair's second CTA is idle)
 ])
 def test_topk_search_random(ops, Q, N, D, k):
     q = oracle.normalize_l2(_randn(Q, D, seed=10))
@@ -161,6 +163,19 @@ def test_topk_search_random(ops, Q, N, D, k):
     # size-independent properties: sorted, no duplicates
     assert (s[:, :-1] >= s[:, 1:]).all()
     assert all(len(set(r)) == k for r in i.cpu().tolist()[:50])
+
+
+def test_topk_search_pair_and_single_cta_kernels_agree(ops, monkeypatch):
+    # the 256 x 256 CTA-pair screen and the single-CTA 128 x 256 screen feed the same exact
+    # re-rank: identical indices and scores (ISB_SCREEN_PAIR=0 selects the single-CTA kernel)
+    Q, N, D, k = 700, 30000, 128, 100
+    q = oracle.normalize_l2(_randn(Q, D, seed=31))
+    db = oracle.normalize_l2(_randn(N, D, seed=32))
+    s2, i2 = _search(ops, q, db, k)
+    monkeypatch.setenv("ISB_SCREEN_PAIR", "0")
+    s1, i1 = _search(ops, q, db, k)
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+    check_topk_against_oracle(q, db, k, s2, i2)
 
 
 def test_topk_search_clustered_and_planted(ops):

@@ -105,7 +105,7 @@ def test_region_exact_second_line_matches_fast_path_and_oracle(R):
     x = s["x"].cuda()
     stats = {}
     d, c, i, n = R.region_descriptors(x, hw, 6, (7, 7), stats=stats)
-    assert stats == {"batches": 1, "batches_resolved_exactly": 0}
+    assert stats == {"batches": 1, "batches_resolved_exactly": 0, "images_resolved_exactly": 0}
     i2, n2, c2, wn2, _, _, _ = R.region_select(x, hw, 6, (7, 7), exact_mode=True)
     torch.cuda.synchronize()
     od, oc, oi, on = oracle.region_descriptor_forward(s["x"], s["cls_w"], s["cls_b"], s["shift"],
@@ -133,6 +133,26 @@ def test_region_near_tied_windows_fall_to_the_exact_line(R):
                                                     s["lin_b"], 6, (7, 7))
     assert torch.allclose(d.cpu(), od, rtol=0, atol=DESC_ATOL)      # identical crops: same descriptor
     assert torch.allclose(c.cpu(), oc, rtol=CLS_RTOL, atol=CLS_ATOL)
+
+
+def test_region_only_the_uncertified_images_are_redone(R):
+    # one constant (all windows tied) image inside an ordinary batch: the certificates list
+    # that image alone, it alone goes through the exact second line, and every image of the
+    # batch still matches the oracle
+    C, H, W, ncls, D = 32, 12, 11, 6, 16
+    s = _synthetic(5, C, H, W, ncls, D, seed=8)
+    s["x"][3] = 0.25
+    hw = _hw(R, s)
+    stats = {}
+    d, c, i, n = R.region_descriptors(s["x"].cuda(), hw, 6, (7, 7), stats=stats)
+    assert stats == {"batches": 1, "batches_resolved_exactly": 1, "images_resolved_exactly": 1}
+    od, oc, oi, on = oracle.region_descriptor_forward(s["x"], s["cls_w"], s["cls_b"], s["shift"], s["lin_w"],
+                                                      s["lin_b"], 6, (7, 7))
+    keep = [0, 1, 2, 4]
+    assert torch.equal(i.cpu()[keep], oi[keep])
+    assert i.cpu()[3].tolist() == [0, 1, 2, 3, 4, 5]           # ties -> lower window index first
+    assert torch.allclose(d.cpu(), od, rtol=0, atol=DESC_ATOL)
+    assert torch.allclose(c.cpu()[keep], oc[keep], rtol=CLS_RTOL, atol=CLS_ATOL)
 
 
 @pytest.mark.parametrize("B,C,H,W,ncls,D", [(6, 64, 14, 14, 20, 32), (3, 256, 20, 24, 464, 32)])

@@ -85,7 +85,7 @@ for hw_size, variant in [(int(s), v) for s in a.sizes.split(",") for v in varian
             for n, (s, t) in zip(["select", "gather", "logits_fixup", "project"], zip(e[:-1], e[1:])):
                 stages[n].append(s.elapsed_time(t))
             stages["total"].append(e[0].elapsed_time(e[4]))
-            uncert += int((n1 + n2).item())
+            uncert += int((n1[0] + n2[0]).item())
             changed_total += int(n_changed.item())
     med = {n: sorted(v)[len(v) // 2] for n, v in stages.items()}
     # streamed: 8 batches back to back over two alternating inputs, certificates read at the end
