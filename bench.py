@@ -330,9 +330,10 @@ def run_b200(a, rank, world, local_rank):
                 "frac": achieved / peak,
                 "traffic": (NCU_SCREEN_TRAFFIC_BYTES if (world == 1 and a.queries == Q_DEFAULT and
                                                          a.db_rows == N_DEFAULT and a.dim == D_DEFAULT) else None),
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_search_screen_1M.txt",
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_search_screen_pair.txt",
                 "algorithmic_bytes": 2.0 * rows_local * a.dim + 2.0 * a.queries * a.dim + 8.0 * a.queries * a.k,
-                "kernel": "gemm_tc_kernel<TopkSched,TopkEpilogue> (tcgen05 screen + streaming top-k)",
+                "kernel": "gemm_tc_pair_kernel<TopkSched,TopkEpilogue> (tcgen05 cta_group::2 screen, 256x256 tiles, "
+                          "streaming top-k epilogue)",
                 "kernel_ms": screen_ms, "peak_source": pk_src + " bf16_tflops_sustained",
                 "frac_of_burst_peak": achieved / pk["bf16_tflops"]}
 
@@ -381,8 +382,8 @@ def run_b200(a, rank, world, local_rank):
 # ------------------------------------------------------------------ side measurements (N = 1)
 # BASELINE.json's metric also names "region descriptors/s" (configs[1]) and the path includes
 # the mining of configs[2]; they are measured here after the headline, on rank 0, a few ms each.
-NCU_SCREEN_TRAFFIC_BYTES = 14.2e9   # dram read + write of the screen kernel at the headline size,
-                                    # profiles/r01_ncu_search_screen_1M.txt (ncu --set full)
+NCU_SCREEN_TRAFFIC_BYTES = 11.3e9   # dram read + write of the screen kernel at the headline size,
+                                    # profiles/r01_ncu_search_screen_pair.txt (ncu --set full)
 
 
 def _median_ms(fn, iters=10, warmup=3, flush=None):

@@ -321,7 +321,7 @@ struct TopkSched {
       const int expected = min(workers, total - wave * workers);
       volatile int* cnt = wave_sync + wave;
       atomicAdd(wave_sync + wave, 1);
-      for (int polls = 0; polls < 8192 && *cnt < expected; ++polls) __nanosleep(100);
+      for (int polls = 0; polls < 2048 && *cnt < expected; ++polls) __nanosleep(100);
     }
     __syncwarp();
   }
