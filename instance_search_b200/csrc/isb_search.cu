@@ -1104,18 +1104,19 @@ static int pick_n_groups(int m_blocks, int n_tiles, int grid) {
   if (lo > n_tiles) lo = n_tiles;
   int hi = lo * 8 + 8;
   if (hi > n_tiles) hi = n_tiles;
-  int best = lo;
-  double best_eff = -1.0;
-  for (int ng = lo; ng <= hi; ++ng) {
+  auto efficiency = [&](int ng) {
     const long long segs = static_cast<long long>(m_blocks) * ng;
     const long long waves = (segs + grid - 1) / grid;
-    const double eff = static_cast<double>(segs) / static_cast<double>(waves * grid);
-    if (eff > best_eff + 1e-9) {
-      best_eff = eff;
-      best = ng;
-    }
-  }
-  return best;
+    return static_cast<double>(segs) / static_cast<double>(waves * grid);
+  };
+  double best_eff = -1.0;
+  for (int ng = lo; ng <= hi; ++ng) best_eff = efficiency(ng) > best_eff ? efficiency(ng) : best_eff;
+  // the FEWEST groups within 1 % of the best wave efficiency: longer segments mean fewer wave
+  // barriers, fewer threshold warm-ups, fewer groups straddling a wave boundary (each straddle
+  // streams the group's database range from HBM again) and a smaller candidate pool
+  for (int ng = lo; ng <= hi; ++ng)
+    if (efficiency(ng) >= best_eff - 0.01) return ng;
+  return lo;
 }
 
 // ISB_SCREEN_PAIR=0 keeps the single-CTA 128 x 256 kernel (A/B switch; the workspace layout

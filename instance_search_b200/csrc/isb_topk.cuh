@@ -19,6 +19,7 @@ namespace isb {
 
 constexpr int kCap = 512;        // private buffer entries per row
 constexpr int kTrig = 256;       // compact when a row holds more than this after a tile
+constexpr int kCompactSlack = 64;   // an in-stream compaction may keep up to kc + this many entries
 constexpr int kMaxCand = 128;    // == ISB_MAX_CANDIDATES
 constexpr int kMaxWaves = 1024;  // wave-barrier counters of the screen scheduler
 
@@ -48,10 +49,15 @@ struct TopkEpiParams {
   float ub_slack;
 };
 
-// Warp-cooperative: keep the `keep` largest of buf[0..cnt) (cnt <= kCap), packed
-// to the front.  Returns the key of the keep-th largest.  All 32 lanes call it
-// with identical arguments.
-__device__ __forceinline__ uint32_t warp_compact_row(uint2* buf, int cnt, int keep, int lane) {
+// Warp-cooperative: keep the largest entries of buf[0..cnt) (cnt <= kCap), packed to the
+// front, and return the threshold key T they all reach.  At least `keep` entries survive and
+// at most keep + slack (n_out): the bit-by-bit select stops as soon as the count of keys >= T
+// is within `slack` of `keep` -- a threshold only has to be a LOWER bound of the keep-th best
+// key, and an early exit saves most of the ~25 select rounds (slack = 0: exactly the keep
+// largest, ties with the keep-th key in slot order).  All 32 lanes call it with identical
+// arguments.
+__device__ __forceinline__ uint32_t warp_compact_row(uint2* buf, int cnt, int keep, int slack, int lane,
+                                                     int& n_out) {
   constexpr int kPer = kCap / 32;
   uint32_t key[kPer], col[kPer];
 #pragma unroll
@@ -75,6 +81,8 @@ __device__ __forceinline__ uint32_t warp_compact_row(uint2* buf, int cnt, int ke
   for (int i = 0; i < kPer; ++i) diff |= (lane + 32 * i < cnt) ? (key[i] ^ k0) : 0u;
   diff = __reduce_or_sync(0xffffffffu, diff);
   uint32_t T = k0;
+  int c_T = cnt;       // count of keys >= T
+  bool exact = true;   // T is the keep-th largest key (all select rounds ran)
   if (diff != 0) {
     const int hb = 31 - __clz(diff);
     T = (hb == 31) ? 0u : (k0 & ~((2u << hb) - 1u));
@@ -85,15 +93,33 @@ __device__ __forceinline__ uint32_t warp_compact_row(uint2* buf, int cnt, int ke
 #pragma unroll
       for (int i = 0; i < kPer; ++i) c += (key[i] >= trial) ? 1 : 0;
       c = __reduce_add_sync(0xffffffffu, c);
-      if (c >= keep) T = trial;
+      if (c >= keep) {
+        T = trial;
+        c_T = c;
+        if (c <= keep + slack && b > 0) { exact = false; break; }
+      }
     }
+  }
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  if (!exact && c_T <= keep + slack) {
+    // keep every entry with key >= T (keep <= c_T <= keep + slack of them)
+    int pos = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const bool ge = key[i] >= T && (lane + 32 * i < cnt);
+      const uint32_t bge = __ballot_sync(0xffffffffu, ge);
+      if (ge) buf[pos + __popc(bge & lt_mask)] = make_uint2(key2f(key[i]), col[i]);
+      pos += __popc(bge);
+    }
+    __syncwarp();
+    n_out = pos;
+    return T;
   }
   int n_gt = 0;
 #pragma unroll
   for (int i = 0; i < kPer; ++i) n_gt += (key[i] > T) ? 1 : 0;
   n_gt = __reduce_add_sync(0xffffffffu, n_gt);
   const int quota_eq = keep - n_gt;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   int pos_gt = 0, pos_eq = 0;
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
@@ -110,6 +136,7 @@ __device__ __forceinline__ uint32_t warp_compact_row(uint2* buf, int cnt, int ke
     pos_eq += __popc(beq);
   }
   __syncwarp();
+  n_out = keep;
   return T;
 }
 
@@ -236,14 +263,16 @@ struct TopkEpilogue {
     }
   }
 
-  __device__ __forceinline__ void compact_rows(uint32_t need, int keep) {
+  // slack: how many entries beyond `keep` a compacted row may retain (0 = exactly keep)
+  __device__ __forceinline__ void compact_rows(uint32_t need, int keep, int slack) {
     while (need) {
       const int r = __ffs(need) - 1;
       need &= need - 1;
       const int c = __shfl_sync(0xffffffffu, cnt, r);
-      const uint32_t T = warp_compact_row(warp_buf + static_cast<size_t>(r) * kCap, c, keep, lane);
+      int kept;
+      const uint32_t T = warp_compact_row(warp_buf + static_cast<size_t>(r) * kCap, c, keep, slack, lane, kept);
       if (lane == r) {
-        cnt = keep;
+        cnt = kept;
         thr = fmaxf(thr, __uint_as_float(key2f(T)));
         atomicMax(p.gthr + row, T);
       }
@@ -265,12 +294,12 @@ struct TopkEpilogue {
     cnt = static_cast<int>(wp - my_buf);
     __syncwarp();
     const uint32_t need = __ballot_sync(0xffffffffu, cnt > kTrig);
-    if (need) compact_rows(need, p.kc);
+    if (need) compact_rows(need, p.kc, kCompactSlack);
   }
 
   __device__ __forceinline__ void end_segment(const Segment& seg) {
     const uint32_t need = __ballot_sync(0xffffffffu, cnt > p.kc);
-    if (need) compact_rows(need, p.kc);
+    if (need) compact_rows(need, p.kc, 0);   // the pool slot holds exactly <= kc entries
     __syncwarp();
 #pragma unroll 1
     for (int r = 0; r < 32; ++r) {
