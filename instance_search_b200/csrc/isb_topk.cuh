@@ -18,7 +18,7 @@
 namespace isb {
 
 constexpr int kCap = 512;        // private buffer entries per row
-constexpr int kTrig = 256;       // compact when a row holds more than this after a tile
+constexpr int kTrig = 256;       // compact when a row holds more than this after a tile (kTrig + 256 <= kCap)
 constexpr int kCompactSlack = 64;   // an in-stream compaction may keep up to kc + this many entries
 constexpr int kMaxCand = 128;    // == ISB_MAX_CANDIDATES
 constexpr int kMaxWaves = 1024;  // wave-barrier counters of the screen scheduler

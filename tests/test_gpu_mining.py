@@ -74,6 +74,8 @@ def test_select_negatives_golden(M, semi):
     (4096, 256, 16, True, 3),
     (1000, 72, 7, True, 3),       # ragged sizes
     (2048, 128, 16, True, 1),     # plain bf16 screen: certificate + brute force must keep it exact
+    (20480, 128, 16, True, 3),    # large enough for the CTA-pair screen (masked epilogue, split operands)
+    (20480, 136, 16, False, 3),   # the same, hard mode, D not a multiple of 64
 ])
 def test_select_negatives_random(M, N, D, per, semi, terms):
     # SURVEY.md 8d cfg 3: E = normalize(center[label] + 0.5 randn), labels i // per

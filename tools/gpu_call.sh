@@ -1,14 +1,9 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
-python -c "
-import json
-d = json.loads(open('gpurun_out/bench_n1.json').read().strip().splitlines()[-1])
-print({k: d[k] for k in ('value', 'ms_per_step', 'e2e', 'clocks')})
-print(d['roofline'])
-"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_pair' --launch-skip 1 -c 1 -f -o gpurun_out/r01_screen_pair_ws python tools/quick_search_bench.py --iters 2 --check 0 > gpurun_out/ncu_pair.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_search_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()"
+timeout 300 python -m pytest tests/test_gpu_core.py tests/test_gpu_mining.py tests/test_gpu_sharded.py -m gpu -x -q 2>&1 | tail -3
+timeout 300 python tools/quick_search_bench.py --iters 8 --check 16 2>&1 | tail -3
+timeout 300 ncu --metrics dram__bytes_read.sum,gpu__time_duration.sum,sm__cycles_elapsed.avg,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,smsp__inst_executed.sum --clock-control none -k regex:'gemm_tc' --launch-skip 1 -c 1 python tools/quick_search_bench.py --iters 2 --check 0 2>&1 | grep -E "dram__bytes|gpu__time|cycles_elapsed|tensor_cycles|inst_executed"
+echo "== shard-sized (N=125000)"
+timeout 300 python tools/quick_search_bench.py --N 125000 --iters 8 --check 16 2>&1 | tail -3
+timeout 300 ncu --metrics dram__bytes_read.sum,gpu__time_duration.sum,sm__cycles_elapsed.avg,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,smsp__inst_executed.sum --clock-control none -k regex:'gemm_tc' --launch-skip 1 -c 1 python tools/quick_search_bench.py --N 125000 --iters 2 --check 0 2>&1 | grep -E "dram__bytes|gpu__time|cycles_elapsed|tensor_cycles|inst_executed"
