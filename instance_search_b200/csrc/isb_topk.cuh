@@ -56,23 +56,29 @@ struct TopkEpiParams {
 // key, and an early exit saves most of the ~25 select rounds (slack = 0: exactly the keep
 // largest, ties with the keep-th key in slot order).  All 32 lanes call it with identical
 // arguments.
+// The row's entries come in `raw` (lane l holds entries l, l + 32, ...: load_row_entries), so
+// that the caller can fetch the next row's while this one is being reduced.
+constexpr int kPerLane = kCap / 32;
+
+__device__ __forceinline__ void load_row_entries(const uint2* buf, int cnt, int lane, uint2 (&raw)[kPerLane]) {
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) {
+    const int j = lane + 32 * i;
+    raw[i] = (j < cnt) ? buf[j] : make_uint2(0u, 0u);
+  }
+}
+
 __device__ __forceinline__ uint32_t warp_compact_row(uint2* buf, int cnt, int keep, int slack, int lane,
-                                                     int& n_out) {
-  constexpr int kPer = kCap / 32;
+                                                     const uint2 (&raw)[kPerLane], int& n_out) {
+  constexpr int kPer = kPerLane;
   uint32_t key[kPer], col[kPer];
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
-    const int j = lane + 32 * i;
-    if (j < cnt) {
-      const uint2 e = buf[j];
-      key[i] = f2key(e.x);
-      col[i] = e.y;
-    } else {
-      key[i] = 0;
-      col[i] = 0;
-    }
+    const bool valid = lane + 32 * i < cnt;
+    key[i] = valid ? f2key(raw[i].x) : 0u;
+    col[i] = raw[i].y;
   }
-  __syncwarp();  // every load above is ordered before every store below
+  __syncwarp();  // every load of this row is ordered before every store below
   // The keys of one row share their leading bits (same sign / exponent): start the
   // bit-by-bit select below the common prefix instead of at bit 31.
   const uint32_t k0 = __shfl_sync(0xffffffffu, key[0], 0);  // entry 0 is valid (cnt > 0)
@@ -263,19 +269,47 @@ struct TopkEpilogue {
     }
   }
 
-  // slack: how many entries beyond `keep` a compacted row may retain (0 = exactly keep)
+  // slack: how many entries beyond `keep` a compacted row may retain (0 = exactly keep).
+  // The rows of a warp tend to need compaction at the same tile (they fill at the same rate
+  // while their thresholds warm up), and the MMA pipe waits for the whole series: the entries
+  // of the next row are fetched (L2 latency) while the current one is being reduced.
   __device__ __forceinline__ void compact_rows(uint32_t need, int keep, int slack) {
-    while (need) {
-      const int r = __ffs(need) - 1;
-      need &= need - 1;
-      const int c = __shfl_sync(0xffffffffu, cnt, r);
-      int kept;
-      const uint32_t T = warp_compact_row(warp_buf + static_cast<size_t>(r) * kCap, c, keep, slack, lane, kept);
-      if (lane == r) {
-        cnt = kept;
-        thr = fmaxf(thr, __uint_as_float(key2f(T)));
-        atomicMax(p.gthr + row, T);
+    uint2 raw_a[kPerLane], raw_b[kPerLane];
+    int r = __ffs(need) - 1;
+    need &= need - 1;
+    int c = __shfl_sync(0xffffffffu, cnt, r);
+    load_row_entries(warp_buf + static_cast<size_t>(r) * kCap, c, lane, raw_a);
+    for (;;) {
+      // ---- row r sits in raw_a; prefetch the next row into raw_b
+      int r2 = -1, c2 = 0;
+      if (need) {
+        r2 = __ffs(need) - 1;
+        need &= need - 1;
+        c2 = __shfl_sync(0xffffffffu, cnt, r2);
+        load_row_entries(warp_buf + static_cast<size_t>(r2) * kCap, c2, lane, raw_b);
       }
+      finish_row(r, c, keep, slack, raw_a);
+      if (r2 < 0) break;
+      // ---- row r2 sits in raw_b; prefetch the next row into raw_a
+      r = -1;
+      if (need) {
+        r = __ffs(need) - 1;
+        need &= need - 1;
+        c = __shfl_sync(0xffffffffu, cnt, r);
+        load_row_entries(warp_buf + static_cast<size_t>(r) * kCap, c, lane, raw_a);
+      }
+      finish_row(r2, c2, keep, slack, raw_b);
+      if (r < 0) break;
+    }
+  }
+
+  __device__ __forceinline__ void finish_row(int r, int c, int keep, int slack, const uint2 (&raw)[kPerLane]) {
+    int kept;
+    const uint32_t T = warp_compact_row(warp_buf + static_cast<size_t>(r) * kCap, c, keep, slack, lane, raw, kept);
+    if (lane == r) {
+      cnt = kept;
+      thr = fmaxf(thr, __uint_as_float(key2f(T)));
+      atomicMax(p.gthr + row, T);
     }
   }
 
