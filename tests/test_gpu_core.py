@@ -178,9 +178,22 @@ def test_topk_search_pair_and_single_cta_kernels_agree(ops, monkeypatch):
     check_topk_against_oracle(q, db, k, s2, i2)
 
 
+def test_topk_search_with_seeded_thresholds(ops, monkeypatch):
+    # ISB_SCREEN_SEED=1: every row's threshold starts at the kc-th best score over the first 2048
+    # database rows (a lower bound of the kc-th best overall) instead of -inf: same result
+    Q, N, D, k = 130, 33000, 72, 100
+    q = oracle.normalize_l2(_randn(Q, D, seed=41))
+    db = oracle.normalize_l2(_randn(N, D, seed=42))
+    s0, i0 = _search(ops, q, db, k)
+    monkeypatch.setenv("ISB_SCREEN_SEED", "1")
+    s1, i1 = _search(ops, q, db, k)
+    assert torch.equal(i0, i1) and torch.equal(s0, s1)
+    check_topk_against_oracle(q, db, k, s1, i1)
+
+
 def test_topk_search_clustered_and_planted(ops):
     # database with near-duplicate clusters + planted exact matches of each query
-    Q, N, D, k = 200, 30000, 128, 50
+    Q, N, D, k = 200, 36000, 128, 50
     centers = _randn(300, D, seed=12)
     lab = torch.randint(0, 300, (N,), generator=torch.Generator().manual_seed(13))
     db = oracle.normalize_l2(centers[lab] + 0.05 * _randn(N, D, seed=14))
