@@ -1,11 +1,21 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_core.py tests/test_gpu_mining.py tests/test_gpu_sharded.py -m gpu -x -q 2>&1 | tail -3
-for seed in 1 0; do
-echo "== seed=$seed N=1M"
-ISB_SCREEN_SEED=$seed timeout 300 python tools/quick_search_bench.py --iters 8 --check 16 2>&1 | tail -3
-echo "== seed=$seed N=125k"
-ISB_SCREEN_SEED=$seed timeout 300 python tools/quick_search_bench.py --N 125000 --iters 8 --check 16 2>&1 | tail -3
-ISB_SCREEN_SEED=$seed timeout 300 ncu --metrics gpu__time_duration.sum,sm__cycles_elapsed.avg,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,smsp__inst_executed.sum --clock-control none -k regex:'gemm_tc_pair|rerank' --launch-skip 2 -c 2 python tools/quick_search_bench.py --N 125000 --iters 2 --check 0 2>&1 | grep -E "gemm_tc|rerank_k|gpu__time|cycles_elapsed|tensor_cycles|inst_executed"
-done
+timeout 600 python -m pytest tests/test_gpu_regions.py tests/test_gpu_dropin.py -m gpu -x -q 2>&1 | tail -3
+timeout 300 python tools/bench_regions.py --sizes 14,32 2>/dev/null | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(d['workload'][36:44], {k: round(v, 4) for k, v in d['ms'].items()})
+"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_regions.csv python tools/bench_regions.py --sizes 14,32 --iters 2 --warmup 1 > /dev/null 2>&1
+python - <<'PY'
+import csv
+rows = [r for r in csv.reader(open('gpurun_out/launches_regions.csv')) if len(r) > 14 and r[0].isdigit()]
+seen = {}
+for r in rows:
+    if 'isb::' in r[4]:
+        key = (r[4][:60], r[8], r[7])
+        seen.setdefault(key, []).append(int(r[14]))
+for k, v in seen.items():
+    print(k[0].replace('void ', ''), k[1], k[2], sorted(v)[len(v)//2], len(v))
+PY
