@@ -1755,7 +1755,9 @@ struct RegionPlan {
   bool fast;       // region_pool_fast_kernel applies
   FastGeom geom;
   int64_t ldp;
-  size_t off_Phi, off_Plo, off_epart, off_screen, off_cand, off_cscreen, off_Ahi, off_Alo, off_logits, total;
+  size_t off_Phi, off_Plo, off_epart, off_screen, off_cand, off_cscreen, off_Ahi, off_Alo, off_logits, off_partials,
+      partials_bytes, total;
+  int resc_splits;   // split-K of the candidates' re-score GEMM (its tiles alone do not fill the machine)
   size_t pool_smem, cand_smem;
   int fast_threads;   // block size of region_pool_fast_kernel
   int stages;     // plane buffers of the fast pooling kernel's prefetch ring
@@ -1867,6 +1869,15 @@ static bool make_region_plan(RegionPlan& p, int64_t B, int C, int H, int W, int 
   p.off_Ahi = off;     off = align_up(off + Abytes, 1024);
   p.off_Alo = off;     off = align_up(off + Abytes, 1024);
   p.off_logits = off;  off = align_up(off + static_cast<size_t>(B) * p.ncand_max * p.ldl * 4, 1024);
+  {
+    const int64_t Mr = B * p.ncand_max;
+    const long long tiles = ((Mr + kBM - 1) / kBM) * ((ncls + kBN - 1) / kBN);
+    p.resc_splits = static_cast<int>(148 / (tiles > 0 ? tiles : 1));
+    if (p.resc_splits < 1) p.resc_splits = 1;
+    if (p.resc_splits > 4) p.resc_splits = 4;
+    p.partials_bytes = p.resc_splits > 1 ? isb_gemm_nt_workspace_bytes(Mr, ncls, C, p.resc_splits) : 0;
+  }
+  p.off_partials = off; off = align_up(off + p.partials_bytes, 1024);
   p.total = off;
   p.cand_smem = static_cast<size_t>((p.nwin + 3) & ~3) * 4;
   return true;
@@ -2002,7 +2013,8 @@ extern "C" int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H
 
   // 4. fp32-grade logits of the candidates: (A_hi, A_lo) . (Wc_hi, Wc_lo)^T + bc
   rc = isb_gemm_nt_split(A_hi, A_lo, p.ldp, cls_w_hi, cls_w_lo, ld_w, B * p.ncand_max, ncls, C, cls_b, logits,
-                         p.ldl, 1, nullptr, 0, stream);
+                         p.ldl, p.resc_splits, p.resc_splits > 1 ? ws + p.off_partials : nullptr, p.partials_bytes,
+                         stream);
   if (rc) return rc;
 
   // 5. final order, outputs, crop norms, certificate

@@ -122,10 +122,10 @@ def test_gemm_nt_split_operands(ops, M, N, K, splits):
     if splits == 1:
         cat = ops.gemm_nt(torch.cat([a_hi, a_lo, a_hi], 1).contiguous(),
                           torch.cat([b_hi, b_hi, b_lo], 1).contiguous(), bias=bias)
-        if K % 64 == 0:   # same k-block sequence => bit-identical accumulation
-            assert torch.equal(got, cat)
-        else:
-            assert torch.allclose(got, cat, rtol=1e-6, atol=1e-6)
+        # same products, different order of the k-blocks (the split kernel interleaves the three
+        # terms of every k-range): equal up to fp32 accumulation order
+        # (the tensor core accumulates 192 k-steps in fp32: ~1e-4 absolute on sums of ~100)
+        assert (got - cat).abs().max().item() <= 1e-5 * cat.abs().max().item()
 
 
 # ------------------------------------------------------------------ top-k search
