@@ -1268,18 +1268,20 @@ region_select_exact_kernel(const float* __restrict__ x, int C, int H, int W, int
 
 
 // ------------------------------------------------------------------ 5. gather
-// One CTA = one image x GG blocks of CBg channels.  Only the rows [r0, r1) of each plane that
-// the image's selected windows touch are staged in shared memory (bulk copies when aligned:
-// one per block when the windows span the whole map, else one per plane), through a ring of
-// NST buffers filled NST - 1 blocks ahead of the arithmetic -- the per-image set-up (window
-// offsets, norms) is paid once per CTA and the loads of the next blocks are in flight while
-// the current one is reduced.  Every thread then produces two consecutive elements of
+// One CTA = one image x 8 warps x G units of CW channels; every warp streams ITS OWN channels:
+// it stages the rows [r0, r1) of its CW planes that the image's selected windows touch (bulk
+// copies when aligned: one per unit when the windows span the whole map, else one per plane)
+// through its own ring of NST slots and its own mbarriers, NST - 1 units ahead of the
+// arithmetic, and never meets the other warps after the per-image set-up (window offsets,
+// norms) -- the CTA-wide barriers of the former block-cooperative loop were its top stall.
+// A warp produces, 64 consecutive outputs per pass, the elements
 //   u[e] = sum_i x[b, c, h_i + dy, w_i + dx] / norm_i + nsel * shift[e],  e = (c, dy, dx)
-// -- the CBg * fh * fw outputs of a block are one contiguous run of the operand row.
+// of its channels -- one contiguous run of the operand row per unit.
 constexpr int kGatherThreads = 256;
-constexpr int kGatherMaxStages = 6;
+constexpr int kGatherWarps = kGatherThreads / 32;
+constexpr int kGatherMaxStages = 4;
 constexpr int kGatherDefaultStages = 2;
-constexpr int kGatherDefaultG = 2;      // channel blocks per CTA on maps of <= 256 pixels, twice that beyond
+constexpr int kGatherDefaultG = 4;      // units per warp
 
 constexpr int kGatherRegWin = 8;
 
@@ -1295,7 +1297,7 @@ __device__ __forceinline__ float lds_f32_off(uint32_t addr) {
   return v;
 }
 
-// The outputs [e_begin, e_end) of one staged channel block.  A warp takes 64 consecutive
+// The outputs [e_begin, e_end) of the channels ONE WARP has staged.  The warp takes 64 consecutive
 // outputs per pass, lane l the elements base + l and base + 32 + l: consecutive lanes read
 // consecutive pixels of a window row (at most 2-way bank conflicts) and store 64 contiguous
 // bytes per instruction.  NW >= 0: the number of summed windows as a compile-time constant --
@@ -1308,9 +1310,9 @@ __device__ __forceinline__ void gather_block(const float* X, int c0, int pl, int
                                              const float (&r_norm)[kGatherRegWin], const int* s_off,
                                              const float* s_norm, int nsel, float fn,
                                              const float* __restrict__ shift, uint16_t* uh, uint16_t* ul) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const uint32_t xs = ptx::smem_u32(X);
-  for (int base = e_begin + warp * 64 + lane; base < e_end; base += 2 * kGatherThreads) {
+  for (int base = e_begin + lane; base < e_end; base += 64) {
     float u[2], sh[2];
     uint32_t a[2];
     bool live[2];
@@ -1351,29 +1353,25 @@ __device__ __forceinline__ void gather_block(const float* X, int c0, int pl, int
 }
 
 template <int FHW>   // FHW = 7: 7 x 7 window with compile-time index arithmetic; 0: generic
-__global__ void __launch_bounds__(kGatherThreads)
+__global__ void __launch_bounds__(kGatherThreads, 4)
 region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, int fw_, int k, int k_sum,
-                     int CBg, int GG, int NST, int row_align, const int* __restrict__ image_list,
+                     int CW, int G, int NST, int row_align, const int* __restrict__ image_list,
                      const int* __restrict__ n_list, const int64_t* __restrict__ idx,
                      const int* __restrict__ nsel_in,
                      const float* __restrict__ win_norm, const float* __restrict__ shift,
                      uint16_t* __restrict__ U_hi, uint16_t* __restrict__ U_lo, int64_t ldu,
                      float* __restrict__ win_mean) {
   extern __shared__ __align__(128) uint8_t gat_smem_raw[];
-  float* X0 = reinterpret_cast<float*>(gat_smem_raw);
   __shared__ int s_off[kSelMaxCand];
   __shared__ float s_norm[kSelMaxCand];
   __shared__ int s_r0, s_r1;
-  __shared__ __align__(8) uint64_t bars[kGatherMaxStages];
+  __shared__ __align__(8) uint64_t bars[kGatherWarps][kGatherMaxStages];
   const int fh = FHW ? FHW : fh_, fw = FHW ? FHW : fw_;
   // optional image list (fix-up pass): grid.y covers the whole batch, rows beyond *n_list exit
   if (image_list != nullptr && static_cast<int>(blockIdx.y) >= *n_list) return;
   const int b = (image_list != nullptr) ? image_list[blockIdx.y] : blockIdx.y;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Wo = W - fw + 1, HW = H * W, area = fh * fw;
-  const int nblk = (C + CBg - 1) / CBg;
-  const int blk0 = blockIdx.x * GG;
-  const int nloc = min(GG, nblk - blk0);
   const int nall = nsel_in[b];                 // windows listed for this image (means are taken of all)
   const int nsel = min(nall, k_sum);           // leading windows summed into the operand
   // window rows of this image: every lane of warp 0 reads one index, the range is a warp reduction
@@ -1395,44 +1393,14 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, 
       r0 = (r0 / row_align) * row_align;                       // keep every plane's range 16-byte aligned
       r1 = min(H, ((r1 + row_align - 1) / row_align) * row_align);
       s_r0 = r0; s_r1 = r1;
-      for (int s = 0; s < NST; ++s) ptx::mbar_init(&bars[s], 1);
+      for (int w = 0; w < kGatherWarps; ++w)
+        for (int st = 0; st < NST; ++st) ptx::mbar_init(&bars[w][st], 1);
       ptx::fence_barrier_init();
     }
   }
   __syncthreads();
   const int r0 = s_r0, nrows = s_r1 - s_r0;
   const int pl = nrows * W;                                  // floats staged per plane
-  const size_t stage_floats = static_cast<size_t>(CBg) * HW;
-  const float* xsrc = x + static_cast<size_t>(b) * C * HW + r0 * W;    // + channel * HW
-  const bool bulk = ((reinterpret_cast<uintptr_t>(xsrc + static_cast<size_t>(blk0) * CBg * HW) & 15) == 0) &&
-                    ((HW & 3) == 0) && ((pl & 3) == 0) && pl > 0;
-  // warp 0 issues the copies of local block j into ring slot j % NST
-  auto issue = [&](int j) {
-    if (tid < 32) {
-      const int c0 = (blk0 + j) * CBg;
-      const int cvalid = min(CBg, C - c0);
-      float* dst = X0 + static_cast<size_t>(j % NST) * stage_floats;
-      uint64_t* bar = &bars[j % NST];
-      const float* src0 = xsrc + static_cast<size_t>(c0) * HW;
-      const uint32_t total = static_cast<uint32_t>(cvalid) * pl * 4u;
-      if (tid == 0) {
-        ptx::fence_proxy_async();   // the slot's previous contents were read through the generic proxy
-        ptx::mbar_arrive_expect_tx(bar, total);
-      }
-      __syncwarp();
-      if (pl == HW) {
-        // whole planes: the channel block is ONE contiguous range -> a few large copies
-        for (uint32_t off = tid * 8192u; off < total; off += 32u * 8192u)
-          ptx::bulk_load_1d(reinterpret_cast<uint8_t*>(dst) + off, reinterpret_cast<const uint8_t*>(src0) + off,
-                            min(8192u, total - off), bar);
-      } else {
-        for (int cb = tid; cb < cvalid; cb += 32)
-          ptx::bulk_load_1d(dst + cb * pl, src0 + static_cast<size_t>(cb) * HW, static_cast<uint32_t>(pl) * 4u, bar);
-      }
-    }
-  };
-  if (bulk)
-    for (int j = 0; j < NST - 1 && j < nloc; ++j) issue(j);
   if (tid < nall) {
     const int win = static_cast<int>(idx[static_cast<size_t>(b) * k + tid]);
     const int h = win / Wo, w = win - h * Wo;
@@ -1441,7 +1409,43 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, 
     // reference's division (model/custom_modules.py:56) changes nothing that survives that rounding
     s_norm[tid] = 1.f / win_norm[static_cast<size_t>(b) * k + tid];
   }
-  __syncthreads();
+  __syncthreads();   // the only CTA-wide meeting points: from here on every warp is on its own
+
+  // this warp's channels: unit u covers [cta_c0 + (u * 8 + warp) * CW, + CW)
+  const int cta_c0 = blockIdx.x * (kGatherWarps * CW * G);
+  const size_t slot_floats = static_cast<size_t>(CW) * HW;
+  float* Xw = reinterpret_cast<float*>(gat_smem_raw) + static_cast<size_t>(warp) * NST * slot_floats;
+  const float* xsrc = x + static_cast<size_t>(b) * C * HW + r0 * W;    // + channel * HW
+  auto unit_c0 = [&](int u) { return cta_c0 + (u * kGatherWarps + warp) * CW; };
+  auto unit_nch = [&](int u) { return max(0, min(CW, C - unit_c0(u))); };
+  const bool bulk = ((reinterpret_cast<uintptr_t>(xsrc) & 15) == 0) && ((HW & 3) == 0) && ((pl & 3) == 0) && pl > 0;
+  // the warp's copies of unit u into ring slot u % NST (all lanes call it)
+  auto issue = [&](int u) {
+    const int nch = unit_nch(u);
+    if (nch > 0) {
+      float* dst = Xw + static_cast<size_t>(u % NST) * slot_floats;
+      uint64_t* bar = &bars[warp][u % NST];
+      const float* src0 = xsrc + static_cast<size_t>(unit_c0(u)) * HW;
+      const uint32_t total = static_cast<uint32_t>(nch) * pl * 4u;
+      if (lane == 0) {
+        ptx::fence_proxy_async();   // the slot's previous contents were read through the generic proxy
+        ptx::mbar_arrive_expect_tx(bar, total);
+      }
+      __syncwarp();
+      if (pl == HW) {
+        // whole planes: the unit is ONE contiguous range -> a few large copies
+        for (uint32_t off = lane * 8192u; off < total; off += 32u * 8192u)
+          ptx::bulk_load_1d(reinterpret_cast<uint8_t*>(dst) + off, reinterpret_cast<const uint8_t*>(src0) + off,
+                            min(8192u, total - off), bar);
+      } else {
+        for (int cb = lane; cb < nch; cb += 32)
+          ptx::bulk_load_1d(dst + cb * pl, src0 + static_cast<size_t>(cb) * HW, static_cast<uint32_t>(pl) * 4u, bar);
+      }
+    }
+  };
+  if (bulk)
+    for (int u = 0; u < NST - 1 && u < G; ++u) issue(u);
+
   const int Kin = C * area;
   const int KinP = (Kin + 7) & ~7;
   const float fn = static_cast<float>(nsel);
@@ -1456,35 +1460,29 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, 
     r_norm[i] = (i < nsel) ? s_norm[i] : 0.f;
   }
 
-  for (int it = 0; it < nloc; ++it) {
-    const int c0 = (blk0 + it) * CBg;
-    const int cvalid = min(CBg, C - c0);
-    float* X = X0 + static_cast<size_t>(it % NST) * stage_floats;
+  for (int u = 0; u < G; ++u) {
+    const int c0 = unit_c0(u);
+    const int nch = unit_nch(u);
+    if (nch <= 0) break;                          // warp-uniform: the following units start even later
+    float* X = Xw + static_cast<size_t>(u % NST) * slot_floats;
     if (bulk) {
-      if (it + NST - 1 < nloc) issue(it + NST - 1);   // into the slot iteration it - 1 has released
-      // one warp polls the mbarrier, the others sleep in the CTA barrier (eight polling warps
-      // took 18 % of the issue slots: ncu source view)
-      if (tid < 32) ptx::mbar_wait(&bars[it % NST], static_cast<uint32_t>((it / NST) & 1));
-      __syncthreads();
+      if (u + NST - 1 < G) issue(u + NST - 1);   // into the slot unit u - 1 has released (syncwarp below)
+      ptx::mbar_wait(&bars[warp][u % NST], static_cast<uint32_t>((u / NST) & 1));
     } else {
       const float* src0 = xsrc + static_cast<size_t>(c0) * HW;
-      for (int i = tid; i < cvalid * pl; i += kGatherThreads) {
+      for (int i = lane; i < nch * pl; i += 32) {
         const int cb = i / pl, o = i - cb * pl;
         X[i] = __ldg(src0 + static_cast<size_t>(cb) * HW + o);
       }
-      __syncthreads();
+      __syncwarp();
     }
     // by-product: the exact fp32 mean of every selected window (row-major sum, then / area --
     // AvgPool2d's own arithmetic, model/siamese.py:187), input of isb_region_logits
     if (win_mean != nullptr) {
       const float farea = static_cast<float>(area);
-      // lanes: 8 consecutive channels (their planes are pl floats apart: 8 distinct banks when
-      // pl % 32 == 4, as at 14 x 14) x 4 windows, instead of 32 channels (4-way conflicts)
-      const int cgroups8 = (cvalid + 7) >> 3;
       const uint32_t xs = ptx::smem_u32(X);
-      for (int t = tid; t < cgroups8 * 8 * nall; t += kGatherThreads) {
-        const int cb = ((t / (8 * nall)) << 3) | (t & 7), i = (t >> 3) % nall;
-        if (cb >= cvalid) continue;
+      for (int t = lane; t < nch * nall; t += 32) {
+        const int i = t / nch, cb = t - i * nch;   // consecutive lanes: consecutive channels of one window
         float sum = 0.f;
         if (FHW == 7) {
           // explicit shared addresses, the seven taps of a row as immediates
@@ -1505,8 +1503,8 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, 
       }
     }
     const int e_begin = c0 * area;
-    // the last block of an image also writes the zero padding [Kin, KinP)
-    const int e_end = (c0 + cvalid >= C) ? KinP : (c0 + cvalid) * area;
+    // the warp that holds the image's last channel also writes the zero padding [Kin, KinP)
+    const int e_end = (c0 + nch >= C) ? KinP : (c0 + nch) * area;
     switch (nsel <= kGatherRegWin ? nsel : -1) {
       case 0: gather_block<0>(X, c0, pl, W, area, fw, Kin, e_begin, e_end, r_off4, r_norm, s_off, s_norm, nsel, fn, shift, uh, ul); break;
       case 1: gather_block<1>(X, c0, pl, W, area, fw, Kin, e_begin, e_end, r_off4, r_norm, s_off, s_norm, nsel, fn, shift, uh, ul); break;
@@ -1519,7 +1517,7 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, 
       case 8: gather_block<8>(X, c0, pl, W, area, fw, Kin, e_begin, e_end, r_off4, r_norm, s_off, s_norm, nsel, fn, shift, uh, ul); break;
       default: gather_block<-1>(X, c0, pl, W, area, fw, Kin, e_begin, e_end, r_off4, r_norm, s_off, s_norm, nsel, fn, shift, uh, ul); break;
     }
-    __syncthreads();   // slot it % NST is free for the copy issued at the top of iteration it + 1
+    __syncwarp();   // slot u % NST is free for the copy issued at the top of unit u + 1
   }
 }
 
@@ -2041,40 +2039,34 @@ extern "C" int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H
   ISB_CHECK_ARG(ldu >= KinP && ldu % 8 == 0 && (reinterpret_cast<uintptr_t>(U_hi) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(U_lo) & 15) == 0, "isb_region_gather: bad ldu / alignment");
   const int64_t HW = H * W;
-  int CBg = 0;
-  // ring slots of <= 32 KB: several CTAs per SM on top of the short ring inside each (measured:
-  // 14 x 14 -> 32 channels, 32 x 32 -> 8 channels per slot)
-  for (int cb : {64, 32, 16, 8, 4, 2}) {
-    if (static_cast<size_t>(cb) * HW * 4 <= 32 * 1024) { CBg = cb; break; }
+  // channels per warp unit: <= 4 KB of planes per ring slot (14 x 14: 4 channels, 32 x 32: 1)
+  int CW = 1;
+  for (int cw : {8, 4, 2, 1}) {
+    if (static_cast<size_t>(cw) * HW * 4 <= 4 * 1024) { CW = cw; break; }
   }
-  if (CBg == 0) {
-    for (int cb : {8, 4, 2}) {
-      if (static_cast<size_t>(cb) * HW * 4 <= 96 * 1024) { CBg = cb; break; }
-    }
+  if (const char* e = getenv("ISB_GATHER_CW")) {
+    const int cw = atoi(e);
+    if (cw >= 1 && cw <= 64) CW = cw;
   }
-  if (const char* e = getenv("ISB_GATHER_CB")) {
-    const int cb = atoi(e);
-    if (cb >= 2 && cb % 2 == 0 && static_cast<size_t>(cb) * HW * 4 <= 96 * 1024) CBg = cb;
-  }
-  ISB_CHECK_ARG(CBg > 0, "isb_region_gather: feature map too large (H*W=%lld)", (long long)HW);
   const int row_align = (W % 4 == 0) ? 1 : ((W % 2 == 0) ? 2 : 4);
-  const size_t stage = static_cast<size_t>(CBg) * HW * 4;
-  const int nblk_g = static_cast<int>((C + CBg - 1) / CBg);
-  // blocks per CTA: the ring needs a few blocks to run ahead of; keep >= 8 waves of CTAs
-  int GG = (HW <= 256) ? kGatherDefaultG : 2 * kGatherDefaultG;
+  const size_t slot = static_cast<size_t>(CW) * HW * 4;            // one warp's ring slot
+  const int units = static_cast<int>((C + kGatherWarps * CW - 1) / (kGatherWarps * CW));   // unit rounds per image
+  // units per warp: the ring needs a few to run ahead of; keep >= 8 waves of CTAs
+  int GG = kGatherDefaultG;
   if (const char* e = getenv("ISB_GATHER_G")) GG = atoi(e);
   if (GG < 1) GG = 1;
-  while (GG > 1 && B * ((nblk_g + GG - 1) / GG) < 148 * 8) GG >>= 1;
-  if (GG > nblk_g) GG = nblk_g;
+  while (GG > 1 && B * ((units + GG - 1) / GG) < 148 * 8) GG >>= 1;
+  if (GG > units) GG = units;
   int NST = kGatherDefaultStages;
   if (const char* e = getenv("ISB_GATHER_STAGES")) NST = atoi(e);
   if (NST < 1) NST = 1;
   if (NST > kGatherMaxStages) NST = kGatherMaxStages;
-  if (NST > GG + 1) NST = GG + 1;                  // no point in more slots than blocks + 1
-  while (NST > 2 && NST * stage > 200 * 1024) --NST;
-  if (NST * stage > 200 * 1024) NST = 1;           // a single 96 KB+ slot: no ring (ISB_GATHER_CB only)
-  const size_t smem = NST * stage;
-  dim3 grid(static_cast<unsigned>((nblk_g + GG - 1) / GG), static_cast<unsigned>(B));
+  if (NST > GG + 1) NST = GG + 1;                  // no point in more slots than units + 1
+  while (NST > 1 && NST * kGatherWarps * slot > 200 * 1024) --NST;
+  const size_t smem = NST * kGatherWarps * slot;
+  ISB_CHECK_ARG(smem <= 200 * 1024, "isb_region_gather: feature map too large (H*W=%lld)", (long long)HW);
+  const int CBg = CW;
+  dim3 grid(static_cast<unsigned>((units + GG - 1) / GG), static_cast<unsigned>(B));
   if (fh == 7 && fw == 7) {
     if (smem > 48 * 1024)
       ISB_CUDA(cudaFuncSetAttribute(region_gather_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -26,7 +26,7 @@ ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--cls-out", type=int, default=0, help="1: also produce cls_out (training); 0: eval, class-max only")
 ap.add_argument("--variants", default="", help="';'-separated tuning variants, each 'ENV=val,ENV=val' (ISB_POOL_STAGES, "
-                "ISB_GATHER_CB / _G / _STAGES); one JSON line per variant and map size")
+                "ISB_GATHER_CW / _G / _STAGES); one JSON line per variant and map size")
 a = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -51,7 +51,7 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 
-TUNABLES = ("ISB_POOL_STAGES", "ISB_GATHER_CB", "ISB_GATHER_G", "ISB_GATHER_STAGES")
+TUNABLES = ("ISB_POOL_STAGES", "ISB_POOL_GENERIC_GEOM", "ISB_GATHER_CW", "ISB_GATHER_G", "ISB_GATHER_STAGES")
 variants = [v for v in a.variants.split(";")] if a.variants else [""]
 for hw_size, variant in [(int(s), v) for s in a.sizes.split(",") for v in variants]:
     H = W = hw_size
