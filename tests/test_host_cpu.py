@@ -122,3 +122,16 @@ def test_label_ids_and_placement_rule():
     assert mining.embeddings_device_dim(P, Net, 1000) == (0, 512)         # feature_dim <= 0 -> net's
     assert mining.embeddings_device_dim(P, Net, 2 ** 20) == (-1, 512)     # N*D*4 > 2^30 -> host
     assert oracle.embeddings_device_dim(0, 0, 2 ** 30, 512, 2 ** 20) == (-1, 512)
+
+
+def test_uncertified_image_lists_are_merged():
+    # the two certificates of the region head report [count, image, image, ...] each; the host
+    # redoes the union of the listed images (regions.region_descriptors)
+    from instance_search_b200.regions import uncertified_images
+    B = 6
+    n_unc = torch.zeros(2, 1 + B, dtype=torch.int32)
+    assert uncertified_images(n_unc) == []
+    n_unc[0, :3] = torch.tensor([2, 4, 1])       # screen certificate: images 4 and 1
+    n_unc[1, :2] = torch.tensor([1, 4])          # selection certificate: image 4 again
+    n_unc[1, 2:] = 5                             # stale entries beyond the count are ignored
+    assert uncertified_images(n_unc) == [1, 4]
