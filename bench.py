@@ -420,6 +420,10 @@ def side_regions(dev, pk):
         ms = _median_ms(lambda: regions.region_descriptors(x, hw, k, (7, 7), want_cls_out=False, stats=stats),
                         flush=flush)
         ms_head = _median_ms(lambda: regions.region_head(x, hw, k, (7, 7), want_cls_out=False), flush=flush)
+        # the pooling pass alone (north_star: >= 70 % of HBM bandwidth): x read once, window means
+        # written as bf16 hi + lo; CUDA events around the one kernel, L2 flushed before every launch
+        ms_pool = _median_ms(lambda: regions.region_pool_probe(x, hw, k + regions.RUNNER_UPS, (7, 7)), flush=flush)
+        rd, wr = regions.region_pool_probe(x, hw, k + regions.RUNNER_UPS, (7, 7))
         # streamed: 8 batches queued back to back over two alternating inputs (each larger than
         # L2, so no batch finds its map cached), certificates read once at the end -- what a
         # pipelined embedding loop sees once launch latency is hidden
@@ -434,6 +438,7 @@ def side_regions(dev, pk):
         ms_stream = _median_ms(stream, iters=5, warmup=2) / nstream
         n_unc_stream = int(torch.stack(pending).sum().item())
         del x2
+        regions._PROBE_CACHE.clear()
         # SURVEY 8d bytes of the bandwidth-bound part: x once + classifier + the bf16 hi+lo operand
         nbytes = 4 * B * C * hwsize * hwsize + 4 * ncls * C + 2 * 2 * B * Kin
         units = B * min((hwsize - 6) ** 2, k)
@@ -442,6 +447,10 @@ def side_regions(dev, pk):
             "pool_select_gather": {"bound": "hbm", "ms": ms_head, "algorithmic_bytes": nbytes,
                                    "achieved": nbytes / (ms_head * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                                    "unit": "GB/s", "frac": nbytes / (ms_head * 1e-3) / 1e9 / pk["hbm_gbs"]},
+            "pooling_kernel": {"kernel": "region_pool_fast_kernel", "bound": "hbm", "ms": ms_pool,
+                               "algorithmic_bytes": rd + wr, "achieved": (rd + wr) / (ms_pool * 1e-3) / 1e9,
+                               "peak": pk["hbm_gbs"], "unit": "GB/s",
+                               "frac": (rd + wr) / (ms_pool * 1e-3) / 1e9 / pk["hbm_gbs"]},
             "projection_ms": ms - ms_head,
             "streamed": {"ms_per_batch": ms_stream, "region_descriptors_per_s": units / (ms_stream * 1e-3),
                          "batches_in_flight": nstream, "uncertified_images_last_pass": n_unc_stream},

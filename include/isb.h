@@ -224,7 +224,9 @@ int isb_gemm_nt_split(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda, c
  * approx_max [B, k] (class-max of the selected windows as seen here) and
  * runner_up [B] (class-max of the best window NOT selected, -inf if none) feed it;
  * both may be NULL.
- * exact_mode != 0: second line for uncertified batches -- the candidates (use
+ * exact_mode < 0: measurement probe -- only the pooling pass runs (window means as bf16
+ * hi / lo into the workspace, energy partials); no output is written.
+ * exact_mode > 0: second line for uncertified batches -- the candidates (use
  * margin = 32 - k) are re-scored from the fp32 inputs with fp64 accumulation; slow,
  * exact, cls_out final.
  *   x [B, C, H, W] fp32 (NCHW)    cls_w [ncls, C] fp32    cls_b [ncls] fp32

@@ -1973,6 +1973,8 @@ extern "C" int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H
   }
   ISB_CUDA(cudaGetLastError());
 
+  if (exact_mode < 0) return ISB_OK;   // measurement probe: the pooling pass alone (outputs undefined)
+
   // 2. window classifier screen + class-max:  screen[m] = max_j (P_hi[m,:] . Wc_hi[j,:] + bc[j])
   CUtensorMap ta, tb;
   rc = make_tmap_bf16_k64(&ta, P_hi, M, C, p.ldp, kBM);

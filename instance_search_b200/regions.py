@@ -60,6 +60,41 @@ def _project(U_hi, U_lo, hw, B):
     return ops.gemm_nt_split(U_hi, U_lo, hw.lin_w_hi, hw.lin_w_lo, splits=splits)
 
 
+_PROBE_CACHE = {}
+
+
+def region_pool_probe(x, hw, k, fsize, margin=WINDOW_MARGIN):
+    """Measurement probe: the pooling pass of isb_region_select alone (exact_mode = -1: x read
+    once, window means written as bf16 hi + lo, per-pixel energy).  Buffers are cached between
+    calls so that a timed call is one memset and one kernel.  Returns (bytes read, bytes written)."""
+    ops._need_cuda(x)
+    B, C, H, W = x.shape
+    fh, fw = fsize
+    ncls = hw.cls_w.size(0)
+    margin = max(0, min(margin, 32 - k))
+    L = _lib.lib()
+    key = (B, C, H, W, ncls, k, margin, x.device)
+    if key not in _PROBE_CACHE:
+        dev = x.device
+        nbytes = L.isb_region_select_workspace_bytes(B, C, H, W, ncls, fh, fw, k, margin)
+        _PROBE_CACHE.clear()
+        _PROBE_CACHE[key] = (
+            torch.empty((B, k), dtype=torch.int64, device=dev), torch.empty((B,), dtype=torch.int32, device=dev),
+            torch.empty((B, ncls, k), dtype=torch.float32, device=dev),
+            torch.empty((B, k), dtype=torch.float32, device=dev), torch.empty((B, k), dtype=torch.float32, device=dev),
+            torch.empty((B,), dtype=torch.float32, device=dev), torch.zeros(1 + B, dtype=torch.int32, device=dev),
+            torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev), nbytes)
+    idx, nsel, cls_out, win_norm, approx_max, runner_up, n_unc, ws, nbytes = _PROBE_CACHE[key]
+    _lib.check(L.isb_region_select(x.data_ptr(), B, C, H, W, hw.cls_w.data_ptr(), hw.cls_w_hi.data_ptr(),
+                                   hw.cls_w_lo.data_ptr(), hw.cls_w_hi.size(1), hw.cls_b.data_ptr(), ncls,
+                                   fh, fw, k, margin, -1, idx.data_ptr(), nsel.data_ptr(),
+                                   cls_out.data_ptr(), win_norm.data_ptr(), approx_max.data_ptr(),
+                                   runner_up.data_ptr(), n_unc.data_ptr(), ws.data_ptr(), nbytes,
+                                   ops._stream()), "isb_region_select")
+    nwin = (H - fh + 1) * (W - fw + 1)
+    return 4 * B * C * H * W, 2 * 2 * B * nwin * ((C + 7) // 8 * 8)
+
+
 def region_select(x, hw, k, fsize, margin=WINDOW_MARGIN, exact_mode=False):
     """a3, first stage: (idx [B,k] int64, nsel [B] int32, cls_out [B,ncls,k], win_norm [B,k],
     approx_max [B,k], runner_up [B], n_uncertified [1] int32).  exact_mode: the slow
@@ -72,7 +107,7 @@ def region_select(x, hw, k, fsize, margin=WINDOW_MARGIN, exact_mode=False):
     nwin = (H - fh + 1) * (W - fw + 1)
     if nwin > LARGE_MAP_WINDOWS:
         margin = 32 - k   # dense maps: the screen's candidate list must reach further down
-    margin = 32 - k if exact_mode else max(0, min(margin, 32 - k))
+    margin = 32 - k if exact_mode is True else max(0, min(margin, 32 - k))
     dev = x.device
     idx = torch.empty((B, k), dtype=torch.int64, device=dev)
     nsel = torch.empty((B,), dtype=torch.int32, device=dev)
@@ -86,7 +121,7 @@ def region_select(x, hw, k, fsize, margin=WINDOW_MARGIN, exact_mode=False):
     ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
     _lib.check(L.isb_region_select(x.data_ptr(), B, C, H, W, hw.cls_w.data_ptr(), hw.cls_w_hi.data_ptr(),
                                    hw.cls_w_lo.data_ptr(), hw.cls_w_hi.size(1), hw.cls_b.data_ptr(), ncls,
-                                   fh, fw, k, margin, 1 if exact_mode else 0, idx.data_ptr(), nsel.data_ptr(),
+                                   fh, fw, k, margin, int(exact_mode), idx.data_ptr(), nsel.data_ptr(),
                                    cls_out.data_ptr(), win_norm.data_ptr(), approx_max.data_ptr(),
                                    runner_up.data_ptr(), n_unc.data_ptr(), ws.data_ptr(), nbytes,
                                    ops._stream()), "isb_region_select")
