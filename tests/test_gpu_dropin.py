@@ -241,3 +241,31 @@ def test_get_embeddings_similarities_and_descriptor_test():
         got = sel.select(couples, epoch, 2)
         want = oracle.select_negatives(S.cpu(), lab, couples, semi).tolist()
         assert [(-1 if g is None else g) for g in got] == want
+
+
+def test_siamese_regions_test_evaluate_matches_the_oracle(capsys):
+    # the evaluation section of the reference's test/siamese_regions_test.py (main, :72-88):
+    # embeddings of both sets, P@1 and mAP, then the same after database-side augmentation
+    from instance_search_b200.train.siamese_regions import get_embeddings
+    from instance_search_b200.test.siamese_regions_test import evaluate
+    net = _toy_region_net(4)
+    gen = torch.Generator().manual_seed(21)
+    ds = [(torch.randn(3, 32, 32, generator=gen), "L%d" % (i % 4), "im%d" % i) for i in range(26)]
+    test_set, ref_set = ds[:8], ds[8:]
+    res = evaluate(net, test_set, ref_set, device=0, dba=-1)
+    assert not net.training
+    t_emb = get_embeddings(net, test_set, 0, 16).cpu()
+    r_emb = get_embeddings(net, ref_set, 0, 16).cpu()
+    sim = t_emb @ r_emb.t()
+    p1 = oracle.precision1(sim, test_set, ref_set, 1)
+    prec1, c, t, mAP = res["plain"]
+    assert (c, t) == (p1[1], 8) and abs(prec1 - p1[0]) < 1e-12
+    assert abs(mAP - oracle.mean_avg_precision(sim, test_set, ref_set, 1)) < 1e-9
+    d_emb = oracle.instance_avg(r_emb, ref_set, -1)
+    sim_d = t_emb @ d_emb.t()
+    p1d = oracle.precision1(sim_d, test_set, ref_set, 1)
+    prec1, c, t, mAP = res["dba"]
+    assert (c, t) == (p1d[1], 8)
+    assert abs(mAP - oracle.mean_avg_precision(sim_d, test_set, ref_set, 1)) < 1e-6
+    out = capsys.readouterr().out
+    assert "Descriptor (TEST): " in out and "Descriptor (TEST DBA k=-1): " in out
