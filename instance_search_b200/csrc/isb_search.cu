@@ -1636,7 +1636,7 @@ static MiningPlan make_mining_plan(int64_t P, int64_t N, int64_t D, int split) {
   return m;
 }
 
-constexpr int kMiningCand = 32;   // candidates re-checked exactly per couple (<= kMaxCand)
+constexpr int kMiningCand = 16;   // candidates re-checked exactly per couple (<= kMaxCand; 32: +0.2 ms, 8: -0.1 ms)
 
 extern "C" size_t isb_select_negatives_workspace_bytes(int64_t P, int64_t N, int64_t D, int split) {
   if (P <= 0 || N <= 0 || D <= 0) return 0;
