@@ -39,6 +39,40 @@ import oracle  # noqa: E402
 
 
 # ----------------------------------------------------------------------------
+# the negative-selection block of train/siamese_regions.py, run from its source
+# ----------------------------------------------------------------------------
+def reference_negative_selection():
+    """train/siamese_regions.py cannot be imported (its ``P`` reads a missing data file at
+    import), so the lines of ``create_batch`` that choose the negative -- from
+    ``ind_exl = lab_indicators[lab]`` to ``_, k = sims.max(0)`` (:106-126) -- are taken from the
+    reference's source file AS TEXT and executed here.  The one line left out is the last of the
+    else branch, ``im3 = train_set[k[0]][0]`` (:127): it indexes a 0-dim tensor, which torch >= 0.4
+    refuses, and it only looks the chosen index up in the data set.  Returns
+    f(similarities, lab_indicators, lab, i1, i2, epoch, train_epoch_switch) -> index or -1."""
+    import textwrap
+    src = open(os.path.join(REF, "train", "siamese_regions.py")).read().split("\n")
+    first = next(i for i, l in enumerate(src) if l.strip() == "ind_exl = lab_indicators[lab]")
+    last = next(i for i, l in enumerate(src) if i > first and l.strip() == "_, k = sims.max(0)")
+    assert src[last + 1].strip() == "im3 = train_set[k[0]][0]", "reference source changed"
+    block = textwrap.dedent("\n".join(src[first:last + 1]))
+    code = compile(block, "train/siamese_regions.py:%d-%d" % (first + 1, last + 1), "exec")
+
+    class _P(object):
+        pass
+
+    def run(similarities, lab_indicators, lab, i1, i2, epoch, train_epoch_switch):
+        P = _P()
+        P.train_epoch_switch = train_epoch_switch
+        ns = {"similarities": similarities, "lab_indicators": lab_indicators, "lab": lab, "i1": i1, "i2": i2,
+              "epoch": epoch, "P": P, "print": lambda *a, **k: None}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")     # uint8 mask indexing is deprecated, not changed
+            exec(code, ns)
+        return int(ns["k"]) if "k" in ns else -1
+    return run
+
+
+# ----------------------------------------------------------------------------
 # import the reference with the two-class shim
 # ----------------------------------------------------------------------------
 def import_reference():
@@ -324,6 +358,17 @@ def main():
     hard = oracle.select_negatives(S, lab, couples, semi_hard=False)
     semi = oracle.select_negatives(S, lab, couples, semi_hard=True)
     assert (semi == -1).any() and (semi >= 0).any()
+    # the reference's own selection lines (executed from its source, see
+    # reference_negative_selection) on every couple, both modes: pins oracle.select_negative
+    ref_select = reference_negative_selection()
+    ds = [(None, "L%d" % int(v), "im%d" % n) for n, v in enumerate(lab)]
+    # torch-0.1 ByteTensor masks index and fill like today's bool masks (masked_fill_ refuses
+    # uint8 since torch 1.2): the indicators go in as bool, the reference lines run unchanged
+    ind = {lab_: m.bool() for lab_, m in oracle.mining.get_lab_indicators(ds).items()}
+    for mode, want in ((False, hard), (True, semi)):
+        epoch = 0 if mode else 5           # P.train_epoch_switch = 2 (train/siamese_regions_p.py)
+        got = torch.tensor([ref_select(S, ind, "L%d" % int(lab[a]), a, b, epoch, 2) for a, b in couples])
+        assert torch.equal(got, want), "oracle.select_negative differs from train/siamese_regions.py:106-126"
     save("mining_tiny", emb=E, lab=lab, couples=np.array(couples), sim=S,
          neg_hard=hard, neg_semi=semi)
     print("oracle == reference on every pinned function; goldens written")

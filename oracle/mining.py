@@ -1,10 +1,13 @@
 """Oracle (test infrastructure): all-pairs similarities and negative selection.
 
-PARITY UNPINNED for ``select_negative``: train/siamese_regions.py cannot be
+``select_negative`` restates train/siamese_regions.py:106-126.  That module cannot be
 imported (its ``P`` reads ``data/CLICIDE_448_train_ms.txt`` at import,
-train/siamese_regions_p.py:51), so the block at :106-129 is restated from
-source.  ``get_lab_indicators`` / ``embeddings_device_dim`` are pinned by
-``oracle/make_goldens.py`` against utils/train_siamese.py imported as-is.
+train/siamese_regions_p.py:51), so ``oracle/make_goldens.py`` takes those lines from the
+reference's source file as text, executes them on the couples of the ``mining_tiny``
+fixture in both modes and asserts that this restatement returns the same indices
+(the only line not executed is ``im3 = train_set[k[0]][0]``, :127 -- a data-set look-up
+that indexes a 0-dim tensor).  ``get_lab_indicators`` / ``embeddings_device_dim`` are
+pinned against utils/train_siamese.py imported as-is.
 """
 
 import torch
