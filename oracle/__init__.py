@@ -20,10 +20,11 @@ run in the build container*: ``oracle/make_goldens.py`` imports
 ``test/instance_avg.py`` unmodified (with a two-class shim for the legacy
 autograd Functions torch >= 1.5 refuses to run), feeds them seeded inputs,
 asserts this package returns bit-identical tensors, and writes the
-input/output vectors to ``tests/golden/*.npz``.  Functions of the reference
-that cannot be imported at all (``train/siamese_regions.py`` reads a missing
-data file at import) are restated from source and marked "parity unpinned"
-in their docstring.
+input/output vectors to ``tests/golden/*.npz``.  ``train/siamese_regions.py``
+cannot be imported (it reads a missing data file at import): the lines of its
+negative-selection block are executed from the reference's source text instead
+(``reference_negative_selection`` in ``oracle/make_goldens.py``) and
+``oracle.select_negative`` is asserted against them.
 
 All arithmetic the reference delegates to ``torch`` is delegated to the
 torch 2.11 CPU build of this image here as well -- that IS north_star's
