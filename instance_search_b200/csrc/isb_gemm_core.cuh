@@ -34,6 +34,27 @@ constexpr uint32_t kStageBytes = kABytes + kBBytes;               // 48 KB
 constexpr uint32_t kRingBytes = kStages * kStageBytes;            // 192 KB
 constexpr uint32_t kGemmSmemBytes = kRingBytes + 1024 /*align*/ + 256 /*barriers*/;
 
+// ------------------------------------------------------------------ role timeline (debug builds)
+// make TIMELINE=1 compiles the CTA-pair kernel with clock64 accounting of where each role
+// waits: the totals land in isb_timeline[blockIdx.x][slot] (cycles) and are read back with
+// isb_debug_timeline().  Off by default: the shipped kernel carries none of it.
+//   0 kernel total   1 producer: wave gate   2 producer: free stage (empty)
+//   3 MMA: accumulator drained (tmem_empty + peer)   4 MMA: stage loaded (full)
+//   5 epilogue warp 2: accumulator ready (tmem_full)   6 epilogue warp 2: tile()   7 tiles
+constexpr int kTimelineSlots = 8;
+#ifdef ISB_TIMELINE
+__device__ long long isb_timeline[256][kTimelineSlots];
+#define ISB_TL_DECL(name) long long name = 0
+#define ISB_TL_BEGIN(t) const long long t = clock64()
+#define ISB_TL_ADD(acc, t) acc += clock64() - t
+#define ISB_TL_STORE(slot, v) isb_timeline[blockIdx.x & 255][slot] = (v)
+#else
+#define ISB_TL_DECL(name)
+#define ISB_TL_BEGIN(t)
+#define ISB_TL_ADD(acc, t)
+#define ISB_TL_STORE(slot, v)
+#endif
+
 struct Segment {
   int m_block;   // rows [m_block*128, +128) of A
   int nt_begin;  // n-tiles [nt_begin, nt_end) of B (256 rows each)
@@ -283,6 +304,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tmem_base = bars->tmem_base;
 
   const int num_segments = sched.num_segments();
+  ISB_TL_BEGIN(tl_kernel0);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -291,14 +313,20 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int stage = 0;
     uint32_t phase = 0;
     int wave = 0;
+    ISB_TL_DECL(tl_gate);
+    ISB_TL_DECL(tl_empty);
     for (int s = pair_id; s < num_segments; s += n_pairs, ++wave) {
       const Segment seg = sched.segment(s);
       const int my_m_block = 2 * seg.m_block + static_cast<int>(rank);
       for (int nt = seg.nt_begin; nt < seg.nt_end; ++nt) {
+        ISB_TL_BEGIN(tl_g0);
         if (leader) sched.gate(seg, nt, wave, n_pairs);
+        ISB_TL_ADD(tl_gate, tl_g0);
         if (lane == 0) {
           for (int kb = seg.kb_begin; kb < seg.kb_end; ++kb) {
+            ISB_TL_BEGIN(tl_e0);
             ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+            ISB_TL_ADD(tl_empty, tl_e0);
             uint8_t* sa = ring + stage * kPairStageBytes;
             uint8_t* sb = sa + kABytes;
             if (leader) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * kPairStageBytes);
@@ -322,6 +350,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       if (leader && lane == 0) sched.leave(seg);
     }
+    if (lane == 0) {
+      ISB_TL_STORE(1, tl_gate);
+      ISB_TL_STORE(2, tl_empty);
+    }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       // ------------------------------------------------------------ MMA issuer (leader)
@@ -329,17 +361,23 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       uint32_t acc_iter = 0;
+      ISB_TL_DECL(tl_drain);
+      ISB_TL_DECL(tl_full);
       for (int s = pair_id; s < num_segments; s += n_pairs) {
         const Segment seg = sched.segment(s);
         for (int nt = seg.nt_begin; nt < seg.nt_end; ++nt, ++acc_iter) {
           const uint32_t buf = acc_iter & 1;
           const uint32_t acc_phase = (acc_iter >> 1) & 1;
+          ISB_TL_BEGIN(tl_d0);
           ptx::mbar_wait(&bars->tmem_empty[buf], acc_phase ^ 1);
           ptx::mbar_wait(&bars->peer_empty[buf], acc_phase ^ 1);
+          ISB_TL_ADD(tl_drain, tl_d0);
           ptx::tc_fence_after();
           const uint32_t tmem_acc = tmem_base + buf * kBN;
           for (int kb = seg.kb_begin; kb < seg.kb_end; ++kb) {
+            ISB_TL_BEGIN(tl_f0);
             ptx::mbar_wait(&bars->full[stage], phase);
+            ISB_TL_ADD(tl_full, tl_f0);
             ptx::tc_fence_after();
             const uint32_t sa = ptx::smem_u32(ring + stage * kPairStageBytes);
             const uint64_t da = ptx::make_smem_desc_k_sw128(sa);
@@ -355,6 +393,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           ptx::umma_commit_pair(&bars->tmem_full[buf], 3);   // both CTAs' accumulators complete
         }
       }
+      ISB_TL_STORE(3, tl_drain);
+      ISB_TL_STORE(4, tl_full);
+      ISB_TL_STORE(7, static_cast<long long>(acc_iter));
     } else if (lane == 0) {
       // ------------------------------------------------------------ drain relay (peer)
       uint32_t acc_iter = 0;
@@ -374,6 +415,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int row_in_tile = lane_group * 32 + lane;
     Epi epi(ep, row_in_tile);
     uint32_t acc_iter = 0;
+    ISB_TL_DECL(tl_ready);
+    ISB_TL_DECL(tl_tile);
     for (int s = pair_id; s < num_segments; s += n_pairs) {
       Segment seg = sched.segment(s);
       seg.m_block = 2 * seg.m_block + static_cast<int>(rank);
@@ -381,15 +424,26 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int nt = seg.nt_begin; nt < seg.nt_end; ++nt, ++acc_iter) {
         const uint32_t buf = acc_iter & 1;
         const uint32_t acc_phase = (acc_iter >> 1) & 1;
+        ISB_TL_BEGIN(tl_r0);
         ptx::mbar_wait(&bars->tmem_full[buf], acc_phase);
+        ISB_TL_ADD(tl_ready, tl_r0);
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + buf * kBN + (static_cast<uint32_t>(lane_group * 32) << 16);
+        ISB_TL_BEGIN(tl_t0);
         epi.tile(seg, nt, tmem_acc, &bars->tmem_empty[buf]);
+        ISB_TL_ADD(tl_tile, tl_t0);
       }
       epi.end_segment(seg);
     }
+    if (warp == kEpiWarp0 && lane == 0) {
+      ISB_TL_STORE(5, tl_ready);
+      ISB_TL_STORE(6, tl_tile);
+    }
   }
 
+  if (threadIdx.x == 0) {
+    ISB_TL_STORE(0, clock64() - tl_kernel0);
+  }
   ptx::tc_fence_before();
   ptx::cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal it
   if (warp == 1) {

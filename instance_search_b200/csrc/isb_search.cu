@@ -1714,3 +1714,13 @@ extern "C" int isb_select_negatives(const float* emb, const uint16_t* emb_hi, co
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;
 }
+
+#ifdef ISB_TIMELINE
+// debug builds (make TIMELINE=1): copies the role timeline of the last CTA-pair screen launch,
+// [256][8] cycle counters (see isb_gemm_core.cuh), to host memory
+extern "C" int isb_debug_timeline(long long* out) {
+  ISB_CUDA(cudaDeviceSynchronize());
+  ISB_CUDA(cudaMemcpyFromSymbol(out, isb::isb_timeline, sizeof(long long) * 256 * isb::kTimelineSlots));
+  return ISB_OK;
+}
+#endif
