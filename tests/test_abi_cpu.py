@@ -100,3 +100,11 @@ def test_product_does_not_import_the_oracle():
                 src = f.read()
             m = re.search(r"^\s*(?:import|from)\s+oracle\b.*$", src, flags=re.M)
             assert m is None, "%s imports the oracle: %s" % (fn, m.group(0))
+
+
+def test_shipped_library_is_not_the_timeline_debug_build():
+    # make TIMELINE=1 (role timeline of the CTA-pair screen) is a debug build: the library the
+    # tests, the bench and the driver load must be the plain one
+    from instance_search_b200 import _lib
+    with pytest.raises(AttributeError):
+        _lib.lib().isb_debug_timeline
