@@ -207,6 +207,36 @@ def time_cpu(q, db, k, repeats=1):
     return best
 
 
+def topk_parity(q, db, k, gpu_scores, gpu_idx, cpu_scores, cpu_idx, tie_atol=5e-7):
+    """GPU top-k of a query sample against the CPU oracle's (torch fp32 mm + topk on the host).
+    rows identical to the oracle are index-exact; a row that differs is adjudicated in fp64 on
+    the union of the two lists: it counts as fp64_adjudicated when the fp64 ranking of that
+    union is the GPU's list AND every differing entry is an fp32-noise tie in the oracle's own
+    scores (gap <= tie_atol); anything else is unexplained."""
+    gs, gi = gpu_scores.cpu(), gpu_idx.cpu()
+    rows = gi.size(0)
+    same = (gi == cpu_idx).all(dim=1)
+    adjudicated, unexplained, max_gap, entries = 0, 0, 0.0, 0
+    for r in (~same).nonzero().flatten().tolist():
+        entries += int((gi[r] != cpu_idx[r]).sum())
+        union = torch.unique(torch.cat([gi[r], cpu_idx[r]]))          # sorted: ties -> lower index
+        s64 = db[union].double() @ q[r].double()
+        order = torch.sort(s64, descending=True, stable=True).indices[:k]
+        pos = (gi[r] != cpu_idx[r]).nonzero().flatten()
+        gap = ((db[gi[r, pos]] * q[r]).sum(1) - cpu_scores[r, pos]).abs().max().item()
+        max_gap = max(max_gap, gap)
+        if torch.equal(union[order], gi[r]) and gap <= tie_atol:
+            adjudicated += 1
+        else:
+            unexplained += 1
+    rel = ((gs - cpu_scores).abs() / cpu_scores.abs().clamp_min(1e-6)).max().item()
+    return {"rows": rows, "index_exact_rows": int(same.sum()), "fp64_adjudicated": adjudicated,
+            "unexplained_rows": unexplained, "entries_differing": entries, "max_tie_gap": max_gap,
+            "tie_atol": tie_atol, "max_rel_score_err": rel, "k": k,
+            "oracle": "torch fp32 mm + topk on the host (oracle.similarity), first %d queries over the "
+                      "full database" % rows}
+
+
 def run_reference(a, rank, world):
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
@@ -234,7 +264,7 @@ def run_reference(a, rank, world):
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(a, 1),
+        "config": workload_config(a, max(1, world)),
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -326,28 +356,40 @@ def run_b200(a, rank, world, local_rank):
     flops = 2.0 * a.queries * rows_local * a.dim          # 2*Q*N*D per launch
     achieved = flops / (screen_ms * 1e-3) / 1e12
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])  # timed inside a long step
+    traffic, traffic_src = None, None
+    if a.queries == Q_DEFAULT and a.dim == D_DEFAULT and a.k == K_DEFAULT:
+        traffic, traffic_src = profile_traffic(rows_local)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak,
-                "traffic": (NCU_SCREEN_TRAFFIC_BYTES if (world == 1 and a.queries == Q_DEFAULT and
-                                                         a.db_rows == N_DEFAULT and a.dim == D_DEFAULT) else None),
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_search_screen_pair.txt",
+                "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes": 2.0 * rows_local * a.dim + 2.0 * a.queries * a.dim + 8.0 * a.queries * a.k,
                 "kernel": "gemm_tc_pair_kernel<TopkSched,TopkEpilogue> (tcgen05 cta_group::2 screen, 256x256 tiles, "
                           "streaming top-k epilogue)",
                 "kernel_ms": screen_ms, "peak_source": pk_src + " bf16_tflops_sustained",
                 "frac_of_burst_peak": achieved / pk["bf16_tflops"]}
 
+    # the result every rank holds after the timed steps (identical on all ranks), for the parity check
+    res_s, res_i = index.search(q_dev, a.k)
+    torch.cuda.synchronize()
+
     line = None
     if rank == 0:
-        cpu = None
-        if world == 1 and not a.no_cpu_baseline:
+        cpu, parity = None, None
+        if not a.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
-            nq = a.cpu_sample_queries
-            db_host = index.local.db_f32[:, :a.dim].cpu()
-            dt = time_cpu(q_host[:nq], db_host, a.k)
-            cpu = {"value": nq / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": "first %d of %d queries over the full %d-row database (%.1f s), torch fp32 "
-                             "mm + topk(%d) on the host" % (nq, a.queries, a.db_rows, dt, a.k)}
+            nq = min(a.cpu_sample_queries, a.queries)
+            if world == 1:
+                db_host = index.local.db_f32[:, :a.dim].cpu()
+            else:   # rank 0 draws the whole database (the same global stream) and keeps it on the host
+                db_host = make_rows_host(a.db_rows, a.dim, SEED, dev)
+            t0 = time.perf_counter()
+            cpu_s, cpu_i = cpu_topk(q_host[:nq], db_host, a.k)
+            dt = time.perf_counter() - t0
+            if world == 1:
+                cpu = {"value": nq / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                       "sample": "first %d of %d queries over the full %d-row database (%.1f s), torch fp32 "
+                                 "mm + topk(%d) on the host" % (nq, a.queries, a.db_rows, dt, a.k)}
+            parity = topk_parity(q_host[:nq], db_host, a.k, res_s[:nq], res_i[:nq], cpu_s, cpu_i)
             del db_host
         # N = 1: bf16 cast, thr init, screen, rerank.  N > 1: bf16 cast, thr init, screen, candidates,
         # global threshold, rerank of the owned candidates, certified merge (NCCL's kernels not counted)
@@ -357,7 +399,7 @@ def run_b200(a, rank, world, local_rank):
             "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16 screen + f64-accumulated f32 re-rank",
             "data": "synthetic (seeded unit-norm Gaussian rows)", "config": workload_config(a, world),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": q_host.numel() * 4,
                     "d2h_bytes_per_step": out_s_host.numel() * 4 + out_i_host.numel() * 8,
@@ -371,7 +413,8 @@ def run_b200(a, rank, world, local_rank):
         if world == 1 and not a.no_secondary:
             del index
             torch.cuda.empty_cache()
-            line["secondary"] = {"region_descriptors": side_regions(dev, pk), "mining": side_mining(dev, pk)}
+            line["secondary"] = {"region_descriptors": side_regions(dev, pk, not a.no_cpu_baseline),
+                                 "mining": side_mining(dev, pk, not a.no_cpu_baseline)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -382,8 +425,32 @@ def run_b200(a, rank, world, local_rank):
 # ------------------------------------------------------------------ side measurements (N = 1)
 # BASELINE.json's metric also names "region descriptors/s" (configs[1]) and the path includes
 # the mining of configs[2]; they are measured here after the headline, on rank 0, a few ms each.
-NCU_SCREEN_TRAFFIC_BYTES = 11.3e9   # dram read + write of the screen kernel at the headline size,
-                                    # profiles/r01_ncu_search_screen_pair.txt (ncu --set full)
+SCREEN_PROFILES = {   # rows of the screened shard -> committed ncu --set full summary of the screen kernel
+    1000000: ("profiles/r02_ncu_search_screen_1M.txt", "profiles/r01_ncu_search_screen_pair.txt"),
+    125000: ("profiles/r02_ncu_search_screen_125k_shard.txt", "profiles/r01_ncu_search_screen_pair_125k_shard.txt"),
+}
+
+
+def profile_traffic(rows_local):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the screen kernel, per launch, parsed from the
+    committed ncu summary of the same shape (a profile, not a measurement of this run: ncu cannot run
+    inside the timed bench).  (None, None) when no capture of this shard size is committed."""
+    for rel in SCREEN_PROFILES.get(int(rows_local), ()):
+        path = os.path.join(ROOT, rel)
+        if not os.path.exists(path):
+            continue
+        total, seen = 0.0, set()
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        with open(path) as f:
+            for ln in f:
+                parts = ln.split()
+                if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") \
+                        and parts[0] not in seen:      # first launch listed in the summary
+                    seen.add(parts[0])
+                    total += float(parts[1]) * scale.get(parts[2], 1.0)
+        if len(seen) == 2:
+            return total, "from profile %s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)" % rel
+    return None, None
 
 
 def _median_ms(fn, iters=10, warmup=3, flush=None):
@@ -401,18 +468,33 @@ def _median_ms(fn, iters=10, warmup=3, flush=None):
     return sorted(ts)[len(ts) // 2]
 
 
-def side_regions(dev, pk):
+def cpu_regions(x_host, host_w, k):
+    """The reference's CPU path for region descriptors: forward_single image by image
+    (model/siamese.py:185-223 via train/siamese_regions.py:31-38), oracle restatement,
+    torch fp32 on all host cores.  Returns (seconds, desc, idx)."""
+    import oracle
+    t0 = time.perf_counter()
+    d, _, i, _ = oracle.region_descriptor_forward(x_host, *host_w, k, (7, 7))
+    return time.perf_counter() - t0, d, i
+
+
+def side_regions(dev, pk, cpu_baseline=True):
     """configs[1]: 256 x 2048 x {14x14, 32x32} fp32 maps -> descriptors (eval path, D=2048, k=6)."""
     from instance_search_b200 import regions
     g = torch.Generator(device=dev).manual_seed(1234 + 2)
     B, C, ncls, D, k = 256, 2048, 464, 2048, 6
     Kin = C * 49
+    lin_w_f32 = torch.randn(D, Kin, device=dev, generator=g) / Kin ** 0.5
     hw = regions.HeadWeights(torch.randn(ncls, C, device=dev, generator=g) / C ** 0.5,
                              0.01 * torch.randn(ncls, device=dev, generator=g),
                              0.01 * torch.randn(Kin, device=dev, generator=g),
-                             torch.randn(D, Kin, device=dev, generator=g) / Kin ** 0.5,
+                             lin_w_f32,
                              0.01 * torch.randn(D, device=dev, generator=g))
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB > L2
+    host_w = None
+    if cpu_baseline:
+        host_w = [t.cpu() for t in (hw.cls_w, hw.cls_b, hw.shift, lin_w_f32, hw.lin_b)]
+    del lin_w_f32
     out = {}
     for hwsize in (14, 32):
         x = torch.relu(torch.randn(B, C, hwsize, hwsize, device=dev, generator=g))
@@ -439,6 +521,23 @@ def side_regions(dev, pk):
         n_unc_stream = int(torch.stack(pending).sum().item())
         del x2
         regions._PROBE_CACHE.clear()
+        cpu, parity = None, None
+        if host_w is not None:
+            # the reference's per-image CPU path on a bounded sample of the same batch, and the GPU
+            # descriptors of those images against it
+            ns = 32 if hwsize == 14 else 16
+            torch.set_num_threads(os.cpu_count() or 1)
+            dt, od, oi = cpu_regions(x[:ns].cpu(), host_w, k)
+            gd, _, gi, _ = regions.region_descriptors(x, hw, k, (7, 7), want_cls_out=False)
+            gd, gi = gd[:ns].cpu().double(), gi[:ns].cpu()
+            u_cpu = ns * min((hwsize - 6) ** 2, k)
+            cpu = {"value": u_cpu / dt, "unit": "region descriptors/s", "cores": torch.get_num_threads(),
+                   "kind": "port", "sample": "first %d of %d images, forward_single looped per image "
+                   "(oracle, torch fp32), %.1f s" % (ns, B, dt)}
+            l2 = (gd - od.double()).norm(dim=1)
+            parity = {"images": ns, "windows_identical_images": int((gi == oi).all(dim=1).sum()),
+                      "max_descriptor_l2_err": float(l2.max()),
+                      "max_1_minus_cos": float((1 - (gd * od.double()).sum(1) / (gd.norm(dim=1) * od.double().norm(dim=1))).max())}
         # SURVEY 8d bytes of the bandwidth-bound part: x once + classifier + the bf16 hi+lo operand
         nbytes = 4 * B * C * hwsize * hwsize + 4 * ncls * C + 2 * 2 * B * Kin
         units = B * min((hwsize - 6) ** 2, k)
@@ -455,13 +554,30 @@ def side_regions(dev, pk):
             "streamed": {"ms_per_batch": ms_stream, "region_descriptors_per_s": units / (ms_stream * 1e-3),
                          "batches_in_flight": nstream, "uncertified_images_last_pass": n_unc_stream},
             "batches_resolved_exactly": stats.get("batches_resolved_exactly", 0),
-            "images_resolved_exactly": stats.get("images_resolved_exactly", 0), "batches": stats.get("batches", 0)}
+            "images_resolved_exactly": stats.get("images_resolved_exactly", 0), "batches": stats.get("batches", 0),
+            "cpu_baseline": cpu, "parity": parity}
         del x
     return {"workload": "region descriptors (eval), 256 x 2048 x HxW fp32 maps, ncls=464, k=6, D=2048 "
                         "(BASELINE configs[1]); L2 flushed between batches", **out}
 
 
-def side_mining(dev, pk):
+def cpu_mining(E, lab, anchors, positives, semi, n_couples):
+    """The reference's CPU path for mining: similarities = mm(E, E.t()) (utils/train_siamese.py:53),
+    then per couple the masked arg-max of train/siamese_regions.py:106-126 (oracle restatement).  The
+    product is timed in full; the per-couple selection on the first n_couples couples and scaled to
+    all of them.  Returns (seconds for all couples, negatives of the sampled couples)."""
+    import oracle
+    t0 = time.perf_counter()
+    S = oracle.mining.all_pairs_similarities(E)
+    t_mm = time.perf_counter() - t0
+    couples = list(zip(anchors[:n_couples].tolist(), positives[:n_couples].tolist()))
+    t0 = time.perf_counter()
+    neg = oracle.select_negatives(S, lab, couples, semi)
+    t_sel = time.perf_counter() - t0
+    return t_mm + t_sel * (anchors.numel() / float(n_couples)), t_mm, neg
+
+
+def side_mining(dev, pk, cpu_baseline=True):
     """configs[2]: all-pairs similarities + (semi-)hard negative of every anchor, 16384 x 2048."""
     from instance_search_b200 import mining
     g = torch.Generator(device=dev).manual_seed(1234 + 3)
@@ -474,12 +590,38 @@ def side_mining(dev, pk):
     idx = mining.MiningIndex(E, lab.int())
     out = {"workload": "negative mining, 16384 x 2048-d descriptors, 16 per label, one couple per anchor "
                        "(BASELINE configs[2])"}
-    flops = 2.0 * N * N * D
+    flops = 2.0 * N * N * D          # 2 N^2 D, whatever the screen issues to get there
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    E_host, lab_host = (E.cpu(), lab.cpu()) if cpu_baseline else (None, None)
     for semi in (True, False):
         ms = _median_ms(lambda: idx.select_negatives(anchors, positives, semi))
-        out["semi_hard" if semi else "hard"] = {
-            "ms": ms, "anchors_per_s": N / (ms * 1e-3), "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
-            "issued_tflops": 3 * flops / (ms * 1e-3) / 1e12, "bruteforce_rows": int(idx.last_bruteforce)}
+        tf = flops / (ms * 1e-3) / 1e12
+        rec = {"ms": ms, "anchors_per_s": N / (ms * 1e-3),
+               "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                            "algorithmic_flops": flops},
+               "bruteforce_rows": int(idx.last_bruteforce), "screen_terms": idx.terms}
+        if cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            nc = 1024
+            dt, t_mm, want = cpu_mining(E_host, lab_host, anchors.cpu(), positives.cpu(), semi, nc)
+            got = idx.select_negatives(anchors, positives, semi)[0][:nc].cpu()
+            rec["cpu_baseline"] = {"value": N / dt, "unit": "anchors/s", "cores": torch.get_num_threads(),
+                                   "kind": "port", "sample": "mm(E, E.t()) in full (%.1f s) + masked arg-max of the "
+                                   "first %d couples scaled to %d (oracle, torch fp32)" % (t_mm, nc, N)}
+            rec["parity"] = {"couples": nc, "identical_negatives": int((got == want).sum())}
+        out["semi_hard" if semi else "hard"] = rec
+    return out
+
+
+def make_rows_host(n, d, seed, device, chunk=131072):
+    """make_rows(n, d, seed) drawn chunk by chunk on `device` (the same global stream every shard
+    is cut from) and moved to host memory: the oracle's copy of a database that is sharded over
+    several GPUs."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = torch.empty((n, d), dtype=torch.float32)
+    for s in range(0, n, chunk):
+        x = torch.randn((min(chunk, n - s), d), generator=g, device=device)
+        out[s:s + chunk] = (x / x.norm(dim=1, keepdim=True)).cpu()
     return out
 
 

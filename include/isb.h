@@ -35,7 +35,7 @@ extern "C" {
 #define ISB_ERR_WORKSPACE 3
 #define ISB_ERR_UNSUPPORTED_DEVICE 4
 
-#define ISB_ABI_VERSION 4
+#define ISB_ABI_VERSION 5
 
 /* Largest k (after the screening margin is added) one search call supports. */
 #define ISB_MAX_CANDIDATES 128
@@ -44,6 +44,31 @@ int isb_abi_version(void);
 const char* isb_last_error(void);
 /* 0 when the current device is compute capability 10.x, else an error code. */
 int isb_check_device(void);
+
+/* Tuning options.  The library reads nothing from the environment: the A/B switches that
+ * let a claim of DESIGN.md be re-measured are set explicitly, process-wide, by the caller.
+ * Defaults are the measured best.  An option is read when a call makes its launch plan; one
+ * that changes a workspace layout (SCREEN_PAIR, SCREEN_SEED, POOL_G) must not change between
+ * a *_workspace_bytes() query and the call it sizes.
+ * isb_set_option(option, value >= 0) sets, value == -1 restores the default;
+ * isb_get_option returns the set value or -1 (default in force / unknown option). */
+enum {
+  ISB_OPT_SCREEN_PAIR = 0,       /* 1 (default): CTA-pair 256 x 256 screen when it fits; 0: single-CTA kernel */
+  ISB_OPT_SCREEN_SEED = 1,       /* 1: seed the screen thresholds from a sample of the database (default 0) */
+  ISB_OPT_SCREEN_WAVESYNC = 2,   /* 1 (default): wave barrier of the screen scheduler; 0: off */
+  ISB_OPT_MINING_KC = 3,         /* candidates re-checked exactly per couple, 1..128 (default 16) */
+  ISB_OPT_POOL_STAGES = 4,       /* ring depth of the pooling kernel (default 3) */
+  ISB_OPT_POOL_G = 5,            /* channel blocks per pooling CTA (default: fills whole waves) */
+  ISB_OPT_POOL_GENERIC_GEOM = 6, /* 1: pooling kernel without compile-time geometry (default 0) */
+  ISB_OPT_REGION_POOL_TC = 7,    /* 1: tensor-core pooling kernel (default 0) */
+  ISB_OPT_TC_DEBUG = 8,          /* ablation flags of the tensor-core pooling kernel (default 0) */
+  ISB_OPT_GATHER_CW = 9,         /* channels per warp unit of the gather kernel */
+  ISB_OPT_GATHER_G = 10,         /* units per warp of the gather kernel */
+  ISB_OPT_GATHER_STAGES = 11,    /* ring depth of the gather kernel */
+  ISB_OPT_COUNT_ = 12
+};
+int isb_set_option(int option, int value);
+int isb_get_option(int option);
 
 /* ---------------------------------------------------------------- a1 / a5
  * y[m, :] = x[m, :] / sqrt(sum_j x[m, j]^2 + eps)          (eps INSIDE the sqrt)
@@ -78,10 +103,14 @@ int isb_f32_to_bf16(const float* x, int64_t rows, int64_t cols, int64_t ldx, uin
  *            fp32 rows accumulated in fp64, sorted, ties -> lower index
  *   stage 2b completeness certificate per query: every database row outside the
  *            candidate list has a screen score <= t_min (the worst candidate's),
- *            so the list provably contains the true top k when
+ *            so the list contains the true top k -- to 8 sigma of the screen noise,
+ *            a statistical statement, not a proof -- when
  *               exact_kth - t_min  >  8 * sigma + 4e-7 * |score|
  *            with sigma = rms(screen - exact) MEASURED on the row's own
- *            candidates.  Rows that fail are appended to uncertified_rows and
+ *            candidates and floored by the noise bf16 operand rounding is expected
+ *            to have on dense rows (1.6e-3 |q||db| / sqrt(D); half of it from 32
+ *            candidates on, 1.5x below: a sigma from a few samples can be ~0).
+ *            Rows that fail are appended to uncertified_rows and
  *            counted in *n_uncertified (both device memory, may both be NULL to
  *            skip the test); the caller resolves them with isb_topk_resolve and,
  *            if still uncertified, isb_topk_exhaustive.
@@ -304,22 +333,35 @@ int isb_descriptor_finalize(const float* y, int64_t B, int64_t D, const float* b
  *              the reference then draws a random negative on the host, :112-129)
  * semi_hard is the reference's `epoch < P.train_epoch_switch`.
  * The rows of a tcgen05 screen GEMM are the anchors; the masks are applied in its
- * streaming top-k epilogue; the <= 128 survivors per couple are re-scored exactly
- * (fp64 accumulation) and the exact conditions re-applied; a couple whose
- * candidate list cannot be certified complete falls to an exhaustive exact pass
- * (counted in *n_bruteforce when non-NULL).
+ * streaming top-k epilogue; the survivors (ISB_OPT_MINING_KC per couple, default 16) are
+ * re-scored exactly (fp64 accumulation) and the exact conditions re-applied.
+ * Certificate per couple: every column outside the candidate list has a screen score <= the
+ * worst candidate's (t_min), hence an exact score <= t_min + eps; the couple is certified when
+ * the exact winner clears that, with
+ *   eps = max(screen_eps, 8 * max(sigma_measured, sigma_floor)),
+ * sigma_measured = rms(screen - exact) over the couple's own candidates.  (Statistical, not a
+ * proof: 8 sigma.)  In semi-hard mode the epilogue also drops columns whose screen score is
+ * >= S[anchor, positive] + max(screen_eps, 8 * sigma_floor); a couple whose measured noise
+ * exceeds that slack is rejected too.
+ *   uncertified_rows != NULL: the rejected couples (indices p) are listed there and counted in
+ *     *n_uncertified; the caller re-runs them with a finer screen (split operands) -- the
+ *     second line, as isb_topk_resolve is for the search.
+ *   uncertified_rows == NULL: they are recomputed by an exhaustive exact pass inside this call
+ *     (counted in *n_uncertified when non-NULL).
  *   emb [N, D] fp32 (unit rows); emb_hi / emb_lo [N, ld] bf16 = isb_f32_to_bf16 parts
- *   0 / 1 of emb: the split operands of the fp32-grade screen
- *   (a_hi.b_hi + a_lo.b_hi + a_hi.b_lo).  emb_lo == NULL: plain bf16 screen.
- *   screen_eps: absolute error bound of the screen scores (2e-5 split, 4e-3 plain)
+ *   0 / 1 of emb.  emb_lo == NULL: plain bf16 screen (one tcgen05 product per tile;
+ *   screen_eps = 0, sigma_floor = the expected bf16 noise 1.6e-3 |a||b| / sqrt(D)).
+ *   emb_lo != NULL: split operands, a_hi.b_hi + a_lo.b_hi + a_hi.b_lo, an fp32-grade screen
+ *   (three products per tile; screen_eps = 2e-5 absolute on unit rows, sigma_floor = 0).
  *   label [N] int32; anchors, positives [P] int64
  *   neg_idx [P] int64; neg_sim [P] fp32 (-2 when none); pos_sim [P] fp32 */
 size_t isb_select_negatives_workspace_bytes(int64_t P, int64_t N, int64_t D, int split);
 int isb_select_negatives(const float* emb, const uint16_t* emb_hi, const uint16_t* emb_lo, int64_t ld,
                          int64_t N, int64_t D, const int32_t* label, const int64_t* anchors,
                          const int64_t* positives, int64_t P, int semi_hard, float screen_eps,
-                         int64_t* neg_idx, float* neg_sim, float* pos_sim, int32_t* n_bruteforce,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         float sigma_floor, int64_t* neg_idx, float* neg_sim, float* pos_sim,
+                         int32_t* uncertified_rows, int32_t* n_uncertified, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- a9 (reduction)
  * precision1's row reduction, utils/metrics.py:11-13:  kth <= 1 -> sim.max(1);

@@ -16,13 +16,15 @@ c_f32 = ctypes.c_float
 c_ptr = ctypes.c_void_p
 c_size = ctypes.c_size_t
 
-ABI_VERSION = 4   # == ISB_ABI_VERSION in include/isb.h
+ABI_VERSION = 5   # == ISB_ABI_VERSION in include/isb.h
 
 # name -> (restype, argtypes); mirrors include/isb.h one to one
 SIGNATURES = {
     "isb_abi_version": (c_int, []),
     "isb_last_error": (ctypes.c_char_p, []),
     "isb_check_device": (c_int, []),
+    "isb_set_option": (c_int, [c_int, c_int]),
+    "isb_get_option": (c_int, [c_int]),
     "isb_l2norm_rows": (c_int, [c_ptr, c_i64, c_i64, c_f32, c_ptr, c_ptr]),
     "isb_shift_rows": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "isb_f32_to_bf16": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_int, c_ptr]),
@@ -60,7 +62,8 @@ SIGNATURES = {
     "isb_descriptor_finalize": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_f32, c_ptr, c_ptr]),
     "isb_select_negatives_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_int]),
     "isb_select_negatives": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64,
-                                     c_int, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+                                     c_int, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size,
+                                     c_ptr]),
     "isb_row_kth_largest": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
     "isb_row_ranks": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_int, c_ptr, c_ptr]),
     "isb_instance_avg": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
@@ -75,6 +78,14 @@ SIGNATURES = {
                             c_int, c_ptr, c_size, c_ptr]),
     "isb_gemm_nt_split": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr,
                                   c_ptr, c_i64, c_int, c_ptr, c_size, c_ptr]),
+}
+
+
+# ISB_OPT_* of include/isb.h
+OPTIONS = {
+    "screen_pair": 0, "screen_seed": 1, "screen_wavesync": 2, "mining_kc": 3, "pool_stages": 4, "pool_g": 5,
+    "pool_generic_geom": 6, "region_pool_tc": 7, "tc_debug": 8, "gather_cw": 9, "gather_g": 10,
+    "gather_stages": 11,
 }
 
 
@@ -110,3 +121,35 @@ def check(rc, what):
     if rc != 0:
         msg = lib().isb_last_error().decode("utf-8", "replace")
         raise IsbError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def set_option(name, value):
+    """Set a tuning option of the library (include/isb.h, ISB_OPT_*); value None or -1
+    restores the default.  The library reads nothing from the environment."""
+    if name not in OPTIONS:
+        raise IsbError("unknown option %r (known: %s)" % (name, ", ".join(sorted(OPTIONS))))
+    check(lib().isb_set_option(OPTIONS[name], -1 if value is None else int(value)), "isb_set_option")
+
+
+def get_option(name):
+    """The explicitly set value of an option, or None when its default is in force."""
+    v = lib().isb_get_option(OPTIONS[name])
+    return None if v < 0 else v
+
+
+class options(object):
+    """``with options(screen_pair=0): ...`` -- set options for a block, restore afterwards."""
+
+    def __init__(self, **kw):
+        self.kw, self.old = kw, {}
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            self.old[k] = get_option(k)
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            set_option(k, v)
+        return False

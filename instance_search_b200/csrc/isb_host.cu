@@ -1,6 +1,7 @@
 // Error state, device checks and TMA tensor-map construction.
 #include "isb_host.cuh"
 
+#include <atomic>
 #include <mutex>
 #include <string.h>
 
@@ -13,6 +14,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// Tuning options (include/isb.h, isb_set_option): explicit, process-wide, -1 = default.
+static std::atomic<int> g_options[ISB_OPT_COUNT_];
+
+int option(int id, int dflt) {
+  if (id < 0 || id >= ISB_OPT_COUNT_) return dflt;
+  const int v = g_options[id].load(std::memory_order_relaxed);
+  return v == 0 ? dflt : v - 1;   // stored biased by one so that zero-initialised means "unset"
 }
 
 int device_sm_count() {
@@ -71,6 +81,18 @@ int make_tmap_bf16_k64(CUtensorMap* map, const void* base, uint64_t rows, uint64
 }  // namespace isb
 
 extern "C" int isb_abi_version(void) { return ISB_ABI_VERSION; }
+
+extern "C" int isb_set_option(int option_id, int value) {
+  ISB_CHECK_ARG(option_id >= 0 && option_id < ISB_OPT_COUNT_, "isb_set_option: unknown option %d", option_id);
+  ISB_CHECK_ARG(value >= -1, "isb_set_option: value must be >= 0, or -1 to restore the default");
+  isb::g_options[option_id].store(value + 1, std::memory_order_relaxed);
+  return ISB_OK;
+}
+
+extern "C" int isb_get_option(int option_id) {
+  if (option_id < 0 || option_id >= ISB_OPT_COUNT_) return -1;
+  return isb::option(option_id, -1);
+}
 
 extern "C" const char* isb_last_error(void) { return isb::g_err; }
 

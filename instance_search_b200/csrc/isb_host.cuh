@@ -15,6 +15,8 @@ namespace isb {
 
 void set_error(const char* fmt, ...);
 int device_sm_count();
+// value of a tuning option (ISB_OPT_*), dflt when it was never set / reset with -1
+int option(int id, int dflt);
 
 #define ISB_CHECK_ARG(cond, ...)            \
   do {                                      \

@@ -1785,8 +1785,7 @@ static bool make_region_plan(RegionPlan& p, int64_t B, int C, int H, int W, int 
     p.fast_threads = (H <= 16 && W <= 16) ? kFastThreadsSmall : kFastThreads;
     // prefetch ring: as many plane buffers (<= want) as leave room for 4 CTAs per SM on small
     // maps (their passes overlap) / fit one SM on large ones
-    const char* st_env = getenv("ISB_POOL_STAGES");
-    int want = st_env ? atoi(st_env) : kPoolDefaultStages;
+    int want = option(ISB_OPT_POOL_STAGES, kPoolDefaultStages);
     if (want < 2) want = 2;
     if (want > kPoolMaxStages) want = kPoolMaxStages;
     const size_t budget = (p.fast_threads == kFastThreadsSmall) ? 55 * 1024 : 224 * 1024;
@@ -1818,11 +1817,10 @@ static bool make_region_plan(RegionPlan& p, int64_t B, int C, int H, int W, int 
   // 64-channel blocks (any window size: Box is built from fh x fw)
   p.tc = false;
   p.eplanes = 1;
-  // Opt-in (ISB_REGION_POOL=tc) while it is slower than the CUDA-core kernel: 229 us vs 202 us
+  // Opt-in (ISB_OPT_REGION_POOL_TC = 1) while it is slower than the CUDA-core kernel: 229 us vs 202 us
   // per 256 x 2048 x 14 x 14 batch (profiles/r01_ncu_pool_tc.txt: latency-bound hand-offs
   // between the roles, 29% of DRAM bandwidth); results are identical either way.
-  const char* pool_mode = getenv("ISB_REGION_POOL");
-  const bool want_tc = pool_mode != nullptr && pool_mode[0] == 't' && pool_mode[1] == 'c';
+  const bool want_tc = option(ISB_OPT_REGION_POOL_TC, 0) == 1;
   if (want_tc && HW <= 256 && HW % 4 == 0 && p.nwin <= 128 && C % kTcCB == 0) {
     TcGeom& t = p.tcg;
     t.nslab = (HW + 63) / 64;
@@ -1836,8 +1834,7 @@ static bool make_region_plan(RegionPlan& p, int64_t B, int C, int H, int W, int 
     const bool items_ok = (kTcCB + t.lanes_c - 1) / t.lanes_c <= kTcMaxItems;
     if (smem <= 227 * 1024 && items_ok) {
       p.tc = true;
-      const char* dbg = getenv("ISB_TC_DEBUG");
-      t.dbg = dbg ? atoi(dbg) : 0;
+      t.dbg = option(ISB_OPT_TC_DEBUG, 0);
       p.CB = kTcCB;
       p.pool_smem = smem;
       p.eplanes = t.lanes_c;
@@ -1849,7 +1846,7 @@ static bool make_region_plan(RegionPlan& p, int64_t B, int C, int H, int W, int 
   // the LARGEST power of two that still fills whole waves of resident CTAs to >= 95 % (fewer
   // prologues, energy partials and ring refills per image; measured: 8 at 14 x 14 with four CTAs
   // per SM -- 16 leaves 3.46 waves, 0.64 instead of 0.71 of HBM -- and 32 at 32 x 32 with one CTA
-  // per SM, 0.80 instead of 0.76).  ISB_POOL_G overrides.
+  // per SM, 0.80 instead of 0.76).  ISB_OPT_POOL_G overrides.
   {
     const int64_t slots = static_cast<int64_t>(device_sm_count()) *
                           ((p.fast && p.fast_threads == kFastThreadsSmall) ? 4 : 1);
@@ -1859,8 +1856,8 @@ static bool make_region_plan(RegionPlan& p, int64_t B, int C, int H, int W, int 
       const int64_t waves = (ctas + slots - 1) / slots;
       if (ctas >= slots && static_cast<double>(ctas) >= 0.95 * static_cast<double>(waves * slots)) p.G = g;
     }
-    if (const char* e = getenv("ISB_POOL_G")) {
-      const int v = atoi(e);
+    {
+      const int v = option(ISB_OPT_POOL_G, 0);
       if (v >= 1 && v <= 128) p.G = v < p.nblk ? v : p.nblk;
     }
   }
@@ -1975,7 +1972,7 @@ extern "C" int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H
     else if (H == 32 && W == 32 && p.CB == 16) kern = region_pool_fast_kernel<32, kFastThreads, 1, 32, 32, 16>;
     else if (p.fast_threads == kFastThreadsSmall) kern = region_pool_fast_kernel<16, kFastThreadsSmall, 4, 0, 0, 0>;
     else kern = region_pool_fast_kernel<32, kFastThreads, 1, 0, 0, 0>;
-    if (getenv("ISB_POOL_GENERIC_GEOM") != nullptr)   // A/B switch: same kernel without the folded constants
+    if (option(ISB_OPT_POOL_GENERIC_GEOM, 0) == 1)   // A/B switch: same kernel without the folded constants
       kern = (p.fast_threads == kFastThreadsSmall) ? region_pool_fast_kernel<16, kFastThreadsSmall, 4, 0, 0, 0>
                                                    : region_pool_fast_kernel<32, kFastThreads, 1, 0, 0, 0>;
     ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pool_smem));
@@ -2062,8 +2059,8 @@ extern "C" int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H
   for (int cw : {8, 4, 2, 1}) {
     if (static_cast<size_t>(cw) * HW * 4 <= 4 * 1024) { CW = cw; break; }
   }
-  if (const char* e = getenv("ISB_GATHER_CW")) {
-    const int cw = atoi(e);
+  {
+    const int cw = option(ISB_OPT_GATHER_CW, 0);
     if (cw >= 1 && cw <= 64) CW = cw;
   }
   const int row_align = (W % 4 == 0) ? 1 : ((W % 2 == 0) ? 2 : 4);
@@ -2071,12 +2068,12 @@ extern "C" int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H
   const int units = static_cast<int>((C + kGatherWarps * CW - 1) / (kGatherWarps * CW));   // unit rounds per image
   // units per warp: the ring needs a few to run ahead of; keep >= 8 waves of CTAs
   int GG = kGatherDefaultG;
-  if (const char* e = getenv("ISB_GATHER_G")) GG = atoi(e);
+  GG = option(ISB_OPT_GATHER_G, GG);
   if (GG < 1) GG = 1;
   while (GG > 1 && B * ((units + GG - 1) / GG) < 148 * 8) GG >>= 1;
   if (GG > units) GG = units;
   int NST = kGatherDefaultStages;
-  if (const char* e = getenv("ISB_GATHER_STAGES")) NST = atoi(e);
+  NST = option(ISB_OPT_GATHER_STAGES, NST);
   if (NST < 1) NST = 1;
   if (NST > kGatherMaxStages) NST = kGatherMaxStages;
   if (NST > GG + 1) NST = GG + 1;                  // no point in more slots than units + 1

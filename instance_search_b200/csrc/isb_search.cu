@@ -97,6 +97,7 @@ struct SelectSmem {
   double sel_score[kMaxCand];
   int sel_col[kMaxCand];
   float sel_screen[kMaxCand];     // screen score of each selected candidate
+  float sel_norm2[kMaxCand];      // squared L2 norm of each selected database row (exact_scores)
 };
 
 // Pick the kc best screen scores among the row's pool entries (4 x 8-bit radix
@@ -181,6 +182,7 @@ __device__ __forceinline__ void exact_scores(SelectSmem& sm, const float* qs,
     if (c < n_sel) {
       const float4* dr = reinterpret_cast<const float4*>(db + static_cast<size_t>(sm.sel_col[c]) * D);
       double acc = 0.0;
+      float n2 = 0.f;
       for (int i = lane; i < D / 4; i += 32) {
         const float4 b = __ldg(dr + i);
         const float4 a = reinterpret_cast<const float4*>(qs)[i];
@@ -188,13 +190,18 @@ __device__ __forceinline__ void exact_scores(SelectSmem& sm, const float* qs,
         acc = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc);
         acc = fma(static_cast<double>(a.z), static_cast<double>(b.z), acc);
         acc = fma(static_cast<double>(a.w), static_cast<double>(b.w), acc);
+        n2 = fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(b.z, b.z, fmaf(b.w, b.w, n2))));
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) sm.sel_score[c] = acc;
+      for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+      }
+      if (lane == 0) { sm.sel_score[c] = acc; sm.sel_norm2[c] = n2; }
     } else if (lane == 0) {
       sm.sel_score[c] = -INFINITY;
       sm.sel_col[c] = 0x7FFFFFFF;
+      sm.sel_norm2[c] = 0.f;
     }
   }
   __syncthreads();
@@ -208,13 +215,44 @@ __device__ __forceinline__ void exact_scores(SelectSmem& sm, const float* qs,
 // row's own candidates.  The row is certified when the exact k-th best score
 // clears t_min by z sigma plus an fp32 accumulation floor; otherwise the caller
 // re-screens it with fp32-grade operands (isb_topk_resolve) or exhaustively.
+// The certificate is statistical (z sigma), not a proof.  A sigma measured on a handful of
+// candidates can be far too small (one sample: ~0), so it is floored by the noise the screen's
+// operand rounding is EXPECTED to have on dense rows, sigma_floor (screen_sigma_floor below; 0
+// for the fp32-grade split-operand screen, whose measured sigma is at fp32-accumulation level).
 __device__ __forceinline__ bool row_certified(const SelectSmem& sm, int kc, double sigma2_sum, int n_sel,
-                                              double kth_exact, float cert_z) {
+                                              double kth_exact, float cert_z, double sigma_floor) {
   if (sm.total < kc) return true;  // nothing was ever dropped for this row
-  const double sigma = sqrt(sigma2_sum / static_cast<double>(n_sel > 0 ? n_sel : 1));
+  const double sigma = fmax(sqrt(sigma2_sum / static_cast<double>(n_sel > 0 ? n_sel : 1)), sigma_floor);
   const double t_min = static_cast<double>(__uint_as_float(key2f(sm.min_key)));
   const double floor_ = 4e-7 * fmax(fabs(kth_exact), fabs(t_min)) + 1e-30;
   return kth_exact - t_min > static_cast<double>(cert_z) * sigma + floor_;
+}
+
+// Expected rms error of a plain-bf16 screen score on dense rows: both operands are rounded to 8
+// significant bits (relative error uniform in +-2^-9, rms 2^-9/sqrt(3)), so a product is off by
+// sqrt(2/3) 2^-9 relative and the sum of D such terms by that times sqrt(sum (a_i b_i)^2) ~
+// |a||b|/sqrt(D).  Half of it is used as the floor when the sample is large (>= 32 candidates
+// measure sigma well), one and a half times it when it is small.
+// qn2: squared norm of the query row, sm.sel_norm2: of the candidates (the largest is taken).
+__device__ __forceinline__ double screen_sigma_floor(const SelectSmem& sm, int n_sel, double qn2, int D) {
+  float bn2 = 0.f;
+  for (int c = 0; c < n_sel; ++c) bn2 = fmaxf(bn2, sm.sel_norm2[c]);
+  const double dense = 1.5947e-3 * sqrt(qn2 * static_cast<double>(bn2) / static_cast<double>(D));
+  return (n_sel >= 32 ? 0.5 : 1.5) * dense;
+}
+
+// squared norm of the query row staged in qs[0..D): every thread returns the same value
+__device__ __forceinline__ double block_norm2(const float* qs, int D, double* red) {
+  double a = 0.0;
+  for (int i = threadIdx.x; i < D; i += kRerankThreads) a = fma(static_cast<double>(qs[i]), static_cast<double>(qs[i]), a);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < kRerankThreads / 32; ++w) t += red[w];
+  __syncthreads();
+  return t;
 }
 
 // Bitonic sort of sm.sel_score / sm.sel_col [kMaxCand], best first (score desc, column
@@ -248,13 +286,14 @@ __device__ __forceinline__ void sort_selected(SelectSmem& sm) {
 __global__ void __launch_bounds__(kRerankThreads)
 rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, int n_groups,
               const uint2* __restrict__ pool, const int* __restrict__ pool_cnt, int kc, int k,
-              int64_t idx_offset, const int* __restrict__ row_map, float cert_z,
+              int64_t idx_offset, const int* __restrict__ row_map, float cert_z, int plain_screen,
               int* __restrict__ unc_rows, int* __restrict__ unc_count,
               float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
   extern __shared__ __align__(16) uint8_t rr_smem[];
   float* qs = reinterpret_cast<float*>(rr_smem);  // [D]
   __shared__ SelectSmem sm;
   __shared__ double s_sig2;
+  __shared__ double s_red[kRerankThreads / 32];
   double* sel_score = sm.sel_score;
   int* sel_col = sm.sel_col;
 
@@ -267,6 +306,9 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, 
   const int n_sel = select_pool_candidates(sm, pool + static_cast<size_t>(prow) * n_groups * kMaxCand,
                                            pool_cnt + static_cast<size_t>(prow) * n_groups, n_groups, kc);
   exact_scores(sm, qs, db, D, n_sel);
+  const double qn2 = (unc_count != nullptr && plain_screen) ? block_norm2(qs, D, s_red) : 0.0;
+  double sigma_floor = 0.0;
+  if (unc_count != nullptr && plain_screen && tid == 0) sigma_floor = screen_sigma_floor(sm, n_sel, qn2, D);
 
   // screen noise of this row: sum over its candidates of (screen - exact)^2
   if (unc_count != nullptr) {
@@ -289,7 +331,7 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, 
     out_idx[static_cast<size_t>(row) * k + j] = ok ? static_cast<int64_t>(sel_col[j]) + idx_offset : -1;
   }
   if (unc_count != nullptr && tid == 0) {
-    const bool ok = (k <= n_sel) && row_certified(sm, kc, s_sig2, n_sel, sel_score[k - 1], cert_z);
+    const bool ok = (k <= n_sel) && row_certified(sm, kc, s_sig2, n_sel, sel_score[k - 1], cert_z, sigma_floor);
     if (!ok) unc_rows[atomicAdd(unc_count, 1)] = row;
   }
 }
@@ -796,19 +838,34 @@ __global__ void __launch_bounds__(kRerankThreads)
 mining_rerank_kernel(const float* __restrict__ emb, int D, const int64_t* __restrict__ anchors,
                      int n_groups, const uint2* __restrict__ pool, const int* __restrict__ pool_cnt,
                      int kc, const double* __restrict__ pos64, int semi_hard, float screen_eps,
-                     int64_t* __restrict__ neg_idx, float* __restrict__ neg_sim, int* __restrict__ flag) {
+                     float sigma_floor, float ub_slack, int64_t* __restrict__ neg_idx,
+                     float* __restrict__ neg_sim, int* __restrict__ flag, int* __restrict__ unc_rows,
+                     int* __restrict__ unc_count) {
   extern __shared__ __align__(16) uint8_t rr_smem[];
   float* qs = reinterpret_cast<float*>(rr_smem);
   __shared__ SelectSmem sm;
   __shared__ double red_s[kRerankThreads / 32];
   __shared__ int red_c[kRerankThreads / 32];
+  __shared__ double s_sig2;
   const int row = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) s_sig2 = 0.0;
   const float* qrow = emb + anchors[row] * D;
   for (int i = tid; i < D / 4; i += kRerankThreads)
     reinterpret_cast<float4*>(qs)[i] = __ldg(reinterpret_cast<const float4*>(qrow) + i);
   const int n_sel = select_pool_candidates(sm, pool + static_cast<size_t>(row) * n_groups * kMaxCand,
                                            pool_cnt + static_cast<size_t>(row) * n_groups, n_groups, kc);
   exact_scores(sm, qs, emb, D, n_sel);
+  // screen noise of this couple: sum over its candidates of (screen - exact)^2
+  {
+    double d2 = 0.0;
+    if (tid < n_sel) {
+      const double d = static_cast<double>(sm.sel_screen[tid]) - sm.sel_score[tid];
+      d2 = d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    if ((tid & 31) == 0 && tid < kMaxCand) atomicAdd(&s_sig2, d2);
+  }
   // reference: excluded if S[i1, j] >= S[i1, i2]  (train/siamese_regions.py:111)
   double s = -INFINITY;
   int c = 0x7FFFFFFF;
@@ -816,19 +873,27 @@ mining_rerank_kernel(const float* __restrict__ emb, int D, const int64_t* __rest
     const double v = sm.sel_score[tid];
     if (!semi_hard || v < pos64[row]) { s = v; c = sm.sel_col[tid]; }
   }
-  block_best(s, c, red_s, red_c);
+  block_best(s, c, red_s, red_c);   // (its barriers also order the s_sig2 atomics)
   if (tid == 0) {
     const bool found = c != 0x7FFFFFFF;
-    // Certificate: every column NOT selected has a screen score <= the worst
-    // selected one, hence an exact score <= that + screen_eps.
+    // Certificate: every column NOT selected has a screen score <= the worst selected one,
+    // hence an exact score <= that + eps, with eps = max(the caller's absolute bound,
+    // kCertZ x the screen noise: measured on this couple's candidates, floored by sigma_floor).
+    const double sigma = fmax(sqrt(s_sig2 / static_cast<double>(n_sel > 0 ? n_sel : 1)),
+                              static_cast<double>(sigma_floor));
+    const double eps = fmax(static_cast<double>(screen_eps), static_cast<double>(kCertZ) * sigma);
     bool certified = true;
     if (sm.total > kc) {
       const float t_min = __uint_as_float(key2f(sm.min_key));
-      certified = found && (static_cast<double>(t_min) + static_cast<double>(screen_eps) < s);
+      certified = found && (static_cast<double>(t_min) + eps < s);
     }
+    // semi-hard: the epilogue dropped the columns with screen >= sim_pos + ub_slack as "surely
+    // excluded"; that holds only while the screen noise stays within the slack
+    if (semi_hard && eps > static_cast<double>(ub_slack)) certified = false;
     neg_idx[row] = found ? static_cast<int64_t>(c) : -1;
     neg_sim[row] = found ? static_cast<float>(s) : -2.f;  // the reference's fill value (:124)
     flag[row] = certified ? 0 : 1;
+    if (!certified && unc_rows != nullptr) unc_rows[atomicAdd(unc_count, 1)] = row;
   }
 }
 
@@ -1149,12 +1214,9 @@ static int pick_n_groups(int m_blocks, int n_tiles, int grid) {
   return lo;
 }
 
-// ISB_SCREEN_PAIR=0 keeps the single-CTA 128 x 256 kernel (A/B switch; the workspace layout
-// follows the plan, so the variable must not change between the size query and the call)
-static bool screen_pair_enabled() {
-  const char* e = getenv("ISB_SCREEN_PAIR");
-  return e == nullptr || e[0] != '0';
-}
+// ISB_OPT_SCREEN_PAIR = 0 keeps the single-CTA 128 x 256 kernel (A/B switch; the workspace layout
+// follows the plan, so the option must not change between the size query and the call)
+static bool screen_pair_enabled() { return option(ISB_OPT_SCREEN_PAIR, 1) != 0; }
 
 static SearchPlan make_search_plan(int64_t Q, int64_t N, int64_t D, int terms = 1, bool allow_pair = true) {
   SearchPlan p;
@@ -1182,10 +1244,9 @@ static SearchPlan make_search_plan(int64_t Q, int64_t N, int64_t D, int terms = 
   p.off_pool = off;     off = align_up(off + static_cast<size_t>(Q) * p.n_groups * kMaxCand * sizeof(uint2), 1024);
   p.off_pool_cnt = off; off = align_up(off + static_cast<size_t>(Q) * p.n_groups * 4, 1024);
   p.off_progress = off; off = align_up(off + static_cast<size_t>(kMaxWaves) * 4, 1024);
-  // Opt-in (ISB_SCREEN_SEED=1): measured on a 125k-row shard the screen gets 0.23 ms faster (4.19 ->
+  // Opt-in (ISB_OPT_SCREEN_SEED = 1): measured on a 125k-row shard the screen gets 0.23 ms faster (4.19 ->
   // 3.96 ms) and the sample GEMM + select cost 0.17 ms -- no net gain yet
-  const char* seed_env = getenv("ISB_SCREEN_SEED");
-  p.seed = terms == 1 && N >= 16ll * kSeedRows && Q >= 128 && seed_env != nullptr && seed_env[0] == '1';
+  p.seed = terms == 1 && N >= 16ll * kSeedRows && Q >= 128 && option(ISB_OPT_SCREEN_SEED, 0) == 1;
   p.off_seed = off;
   if (p.seed) off = align_up(off + static_cast<size_t>(Q) * kSeedRows * 4, 1024);
   p.total = off;
@@ -1229,11 +1290,10 @@ int launch_topk_screen(const uint16_t* a_bf16, const uint16_t* a_lo, int64_t lda
         sample, Q, kSeedRows, kc, gthr);
     ISB_CUDA(cudaGetLastError());
   }
-  // wave barrier of the scheduler: ISB_SCREEN_WAVESYNC=0 switches it off
+  // wave barrier of the scheduler: ISB_OPT_SCREEN_WAVESYNC = 0 switches it off
   int* progress = nullptr;
   int window = 0;
-  const char* wsync = getenv("ISB_SCREEN_WAVESYNC");
-  if ((wsync == nullptr || wsync[0] != '0') && plan.grid >= device_sm_count() / 2) {
+  if (option(ISB_OPT_SCREEN_WAVESYNC, 1) != 0 && plan.grid >= device_sm_count() / 2) {
     progress = reinterpret_cast<int*>(ws + plan.off_progress);
     ISB_CUDA(cudaMemsetAsync(progress, 0, static_cast<size_t>(kMaxWaves) * 4, st));
   }
@@ -1356,8 +1416,8 @@ extern "C" int isb_topk_screen(const float* q, int64_t Q, const uint16_t* db_bf1
 
 static int launch_rerank(const char* fn, const float* q, const float* db_f32, int64_t D, int64_t n_rows,
                          const SearchPlan& plan, uint8_t* ws, int kc, int k, int64_t idx_offset,
-                         const int* row_map, int32_t* unc_rows, int32_t* unc_count, float* out_scores,
-                         int64_t* out_idx, cudaStream_t st) {
+                         const int* row_map, int plain_screen, int32_t* unc_rows, int32_t* unc_count,
+                         float* out_scores, int64_t* out_idx, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(D) * 4;
   ISB_CHECK_ARG(smem <= 160 * 1024, "%s: D too large for the re-rank kernel", fn);
   if (smem > 48 * 1024)
@@ -1365,8 +1425,8 @@ static int launch_rerank(const char* fn, const float* q, const float* db_f32, in
   if (unc_count != nullptr) ISB_CUDA(cudaMemsetAsync(unc_count, 0, 4, st));
   rerank_kernel<<<static_cast<unsigned>(n_rows), kRerankThreads, smem, st>>>(
       q, db_f32, static_cast<int>(D), plan.n_groups, reinterpret_cast<const uint2*>(ws + plan.off_pool),
-      reinterpret_cast<const int*>(ws + plan.off_pool_cnt), kc, k, idx_offset, row_map, kCertZ, unc_rows,
-      unc_count, out_scores, out_idx);
+      reinterpret_cast<const int*>(ws + plan.off_pool_cnt), kc, k, idx_offset, row_map, kCertZ, plain_screen,
+      unc_rows, unc_count, out_scores, out_idx);
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;
 }
@@ -1388,7 +1448,7 @@ extern "C" int isb_topk_rerank(const float* q, int64_t Q, const float* db_f32, i
   if (rc) return rc;
   int kc = k + margin;
   if (kc > N) kc = static_cast<int>(N);
-  return launch_rerank("isb_topk_rerank", q, db_f32, D, Q, plan, ws, kc, k, idx_offset, nullptr,
+  return launch_rerank("isb_topk_rerank", q, db_f32, D, Q, plan, ws, kc, k, idx_offset, nullptr, 1,
                        uncertified_rows, n_uncertified, out_scores, out_idx, static_cast<cudaStream_t>(stream));
 }
 
@@ -1434,7 +1494,7 @@ extern "C" int isb_topk_resolve(const float* q, const float* db_f32, const uint1
   rc = launch_topk_screen(a_hi, a_lo, plan.ldq, n_rows, db_bf16, db_lo_bf16, ld_bf16, N, D, kc, plan, ws,
                           nullptr, nullptr, nullptr, 0.f, st);
   if (rc) return rc;
-  return launch_rerank("isb_topk_resolve", q, db_f32, D, n_rows, plan, ws, kc, k, idx_offset, rows,
+  return launch_rerank("isb_topk_resolve", q, db_f32, D, n_rows, plan, ws, kc, k, idx_offset, rows, 0,
                        uncertified_rows, n_uncertified, out_scores, out_idx, st);
 }
 
@@ -1646,12 +1706,16 @@ extern "C" size_t isb_select_negatives_workspace_bytes(int64_t P, int64_t N, int
 extern "C" int isb_select_negatives(const float* emb, const uint16_t* emb_hi, const uint16_t* emb_lo,
                                     int64_t ld, int64_t N, int64_t D, const int32_t* label,
                                     const int64_t* anchors, const int64_t* positives, int64_t P,
-                                    int semi_hard, float screen_eps, int64_t* neg_idx, float* neg_sim,
-                                    float* pos_sim, int32_t* n_bruteforce, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+                                    int semi_hard, float screen_eps, float sigma_floor, int64_t* neg_idx,
+                                    float* neg_sim, float* pos_sim, int32_t* uncertified_rows,
+                                    int32_t* n_uncertified, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
   ISB_CHECK_ARG(emb && emb_hi && label && anchors && positives && neg_idx && neg_sim && pos_sim,
                 "isb_select_negatives: null pointer");
   ISB_CHECK_ARG(P > 0 && N > 0 && D > 0 && N < (1ll << 31) && P < (1ll << 31), "isb_select_negatives: bad shape");
+  ISB_CHECK_ARG(uncertified_rows == nullptr || n_uncertified != nullptr,
+                "isb_select_negatives: uncertified_rows needs n_uncertified");
+  ISB_CHECK_ARG(screen_eps >= 0.f && sigma_floor >= 0.f, "isb_select_negatives: negative error bound");
   ISB_CHECK_ARG(D % 8 == 0 && ld % 8 == 0 && ld >= D, "isb_select_negatives: D and ld must be multiples of 8, ld >= D");
   ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(emb) & 15) == 0 && (reinterpret_cast<uintptr_t>(emb_hi) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(emb_lo) & 15) == 0, "isb_select_negatives: inputs must be 16-byte aligned");
@@ -1682,21 +1746,19 @@ extern "C" int isb_select_negatives(const float* emb, const uint16_t* emb_hi, co
   pair_dot_kernel<<<static_cast<unsigned>((P * 32 + 255) / 256), 256, 0, st>>>(emb, (int)D, anchors, positives, P, pos64, pos32);
   ISB_CUDA(cudaGetLastError());
   ISB_CUDA(cudaMemcpyAsync(pos_sim, pos32, static_cast<size_t>(P) * 4, cudaMemcpyDeviceToDevice, st));
-  if (n_bruteforce != nullptr) ISB_CUDA(cudaMemsetAsync(n_bruteforce, 0, 4, st));
+  if (n_uncertified != nullptr) ISB_CUDA(cudaMemsetAsync(n_uncertified, 0, 4, st));
 
   // One negative per couple is wanted: a short candidate list is enough -- the certificate
   // (worst candidate's screen score + screen_eps < the exact winner) sends the rows it is not
   // enough for to the brute-force pass.  The exact re-check gathers kc rows of D floats per
   // couple: 128 candidates were 17 GB of random 8 KB reads at the 16k x 2048 configuration.
-  int kc = kMiningCand;
-  if (const char* e = getenv("ISB_MINING_KC")) {
-    const int v = atoi(e);
-    if (v >= 1 && v <= kMaxCand) kc = v;
-  }
+  int kc = option(ISB_OPT_MINING_KC, kMiningCand);
+  if (kc < 1 || kc > kMaxCand) kc = kMiningCand;
   if (kc > N) kc = static_cast<int>(N);
   // semi-hard: columns scoring >= sim_pos (+ the screen's error bound) are masked in the epilogue
+  const float ub_slack = fmaxf(screen_eps, kCertZ * sigma_floor);
   rc = launch_topk_screen(a_hi, a_lo, ld, P, emb_hi, emb_lo, ld, N, D, kc, mp.sp, ws, label, row_label,
-                          semi_hard ? pos32 : nullptr, screen_eps, st);
+                          semi_hard ? pos32 : nullptr, ub_slack, st);
   if (rc) return rc;
   const size_t smem = static_cast<size_t>(D) * 4;
   ISB_CHECK_ARG(smem <= 160 * 1024, "isb_select_negatives: D too large");
@@ -1706,12 +1768,14 @@ extern "C" int isb_select_negatives(const float* emb, const uint16_t* emb_hi, co
   }
   mining_rerank_kernel<<<static_cast<unsigned>(P), kRerankThreads, smem, st>>>(
       emb, (int)D, anchors, mp.sp.n_groups, reinterpret_cast<const uint2*>(ws + mp.sp.off_pool),
-      reinterpret_cast<const int*>(ws + mp.sp.off_pool_cnt), kc, pos64, semi_hard, screen_eps, neg_idx,
-      neg_sim, flag);
+      reinterpret_cast<const int*>(ws + mp.sp.off_pool_cnt), kc, pos64, semi_hard, screen_eps, sigma_floor,
+      ub_slack, neg_idx, neg_sim, flag, uncertified_rows, n_uncertified);
   ISB_CUDA(cudaGetLastError());
-  mining_bruteforce_kernel<<<static_cast<unsigned>(P), kRerankThreads, smem, st>>>(
-      emb, (int)N, (int)D, label, anchors, pos64, semi_hard, flag, neg_idx, neg_sim, n_bruteforce);
-  ISB_CUDA(cudaGetLastError());
+  if (uncertified_rows == nullptr) {   // no second line requested: resolve the rejected couples here
+    mining_bruteforce_kernel<<<static_cast<unsigned>(P), kRerankThreads, smem, st>>>(
+        emb, (int)N, (int)D, label, anchors, pos64, semi_hard, flag, neg_idx, neg_sim, n_uncertified);
+    ISB_CUDA(cudaGetLastError());
+  }
   return ISB_OK;
 }
 

@@ -10,7 +10,9 @@ from . import _lib, ops
 from ._lib import IsbError
 
 SCREEN_EPS_3TERM = 2e-5   # absolute error bound of the [hi|lo|hi].[hi|hi|lo] screen, unit rows
-SCREEN_EPS_1TERM = 4e-3   # worst case 2^-8 for plain bf16 operands
+# plain bf16 screen: expected rms error of a score on dense rows, both operands rounded to 8
+# significant bits: sqrt(2/3) 2^-9 |a||b| / sqrt(D)  (include/isb.h, isb_select_negatives)
+SIGMA_BF16 = 1.5947e-3
 
 
 def label_ids(dataset):
@@ -57,10 +59,20 @@ def all_pairs_similarities(emb, terms=3):
 
 
 class MiningIndex(object):
-    """Embeddings of the reference set prepared for negative selection."""
+    """Embeddings of the reference set prepared for negative selection.
 
-    def __init__(self, emb, labels, terms=3):
+    terms=1 (default): ONE bf16 tcgen05 product per tile screens all couples; every couple carries
+    a completeness certificate (8 sigma of the measured screen noise), and the couples it
+    rejects -- and only those -- are re-screened with fp32-grade split operands (three products
+    per tile) and, failing that, exhaustively: the same three lines as the search
+    (isb_topk_search -> isb_topk_resolve -> isb_topk_exhaustive).  Costs one 4-byte
+    device->host read per call.  terms=3: every couple goes through the split-operand screen
+    (no host read; exhaustive pass in the same call)."""
+
+    def __init__(self, emb, labels, terms=1):
         ops._need_cuda(emb)
+        if terms not in (1, 3):
+            raise IsbError("terms must be 1 or 3")
         emb = ops._f32c(emb)
         self.N, self.dim = emb.shape
         pad = (-self.dim) % 8
@@ -70,10 +82,33 @@ class MiningIndex(object):
         self.labels = labels.to(device=emb.device, dtype=torch.int32).contiguous()
         if self.labels.numel() != self.N:
             raise IsbError("one label id per embedding expected")
+        self.terms = terms
         self.emb_hi = ops.to_bf16(self.emb, 0)
-        self.emb_lo = ops.to_bf16(self.emb, 1) if terms == 3 else None
-        self.eps = SCREEN_EPS_3TERM if terms == 3 else SCREEN_EPS_1TERM
-        self.last_bruteforce = None
+        self._emb_lo = ops.to_bf16(self.emb, 1) if terms == 3 else None
+        # sigma floor of the plain screen's certificate: expected bf16 noise for the largest rows
+        self.sigma_floor = SIGMA_BF16 * float(self.emb.square().sum(1).max()) / self.emb.size(1) ** 0.5
+        self.last_bruteforce = None      # device int32 [1]: couples answered by the exhaustive pass
+        self.last_second_line = 0        # couples the plain screen's certificate rejected (terms=1)
+
+    def _lo(self):
+        if self._emb_lo is None:
+            self._emb_lo = ops.to_bf16(self.emb, 1)
+        return self._emb_lo
+
+    def _select(self, anchors, positives, semi_hard, split, unc_rows, n_unc, out):
+        L = _lib.lib()
+        D, P = self.emb.size(1), anchors.numel()
+        nbytes = L.isb_select_negatives_workspace_bytes(P, self.N, D, 1 if split else 0)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.emb.device)
+        neg_idx, neg_sim, pos_sim = out
+        _lib.check(L.isb_select_negatives(self.emb.data_ptr(), self.emb_hi.data_ptr(),
+                                          self._lo().data_ptr() if split else 0, self.emb_hi.size(1), self.N, D,
+                                          self.labels.data_ptr(), anchors.data_ptr(), positives.data_ptr(), P,
+                                          1 if semi_hard else 0, SCREEN_EPS_3TERM if split else 0.0,
+                                          0.0 if split else self.sigma_floor,
+                                          neg_idx.data_ptr(), neg_sim.data_ptr(), pos_sim.data_ptr(),
+                                          ops._ptr(unc_rows), n_unc.data_ptr(), ws.data_ptr(), nbytes,
+                                          ops._stream()), "isb_select_negatives")
 
     def select_negatives(self, anchors, positives, semi_hard):
         """One negative per positive couple (anchors[p], positives[p]).
@@ -91,17 +126,20 @@ class MiningIndex(object):
         pos_sim = torch.empty(P, dtype=torch.float32, device=dev)
         if P == 0:
             return neg_idx, neg_sim, pos_sim
-        nb = torch.zeros(1, dtype=torch.int32, device=dev)
-        L = _lib.lib()
-        D = self.emb.size(1)
-        nbytes = L.isb_select_negatives_workspace_bytes(P, self.N, D, 0 if self.emb_lo is None else 1)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _lib.check(L.isb_select_negatives(self.emb.data_ptr(), self.emb_hi.data_ptr(),
-                                          ops._ptr(self.emb_lo), self.emb_hi.size(1), self.N, D,
-                                          self.labels.data_ptr(), anchors.data_ptr(),
-                                          positives.data_ptr(), P, 1 if semi_hard else 0, self.eps,
-                                          neg_idx.data_ptr(), neg_sim.data_ptr(), pos_sim.data_ptr(),
-                                          nb.data_ptr(), ws.data_ptr(), nbytes, ops._stream()),
-                   "isb_select_negatives")
-        self.last_bruteforce = nb
+        n_unc = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self.terms == 3:
+            self._select(anchors, positives, semi_hard, True, None, n_unc, (neg_idx, neg_sim, pos_sim))
+            self.last_bruteforce, self.last_second_line = n_unc, 0
+            return neg_idx, neg_sim, pos_sim
+        unc_rows = torch.empty(P, dtype=torch.int32, device=dev)
+        self._select(anchors, positives, semi_hard, False, unc_rows, n_unc, (neg_idx, neg_sim, pos_sim))
+        n_bad = int(n_unc.item())            # the one 4-byte D2H read of the exactness guarantee
+        self.last_second_line = n_bad
+        self.last_bruteforce = torch.zeros(1, dtype=torch.int32, device=dev)
+        if n_bad:
+            rows = unc_rows[:n_bad].long()
+            sub = tuple(torch.empty(n_bad, dtype=t.dtype, device=dev) for t in (neg_idx, neg_sim, pos_sim))
+            self._select(anchors[rows].contiguous(), positives[rows].contiguous(), semi_hard, True, None,
+                         self.last_bruteforce, sub)
+            neg_idx[rows], neg_sim[rows] = sub[0], sub[1]
         return neg_idx, neg_sim, pos_sim

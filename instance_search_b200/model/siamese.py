@@ -1,5 +1,7 @@
 """Drop-in for the descriptor nets of the reference's ``model/siamese.py``.
 
+    TuneClassif            model/siamese.py:10-54   (construction + plain forward only)
+    TuneClassifSub         model/siamese.py:57-89   (what get_siamese_net wraps, train/siamese_regions.py:161)
     DescriptorNet          model/siamese.py:92-130
     RegionDescriptorNet    model/siamese.py:133-231
 
@@ -27,9 +29,16 @@ from .nn_utils import convolutionalize, extract_layers, get_feature_size, set_un
 
 class _HeadCache(object):
     """Tensor-core-ready copies of the head parameters, rebuilt when any of them
-    changes (in-place updates bump ``_version``; re-assignment changes data_ptr)."""
+    changes.  In-place updates bump ``_version`` and re-assignment changes data_ptr, but
+    writes through ``.data`` (``p.data.copy_()``, the reference's way of loading weights,
+    and Shift.reset_parameters) do neither: the owning module therefore also calls
+    ``invalidate()`` from ``train()``, ``_load_from_state_dict`` and ``_apply`` -- every
+    train -> eval transition rebuilds the copies."""
 
     def __init__(self):
+        self.key, self.hw = None, None
+
+    def invalidate(self):
         self.key, self.hw = None, None
 
     def get(self, params, terms, build):
@@ -40,7 +49,82 @@ class _HeadCache(object):
         return self.hw
 
 
-class DescriptorNet(nn.Module):
+class _CachedHeadMixin(object):
+    """Invalidation hooks of the cached head operands (see _HeadCache)."""
+
+    def invalidate_head_cache(self):
+        """Call after writing head parameters through ``.data`` while in eval mode."""
+        cache = self.__dict__.get("_cache")
+        if cache is not None:
+            cache.invalidate()
+
+    def train(self, mode=True):
+        self.invalidate_head_cache()
+        return super(_CachedHeadMixin, self).train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_head_cache()
+        return super(_CachedHeadMixin, self)._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.invalidate_head_cache()
+        return super(_CachedHeadMixin, self).load_state_dict(*args, **kwargs)
+
+
+class TuneClassif(nn.Module):
+    """Classifier fine-tuned from a pretrained net: trunk / spatial reduction / classifier
+    with the last FC resized to ``num_classes``.  reference: model/siamese.py:10-54.
+    Only what the region-descriptor path needs of it -- it is the net that
+    ``get_siamese_net`` hands to RegionDescriptorNet (train/siamese_regions.py:161-164) --
+    runs in PyTorch; the classification track that trains it is out of scope."""
+
+    def __init__(self, net, num_classes, untrained=-1, reduc=True):
+        super(TuneClassif, self).__init__()
+        self.features, self.feature_reduc, self.classifier = extract_layers(net)
+        set_untrained_blocks([self.features, self.classifier], untrained)
+        names = list(self.classifier._modules.keys())
+        last = self.classifier._modules[names[-1]]
+        if not isinstance(last, nn.Linear) or last.out_features != num_classes:      # :27-31
+            self.classifier._modules[names[-1]] = nn.Linear(last.in_features, num_classes)
+        self.feature_size = num_classes
+        if not reduc:                                                                # :34-46
+            factor = 1
+            for m in self.feature_reduc:
+                ks = m.kernel_size
+                factor *= ks[0] * ks[1] if isinstance(ks, (tuple, list)) else ks * ks
+            first = self.classifier._modules[names[0]]
+            self.classifier._modules[names[0]] = nn.Linear(first.in_features * factor, first.out_features)
+            self.feature_reduc = nn.Sequential()
+
+    def forward(self, x):
+        x = self.feature_reduc(self.features(x))
+        return self.classifier(x.view(x.size(0), -1))
+
+
+class TuneClassifSub(TuneClassif):
+    """TuneClassif whose FC layers are convolutionalised so every sub-window of the map is
+    classified.  reference: model/siamese.py:57-89"""
+
+    def __init__(self, net, num_classes, feature_size2d, untrained=-1):
+        super(TuneClassifSub, self).__init__(net, num_classes, untrained, reduc=True)
+        reduc_count = sum(1 for _ in self.feature_reduc)
+        if reduc_count > 0:
+            self.feature_reduc = nn.Sequential(nn.AvgPool2d(tuple(feature_size2d), stride=1))
+        count = 0
+        for name, module in self.classifier._modules.items():
+            if isinstance(module, nn.Linear):
+                size2d = (1, 1) if (reduc_count > 0 or count > 0) else tuple(feature_size2d)
+                self.classifier._modules[name] = convolutionalize(module, size2d)
+                count += 1
+
+    def forward_single(self, x):
+        return self.classifier(self.feature_reduc(self.features(x)))
+
+    def forward(self, *scales):
+        return [self.forward_single(x) for x in scales]
+
+
+class DescriptorNet(_CachedHeadMixin, nn.Module):
     """Global descriptor: trunk -> flatten -> L2 -> Shift -> Linear -> L2.
     reference: model/siamese.py:92-130"""
 
@@ -89,7 +173,7 @@ class DescriptorNet(nn.Module):
             return self.forward_single(x1)
 
 
-class RegionDescriptorNet(nn.Module):
+class RegionDescriptorNet(_CachedHeadMixin, nn.Module):
     """Top-k region descriptor. reference: model/siamese.py:133-231"""
 
     projection_terms = 3

@@ -2,6 +2,7 @@
 
     get_embeddings              train/siamese_regions.py:26-41
     negative selection          train/siamese_regions.py:106-129 (create_batch)
+    get_siamese_net             train/siamese_regions.py:157-168
 
 The reference embeds ONE image per forward (``fold_batches(..., 1)``, an H2D copy
 and a Python iteration per image).  Here consecutive images of identical size
@@ -68,3 +69,24 @@ class NegativeSelector(object):
         b = torch.tensor([c[1] for c in couples], dtype=torch.int64)
         neg, _, _ = self.index.select_negatives(a, b, epoch < train_epoch_switch)   # :107
         return [None if v < 0 else v for v in neg.tolist()]
+
+
+def get_siamese_net(P, pretrained=True, base_net=None):
+    """The net of the region-siamese track: torchvision trunk -> TuneClassifSub ->
+    RegionDescriptorNet, optional checkpoints, moved to ``P.cuda_device``.
+    reference: train/siamese_regions.py:157-168.  ``P`` is passed explicitly (the
+    reference reads a module-global); ``pretrained=False`` / ``base_net`` exist because the
+    torchvision weights need a download the reference takes for granted."""
+    from ..model.siamese import RegionDescriptorNet, TuneClassifSub
+    if base_net is None:
+        import torchvision.models as models
+        model = models.resnet152 if P.cnn_model.lower() == 'resnet152' else models.alexnet
+        base_net = model(weights="DEFAULT" if pretrained else None)
+    class_net = TuneClassifSub(base_net, P.num_classes, P.feature_size2d, untrained=P.untrained_blocks)
+    if getattr(P, "classif_model", None):
+        class_net.load_state_dict(torch.load(P.classif_model, map_location="cpu"))
+    net = RegionDescriptorNet(class_net, P.regions_k, P.feature_dim, P.feature_size2d,
+                              untrained=P.untrained_blocks)
+    if getattr(P, "preload_net", None):
+        net.load_state_dict(torch.load(P.preload_net, map_location="cpu"))
+    return net.cuda() if P.cuda_device >= 0 else net

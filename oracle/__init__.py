@@ -43,6 +43,7 @@ from .mining import (  # noqa: F401
     get_lab_indicators,
     embeddings_device_dim,
     select_negative,
+    select_negative_row,
     select_negatives,
 )
 from .instance_avg import instance_avg  # noqa: F401

@@ -50,6 +50,22 @@ def all_pairs_similarities(embeddings):
     return torch.mm(embeddings, embeddings.t())
 
 
+def select_negative_row(row, lab_indicator, i2, semi_hard):
+    """The body of select_negative on ONE row of the similarity matrix (row = S[i1, :], so
+    large data sets can be checked without materialising S: mm(E[i1:i1+1], E.t()) is that row).
+    reference: train/siamese_regions.py:106-126."""
+    ind_exl = lab_indicator
+    sim_pos = row[i2]
+    if semi_hard:
+        ind_exl = ind_exl | row.ge(sim_pos).to(torch.uint8)
+    if int(ind_exl.sum()) >= row.size(0):
+        return -1
+    sims = row.clone()
+    sims[ind_exl.bool()] = -2
+    _, k = sims.max(0)
+    return int(k)
+
+
 def select_negative(similarities, lab_indicator, i1, i2, semi_hard):
     """Negative for the positive couple (i1, i2).
 
@@ -59,16 +75,7 @@ def select_negative(similarities, lab_indicator, i1, i2, semi_hard):
     negative, or -1 when every item is excluded (the reference then falls back
     to ``choose_rand_neg``, utils/dataset.py:57-61 -- host RNG, out of scope).
     """
-    ind_exl = lab_indicator
-    sim_pos = similarities[i1, i2]
-    if semi_hard:
-        ind_exl = ind_exl | similarities[i1].ge(sim_pos).to(torch.uint8)
-    if int(ind_exl.sum()) >= similarities.size(0):
-        return -1
-    sims = similarities[i1].clone()
-    sims[ind_exl.bool()] = -2
-    _, k = sims.max(0)
-    return int(k)
+    return select_negative_row(similarities[i1], lab_indicator, i2, semi_hard)
 
 
 def select_negatives(similarities, label_ids, couples, semi_hard):

@@ -1,8 +1,13 @@
 """Shared parity checks (test infrastructure)."""
 
+import json
+import os
+
 import torch
 
 import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # north_star: "scores must agree within 1e-5 relative"
 SCORE_RTOL = 1e-5
@@ -10,16 +15,59 @@ SCORE_RTOL = 1e-5
 # scores differ by less than fp32 accumulation noise; such a disagreement with
 # the fp32 oracle is accepted only if the oracle's own scores of the two rows
 # are this close, and the fp64 adjudicator sides with us.
-FP32_TIE_ATOL = 2e-6
+# Unit-norm rows: |score| <= 1, fp32 dot noise is a few 1e-8 (measured on the B200
+# box: largest accepted gap 1.8e-7 over the whole suite, gpurun_out/parity_achieved.jsonl).
+FP32_TIE_ATOL = 5e-7
+# ... and such disagreements are rare: at most this fraction of the Q*k returned
+# entries (+2) may differ from the fp32 oracle
+FP32_TIE_MAX_FRACTION = 2e-3
+
+# region descriptors (unit-norm rows, split-operand fp32-grade projection): per-row L2
+# error against the oracle's descriptor, and 1 - cosine in fp64.  Measured on the box:
+# see gpurun_out/parity_achieved.jsonl / DESIGN.md section 2.
+DESC_L2_TOL = 4e-6
+DESC_COS_TOL = 1e-10
 
 
-def check_topk_against_oracle(q, db, k, scores, idx, f64_exact=True):
-    """q, db CPU fp32; scores/idx = result of the CUDA path (any device)."""
+def record(kind, **values):
+    """Append the achieved error of a parity check to gpurun_out/parity_achieved.jsonl
+    (only when that directory exists: the GPU box visit) so tolerances can be pinned to
+    what is measured."""
+    d = os.path.join(ROOT, "gpurun_out")
+    if not os.path.isdir(d):
+        return
+    test = os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0]
+    with open(os.path.join(d, "parity_achieved.jsonl"), "a") as f:
+        f.write(json.dumps(dict(kind=kind, test=test, **values)) + "\n")
+
+
+def check_descriptors(got, want, l2_tol=DESC_L2_TOL, cos_tol=DESC_COS_TOL, unit=True):
+    """got/want [B, D] descriptors (model/siamese.py:222: unit-norm rows).  Asserts the
+    per-row L2 error and 1 - cosine (fp64) and records what was achieved."""
+    g, w = got.detach().cpu().double(), want.detach().cpu().double()
+    assert g.shape == w.shape
+    if g.numel() == 0:
+        return 0.0
+    l2 = (g - w).norm(dim=1)
+    cos = (g * w).sum(1) / (g.norm(dim=1) * w.norm(dim=1)).clamp_min(1e-300)
+    record("descriptor", rows=g.size(0), dim=g.size(1), max_l2=float(l2.max()), max_1mcos=float((1 - cos).max()),
+           max_abs=float((g - w).abs().max()))
+    assert float(l2.max()) <= l2_tol, "descriptor L2 error %g > %g" % (float(l2.max()), l2_tol)
+    assert float((1 - cos).max()) <= cos_tol, "1 - cosine %g > %g" % (float((1 - cos).max()), cos_tol)
+    if unit:
+        assert float((g.norm(dim=1) - 1).abs().max()) <= 1e-6
+    return float(l2.max())
+
+
+def check_topk_against_oracle(q, db, k, scores, idx, f64_exact=True, oracle_result=None):
+    """q, db CPU fp32; scores/idx = result of the CUDA path (any device).  Returns the
+    number of entries that differ from the fp32 oracle (all of them fp32-noise ties that
+    the fp64 ranking decides our way; bounded by FP32_TIE_MAX_FRACTION)."""
     scores, idx = scores.cpu(), idx.cpu()
-    o_s, o_i = oracle.topk_search(q, db, k)
-    a_s, a_i = oracle.topk_search_f64(q, db, k)
+    o_s, o_i = oracle.topk_search(q, db, k) if oracle_result is None else oracle_result
     # 1. index-exact against the fp64 adjudicator
     if f64_exact:
+        a_s, a_i = oracle.topk_search_f64(q, db, k)
         bad = (idx != a_i).any(dim=1).nonzero().flatten()
         if bad.numel():
             # an fp64 tie/near-tie (|d| < 1e-13) is the only excuse
@@ -28,18 +76,23 @@ def check_topk_against_oracle(q, db, k, scores, idx, f64_exact=True):
                 mine = (q[r].double() * db[idx[r, pos]].double()).sum(1)
                 assert torch.allclose(mine, a_s[r, pos], rtol=0, atol=1e-13), \
                     "row %d: indices differ from the fp64 ranking" % r
+        assert torch.allclose(scores.double(), a_s, rtol=2e-7, atol=1e-9)
     # 2. scores: within 1e-5 relative of the reference fp32 path
-    assert torch.allclose(scores, o_s, rtol=SCORE_RTOL, atol=1e-7), \
-        "max rel score err %g" % ((scores - o_s).abs() / o_s.abs().clamp_min(1e-6)).max()
-    assert torch.allclose(scores.double(), a_s, rtol=2e-7, atol=1e-9)
+    rel = ((scores - o_s).abs() / o_s.abs().clamp_min(1e-6)).max() if scores.numel() else 0.0
+    assert torch.allclose(scores, o_s, rtol=SCORE_RTOL, atol=1e-7), "max rel score err %g" % rel
     # 3. against the fp32 oracle: identical except fp32-noise ties
     mism = (idx != o_i)
     n_mism = int(mism.sum())
+    max_gap = 0.0
     if n_mism:
         rows, cols = mism.nonzero(as_tuple=True)
         # oracle's fp32 score of the row we returned at that position
         s_mine = (q[rows] * db[idx[rows, cols]]).sum(1)
         gap = (s_mine - o_s[rows, cols]).abs()
-        assert float(gap.max()) <= FP32_TIE_ATOL, \
-            "index mismatch not explained by fp32 noise: gap %g" % gap.max()
+        max_gap = float(gap.max())
+        assert max_gap <= FP32_TIE_ATOL, "index mismatch not explained by fp32 noise: gap %g" % max_gap
+        assert n_mism <= FP32_TIE_MAX_FRACTION * idx.numel() + 2, \
+            "%d of %d entries differ from the fp32 oracle" % (n_mism, idx.numel())
+    record("topk", Q=q.size(0), N=db.size(0), D=q.size(1), k=k, mismatches_vs_f32=n_mism, max_tie_gap=max_gap,
+           max_rel_score_err=float(rel))
     return n_mism

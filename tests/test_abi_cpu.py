@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported_and_bound(L):
 
 
 def test_abi_version(L):
-    assert L.isb_abi_version() == 4
+    assert L.isb_abi_version() == 5
 
 
 def test_argument_errors_need_no_gpu(L):
@@ -108,3 +108,22 @@ def test_shipped_library_is_not_the_timeline_debug_build():
     from instance_search_b200 import _lib
     with pytest.raises(AttributeError):
         _lib.lib().isb_debug_timeline
+
+
+def test_options_are_explicit_not_environment(L, monkeypatch):
+    # the library reads nothing from the environment (round-1 A/B switches were getenv calls)
+    from instance_search_b200 import _lib
+    monkeypatch.setenv("ISB_MINING_KC", "8")
+    assert _lib.get_option("mining_kc") is None
+    with _lib.options(mining_kc=8, screen_pair=0):
+        assert _lib.get_option("mining_kc") == 8 and _lib.get_option("screen_pair") == 0
+    assert _lib.get_option("mining_kc") is None and _lib.get_option("screen_pair") is None
+    assert L.isb_set_option(999, 1) == 1 and b"unknown option" in L.isb_last_error()
+    with pytest.raises(_lib.IsbError):
+        _lib.set_option("no_such_option", 1)
+    # (the static CUDA runtime inside the .so imports getenv, so the check is on our sources)
+    import glob
+    import os
+    csrc = os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc")
+    for f in glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh")):
+        assert "getenv" not in open(f).read(), f

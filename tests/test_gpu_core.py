@@ -165,28 +165,31 @@ def test_topk_search_random(ops, Q, N, D, k):
     assert all(len(set(r)) == k for r in i.cpu().tolist()[:50])
 
 
-def test_topk_search_pair_and_single_cta_kernels_agree(ops, monkeypatch):
+def test_topk_search_pair_and_single_cta_kernels_agree(ops):
     # the 256 x 256 CTA-pair screen and the single-CTA 128 x 256 screen feed the same exact
-    # re-rank: identical indices and scores (ISB_SCREEN_PAIR=0 selects the single-CTA kernel)
+    # re-rank: identical indices and scores (option screen_pair=0 selects the single-CTA kernel)
+    from instance_search_b200 import _lib
     Q, N, D, k = 700, 30000, 128, 100
     q = oracle.normalize_l2(_randn(Q, D, seed=31))
     db = oracle.normalize_l2(_randn(N, D, seed=32))
     s2, i2 = _search(ops, q, db, k)
-    monkeypatch.setenv("ISB_SCREEN_PAIR", "0")
-    s1, i1 = _search(ops, q, db, k)
+    with _lib.options(screen_pair=0):
+        s1, i1 = _search(ops, q, db, k)
+    assert _lib.get_option("screen_pair") is None      # restored
     assert torch.equal(i1, i2) and torch.equal(s1, s2)
     check_topk_against_oracle(q, db, k, s2, i2)
 
 
-def test_topk_search_with_seeded_thresholds(ops, monkeypatch):
-    # ISB_SCREEN_SEED=1: every row's threshold starts at the kc-th best score over the first 2048
+def test_topk_search_with_seeded_thresholds(ops):
+    # option screen_seed=1: every row's threshold starts at the kc-th best score over the first 2048
     # database rows (a lower bound of the kc-th best overall) instead of -inf: same result
     Q, N, D, k = 130, 33000, 72, 100
     q = oracle.normalize_l2(_randn(Q, D, seed=41))
     db = oracle.normalize_l2(_randn(N, D, seed=42))
+    from instance_search_b200 import _lib
     s0, i0 = _search(ops, q, db, k)
-    monkeypatch.setenv("ISB_SCREEN_SEED", "1")
-    s1, i1 = _search(ops, q, db, k)
+    with _lib.options(screen_seed=1):
+        s1, i1 = _search(ops, q, db, k)
     assert torch.equal(i0, i1) and torch.equal(s0, s1)
     check_topk_against_oracle(q, db, k, s1, i1)
 
@@ -274,6 +277,20 @@ def test_topk_search_idx_offset_and_merge(ops):
         cs.append(s), ci.append(i)
     ms, mi = ops.topk_merge(torch.stack(cs), torch.stack(ci))
     assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+
+
+def test_topk_small_margin_is_not_certified_by_a_one_sample_sigma(ops):
+    # k = 1, margin = 0: sigma comes from ONE candidate and can be ~0; the expected-bf16-noise
+    # floor keeps such a row from being certified on a gap far below the screen noise.  The
+    # result must still be the fp64 arg-max for every row (rows the floor rejects are resolved).
+    Q, N, D = 300, 40000, 256
+    q = oracle.normalize_l2(_randn(Q, D, seed=51))
+    db = oracle.normalize_l2(_randn(N, D, seed=52))
+    stats = {}
+    s, i = _search(ops, q, db, 1, margin=0, stats=stats)
+    a_s, a_i = oracle.topk_search_f64(q, db, 1)
+    assert torch.equal(i.cpu(), a_i)
+    assert stats["resolved_fp32_grade"] >= 1      # top-2 gaps below 8 sigma exist among 300 rows
 
 
 def test_topk_search_errors(ops):

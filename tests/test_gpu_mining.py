@@ -73,7 +73,9 @@ def test_select_negatives_golden(M, semi):
     (2048, 128, 16, True, 3),
     (4096, 256, 16, True, 3),
     (1000, 72, 7, True, 3),       # ragged sizes
-    (2048, 128, 16, True, 1),     # plain bf16 screen: certificate + brute force must keep it exact
+    (2048, 128, 16, True, 1),     # plain bf16 screen (the default): certificate + second line keep it exact
+    (2048, 128, 16, False, 1),
+    (20480, 128, 16, True, 1),    # CTA-pair screen, plain operands
     (20480, 128, 16, True, 3),    # large enough for the CTA-pair screen (masked epilogue, split operands)
     (20480, 136, 16, False, 3),   # the same, hard mode, D not a multiple of 64
 ])
@@ -97,8 +99,30 @@ def test_select_negatives_random(M, N, D, per, semi, terms):
     assert (lab[neg.cpu()[valid]] != lab[anchors[valid]]).all()
     if semi:
         assert (nsim.cpu()[valid] < psim.cpu()[valid]).all()
-    if terms == 3:
-        assert int(idx.last_bruteforce) <= 2
+    assert int(idx.last_bruteforce) <= 2
+    if terms == 1:
+        assert idx.last_second_line <= len(anchors) // 20    # the plain screen certifies nearly every couple
+
+
+def test_select_negatives_dense_neighbourhoods_fall_to_the_second_line(M):
+    # negatives packed within bf16 noise of each other (all rows = one direction + 1e-4 noise, every
+    # item its own label pair): the plain screen cannot certify, the split-operand second line /
+    # the exhaustive pass answer -- and the answer is still the fp64 arg-max
+    g = torch.Generator().manual_seed(77)
+    N, D = 3000, 128
+    base = torch.randn(1, D, generator=g)
+    E = oracle.normalize_l2(base + 3e-3 * torch.randn(N, D, generator=g))
+    lab = torch.arange(N) // 2
+    anchors = torch.arange(0, 200, 2)
+    positives = anchors + 1
+    idx = M.MiningIndex(E.cuda(), lab)
+    neg, nsim, psim = idx.select_negatives(anchors, positives, False)
+    S64 = E.double() @ E.double().t()
+    for p, (a, b) in enumerate(zip(anchors.tolist(), positives.tolist())):
+        s = S64[a].clone()
+        s[lab == lab[a]] = -2
+        assert int(neg[p]) == int(s.argmax())
+    assert idx.last_second_line > 0
 
 
 def test_lab_indicators_and_device_rule(M):

@@ -6,12 +6,12 @@ import torch
 
 import oracle
 from conftest import load_golden
+from parity import check_descriptors
 
 pytestmark = pytest.mark.gpu
 
-# descriptor components: the projection runs as a 3-product bf16 expansion
-# (fp32-grade, ~1e-5 relative); unit-norm rows => absolute tolerance
-DESC_ATOL = 3e-5
+# descriptors: per-row L2 error <= parity.DESC_L2_TOL and 1 - cosine <= 1e-10 against the
+# oracle (the projection runs as a 3-product bf16 expansion, fp32-grade): check_descriptors
 CLS_RTOL = 1e-5   # cls_out: fp32 dot products of the exact window means (isb_region_logits)
 CLS_ATOL = 2e-6   # fp32 summation-order noise on logits that cancel to ~0
 
@@ -35,7 +35,7 @@ def test_region_tiny_golden(R, tag):
     d, c, i, n = R.region_descriptors(g["x_" + tag].cuda(), hw, g["k"], fs)
     assert torch.equal(i.cpu(), g["idx_" + tag])                 # index-exact windows
     assert torch.allclose(c.cpu(), g["cls_out_" + tag], rtol=CLS_RTOL, atol=CLS_ATOL)
-    assert torch.allclose(d.cpu(), g["desc_" + tag], rtol=0, atol=DESC_ATOL)
+    check_descriptors(d, g["desc_" + tag])
     nw = (g["x_" + tag].size(2) - 6) * (g["x_" + tag].size(3) - 6)
     assert n.tolist() == [min(nw, g["k"])] * 3
     assert torch.allclose(d.norm(dim=1).cpu(), torch.ones(3), atol=1e-5)
@@ -47,14 +47,14 @@ def test_region_resnet18_head_golden(R):
     d, c, i, n = R.region_descriptors(g["x"].cuda(), hw, g["k"], tuple(int(v) for v in g["fsize"]))
     assert torch.equal(i.cpu(), g["idx"])
     assert torch.allclose(c.cpu(), g["cls_out"], rtol=CLS_RTOL, atol=CLS_ATOL)
-    assert torch.allclose(d.cpu(), g["desc"], rtol=0, atol=DESC_ATOL)
+    check_descriptors(d, g["desc"])
 
 
 def test_descriptor_head_golden(R):
     g = load_golden("descriptor_tiny")
     hw = R.HeadWeights(None, None, g["shift"].cuda(), g["lin_w"].cuda(), g["lin_b"].cuda())
     d = R.global_descriptors(g["x"].cuda(), hw)
-    assert torch.allclose(d.cpu(), g["desc"], rtol=0, atol=DESC_ATOL)
+    check_descriptors(d, g["desc"])
 
 
 def _synthetic(B, C, H, W, ncls, D, seed):
@@ -85,7 +85,7 @@ def test_region_random_vs_oracle(R, B, C, H, W, ncls, D, k):
     assert torch.equal(n.cpu().long(), on)
     assert torch.equal(i.cpu(), oi)
     assert torch.allclose(c.cpu(), oc, rtol=CLS_RTOL, atol=CLS_ATOL)
-    assert torch.allclose(d.cpu(), od, rtol=0, atol=DESC_ATOL)
+    check_descriptors(d, od)
 
 
 def test_region_plain_bf16_projection_is_close(R):
@@ -114,7 +114,7 @@ def test_region_exact_second_line_matches_fast_path_and_oracle(R):
     assert torch.allclose(c2.cpu(), oc, rtol=CLS_RTOL, atol=CLS_ATOL)
     assert torch.allclose(c.cpu(), oc, rtol=CLS_RTOL, atol=CLS_ATOL)
     U_hi, U_lo, _ = R.region_gather(x, hw, 6, (7, 7), i2, n2, wn2, want_means=False)
-    assert torch.allclose(R.region_project(U_hi, U_lo, hw, n2).cpu(), od, rtol=0, atol=DESC_ATOL)
+    check_descriptors(R.region_project(U_hi, U_lo, hw, n2), od)
 
 
 def test_region_near_tied_windows_fall_to_the_exact_line(R):
@@ -131,7 +131,7 @@ def test_region_near_tied_windows_fall_to_the_exact_line(R):
     assert i.cpu().tolist() == [[0, 1, 2, 3, 4, 5]] * 2
     od, oc, _, _ = oracle.region_descriptor_forward(s["x"], s["cls_w"], s["cls_b"], s["shift"], s["lin_w"],
                                                     s["lin_b"], 6, (7, 7))
-    assert torch.allclose(d.cpu(), od, rtol=0, atol=DESC_ATOL)      # identical crops: same descriptor
+    check_descriptors(d, od)      # identical crops: same descriptor
     assert torch.allclose(c.cpu(), oc, rtol=CLS_RTOL, atol=CLS_ATOL)
 
 
@@ -151,7 +151,7 @@ def test_region_only_the_uncertified_images_are_redone(R):
     keep = [0, 1, 2, 4]
     assert torch.equal(i.cpu()[keep], oi[keep])
     assert i.cpu()[3].tolist() == [0, 1, 2, 3, 4, 5]           # ties -> lower window index first
-    assert torch.allclose(d.cpu(), od, rtol=0, atol=DESC_ATOL)
+    check_descriptors(d, od)
     assert torch.allclose(c.cpu()[keep], oc[keep], rtol=CLS_RTOL, atol=CLS_ATOL)
 
 
