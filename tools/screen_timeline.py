@@ -1,7 +1,7 @@
 """Where the roles of the CTA-pair screen kernel wait.  Needs the debug build:
 
-    make -C instance_search_b200/csrc clean && make -C instance_search_b200/csrc TIMELINE=1
-    python tools/screen_timeline.py --N 125000          # (rebuild without TIMELINE afterwards)
+    make -C instance_search_b200/csrc timeline          # -> instance_search_b200/libisb_timeline.so
+    python tools/screen_timeline.py --N 125000
 
 Runs one search and prints, per slot of isb_timeline (isb_gemm_core.cuh), the mean over the
 leader / peer CTAs as cycles and as a share of the kernel's own duration."""
@@ -22,12 +22,12 @@ ap.add_argument("--D", type=int, default=2048)
 ap.add_argument("--k", type=int, default=100)
 a = ap.parse_args()
 
+_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libisb_timeline.so")   # the instrumented build
 L = _lib.lib()
-if not hasattr(L, "isb_debug_timeline"):
-    try:
-        L.isb_debug_timeline
-    except AttributeError:
-        sys.exit("libisb.so was built without TIMELINE=1")
+try:
+    L.isb_debug_timeline
+except AttributeError:
+    sys.exit("libisb_timeline.so lacks isb_debug_timeline: build it with `make timeline`")
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(1234)
 db = torch.randn(a.N, a.D, device=dev, generator=g)
