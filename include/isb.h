@@ -324,6 +324,31 @@ int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H, int64_t W
 int isb_descriptor_finalize(const float* y, int64_t B, int64_t D, const float* bias,
                             const int32_t* nsel, float eps, float* desc, void* stream);
 
+/* ---------------------------------------------------------------- f3: backward of the fused head
+ * Training path of RegionDescriptorNet (model/siamese.py:199-222 with the backward passes of
+ * model/custom_modules.py:20-25 (Shift) and :59-67 (NormalizeL2)), batched.  With, per image b and
+ * selected window i < nsel[b] at idx[b, i]:  crop_i = the flattened C x fh x fw crop,
+ *   u_b = sum_i crop_i / sqrt(|crop_i|^2 + eps) + nsel[b] * shift,   y_b = W u_b + nsel[b] * bias,
+ *   cls_out[b, :, i] = Wc mean_i + bc,
+ * the dense parts (g_u = g_y W, dW = g_y^T u, dWc = g_cls^T mean, g_mean = g_cls Wc) are
+ * isb_gemm_nt_split calls; these two entry points are the glue around them.
+ *
+ * isb_region_crop_stats: crop_norm2[b, i] = |crop_i|^2, crop_dot[b, i] = <crop_i, g_u[b, :]>
+ *   (0 when g_u == NULL), win_mean[b, i, :] = per-channel window means (may be NULL); slots
+ *   i >= nsel[b] give 0.  g_u [B, ldg] fp32 is the gradient w.r.t. u.
+ * isb_region_scatter_grad: g_x[b, c, h, w] = sum over the windows i covering (h, w) of
+ *     g_u[b, j] / n_i - x[b, c, h, w] * crop_dot[b, i] / n_i^3  +  g_mean[b, i, c] / (fh * fw),
+ *   n_i = sqrt(crop_norm2[b, i] + eps), j = the crop element (c, h - r_i, w - c_i).
+ *   g_u / g_mean may be NULL (no descriptor / no cls_out gradient).  Gather form: no atomics,
+ *   overlapping windows add in a fixed order.  k <= 32. */
+int isb_region_crop_stats(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int fh, int fw, int k,
+                          const int64_t* idx, const int32_t* nsel, const float* g_u, int64_t ldg,
+                          float* crop_norm2, float* crop_dot, float* win_mean, void* stream);
+int isb_region_scatter_grad(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int fh, int fw, int k,
+                            const int64_t* idx, const int32_t* nsel, const float* g_u, int64_t ldg,
+                            const float* crop_norm2, const float* crop_dot, const float* g_mean, float eps,
+                            float* g_x, void* stream);
+
 /* ---------------------------------------------------------------- a11 + a13
  * Negative selection of create_batch, train/siamese_regions.py:106-129 (same
  * code train/siamese_descriptor.py:108-131), for P positive couples at once and
@@ -341,8 +366,8 @@ int isb_descriptor_finalize(const float* y, int64_t B, int64_t D, const float* b
  *   eps = max(screen_eps, 8 * max(sigma_measured, sigma_floor)),
  * sigma_measured = rms(screen - exact) over the couple's own candidates.  (Statistical, not a
  * proof: 8 sigma.)  In semi-hard mode the epilogue also drops columns whose screen score is
- * >= S[anchor, positive] + max(screen_eps, 8 * sigma_floor); a couple whose measured noise
- * exceeds that slack is rejected too.
+ * >= S[anchor, positive] + max(screen_eps, 16 * sigma_floor); a couple whose eps exceeds
+ * that slack is rejected too.
  *   uncertified_rows != NULL: the rejected couples (indices p) are listed there and counted in
  *     *n_uncertified; the caller re-runs them with a finer screen (split operands) -- the
  *     second line, as isb_topk_resolve is for the search.

@@ -5,4 +5,5 @@ own Python operator surface.  See DESIGN.md / INTEGRATION.md.
 """
 
 from . import _lib, ops  # noqa: F401
+from . import torch_ops  # noqa: F401  (registers torch.ops.isb.*)
 from ._lib import IsbError  # noqa: F401

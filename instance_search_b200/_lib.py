@@ -59,6 +59,10 @@ SIGNATURES = {
                                   c_ptr, c_ptr, c_ptr]),
     "isb_region_gather": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_ptr,
                                   c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    "isb_region_crop_stats": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr,
+                                      c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "isb_region_scatter_grad": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr,
+                                        c_i64, c_ptr, c_ptr, c_ptr, c_f32, c_ptr, c_ptr]),
     "isb_descriptor_finalize": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_f32, c_ptr, c_ptr]),
     "isb_select_negatives_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_int]),
     "isb_select_negatives": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64,

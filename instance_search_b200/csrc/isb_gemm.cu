@@ -26,57 +26,88 @@ struct StoreEpilogue {
   __device__ __forceinline__ void begin_segment(const Segment&) {}
   __device__ __forceinline__ void end_segment(const Segment&) {}
 
+  // pass nt of a segment = chunk nt of the split's k-range (PlainSched): the first pass stores
+  // the tile (+ bias), the later ones add to it -- every output element is owned by exactly one
+  // thread of one CTA, so the read-modify-write is plain, ordered and deterministic (the slab
+  // stays in L2 between passes)
   __device__ __forceinline__ void tile(const Segment& seg, int nt, uint32_t tmem_acc,
                                        uint64_t* tmem_empty_bar) {
     const int row = seg.m_block * kBM + row_in_tile;
     float* orow = p.out + static_cast<long long>(seg.aux) * p.split_stride +
                   static_cast<long long>(row) * p.ldo;
-    const int col0 = nt * kBN;
-    uint32_t v[2][32];
-    ptx::tmem_ld_32x32b_x32(tmem_acc, v[0]);
-#pragma unroll
-    for (int c = 0; c < kBN / 32; ++c) {
+    const int col0 = seg.n_tile * kBN;
+    const bool first = nt == seg.nt_begin;
+    uint32_t v0[32], v1[32];
+    ptx::tmem_ld_32x32b_x32(tmem_acc, v0);
+#pragma unroll 1
+    for (int it = 0; it < kBN / 64; ++it) {
       ptx::tmem_ld_wait();
-      if (c + 1 < kBN / 32) {
-        ptx::tmem_ld_32x32b_x32(tmem_acc + (c + 1) * 32, v[(c + 1) & 1]);
+      ptx::tmem_ld_32x32b_x32(tmem_acc + it * 64 + 32, v1);
+      emit(v0, orow, row, col0 + it * 64, first);
+      ptx::tmem_ld_wait();
+      if (it + 1 < kBN / 64) {
+        ptx::tmem_ld_32x32b_x32(tmem_acc + it * 64 + 64, v0);
       } else {
+        // the whole accumulator is in registers: hand the TMEM buffer back
         ptx::tc_fence_before();
         ptx::mbar_arrive(tmem_empty_bar);
       }
-      const int cb = col0 + c * 32;
-      if (row < p.M && cb < p.N) {
-        const uint32_t(&x)[32] = v[c & 1];
-        if (p.vec_ok && cb + 32 <= p.N) {
+      emit(v1, orow, row, col0 + it * 64 + 32, first);
+    }
+  }
+
+  __device__ __forceinline__ void emit(const uint32_t (&x)[32], float* orow, int row, int cb, bool first) {
+    if (row < p.M && cb < p.N) {
+      if (p.vec_ok && cb + 32 <= p.N) {
+        float4* o4 = reinterpret_cast<float4*>(orow + cb);
+        if (first) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(__uint_as_float(x[j]), __uint_as_float(x[j + 1]),
-                                   __uint_as_float(x[j + 2]), __uint_as_float(x[j + 3]));
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(__uint_as_float(x[4 * j]), __uint_as_float(x[4 * j + 1]),
+                                   __uint_as_float(x[4 * j + 2]), __uint_as_float(x[4 * j + 3]));
             if (p.bias != nullptr) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cb + j));
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cb) + j);
               o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
             }
-            *reinterpret_cast<float4*>(orow + cb + j) = o;
+            o4[j] = o;
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (cb + j < p.N) {
-              float o = __uint_as_float(x[j]);
+          for (int j = 0; j < 8; ++j) {
+            float4 o = o4[j];
+            o.x += __uint_as_float(x[4 * j]); o.y += __uint_as_float(x[4 * j + 1]);
+            o.z += __uint_as_float(x[4 * j + 2]); o.w += __uint_as_float(x[4 * j + 3]);
+            o4[j] = o;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (cb + j < p.N) {
+            float o = __uint_as_float(x[j]);
+            if (first) {
               if (p.bias != nullptr) o += __ldg(p.bias + cb + j);
-              orow[cb + j] = o;
+            } else {
+              o += orow[cb + j];
             }
+            orow[cb + j] = o;
           }
         }
       }
-      __syncwarp();
     }
+    __syncwarp();
   }
 };
 
 // One n-tile per segment.  m-block varies fastest so the CTAs running
 // concurrently share a B tile; then the k-split, then the n-tile.
+// The k-range of a segment is accumulated in passes of at most chunk_kb k-blocks (see the
+// scheduler interface in isb_gemm_core.cuh): pass c of the segment covers k-blocks
+// [kb_begin + c * chunk_kb, ...) and the epilogue sums the passes in fp32.
+constexpr int kAccChunkKb = 32;   // 128 tcgen05.mma accumulation steps per chunk
+
 struct PlainSched {
-  int m_blocks, n_tiles, k_blocks, splits;
+  int m_blocks, n_tiles, k_blocks, splits, chunk_kb;
   __device__ __forceinline__ void gate(const Segment&, int, int, int) const {}
   __device__ __forceinline__ void leave(const Segment&) const {}
   __device__ __forceinline__ int num_segments() const { return m_blocks * n_tiles * splits; }
@@ -86,12 +117,18 @@ struct PlainSched {
     seg.m_block = s - t * m_blocks;
     const int nt = t / splits;
     const int sp = t - nt * splits;
-    seg.nt_begin = nt;
-    seg.nt_end = nt + 1;
     seg.kb_begin = static_cast<int>(static_cast<long long>(sp) * k_blocks / splits);
     seg.kb_end = static_cast<int>(static_cast<long long>(sp + 1) * k_blocks / splits);
+    seg.nt_begin = 0;                                              // passes = chunks of the k-range
+    seg.nt_end = (seg.kb_end - seg.kb_begin + chunk_kb - 1) / chunk_kb;
     seg.aux = sp;
+    seg.n_tile = nt;
     return seg;
+  }
+  __device__ __forceinline__ int b_tile(const Segment& seg, int) const { return seg.n_tile; }
+  __device__ __forceinline__ void kb_range(const Segment& seg, int pass, int& kb0, int& kb1) const {
+    kb0 = seg.kb_begin + pass * chunk_kb;
+    kb1 = min(kb0 + chunk_kb, seg.kb_end);
   }
 };
 
@@ -162,7 +199,11 @@ static int gemm_nt_impl(const char* fn, const uint16_t* A, const uint16_t* A_lo,
     if (rc) return rc;
   }
 
-  PlainSched sched{m_blocks, n_tiles, k_blocks, splits};
+  // accumulation chunks: equal parts of at most kAccChunkKb k-blocks of every split's range
+  const int kb_split = (k_blocks + splits - 1) / splits;
+  const int n_chunks = (kb_split + kAccChunkKb - 1) / kAccChunkKb;
+  const int chunk_kb = (kb_split + n_chunks - 1) / n_chunks;
+  PlainSched sched{m_blocks, n_tiles, k_blocks, splits, chunk_kb};
   StoreEpiParams ep;
   ep.M = static_cast<int>(M);
   ep.N = static_cast<int>(N);

@@ -62,7 +62,25 @@ struct Segment {
   int kb_begin;  // k-blocks [kb_begin, kb_end) (64 columns each)
   int kb_end;
   int aux;       // scheduler-defined (n-group id / k-split id)
+  int n_tile;    // chunked schedulers: the one n-tile of B the whole segment works on
 };
+
+// Scheduler interface (besides num_segments / segment / gate / leave): every pass `nt` of a
+// segment produces one accumulator tile
+//   int  b_tile(seg, nt)              n-tile of B loaded for the pass (plain schedulers: nt)
+//   void kb_range(seg, nt, kb0, kb1)  k-blocks accumulated in the pass (plain: the segment's)
+// A chunked scheduler (PlainSched with chunk_kb) runs SEVERAL passes over the same output tile,
+// each over a slice of the k-range: the tensor core's fp32 accumulator loses low bits on every
+// one of the thousands of accumulation steps of a long chain (measured: 3.6e-4 relative on a
+// 300k-long chain, 5e-6 on 2k-long ones, tools/gemm_precision.py), so long contractions are cut
+// into chunks whose partial tiles the epilogue adds up in fp32 outside the tensor core.
+// Plain schedulers get the two trivial members from ISB_PLAIN_SEGMENT_PASSES.
+#define ISB_PLAIN_SEGMENT_PASSES                                                                    \
+  __device__ __forceinline__ int b_tile(const Segment&, int nt) const { return nt; }                \
+  __device__ __forceinline__ void kb_range(const Segment& seg, int, int& kb0, int& kb1) const {     \
+    kb0 = seg.kb_begin;                                                                             \
+    kb1 = seg.kb_end;                                                                               \
+  }
 
 struct GemmSmem {
   uint64_t full[kStages];
@@ -138,7 +156,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int nt = seg.nt_begin; nt < seg.nt_end; ++nt) {
         sched.gate(seg, nt, wave, gridDim.x);
         if (lane == 0) {
-          for (int kb = seg.kb_begin; kb < seg.kb_end; ++kb) {
+          int kb0, kb1;
+          sched.kb_range(seg, nt, kb0, kb1);
+          const int bt = sched.b_tile(seg, nt);
+          for (int kb = kb0; kb < kb1; ++kb) {
             ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* sa = ring + stage * kStageBytes;
             uint8_t* sb = sa + kABytes;
@@ -155,7 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // A (queries / activations) is re-read for every n-tile: keep it in L2.
             ptx::tma_load_2d(sa, ma, &bars->full[stage], kk * kBK, seg.m_block * kBM,
                              ptx::kEvictLast);
-            ptx::tma_load_2d(sb, mb, &bars->full[stage], kk * kBK, nt * kBN,
+            ptx::tma_load_2d(sb, mb, &bars->full[stage], kk * kBK, bt * kBN,
                              ptx::kEvictNormal);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
@@ -179,7 +200,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           ptx::mbar_wait(&bars->tmem_empty[buf], acc_phase ^ 1);
           ptx::tc_fence_after();
           const uint32_t tmem_acc = tmem_base + buf * kBN;
-          for (int kb = seg.kb_begin; kb < seg.kb_end; ++kb) {
+          int kb0, kb1;
+          sched.kb_range(seg, nt, kb0, kb1);
+          for (int kb = kb0; kb < kb1; ++kb) {
             ptx::mbar_wait(&bars->full[stage], phase);
             ptx::tc_fence_after();
             const uint32_t sa = ptx::smem_u32(ring + stage * kStageBytes);
@@ -190,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in
               // the (addr >> 4) start-address field
               ptx::umma_bf16(tmem_acc, da + 2 * k, db + 2 * k, idesc,
-                             (kb > seg.kb_begin || k > 0) ? 1u : 0u);
+                             (kb > kb0 || k > 0) ? 1u : 0u);
             }
             ptx::umma_commit(&bars->empty[stage]);  // smem slot free once these MMAs retire
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -323,7 +346,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (leader) sched.gate(seg, nt, wave, n_pairs);
         ISB_TL_ADD(tl_gate, tl_g0);
         if (lane == 0) {
-          for (int kb = seg.kb_begin; kb < seg.kb_end; ++kb) {
+          int kb0, kb1;
+          sched.kb_range(seg, nt, kb0, kb1);
+          const int bt = sched.b_tile(seg, nt);
+          for (int kb = kb0; kb < kb1; ++kb) {
             ISB_TL_BEGIN(tl_e0);
             ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
             ISB_TL_ADD(tl_empty, tl_e0);
@@ -341,7 +367,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const CUtensorMap* ma = (term == 1) ? &tmap_a_lo : &tmap_a;
             const CUtensorMap* mb = (term == 2) ? &tmap_b_lo : &tmap_b;
             ptx::tma_load_2d_pair(sa, ma, full_leader, kk * kBK, my_m_block * kBM, ptx::kEvictLast);
-            ptx::tma_load_2d_pair(sb, mb, full_leader, kk * kBK, nt * kBN + static_cast<int>(rank) * kPairBRows,
+            ptx::tma_load_2d_pair(sb, mb, full_leader, kk * kBK, bt * kBN + static_cast<int>(rank) * kPairBRows,
                                   ptx::kEvictNormal);
             if (++stage == kPairStages) { stage = 0; phase ^= 1; }
           }
@@ -374,7 +400,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           ISB_TL_ADD(tl_drain, tl_d0);
           ptx::tc_fence_after();
           const uint32_t tmem_acc = tmem_base + buf * kBN;
-          for (int kb = seg.kb_begin; kb < seg.kb_end; ++kb) {
+          int kb0, kb1;
+          sched.kb_range(seg, nt, kb0, kb1);
+          for (int kb = kb0; kb < kb1; ++kb) {
             ISB_TL_BEGIN(tl_f0);
             ptx::mbar_wait(&bars->full[stage], phase);
             ISB_TL_ADD(tl_full, tl_f0);
@@ -385,7 +413,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k) {
               ptx::umma_bf16_pair(tmem_acc, da + 2 * k, db + 2 * k, idesc,
-                                  (kb > seg.kb_begin || k > 0) ? 1u : 0u);
+                                  (kb > kb0 || k > 0) ? 1u : 0u);
             }
             ptx::umma_commit_pair(&bars->empty[stage], 3);   // both CTAs' slots are free
             if (++stage == kPairStages) { stage = 0; phase ^= 1; }

@@ -898,6 +898,7 @@ struct RowMaxEpilogue {
 
 // one segment = one m-block x ALL n-tiles (the max runs over every class)
 struct RowSched {
+  ISB_PLAIN_SEGMENT_PASSES
   int m_blocks, n_tiles, k_blocks;
   __device__ __forceinline__ void gate(const Segment&, int, int, int) const {}
   __device__ __forceinline__ void leave(const Segment&) const {}
@@ -905,7 +906,7 @@ struct RowSched {
   __device__ __forceinline__ Segment segment(int s) const {
     Segment seg;
     seg.m_block = s; seg.nt_begin = 0; seg.nt_end = n_tiles;
-    seg.kb_begin = 0; seg.kb_end = k_blocks; seg.aux = 0;
+    seg.kb_begin = 0; seg.kb_end = k_blocks; seg.aux = 0; seg.n_tile = 0;
     return seg;
   }
 };

@@ -1756,7 +1756,9 @@ extern "C" int isb_select_negatives(const float* emb, const uint16_t* emb_hi, co
   if (kc < 1 || kc > kMaxCand) kc = kMiningCand;
   if (kc > N) kc = static_cast<int>(N);
   // semi-hard: columns scoring >= sim_pos (+ the screen's error bound) are masked in the epilogue
-  const float ub_slack = fmaxf(screen_eps, kCertZ * sigma_floor);
+  // twice the certificate's z: sigma measured on ~16 candidates scatters by ~20 % around the
+  // floor, and a couple is rejected when its measured noise exceeds the slack
+  const float ub_slack = fmaxf(screen_eps, 2.f * kCertZ * sigma_floor);
   rc = launch_topk_screen(a_hi, a_lo, ld, P, emb_hi, emb_lo, ld, N, D, kc, mp.sp, ws, label, row_label,
                           semi_hard ? pos32 : nullptr, ub_slack, st);
   if (rc) return rc;

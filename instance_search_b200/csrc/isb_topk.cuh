@@ -354,6 +354,7 @@ struct TopkEpilogue {
 // CTAs running concurrently stream the SAME database tiles (one HBM read, the
 // rest L2 hits) while the whole query matrix stays L2-resident.
 struct TopkSched {
+  ISB_PLAIN_SEGMENT_PASSES
   int m_blocks, n_tiles, n_groups, k_blocks;
   // Wave barrier.  Segments are handed out round-robin, so the workers (CTAs or CTA pairs) go
   // through them in waves; the row blocks of one n-group stream the same database tiles and
@@ -373,6 +374,7 @@ struct TopkSched {
     seg.kb_begin = 0;
     seg.kb_end = k_blocks;
     seg.aux = g;
+    seg.n_tile = 0;
     return seg;
   }
   // called by ALL 32 lanes of the producer warp before n-tile nt of the segment is loaded;

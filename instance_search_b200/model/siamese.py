@@ -14,15 +14,19 @@ checkpoints load and its callers run unchanged.  The trunk (``features``) stays
 in PyTorch.  Everything after it runs, without autograd, as the fused CUDA head
 of ``instance_search_b200.regions`` for the WHOLE batch at once -- the result
 equals the reference's batch-1 forward (:184) looped over the images.  When a
-gradient is required (training), the head is composed per image exactly as the
-reference composes it (:185-223), from this package's NormalizeL2 / Shift
-(CUDA forward + backward kernels) and torch's conv / linear autograd.
+gradient is required (training), the same fused head runs under autograd
+(``regions_autograd.RegionHeadFunction``: split-operand tcgen05 GEMMs for the weight /
+operand gradients, a gather kernel for the crop gradients), still batched.  Nets whose
+classifier is not AvgPool + one 1x1 conv (AlexNet's two-FC classifier) are composed per
+image as the reference composes them (:185-223) from this package's NormalizeL2 / Shift
+and torch's conv / linear autograd (``_forward_single_composed``, also the checker of the
+fused backward in the tests).
 """
 
 import torch
 import torch.nn as nn
 
-from .. import regions
+from .. import regions, regions_autograd
 from .custom_modules import NormalizeL2, Shift
 from .nn_utils import convolutionalize, extract_layers, get_feature_size, set_untrained_blocks
 
@@ -258,9 +262,13 @@ class RegionDescriptorNet(_CachedHeadMixin, nn.Module):
         treated as the reference's batch-1 call (model/siamese.py:184).  want_cls_out=False
         (what the eval-mode forward needs, :231) skips the logits output: cls_out is None."""
         x = self.features(x)
-        if self._needs_grad(x) or not self._fusable():
+        if not self._fusable():
             outs = [self._forward_single_composed(x[b:b + 1]) for b in range(x.size(0))]
             return torch.cat([d for d, _ in outs], 0), torch.cat([c for _, c in outs], 0)
+        if self._needs_grad(x):
+            # training: the same fused head under autograd (regions_autograd), whole batch at once
+            return regions_autograd.region_head(x, self.classifier[0], self.feature_reduc1[1],
+                                                self.feature_reduc1[2], self._head(), self.k, self.feature_size2d)
         desc, cls_out, _, _ = regions.region_descriptors(x.detach(), self._head(), self.k, self.feature_size2d,
                                                           want_cls_out=want_cls_out)
         return desc, cls_out

@@ -1,4 +1,5 @@
-"""Tensor-level wrappers of the C ABI, registered as torch custom ops (``isb::*``).
+"""Tensor-level wrappers of the C ABI (ctypes -> libisb.so).  ``torch_ops.py`` registers them
+as torch custom ops (``torch.ops.isb.*``).
 
 PyTorch is plumbing here: it owns device memory and the current stream; every
 computation below happens in libisb.so.  CUDA tensors only -- a CPU tensor is
@@ -205,6 +206,57 @@ def topk_search_workspace(Q, N, D, k, margin, device):
     return torch.empty(n, dtype=torch.uint8, device=device)
 
 
+def topk_candidates(q, db_bf16, k, kc, workspace=None, events=None, dim=None):
+    """Sharded search, local stage 1 (isb_topk_screen + isb_topk_candidates): screen one shard and
+    list its kc best screen entries per query.  q [Q, D] fp32, db_bf16 [N, ld] (to_bf16 of the
+    shard); dim = the true D when the bf16 rows are padded.  Returns (cand_screen [Q, kc] fp32,
+    cand_col [Q, kc] int32 local row; -inf / -1 where the shard has fewer than kc rows)."""
+    _need_cuda(q, db_bf16)
+    q = _f32c(q)
+    Q, D = q.shape
+    N = db_bf16.size(0)
+    k_eff = min(k, N)
+    margin = min(kc, N) - k_eff
+    cand_screen = torch.empty((Q, kc), dtype=torch.float32, device=q.device)
+    cand_col = torch.empty((Q, kc), dtype=torch.int32, device=q.device)
+    if Q == 0:
+        return cand_screen, cand_col
+    L = _lib.lib()
+    nbytes = L.isb_topk_search_workspace_bytes(Q, N, D, k_eff, margin)
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+    if events is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(L.isb_topk_screen(q.data_ptr(), Q, db_bf16.data_ptr(), N, D, db_bf16.size(1), k_eff, margin,
+                                 workspace.data_ptr(), workspace.numel(), _stream()), "isb_topk_screen")
+    if events is not None:
+        e1.record()
+        events.append((e0, e1))
+    _lib.check(L.isb_topk_candidates(Q, N, D, k_eff, margin, kc, cand_screen.data_ptr(), cand_col.data_ptr(),
+                                     workspace.data_ptr(), workspace.numel(), _stream()), "isb_topk_candidates")
+    return cand_screen, cand_col
+
+
+def topk_rerank_owned(q, db_f32, k, cand_screen, cand_col, thr):
+    """Sharded search, local stage 2 (isb_topk_rerank_owned): exact scores of this shard's
+    candidates at or above the global threshold, best first, as packed rows [Q, 2k + 2] int32
+    words: k scores (fp32 bits, -inf padded) | k local rows (-1 padded) | sum (screen - exact)^2 |
+    candidates scored (fp32 bits) -- what the second all-gather exchanges."""
+    _need_cuda(q, db_f32, cand_screen, cand_col, thr)
+    q, db_f32 = _f32c(q), _f32c(db_f32)
+    Q, kc = cand_screen.shape
+    N, D = db_f32.shape
+    packed = torch.empty((Q, 2 * k + 2), dtype=torch.int32, device=q.device)
+    if Q == 0:
+        return packed
+    _lib.check(_lib.lib().isb_topk_rerank_owned(
+        q.data_ptr(), Q, db_f32.data_ptr(), N, D, k, kc, _f32c(cand_screen).data_ptr(),
+        cand_col.contiguous().data_ptr(), _f32c(thr).data_ptr(), packed.data_ptr(), _stream()),
+        "isb_topk_rerank_owned")
+    return packed
+
+
 def topk_merge(cand_scores, cand_idx):
     """[R, Q, k] per-shard results -> the k best per query (ties -> lower index)."""
     _need_cuda(cand_scores, cand_idx)
@@ -355,58 +407,3 @@ def triplet_loss_backward(anchor, pos, neg, clamp, grad_out, size_average=True, 
                                                     ga.data_ptr(), gp.data_ptr(), gn.data_ptr(), _stream()),
                "isb_triplet_loss_backward")
     return ga, gp, gn
-
-
-# ------------------------------------------------------- torch.library registration
-# The same entry points as dispatcher ops (CUDA only; no CPU kernel is registered,
-# so calling them with CPU tensors raises NotImplementedError from the dispatcher).
-def _register():
-    try:
-        from torch.library import custom_op
-    except ImportError:  # pragma: no cover
-        return
-
-    @custom_op("isb::l2norm_rows", mutates_args=(), device_types="cuda")
-    def _l2norm(x: torch.Tensor, eps: float) -> torch.Tensor:
-        return l2norm_rows(x, eps)
-
-    @_l2norm.register_fake
-    def _(x, eps):
-        return torch.empty_like(x)
-
-    @custom_op("isb::shift_rows", mutates_args=(), device_types="cuda")
-    def _shift(x: torch.Tensor, param: torch.Tensor) -> torch.Tensor:
-        return shift_rows(x, param)
-
-    @_shift.register_fake
-    def _(x, param):
-        return torch.empty_like(x)
-
-    @custom_op("isb::topk_search", mutates_args=(), device_types="cuda")
-    def _search(q: torch.Tensor, db_f32: torch.Tensor, db_bf16: torch.Tensor, k: int,
-                margin: int, idx_offset: int) -> tuple[torch.Tensor, torch.Tensor]:
-        return topk_search(q, db_f32, db_bf16, k, margin, idx_offset)
-
-    @custom_op("isb::gemm_nt_split", mutates_args=(), device_types="cuda")
-    def _gemm_split(a_hi: torch.Tensor, a_lo: torch.Tensor, b_hi: torch.Tensor, b_lo: torch.Tensor,
-                    splits: int) -> torch.Tensor:
-        return gemm_nt_split(a_hi, a_lo, b_hi, b_lo, None, splits)
-
-    @_gemm_split.register_fake
-    def _(a_hi, a_lo, b_hi, b_lo, splits):
-        return a_hi.new_empty((a_hi.size(0), b_hi.size(0)), dtype=torch.float32)
-
-    @_search.register_fake
-    def _(q, db_f32, db_bf16, k, margin, idx_offset):
-        return (q.new_empty((q.size(0), k)), q.new_empty((q.size(0), k), dtype=torch.int64))
-
-    @custom_op("isb::gemm_nt", mutates_args=(), device_types="cuda")
-    def _gemm(a: torch.Tensor, b: torch.Tensor, splits: int) -> torch.Tensor:
-        return gemm_nt(a, b, None, splits)
-
-    @_gemm.register_fake
-    def _(a, b, splits):
-        return a.new_empty((a.size(0), b.size(0)), dtype=torch.float32)
-
-
-_register()

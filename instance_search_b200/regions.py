@@ -181,15 +181,30 @@ def region_logits(win_mean, hw, k, nsel_in, idx_in, norm_in, approx_max, runner_
     return idx, norm, nsel, cls_out, changed, n_changed, n_unc
 
 
-def region_project(U_hi, U_lo, hw, nsel):
-    """a4 projection + a5: desc = l2norm(u . W^T + nsel * bias)."""
-    B = U_hi.size(0)
-    y = _project(U_hi, U_lo, hw, B)
-    desc = torch.empty((B, hw.D), dtype=torch.float32, device=U_hi.device)
-    _lib.check(_lib.lib().isb_descriptor_finalize(y.data_ptr(), B, hw.D, ops._ptr(hw.lin_b), nsel.data_ptr(),
-                                                  1e-10, desc.data_ptr(), ops._stream()),
+def descriptor_finalize(y, bias, nsel, eps=1e-10):
+    """a4 (bias) + a5: desc = l2norm(y + nsel * bias); nsel None = 1 (DescriptorNet).
+    reference: model/siamese.py:220-222."""
+    ops._need_cuda(y, bias, nsel)
+    y = ops._f32c(y)
+    B, D = y.shape
+    desc = torch.empty((B, D), dtype=torch.float32, device=y.device)
+    if B == 0:
+        return desc
+    if nsel is not None:
+        nsel = nsel.to(torch.int32).contiguous()
+    _lib.check(_lib.lib().isb_descriptor_finalize(y.data_ptr(), B, D, ops._ptr(None if bias is None else ops._f32c(bias)),
+                                                  ops._ptr(nsel), float(eps), desc.data_ptr(), ops._stream()),
                "isb_descriptor_finalize")
     return desc
+
+
+def region_project(U_hi, U_lo, hw, nsel, extras=None):
+    """a4 projection + a5: desc = l2norm(u . W^T + nsel * bias).  extras (dict): receives
+    'y' = u . W^T, what the backward of the final normalisation needs."""
+    y = _project(U_hi, U_lo, hw, U_hi.size(0))
+    if extras is not None:
+        extras["y"] = y
+    return descriptor_finalize(y, hw.lin_b, nsel)
 
 
 def region_head(x, hw, k, fsize, margin=WINDOW_MARGIN, want_cls_out=True):
@@ -211,13 +226,16 @@ def region_head(x, hw, k, fsize, margin=WINDOW_MARGIN, want_cls_out=True):
     return U_hi, U_lo, idx, nsel, cls_out, torch.stack([n1, n2])
 
 
-def region_descriptors_async(x, hw, k, fsize, margin=WINDOW_MARGIN, want_cls_out=True):
+def region_descriptors_async(x, hw, k, fsize, margin=WINDOW_MARGIN, want_cls_out=True, extras=None):
     """The certified fast path with nothing read back: (desc, cls_out, idx, nsel,
     n_uncertified [2, 1 + B] device int32).  The caller checks n_uncertified[:, 0] whenever
     it likes (e.g. after queueing the next batch) and, if it is non-zero, patches the
-    listed images with region_descriptors_fix."""
+    listed images with region_descriptors_fix.  extras (dict): receives the projection's
+    operand and output ('U_hi', 'U_lo', 'y') for the backward pass."""
     U_hi, U_lo, idx, nsel, cls_out, n_unc = region_head(x, hw, k, fsize, margin, want_cls_out)
-    desc = region_project(U_hi, U_lo, hw, nsel)
+    if extras is not None:
+        extras["U_hi"], extras["U_lo"] = U_hi, U_lo
+    desc = region_project(U_hi, U_lo, hw, nsel, extras)
     return desc, cls_out, idx, nsel, n_unc
 
 
@@ -230,27 +248,35 @@ def uncertified_images(n_unc):
     return sorted(bad)
 
 
-def region_descriptors_exact(x, hw, k, fsize):
+def region_descriptors_exact(x, hw, k, fsize, extras=None):
     """The fp64-exact second line (candidates = 32 windows, everything re-scored from the
     fp32 inputs): what uncertified images are redone with."""
     idx, nsel, cls_out, win_norm, _, _, _ = region_select(x, hw, k, fsize, exact_mode=True)
     U_hi, U_lo, _ = region_gather(x, hw, k, fsize, idx, nsel, win_norm, want_means=False)
-    return region_project(U_hi, U_lo, hw, nsel), cls_out, idx, nsel
+    if extras is not None:
+        extras["U_hi"], extras["U_lo"] = U_hi, U_lo
+    return region_project(U_hi, U_lo, hw, nsel, extras), cls_out, idx, nsel
 
 
-def region_descriptors_fix(x, hw, k, fsize, bad, desc, cls_out, idx, nsel):
+def region_descriptors_fix(x, hw, k, fsize, bad, desc, cls_out, idx, nsel, extras=None):
     """Redo the images ``bad`` (list of batch indices) with the exact second line and patch
-    the fast path's outputs in place."""
+    the fast path's outputs (and the backward's operands in ``extras``) in place."""
     sel = torch.tensor(bad, dtype=torch.int64, device=x.device)
-    d2, c2, i2, n2 = region_descriptors_exact(x.index_select(0, sel).contiguous(), hw, k, fsize)
+    sub = {} if extras is not None else None
+    d2, c2, i2, n2 = region_descriptors_exact(x.index_select(0, sel).contiguous(), hw, k, fsize, sub)
     desc.index_copy_(0, sel, d2)
     idx.index_copy_(0, sel, i2)
     nsel.index_copy_(0, sel, n2)
     if cls_out is not None:
         cls_out.index_copy_(0, sel, c2)
+    if extras is not None:
+        for name in ("U_hi", "U_lo", "y"):
+            if extras.get(name) is not None:
+                extras[name].index_copy_(0, sel, sub[name])
 
 
-def region_descriptors(x, hw, k, fsize, margin=WINDOW_MARGIN, exact=True, stats=None, want_cls_out=True):
+def region_descriptors(x, hw, k, fsize, margin=WINDOW_MARGIN, exact=True, stats=None, want_cls_out=True,
+                       extras=None):
     """x [B, C, H, W] trunk feature maps -> (desc [B, D], cls_out [B, ncls, k],
     idx [B, k], nsel [B]).  reference: model/siamese.py:187-223 per image.
 
@@ -259,7 +285,7 @@ def region_descriptors(x, hw, k, fsize, margin=WINDOW_MARGIN, exact=True, stats=
     the projection has been queued so the GPU does not idle during the round trip);
     the images they reject -- and only those -- are redone with the fp64-exact second
     line.  exact=False skips the read-back (no host sync)."""
-    desc, cls_out, idx, nsel, n_unc = region_descriptors_async(x, hw, k, fsize, margin, want_cls_out)
+    desc, cls_out, idx, nsel, n_unc = region_descriptors_async(x, hw, k, fsize, margin, want_cls_out, extras)
     if exact:
         n_bad = int(n_unc[:, 0].sum().item())
         if stats is not None:
@@ -270,8 +296,51 @@ def region_descriptors(x, hw, k, fsize, margin=WINDOW_MARGIN, exact=True, stats=
             bad = uncertified_images(n_unc)
             if stats is not None:
                 stats["images_resolved_exactly"] += len(bad)
-            region_descriptors_fix(x, hw, k, fsize, bad, desc, cls_out, idx, nsel)
+            region_descriptors_fix(x, hw, k, fsize, bad, desc, cls_out, idx, nsel, extras)
     return desc, cls_out, idx, nsel
+
+
+# ------------------------------------------------------------------ backward glue (f3)
+def crop_stats(x, k, fsize, idx, nsel, g_u=None, want_means=True):
+    """Per selected window: (|crop|^2 [B, k], <crop, g_u[b]> [B, k], window means [B, k, C] or
+    None) -- isb_region_crop_stats.  g_u [B, ld] fp32 (gradient w.r.t. the projection operand)."""
+    ops._need_cuda(x, idx, nsel, g_u)
+    x = ops._f32c(x)
+    B, C, H, W = x.shape
+    n2 = torch.empty((B, k), dtype=torch.float32, device=x.device)
+    dot = torch.empty((B, k), dtype=torch.float32, device=x.device)
+    means = torch.empty((B, k, C), dtype=torch.float32, device=x.device) if want_means else None
+    if B == 0:
+        return n2, dot, means
+    if g_u is not None:
+        g_u = ops._f32c(g_u)
+    _lib.check(_lib.lib().isb_region_crop_stats(
+        x.data_ptr(), B, C, H, W, fsize[0], fsize[1], k, idx.contiguous().data_ptr(),
+        nsel.to(torch.int32).contiguous().data_ptr(), ops._ptr(g_u), 0 if g_u is None else g_u.size(1),
+        n2.data_ptr(), dot.data_ptr(), ops._ptr(means), ops._stream()), "isb_region_crop_stats")
+    return n2, dot, means
+
+
+def scatter_grad(x, k, fsize, idx, nsel, g_u, n2, dot, g_mean, eps=1e-10):
+    """g_x [B, C, H, W]: gradient of the head w.r.t. the feature map from the gradient of the
+    projection operand (g_u, through the crops' L2 normalisation) and of the window means
+    (g_mean [B, k, C], through the sliding mean) -- isb_region_scatter_grad."""
+    ops._need_cuda(x, idx, nsel, g_u, g_mean)
+    x = ops._f32c(x)
+    B, C, H, W = x.shape
+    g_x = torch.empty_like(x)
+    if B == 0:
+        return g_x
+    if g_u is not None:
+        g_u = ops._f32c(g_u)
+    if g_mean is not None:
+        g_mean = ops._f32c(g_mean)
+    _lib.check(_lib.lib().isb_region_scatter_grad(
+        x.data_ptr(), B, C, H, W, fsize[0], fsize[1], k, idx.contiguous().data_ptr(),
+        nsel.to(torch.int32).contiguous().data_ptr(), ops._ptr(g_u), 0 if g_u is None else g_u.size(1),
+        ops._f32c(n2).data_ptr(), ops._f32c(dot).data_ptr(), ops._ptr(g_mean), float(eps), g_x.data_ptr(),
+        ops._stream()), "isb_region_scatter_grad")
+    return g_x
 
 
 def global_descriptors(x, hw):
@@ -285,8 +354,4 @@ def global_descriptors(x, hw):
         raise IsbError("flattened features (%d) != projection in_features (%d)" % (flat.size(1), hw.Kin))
     u = ops.shift_rows(ops.l2norm_rows(flat), hw.shift)
     y = _project(ops.to_bf16(u, 0), ops.to_bf16(u, 1) if hw.terms == 3 else None, hw, B)
-    desc = torch.empty((B, hw.D), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().isb_descriptor_finalize(y.data_ptr(), B, hw.D, ops._ptr(hw.lin_b), 0, 1e-10,
-                                                  desc.data_ptr(), ops._stream()),
-               "isb_descriptor_finalize")
-    return desc
+    return descriptor_finalize(y, hw.lin_b, None)

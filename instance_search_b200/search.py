@@ -101,33 +101,14 @@ class DescriptorIndex(object):
         entries per query: (cand_screen [Q, kc] fp32, cand_col [Q, kc] int32 local row;
         -inf / -1 where the shard has fewer than kc rows)."""
         q = self._queries(q)
-        Q, N = q.size(0), len(self)
-        k_eff = min(k, N)
-        margin = min(kc, N) - k_eff
-        cand_screen = torch.empty((Q, kc), dtype=torch.float32, device=q.device)
-        cand_col = torch.empty((Q, kc), dtype=torch.int32, device=q.device)
-        if Q == 0:
-            return cand_screen, cand_col
-        ws = self._screen(q, k_eff, margin, events)
-        ops._lib.check(ops._lib.lib().isb_topk_candidates(
-            Q, N, self.db_f32.size(1), k_eff, margin, kc, cand_screen.data_ptr(), cand_col.data_ptr(),
-            ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "isb_topk_candidates")
-        return cand_screen, cand_col
+        k_eff = min(k, len(self))
+        self._workspace(q.size(0), k_eff, min(kc, len(self)) - k_eff)
+        return ops.topk_candidates(q, self.db_bf16, k, kc, workspace=self._ws, events=events)
 
     def rerank_owned(self, q, k, cand_screen, cand_col, thr):
         """Sharded search, local stage 2: exact scores of this shard's candidates at or above
-        the global threshold, best first, as packed rows [Q, 2k + 2] int32 words: k scores
-        (fp32 bits, -inf padded) | k local rows (-1 padded) | sum (screen - exact)^2 |
-        candidates scored (fp32 bits) -- what the second all-gather exchanges."""
-        q = self._queries(q)
-        Q, kc = cand_screen.shape
-        packed = torch.empty((Q, 2 * k + 2), dtype=torch.int32, device=q.device)
-        N, D = self.db_f32.shape
-        ops._lib.check(ops._lib.lib().isb_topk_rerank_owned(
-            q.data_ptr(), Q, self.db_f32.data_ptr(), N, D, k, kc, cand_screen.data_ptr(),
-            cand_col.data_ptr(), thr.data_ptr(), packed.data_ptr(),
-            torch.cuda.current_stream().cuda_stream), "isb_topk_rerank_owned")
-        return packed
+        the global threshold, packed for the second all-gather (ops.topk_rerank_owned)."""
+        return ops.topk_rerank_owned(self._queries(q), self.db_f32, k, cand_screen, cand_col, thr)
 
     def search(self, q, k, margin=None, events=None, exact=True):
         """(scores [Q, k] fp32, idx [Q, k] int64 global), best first.

@@ -16,16 +16,19 @@ SCORE_RTOL = 1e-5
 # the fp32 oracle is accepted only if the oracle's own scores of the two rows
 # are this close, and the fp64 adjudicator sides with us.
 # Unit-norm rows: |score| <= 1, fp32 dot noise is a few 1e-8 (measured on the B200
-# box: largest accepted gap 1.8e-7 over the whole suite, gpurun_out/parity_achieved.jsonl).
-FP32_TIE_ATOL = 5e-7
+# box: largest accepted gap 1.04e-7 over the whole suite, profiles/r02_parity_achieved.jsonl).
+FP32_TIE_ATOL = 2.5e-7
 # ... and such disagreements are rare: at most this fraction of the Q*k returned
 # entries (+2) may differ from the fp32 oracle
 FP32_TIE_MAX_FRACTION = 2e-3
 
 # region descriptors (unit-norm rows, split-operand fp32-grade projection): per-row L2
-# error against the oracle's descriptor, and 1 - cosine in fp64.  Measured on the box:
-# see gpurun_out/parity_achieved.jsonl / DESIGN.md section 2.
-DESC_L2_TOL = 4e-6
+# error against the oracle's descriptor, and 1 - cosine in fp64.  The floor is the 16-bit
+# (hi + lo bf16) representation of the two operands: 4.3e-6 relative on the projection at
+# K = 100352 even with exact accumulation (tools/gemm_precision.py), 3e-6 .. 6.3e-6 measured
+# over the suite (profiles/r02_parity_achieved.jsonl); torch's own fp32 matmul on the GPU is
+# 5.9e-6 from the fp64 product on the same operands.  Tolerance = 1.6 x the largest measured.
+DESC_L2_TOL = 1e-5
 DESC_COS_TOL = 1e-10
 
 

@@ -171,27 +171,53 @@ def test_region_descriptor_net_eval_matches_oracle_and_reloads():
         assert torch.allclose(net(x), -desc, atol=1e-6)
 
 
-def test_region_descriptor_net_train_mode_composed_path():
-    net = _toy_region_net(2)
-    for p in net.classifier.parameters():
+def _train_mode_grads(net, x, g_desc, g_cls, composed):
+    """Gradients of (desc, cls_out) w.r.t. the head parameters and the input images, through the
+    fused autograd head or through the reference composition (_forward_single_composed per image)."""
+    for p in net.parameters():
+        p.grad = None
+    xi = x.clone().requires_grad_(True)
+    fmap = net.features(xi)
+    if composed:
+        outs = [net._forward_single_composed(fmap[b:b + 1]) for b in range(fmap.size(0))]
+        desc, cls_out = torch.cat([d for d, _ in outs], 0), torch.cat([c for _, c in outs], 0)
+    else:
+        desc, cls_out = net.forward_single(xi)
+    ((desc * g_desc).sum() + (cls_out * g_cls).sum()).backward()
+    conv, shift, lin = net.classifier[0], net.feature_reduc1[1], net.feature_reduc1[2]
+    grads = {"x": xi.grad, "cls_w": conv.weight.grad, "cls_b": conv.bias.grad, "shift": shift.param.grad,
+             "lin_w": lin.weight.grad, "lin_b": lin.bias.grad}
+    return desc.detach(), cls_out.detach(), {k: v.detach().clone() for k, v in grads.items()}
+
+
+@pytest.mark.parametrize("B,h,w,k", [(3, 32, 32, 6), (2, 36, 44, 6), (4, 16, 18, 12)])
+def test_region_descriptor_net_train_mode_fused_backward_matches_composed_path(B, h, w, k):
+    # training (model/siamese.py:225-229): the fused head under autograd (regions_autograd) against the
+    # reference composition per image on torch's conv / linear autograd -- outputs and every gradient
+    net = _toy_region_net(2, k=k)
+    for p in list(net.classifier.parameters()) + list(net.feature_reduc1.parameters()):
         p.requires_grad = True
-    for p in net.feature_reduc1.parameters():
-        p.requires_grad = True
-    x = _randn(2, 3, 32, 32, seed=12).cuda()
+    x = _randn(B, 3, h, w, seed=12).cuda()
     torch.backends.cudnn.allow_tf32 = False          # the composed path's conv / linear in true fp32
     torch.backends.cuda.matmul.allow_tf32 = False
-    with torch.no_grad():
-        fused_desc, fused_cls = net.forward_single(x)
     from instance_search_b200.model.nn_utils import set_net_train
     set_net_train(net, True)                              # train mode, BatchNorm kept frozen (as the reference)
     out = net(x, x)                                       # train: tuple of (desc, cls_out) per input
-    assert isinstance(out, tuple) and len(out) == 2
-    desc, cls_out = out[0]
-    check_descriptors(desc, fused_desc)
-    assert torch.allclose(cls_out, fused_cls, rtol=1e-4, atol=1e-5)
-    (desc.sum() + cls_out.sum()).backward()
-    assert net.feature_reduc1[1].param.grad is not None and net.classifier[0].weight.grad is not None
-    assert float(net.feature_reduc1[2].weight.grad.abs().sum()) > 0
+    assert isinstance(out, tuple) and len(out) == 2 and out[0][0].requires_grad
+    g_desc = _randn(B, 16, seed=13).cuda()
+    g_cls = _randn(B, 5, k, seed=14).cuda()
+    d0, c0, want = _train_mode_grads(net, x, g_desc, g_cls, composed=True)
+    d1, c1, got = _train_mode_grads(net, x, g_desc, g_cls, composed=False)
+    check_descriptors(d1, d0)
+    assert torch.allclose(c1, c0, rtol=1e-4, atol=1e-5)
+    for name in want:
+        scale = want[name].abs().max().item()
+        err = (got[name] - want[name]).abs().max().item()
+        assert err <= 1e-5 * scale + 1e-9, (name, err, scale)
+    # eval-mode forward of the same net is the same descriptor
+    net.eval()
+    with torch.no_grad():
+        check_descriptors(net(x), d1, l2_tol=1e-6)
 
 
 def test_descriptor_net_eval_matches_oracle():

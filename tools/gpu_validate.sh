@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 rm -f gpurun_out/parity_achieved.jsonl
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader
 nproc; free -g | head -2
-timeout 1500 python -m pytest tests -m gpu -q -x --durations=15 2>&1 | tail -40 > gpurun_out/gputest.log; tail -25 gpurun_out/gputest.log
+timeout 1500 python -m pytest tests -m gpu -q --durations=15 2>&1 | tail -40 > gpurun_out/gputest.log; tail -25 gpurun_out/gputest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()"
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -3 gpurun_out/bench_n1.err
 python - <<'PY'
