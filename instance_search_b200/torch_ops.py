@@ -218,6 +218,24 @@ def global_descriptors(x: T, shift: T, lin_w_hi: T, lin_w_lo: Optional[T], lin_b
     return _regions.global_descriptors(x, hw)
 
 
+def _cstats_fake(x, idx, nsel, g_u, fh, fw):
+    B, C, k = x.size(0), x.size(1), idx.size(1)
+    return x.new_empty((B, k)), x.new_empty((B, k)), x.new_empty((B, k, C))
+
+
+@_op("region_crop_stats", _cstats_fake)
+def region_crop_stats(x: T, idx: T, nsel: T, g_u: Optional[T], fh: int, fw: int) -> Tuple[T, T, T]:
+    """Backward glue of the fused head: (|crop|^2, <crop, g_u>, window means) per selected window."""
+    return _regions.crop_stats(x, idx.size(1), (fh, fw), idx, nsel, g_u, want_means=True)
+
+
+@_op("region_scatter_grad", lambda x, idx, nsel, g_u, n2, dot, g_mean, fh, fw, eps: torch.empty_like(x))
+def region_scatter_grad(x: T, idx: T, nsel: T, g_u: Optional[T], n2: T, dot: T, g_mean: Optional[T], fh: int,
+                        fw: int, eps: float) -> T:
+    """Backward glue of the fused head: gradient w.r.t. the feature map (gather form)."""
+    return _regions.scatter_grad(x, idx.size(1), (fh, fw), idx, nsel, g_u, n2, dot, g_mean, eps)
+
+
 # ---------------------------------------------------------------- mining (a11-a13)
 def _neg_fake(emb, labels, anchors, positives, semi_hard, terms):
     P = anchors.size(0)

@@ -23,6 +23,7 @@ ENTRY_TO_OP = {
     "isb_region_select_workspace_bytes": None, "isb_region_select": "region_select",
     "isb_region_logits": "region_logits", "isb_region_gather": "region_gather",
     "isb_descriptor_finalize": "descriptor_finalize",
+    "isb_region_crop_stats": "region_crop_stats", "isb_region_scatter_grad": "region_scatter_grad",
     "isb_select_negatives_workspace_bytes": None, "isb_select_negatives": "select_negatives",
     "isb_row_kth_largest": "row_kth_largest", "isb_row_ranks": "row_ranks", "isb_instance_avg": "instance_avg",
     "isb_l2norm_rows_backward": "l2norm_rows_backward", "isb_col_sums": "col_sums",
@@ -85,6 +86,9 @@ def test_fake_shape_functions_trace_without_a_gpu():
         assert r[0].shape == (B, k) and r[3].shape == (B, ncls, k)
         assert o.descriptor_finalize(_f(B, D), _f(D), nsel, 1e-10).shape == (B, D)
         assert o.descriptor_finalize(_f(B, D), None, None, 1e-10).shape == (B, D)
+        n2, dot, means = o.region_crop_stats(fm, idx, nsel, _f(B, Kin), fh, fh)
+        assert n2.shape == (B, 8) and means.shape == (B, 8, C)
+        assert o.region_scatter_grad(fm, idx, nsel, _f(B, Kin), n2, dot, None, fh, fh, 1e-10).shape == fm.shape
         lw = _f(D, Kin, dtype=bf)
         d, c, i, n = o.region_descriptors(fm, cw, cwb, cwb, _f(ncls), _f(Kin), lw, lw, _f(D), fh, fh, k, 1.0)
         assert d.shape == (B, D) and c.shape == (B, ncls, k) and i.shape == (B, k) and n.dtype == i32
