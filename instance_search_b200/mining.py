@@ -8,6 +8,7 @@ import torch
 
 from . import _lib, ops
 from ._lib import IsbError
+from .sharding import all_gather_rows, shard_bounds
 
 SCREEN_EPS_3TERM = 2e-5   # absolute error bound of the [hi|lo|hi].[hi|hi|lo] screen, unit rows
 # plain bf16 screen: expected rms error of a score on dense rows, both operands rounded to 8
@@ -143,3 +144,42 @@ class MiningIndex(object):
                          self.last_bruteforce, sub)
             neg_idx[rows], neg_sim[rows] = sub[0], sub[1]
         return neg_idx, neg_sim, pos_sim
+
+
+class ShardedMiner(object):
+    """Negative selection over several GPUs: the embeddings are replicated
+    (every rank holds all of E: 134 MB at 16k x 2048), the positive couples are split contiguously
+    across the ranks, every rank selects the negatives of ITS couples (MiningIndex, no exchange on
+    the data path), and ONE all-gather of the packed results -- 16 bytes per couple -- gives every
+    rank the full answer.  Identical to MiningIndex.select_negatives on one GPU.
+
+    reference: train/siamese_regions.py:106-129 over the matrix of utils/train_siamese.py:48-55
+    (single device there)."""
+
+    def __init__(self, emb, labels, rank=0, world_size=1, group=None, terms=1):
+        self.rank, self.world_size, self.group = rank, world_size, group
+        self.index = self._make_index(emb, labels, terms)
+
+    # hooks (the gloo CPU test replaces them to exercise the plumbing)
+    def _make_index(self, emb, labels, terms):
+        return MiningIndex(emb, labels, terms=terms)
+
+    def _local_select(self, anchors, positives, semi_hard):
+        return self.index.select_negatives(anchors, positives, semi_hard)
+
+    def select_negatives(self, anchors, positives, semi_hard):
+        """Collective: every rank passes the SAME couples; returns (neg_idx [P] int64, neg_sim [P],
+        pos_sim [P]) of all couples on every rank."""
+        anchors = torch.as_tensor(anchors, dtype=torch.int64)
+        positives = torch.as_tensor(positives, dtype=torch.int64)
+        P = anchors.numel()
+        lo, hi = shard_bounds(P, self.world_size)[self.rank]
+        neg, nsim, psim = self._local_select(anchors[lo:hi], positives[lo:hi], semi_hard)
+        if self.world_size == 1:
+            return neg, nsim, psim
+        # pack (neg int64 | the two fp32 similarities as one 64-bit word) -> one collective
+        sims = torch.stack([nsim.float(), psim.float()], 1).contiguous().view(torch.int64)     # [p, 1]
+        packed = torch.cat([neg.view(-1, 1), sims.view(-1, 1)], 1)                              # [p, 2]
+        full = all_gather_rows(packed, P, self.rank, self.world_size, self.group)
+        sims = full[:, 1].contiguous().view(torch.float32).view(-1, 2)
+        return full[:, 0].contiguous(), sims[:, 0].contiguous(), sims[:, 1].contiguous()

@@ -19,17 +19,7 @@ import torch
 
 from . import ops
 from ._lib import IsbError
-
-
-def shard_bounds(n_rows, world_size):
-    """Row range [lo, hi) of every rank: as even as possible, contiguous."""
-    base, extra = divmod(n_rows, world_size)
-    bounds, lo = [], 0
-    for r in range(world_size):
-        hi = lo + base + (1 if r < extra else 0)
-        bounds.append((lo, hi))
-        lo = hi
-    return bounds
+from .sharding import shard_bounds  # noqa: F401  (re-exported: callers import it from here)
 
 
 class DescriptorIndex(object):

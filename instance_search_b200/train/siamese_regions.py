@@ -16,11 +16,23 @@ import torch
 from .. import mining
 
 
-def get_embeddings(net, dataset, device, out_size, batch_size=32, transform=None):
+def get_embeddings(net, dataset, device, out_size, batch_size=32, transform=None, rank=0, world_size=1,
+                   group=None):
     """Descriptors [len(dataset), out_size] of a reference-style data set (list of
     ``(image tensor [3, h, w], label, name)``), stored on ``device`` (>= 0: current
     CUDA device, < 0: host -- utils/general.py:94-98).
-    reference: train/siamese_regions.py:26-41 (net must be in eval mode)."""
+    reference: train/siamese_regions.py:26-41 (net must be in eval mode).
+
+    world_size > 1: collective over a torch.distributed group, one process
+    per GPU with a replica of the net -- the images are split contiguously across the ranks
+    (independent units, no exchange on the data path), every rank embeds its slice, and one
+    all-gather of the [n / R, D] blocks gives every rank the full matrix."""
+    if world_size > 1:
+        from ..sharding import all_gather_rows, shard_bounds
+        lo, hi = shard_bounds(len(dataset), world_size)[rank]
+        local = get_embeddings(net, dataset[lo:hi], 0, out_size, batch_size, transform)
+        full = all_gather_rows(local, len(dataset), rank, world_size, group)
+        return full if device >= 0 else full.cpu()
     n = len(dataset)
     out = torch.empty((n, out_size), dtype=torch.float32, device="cuda")
     i = 0
@@ -55,9 +67,10 @@ class NegativeSelector(object):
     from a row of the N x N matrix -- which is never materialised here.
     """
 
-    def __init__(self, embeddings, dataset):
+    def __init__(self, embeddings, dataset, rank=0, world_size=1, group=None):
         ids, self.labels = mining.label_ids(dataset)
-        self.index = mining.MiningIndex(embeddings.cuda(), ids)
+        # world_size > 1: the couples of every select() are split across the ranks (ShardedMiner)
+        self.index = mining.ShardedMiner(embeddings.cuda(), ids, rank, world_size, group)
 
     def select(self, couples, epoch, train_epoch_switch):
         """couples: sequence of (i1, i2).  Returns a list with, per couple, the index
