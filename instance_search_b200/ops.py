@@ -122,41 +122,78 @@ def gemm_nt_split(a_hi, a_lo, b_hi, b_lo, bias=None, splits=1, k=None):
 
 
 # ---------------------------------------------------------------------- search
+class ExactnessTicket(object):
+    """The host side of the exactness guarantee, deferred.  The completeness certificate leaves
+    the number of rows it rejected in device memory; reading it is the one device->host
+    round trip of a search.  A ticket holds that count on its way to pinned host memory (copy
+    queued behind the search, an event after it) so that the caller can queue MORE work --
+    the next batch's search -- before it waits: ``resolve()`` waits for the event and, on the
+    rare batch that has uncertified rows, re-runs them (fp32-grade re-screen / exhaustive pass)
+    and patches the result tensors in place.  A result must not be consumed before its ticket is
+    resolved."""
+
+    def __init__(self, n_unc, fixup):
+        if n_unc.is_cuda:
+            self._host = torch.empty(1, dtype=torch.int32).pin_memory()
+            self._host.copy_(n_unc, non_blocking=True)
+            self._event = torch.cuda.Event()
+            self._event.record()
+        else:   # host tensors (the gloo plumbing tests): nothing to wait for
+            self._host, self._event = n_unc.reshape(-1)[:1].clone(), None
+        self._fixup = fixup
+        self.n_uncertified = None
+
+    def resolve(self):
+        if self.n_uncertified is None:
+            if self._event is not None:
+                self._event.synchronize()
+            self.n_uncertified = int(self._host[0])
+            self._fixup(self.n_uncertified)
+            self._fixup = None
+        return self.n_uncertified
+
+
 def resolve_uncertified(q, db_f32, db_bf16, db_lo, k, margin, idx_offset, scores, idx, unc_rows, n_unc,
-                        stats=None):
+                        stats=None, defer=False):
     """Host side of the exactness guarantee (include/isb.h, stage 2b): read the
     number of rows the bf16 screen could not certify (ONE 4-byte D2H read; it is 0
     on ordinary data), re-screen those with fp32-grade split operands, and search
     exhaustively whatever is still uncertified.  db_lo: bf16 lo term of db_f32 or a
-    zero-argument callable that builds it on first need.  Returns db_lo (built or not)."""
+    zero-argument callable that builds it on first need.  defer=True: nothing is read
+    here; returns an ExactnessTicket to resolve later."""
     L = _lib.lib()
-    n1 = int(n_unc.item())
-    n2 = 0
     N, D = db_f32.shape
-    if n1 > 0:
-        if callable(db_lo):
-            db_lo = db_lo()
-        rows = unc_rows[:n1].clone()
-        nb = L.isb_topk_resolve_workspace_bytes(n1, N, D)
-        ws = torch.empty(nb, dtype=torch.uint8, device=q.device)
-        _lib.check(L.isb_topk_resolve(q.data_ptr(), db_f32.data_ptr(), db_bf16.data_ptr(), db_lo.data_ptr(),
-                                      N, D, db_bf16.size(1), int(k), int(margin), int(idx_offset),
-                                      rows.data_ptr(), n1, scores.data_ptr(), idx.data_ptr(),
-                                      unc_rows.data_ptr(), n_unc.data_ptr(), ws.data_ptr(), nb, _stream()),
-                   "isb_topk_resolve")
-        n2 = int(n_unc.item())
-        if n2 > 0:
-            rows = unc_rows[:n2].clone()
-            nb = L.isb_topk_exhaustive_workspace_bytes(n2, N, int(k))
+
+    def fixup(n1):
+        n2 = 0
+        if n1 > 0:
+            lo = db_lo() if callable(db_lo) else db_lo
+            rows = unc_rows[:n1].clone()
+            nb = L.isb_topk_resolve_workspace_bytes(n1, N, D)
             ws = torch.empty(nb, dtype=torch.uint8, device=q.device)
-            _lib.check(L.isb_topk_exhaustive(q.data_ptr(), db_f32.data_ptr(), N, D, int(k), int(idx_offset),
-                                             rows.data_ptr(), n2, scores.data_ptr(), idx.data_ptr(),
-                                             ws.data_ptr(), nb, _stream()), "isb_topk_exhaustive")
-    if stats is not None:
-        stats["rows"] = stats.get("rows", 0) + q.size(0)
-        stats["resolved_fp32_grade"] = stats.get("resolved_fp32_grade", 0) + n1
-        stats["resolved_exhaustive"] = stats.get("resolved_exhaustive", 0) + n2
-    return db_lo
+            _lib.check(L.isb_topk_resolve(q.data_ptr(), db_f32.data_ptr(), db_bf16.data_ptr(), lo.data_ptr(),
+                                          N, D, db_bf16.size(1), int(k), int(margin), int(idx_offset),
+                                          rows.data_ptr(), n1, scores.data_ptr(), idx.data_ptr(),
+                                          unc_rows.data_ptr(), n_unc.data_ptr(), ws.data_ptr(), nb, _stream()),
+                       "isb_topk_resolve")
+            n2 = int(n_unc.item())
+            if n2 > 0:
+                rows = unc_rows[:n2].clone()
+                nb = L.isb_topk_exhaustive_workspace_bytes(n2, N, int(k))
+                ws = torch.empty(nb, dtype=torch.uint8, device=q.device)
+                _lib.check(L.isb_topk_exhaustive(q.data_ptr(), db_f32.data_ptr(), N, D, int(k), int(idx_offset),
+                                                 rows.data_ptr(), n2, scores.data_ptr(), idx.data_ptr(),
+                                                 ws.data_ptr(), nb, _stream()), "isb_topk_exhaustive")
+        if stats is not None:
+            stats["rows"] = stats.get("rows", 0) + q.size(0)
+            stats["resolved_fp32_grade"] = stats.get("resolved_fp32_grade", 0) + n1
+            stats["resolved_exhaustive"] = stats.get("resolved_exhaustive", 0) + n2
+
+    ticket = ExactnessTicket(n_unc, fixup)
+    if defer:
+        return ticket
+    ticket.resolve()
+    return None
 
 
 def topk_search(q, db_f32, db_bf16, k, margin=None, idx_offset=0, workspace=None, exact=True,

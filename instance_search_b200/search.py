@@ -100,8 +100,12 @@ class DescriptorIndex(object):
         the global threshold, packed for the second all-gather (ops.topk_rerank_owned)."""
         return ops.topk_rerank_owned(self._queries(q), self.db_f32, k, cand_screen, cand_col, thr)
 
-    def search(self, q, k, margin=None, events=None, exact=True):
+    def search(self, q, k, margin=None, events=None, exact=True, defer=False):
         """(scores [Q, k] fp32, idx [Q, k] int64 global), best first.
+
+        defer=True: returns (scores, idx, ticket) without any host synchronisation; the
+        caller resolves the ticket (ops.ExactnessTicket) before it consumes the result --
+        after it has queued the next batch, so the GPU never idles on the round trip.
 
         exact=True: rows whose candidate list the bf16 screen cannot certify
         complete are re-screened with fp32-grade operands / exhaustively
@@ -132,10 +136,11 @@ class DescriptorIndex(object):
                                          self.row_offset, scores.data_ptr(), idx.data_ptr(),
                                          ops._ptr(unc_rows), ops._ptr(n_unc),
                                          ws.data_ptr(), ws.numel(), st), "isb_topk_rerank")
+        ticket = None
         if exact:
-            ops.resolve_uncertified(q, self.db_f32, self.db_bf16, self._lo, k_eff, margin, self.row_offset,
-                                    scores, idx, unc_rows, n_unc, self.stats)
-        return scores, idx
+            ticket = ops.resolve_uncertified(q, self.db_f32, self.db_bf16, self._lo, k_eff, margin, self.row_offset,
+                                             scores, idx, unc_rows, n_unc, self.stats, defer=defer)
+        return (scores, idx, ticket) if defer else (scores, idx)
 
 
 class ShardedIndex(object):
@@ -162,8 +167,8 @@ class ShardedIndex(object):
     def _make_local(self, local_db, row_offset):
         return DescriptorIndex(local_db, row_offset)
 
-    def _local_search(self, q, k, events=None):
-        return self.local.search(q, k, events=events)
+    def _local_search(self, q, k, events=None, defer=False):
+        return self.local.search(q, k, events=events, defer=defer)
 
     def _merge(self, cand_scores, cand_idx):
         return ops.topk_merge(cand_scores, cand_idx)
@@ -197,25 +202,24 @@ class ShardedIndex(object):
         host->device copies)."""
         if self.world_size == 1 or q_host.size(0) < self.world_size:
             return q_host.to(self.device, non_blocking=True)
-        import torch.distributed as dist
-        Q = q_host.size(0)
-        bounds = shard_bounds(Q, self.world_size)
-        per = bounds[0][1] - bounds[0][0]            # the largest slice
-        lo, hi = bounds[self.rank]
-        part = torch.zeros((per, q_host.size(1)), dtype=q_host.dtype, device=self.device)
-        part[:hi - lo].copy_(q_host[lo:hi], non_blocking=True)
-        full = torch.empty((self.world_size * per, q_host.size(1)), dtype=q_host.dtype, device=self.device)
-        dist.all_gather_into_tensor(full, part, group=self.group)
-        if per * self.world_size == Q:
-            return full
-        keep = torch.cat([torch.arange(r * per, r * per + (b[1] - b[0]), device=self.device)
-                          for r, b in enumerate(bounds)])
-        return full.index_select(0, keep)
+        lo, hi = shard_bounds(q_host.size(0), self.world_size)[self.rank]
+        return self.gather_queries(q_host[lo:hi].to(self.device, non_blocking=True), q_host.size(0))
 
-    def search(self, q, k, events=None, exchange=True):
+    def gather_queries(self, part, n_queries):
+        """part: this rank's shard_bounds slice of the query rows, already on the device (e.g.
+        uploaded on a copy stream while the previous batch was searched) -> all n_queries rows
+        on every rank (one NVLink all-gather)."""
+        from .sharding import all_gather_rows
+        return all_gather_rows(part, n_queries, self.rank, self.world_size, self.group)
+
+    def search(self, q, k, events=None, exchange=True, defer=False):
         """(scores [Q, kk] fp32, idx [Q, kk] int64 global), kk = min(k, n_total), best first,
         identical on every rank.  q: the same queries on every rank (CUDA tensor, or a pinned
         host tensor -> upload_queries).
+
+        defer=True: returns (scores, idx, ticket): no host synchronisation inside; resolve the
+        ticket (collectively, on every rank) before consuming the result -- typically after the
+        next batch has been queued.
 
         exchange=True (default): candidate exchange -- the shards all-gather the screen scores
         of their candidates, agree on the global (k + margin)-th best and re-rank only their
@@ -226,26 +230,38 @@ class ShardedIndex(object):
         if not q.is_cuda and self.device.type == "cuda":
             q = self.upload_queries(q)
         if self.world_size == 1:
-            return self._local_search(q, min(k, self.hi - self.lo), events)
+            return self._local_search(q, min(k, self.hi - self.lo), events, defer)
         if not exchange:
-            return self._search_replicated_rerank(q, k, events)
+            r = self._search_replicated_rerank(q, k, events)
+            return r + (None,) if defer else r
         kk = min(k, self.n_total)
         kc = min(kk + ops.DEFAULT_MARGIN, ops.MAX_CANDIDATES)
         cand_screen, cand_col = self._local_candidates(q, kk, kc, events)
         thr = self._global_threshold(self._gather(cand_screen))
         packed = self._rerank_owned(q, kk, cand_screen, cand_col, thr)
         ms, mi, unc_rows, n_unc = self._merge_certified(self._gather(packed), thr, kk)
-        n_bad = int(n_unc.item())           # the one 4-byte D2H read of the exactness guarantee
-        self.stats["rows"] = self.stats.get("rows", 0) + q.size(0)
-        self.stats["resolved_locally_exact"] = self.stats.get("resolved_locally_exact", 0) + n_bad
-        if n_bad:
-            # rows the global certificate rejects: every shard answers them with its own
-            # certified search (fp32-grade re-screen / exhaustive as needed), plain merge
-            rows = unc_rows[:n_bad].long().sort().values   # same order on every rank
-            rs, ri = self._search_replicated_rerank(q.index_select(0, rows), k, None)
-            ms.index_copy_(0, rows, rs)
-            mi.index_copy_(0, rows, ri)
+
+        def fixup(n_bad):
+            self.stats["rows"] = self.stats.get("rows", 0) + q.size(0)
+            self.stats["resolved_locally_exact"] = self.stats.get("resolved_locally_exact", 0) + n_bad
+            if n_bad:
+                # rows the global certificate rejects (the same on every rank): every shard answers
+                # them with its own certified search (fp32-grade re-screen / exhaustive as needed),
+                # plain merge
+                rows = unc_rows[:n_bad].long().sort().values   # same order on every rank
+                rs, ri = self._search_replicated_rerank(q.index_select(0, rows), k, None)
+                ms.index_copy_(0, rows, rs)
+                mi.index_copy_(0, rows, ri)
+
+        # the one 4-byte D2H read of the exactness guarantee (deferred: off the critical path)
+        ticket = self._ticket(n_unc, fixup)
+        if defer:
+            return ms, mi, ticket
+        ticket.resolve()
         return ms, mi
+
+    def _ticket(self, n_unc, fixup):
+        return ops.ExactnessTicket(n_unc, fixup)
 
     def _search_replicated_rerank(self, q, k, events=None):
         k_local = min(k, self.hi - self.lo)
