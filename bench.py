@@ -47,7 +47,9 @@ def parse():
     ap.add_argument("--cpu-sample-queries", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true",
-                    help="skip the region-descriptor / mining side measurements (N=1 only)")
+                    help="skip the side measurements: region descriptors / mining (N=1 only) and the "
+                         "end-to-end configs[4] leg (every N)")
+    ap.add_argument("--e2e-db-rows", type=int, default=10000000)
     return ap.parse_args()
 
 
@@ -479,6 +481,12 @@ def run_b200(a, rank, world, local_rank):
             torch.cuda.empty_cache()
             line["secondary"] = {"region_descriptors": side_regions(dev, pk, not a.no_cpu_baseline),
                                  "mining": side_mining(dev, pk, not a.no_cpu_baseline)}
+    if not a.no_secondary:
+        index = None
+        torch.cuda.empty_cache()
+        e2e = side_e2e(a, dev, rank, world, not a.no_cpu_baseline)      # collective: every rank runs it
+        if line is not None:
+            line.setdefault("secondary", {})["e2e_instance_search"] = e2e
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -674,6 +682,92 @@ def side_mining(dev, pk, cpu_baseline=True):
                                    "first %d couples scaled to %d (oracle, torch fp32)" % (t_mm, nc, N)}
             rec["parity"] = {"couples": nc, "identical_negatives": int((got == want).sum())}
         out["semi_hard" if semi else "hard"] = rec
+    return out
+
+
+def side_e2e(a, dev, rank, world, cpu_baseline=True):
+    """BASELINE configs[4]: ResNet-152 trunk (PyTorch, random init, 448-px input -> 14 x 14 maps) ->
+    region descriptors (fused CUDA head, D = 512, k = 6) -> top-100 over a synthetic 10M x 512-d
+    database, row-sharded over the N ranks (images data-parallel, descriptors all-gathered, candidate
+    exchange over NCCL).  Collective: every rank calls it.  Rank 0 also checks the returned top-100 of
+    a query sample against the CPU oracle over the full database."""
+    import torch.distributed as dist
+    import torchvision
+    from instance_search_b200 import regions
+    from instance_search_b200.model.siamese import RegionDescriptorNet
+    from instance_search_b200.search import ShardedIndex, shard_bounds
+    from instance_search_b200.sharding import all_gather_rows
+    n_db, dim, k, per_gpu, batch, px = a.e2e_db_rows, 512, 100, 128, 32, 448
+    torch.manual_seed(0)
+    trunk = torchvision.models.resnet152(weights=None, num_classes=464)
+    net = RegionDescriptorNet(trunk, 6, dim, (7, 7)).to(dev).eval()
+    lo, hi = shard_bounds(n_db, world)[rank]
+    index = ShardedIndex(make_rows_slice(n_db, dim, 1234 + 5, dev, lo, hi), n_db, rank, world)
+    g = torch.Generator().manual_seed(100 + rank)
+    mean = torch.tensor([0.36, 0.30, 0.28]).view(1, 3, 1, 1)
+    std = torch.tensor([0.21, 0.20, 0.20]).view(1, 3, 1, 1)
+    images = ((torch.rand(per_gpu, 3, px, px, generator=g) - mean) / std).pin_memory()
+    n_img = per_gpu * world
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def one_pass():
+        marks, descs = [], []
+        e = [ev() for _ in range(3)]
+        e[0].record()
+        with torch.no_grad():
+            for s in range(0, per_gpu, batch):
+                x = images[s:s + batch].to(dev, non_blocking=True)
+                m0, m1, m2 = ev(), ev(), ev()
+                m0.record()
+                fmap = net.features(x)                    # PyTorch trunk (north_star: stays in PyTorch)
+                m1.record()
+                descs.append(regions.region_descriptors(fmap, net._head(), net.k, net.feature_size2d,
+                                                        want_cls_out=False)[0])
+                m2.record()
+                marks.append((m0, m1, m2))
+        q = all_gather_rows(torch.cat(descs), n_img, rank, world)       # [n_img, 512] on every rank
+        e[1].record()
+        scores, idx = index.search(q, k)
+        e[2].record()
+        return marks, e, q, scores, idx
+
+    times = []
+    for it in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        marks, e, q, scores, idx = one_pass()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if it >= 1:
+            times.append((sum(m0.elapsed_time(m1) for m0, m1, _ in marks),
+                          sum(m1.elapsed_time(m2) for _, m1, m2 in marks), e[1].elapsed_time(e[2]),
+                          e[0].elapsed_time(e[2])))
+    best = min(times, key=lambda t: t[3])
+    ms = torch.tensor(best, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    tr, hd, se, tot = [float(v) for v in ms.tolist()]
+    out = None
+    if rank == 0:
+        out = {"workload": "end-to-end instance search (BASELINE configs[4]): ResNet-152 trunk (PyTorch, %d px) -> region "
+                           "descriptors (D=%d, k=6) -> top-%d over %d x %d-d database, %d GPU(s), %d images per GPU"
+                           % (px, dim, k, n_db, dim, world, per_gpu),
+               "n_gpus": world, "images": n_img, "ms": {"trunk": tr, "region_head": hd, "search": se, "total": tot},
+               "images_per_s_end_to_end": n_img / (tot * 1e-3), "search_queries_per_s": n_img / (se * 1e-3),
+               "region_head_images_per_s": n_img / (hd * 1e-3), "parity": None}
+        if cpu_baseline:
+            nq = min(32, n_img)
+            db_host = make_rows_host(n_db, dim, 1234 + 5, dev)
+            qh = q[:nq].cpu()
+            cs, ci = cpu_topk(qh, db_host, k)
+            out["parity"] = topk_parity(qh, db_host, k, scores[:nq], idx[:nq], cs, ci)
+            del db_host
+    del index, net
+    torch.cuda.empty_cache()
     return out
 
 

@@ -1121,11 +1121,16 @@ region_finalize_select_kernel(const float* __restrict__ logits, int ldl, int ncl
 }
 
 // ------------------------------------------------------------------ 4b. exact selection (second line)
-// For batches the fast path could not certify: one CTA per image re-scores up to 32
-// candidates of the screen EXACTLY -- window means and logits from the fp32 inputs
-// with fp64 accumulation -- and selects from those.  Slow (each CTA streams the whole
-// classifier), used only when isb_region_select / isb_region_logits report
-// uncertified images.
+// For images the fast path could not certify: one CTA per image re-scores candidates of the
+// screen EXACTLY -- window means and logits from the fp32 inputs with fp64 accumulation -- in
+// ROUNDS: the first round scores the 32 best windows of the screen; while the completeness
+// certificate fails (a window not yet scored could still belong to the top k: its screen score is
+// within 8 sigma of the exact k-th best), the slots of the candidates that fell out of the top k
+// are refilled with the next best windows of the screen and scored, until the certificate holds
+// or every window of the map has been scored exactly -- so the result is never left
+// uncertified (the round-1 second line scored 32 candidates once and could return a list it had
+// flagged incomplete).  Slow (each round streams the whole classifier up to four times per
+// CTA), used only for the images isb_region_select / isb_region_logits report.
 constexpr int kSelChunk = 8;      // candidates re-scored per pass over the classifier weights
 
 __global__ void __launch_bounds__(kSelThreads)
@@ -1147,98 +1152,136 @@ region_select_exact_kernel(const float* __restrict__ x, int C, int H, int W, int
   __shared__ float cand_max[kSelMaxCand];
   __shared__ int order[kSelMaxCand];
   __shared__ float cand_scr[kSelMaxCand];
+  __shared__ int fresh[kSelMaxCand];      // slots to (re)score in this round
+  __shared__ int s_nfresh, s_done, s_scored;
+  __shared__ float s_s2;
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* xb = x + static_cast<size_t>(b) * C * HW;
+  const int nsel = min(nwin, k);
 
   for (int i = tid; i < nwin; i += kSelThreads) sc[i] = screen[static_cast<size_t>(b) * nwin + i];
-  __syncthreads();
-  // ---- candidates: the ncand best windows of the screen
-  for (int c = 0; c < ncand; ++c) {
-    float v = -INFINITY;
-    int vi = 0x7FFFFFFF;
-    for (int i = tid; i < nwin; i += kSelThreads) {
-      const float s = sc[i];
-      if (s > v || (s == v && i < vi)) { v = s; vi = i; }
-    }
-    float bv; int bi;
-    block_argmax(v, vi, s_val, s_idx, bv, bi);
-    if (tid == 0) { cand[c] = bi; cand_scr[c] = bv; sc[bi] = -INFINITY; }
-    __syncthreads();
-  }
-  // ---- exact logits of the candidates (fp64 accumulation of fp32 products)
-  const double inv_area = 1.0 / static_cast<double>(fh * fw);
-  for (int c0 = 0; c0 < ncand; c0 += kSelChunk) {
-    const int nc = min(kSelChunk, ncand - c0);
-    for (int i = tid; i < nc * C; i += kSelThreads) {
-      const int ci = i / C, ch = i - ci * C;
-      const int win = cand[c0 + ci];
-      const int h = win / Wo, w = win - h * Wo;
-      const float* pl = xb + static_cast<size_t>(ch) * HW + h * W + w;
-      double s = 0.0;
-      for (int dy = 0; dy < fh; ++dy)
-        for (int dx = 0; dx < fw; ++dx) s += static_cast<double>(__ldg(pl + dy * W + dx));
-      pooled[ci * C + ch] = static_cast<float>(s * inv_area);
-    }
-    __syncthreads();
-    for (int j = warp; j < ncls; j += kSelThreads / 32) {
-      const float* wr = cls_w + static_cast<size_t>(j) * C;
-      double acc[kSelChunk];
-#pragma unroll
-      for (int t = 0; t < kSelChunk; ++t) acc[t] = 0.0;
-      for (int ch = lane; ch < C; ch += 32) {
-        const double wv = static_cast<double>(__ldg(wr + ch));
-#pragma unroll
-        for (int t = 0; t < kSelChunk; ++t)
-          if (t < nc) acc[t] = fma(wv, static_cast<double>(pooled[t * C + ch]), acc[t]);
-      }
-#pragma unroll
-      for (int t = 0; t < kSelChunk; ++t) {
-        double a = acc[t];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0 && t < nc)
-          logits[(c0 + t) * ncls + j] = static_cast<float>(a + static_cast<double>(__ldg(cls_b + j)));
-      }
-    }
-    __syncthreads();
-  }
-  // ---- exact class-max of every candidate
-  for (int c = warp; c < ncand; c += kSelThreads / 32) {
-    float m = -INFINITY;
-    for (int j = lane; j < ncls; j += 32) m = fmaxf(m, logits[c * ncls + j]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) cand_max[c] = m;
-  }
-  __syncthreads();
-  const int nsel = min(nwin, k);
   if (tid == 0) {
-    // rank the (<= 32) candidates: value desc, window index asc
-    for (int c = 0; c < ncand; ++c) order[c] = c;
-    for (int i = 1; i < ncand; ++i) {
-      const int o = order[i];
-      int j = i - 1;
-      while (j >= 0 && (cand_max[order[j]] < cand_max[o] ||
-                        (cand_max[order[j]] == cand_max[o] && cand[order[j]] > cand[o]))) {
-        order[j + 1] = order[j];
-        --j;
+    s_nfresh = ncand;                     // round 1: every slot is fresh
+    for (int c = 0; c < ncand; ++c) fresh[c] = c;
+    s_done = 0; s_scored = 0; s_s2 = 0.f;
+  }
+  __syncthreads();
+  const double inv_area = 1.0 / static_cast<double>(fh * fw);
+  for (;;) {
+    const int nfresh = s_nfresh;
+    // ---- fill the fresh slots with the best windows of the screen not scored yet
+    for (int f = 0; f < nfresh; ++f) {
+      float v = -INFINITY;
+      int vi = 0x7FFFFFFF;
+      for (int i = tid; i < nwin; i += kSelThreads) {
+        const float s = sc[i];
+        if (s > v || (s == v && i < vi)) { v = s; vi = i; }
       }
-      order[j + 1] = o;
+      float bv; int bi;
+      block_argmax(v, vi, s_val, s_idx, bv, bi);
+      if (tid == 0) { cand[fresh[f]] = bi; cand_scr[fresh[f]] = bv; sc[bi] = -INFINITY; }
+      __syncthreads();
     }
-    nsel_out[b] = nsel;
-    if (nwin > ncand && n_uncertified != nullptr) {   // completeness of the screen's candidate list
-      float t_min = INFINITY, s2 = 0.f;
-      for (int c = 0; c < ncand; ++c) {
-        t_min = fminf(t_min, cand_scr[c]);
-        const float d = cand_scr[c] - cand_max[c];
+    // ---- exact logits of the fresh candidates (fp64 accumulation of fp32 products)
+    for (int c0 = 0; c0 < nfresh; c0 += kSelChunk) {
+      const int nc = min(kSelChunk, nfresh - c0);
+      for (int i = tid; i < nc * C; i += kSelThreads) {
+        const int ci = i / C, ch = i - ci * C;
+        const int win = cand[fresh[c0 + ci]];
+        const int h = win / Wo, w = win - h * Wo;
+        const float* pl = xb + static_cast<size_t>(ch) * HW + h * W + w;
+        double s = 0.0;
+        for (int dy = 0; dy < fh; ++dy)
+          for (int dx = 0; dx < fw; ++dx) s += static_cast<double>(__ldg(pl + dy * W + dx));
+        pooled[ci * C + ch] = static_cast<float>(s * inv_area);
+      }
+      __syncthreads();
+      for (int j = warp; j < ncls; j += kSelThreads / 32) {
+        const float* wr = cls_w + static_cast<size_t>(j) * C;
+        double acc[kSelChunk];
+#pragma unroll
+        for (int t = 0; t < kSelChunk; ++t) acc[t] = 0.0;
+        for (int ch = lane; ch < C; ch += 32) {
+          const double wv = static_cast<double>(__ldg(wr + ch));
+#pragma unroll
+          for (int t = 0; t < kSelChunk; ++t)
+            if (t < nc) acc[t] = fma(wv, static_cast<double>(pooled[t * C + ch]), acc[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < kSelChunk; ++t) {
+          double a = acc[t];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+          if (lane == 0 && t < nc)
+            logits[fresh[c0 + t] * ncls + j] = static_cast<float>(a + static_cast<double>(__ldg(cls_b + j)));
+        }
+      }
+      __syncthreads();
+    }
+    // ---- exact class-max of the fresh candidates
+    for (int f = warp; f < nfresh; f += kSelThreads / 32) {
+      const int c = fresh[f];
+      float m = -INFINITY;
+      for (int j = lane; j < ncls; j += 32) m = fmaxf(m, logits[c * ncls + j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) cand_max[c] = m;
+    }
+    __syncthreads();
+    // ---- best screen score among the windows not scored yet
+    float rem = -INFINITY;
+    {
+      float v = -INFINITY;
+      int vi = 0x7FFFFFFF;
+      for (int i = tid; i < nwin; i += kSelThreads) {
+        const float s = sc[i];
+        if (s > v || (s == v && i < vi)) { v = s; vi = i; }
+      }
+      int bi;
+      block_argmax(v, vi, s_val, s_idx, rem, bi);
+    }
+    if (tid == 0) {
+      // rank the (<= 32) candidates: value desc, window index asc
+      for (int c = 0; c < ncand; ++c) order[c] = c;
+      for (int i = 1; i < ncand; ++i) {
+        const int o = order[i];
+        int j = i - 1;
+        while (j >= 0 && (cand_max[order[j]] < cand_max[o] ||
+                          (cand_max[order[j]] == cand_max[o] && cand[order[j]] > cand[o]))) {
+          order[j + 1] = order[j];
+          --j;
+        }
+        order[j + 1] = o;
+      }
+      // screen noise, measured on everything scored so far
+      float s2 = s_s2;
+      for (int f = 0; f < nfresh; ++f) {
+        const float d = cand_scr[fresh[f]] - cand_max[fresh[f]];
         s2 += d * d;
       }
-      const float sigma = sqrtf(s2 / static_cast<float>(ncand));
+      s_s2 = s2;
+      s_scored += nfresh;
+      const float sigma = sqrtf(s2 / static_cast<float>(s_scored));
       const float kth = cand_max[order[nsel - 1]];
-      if (!(kth - t_min > 8.f * sigma + 4e-7f * fmaxf(fabsf(kth), fabsf(t_min))))
-        n_uncertified[1 + atomicAdd(n_uncertified, 1)] = b;   // count, then the list of images
+      // completeness: no window left (rem = -inf), or the best one left cannot reach the k-th
+      const bool complete = rem == -INFINITY ||
+                            (kth - rem > 8.f * sigma + 4e-7f * fmaxf(fabsf(kth), fabsf(rem)));
+      const int nfree = ncand - nsel;   // slots outside the top k: refilled in the next round
+      if (complete) {
+        s_done = 1;
+      } else if (nfree <= 0) {          // k fills every slot: cannot continue, report the image
+        s_done = 1;
+        if (n_uncertified != nullptr) n_uncertified[1 + atomicAdd(n_uncertified, 1)] = b;
+      } else {
+        const int left = nwin - s_scored;                 // > 0 here: rem is a real window's score
+        s_nfresh = nfree < left ? nfree : left;
+        for (int f = 0; f < s_nfresh; ++f) fresh[f] = order[nsel + f];
+      }
     }
+    __syncthreads();
+    if (s_done) break;
   }
+  if (tid == 0) nsel_out[b] = nsel;
   __syncthreads();
   for (int i = tid; i < k; i += kSelThreads)
     idx[static_cast<size_t>(b) * k + i] = (i < nsel) ? static_cast<int64_t>(cand[order[i]]) : -1;

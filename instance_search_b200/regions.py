@@ -249,9 +249,14 @@ def uncertified_images(n_unc):
 
 
 def region_descriptors_exact(x, hw, k, fsize, extras=None):
-    """The fp64-exact second line (candidates = 32 windows, everything re-scored from the
-    fp32 inputs): what uncertified images are redone with."""
-    idx, nsel, cls_out, win_norm, _, _, _ = region_select(x, hw, k, fsize, exact_mode=True)
+    """The fp64-exact second line (rounds of up to 32 candidate windows re-scored from the fp32
+    inputs until the completeness certificate holds or the whole map has been scored): what
+    uncertified images are redone with.  Complete by construction; the one case it cannot
+    finish (k fills all 32 candidate slots of a larger map) raises."""
+    idx, nsel, cls_out, win_norm, _, _, n_unc = region_select(x, hw, k, fsize, exact_mode=True)
+    if k >= 32 and int(n_unc[0]):
+        raise IsbError("region_descriptors_exact: %d image(s) could not be certified with k = %d "
+                       "(k must leave free candidate slots: k < 32)" % (int(n_unc[0]), k))
     U_hi, U_lo, _ = region_gather(x, hw, k, fsize, idx, nsel, win_norm, want_means=False)
     if extras is not None:
         extras["U_hi"], extras["U_lo"] = U_hi, U_lo

@@ -96,16 +96,19 @@ class DescriptorFile(object):
                  for _ in range(2)]
         events = [None, None]
         rows = self._rows()
-        for i, s in enumerate(range(lo, hi, chunk_rows)):
-            e = min(s + chunk_rows, hi)
-            buf = stage[i & 1]
-            if events[i & 1] is not None:
-                events[i & 1].synchronize()          # the previous copy out of this buffer is done
-            np.copyto(buf[:e - s].numpy(), rows[s:e])
-            out[s - lo:e - lo].copy_(buf[:e - s], non_blocking=True)
-            events[i & 1] = torch.cuda.Event()
-            events[i & 1].record()
-        torch.cuda.current_stream().synchronize()
+        # copies, events and the final wait all on the TARGET device's current stream (the caller's
+        # current device may be another one)
+        with torch.cuda.device(device):
+            for i, s in enumerate(range(lo, hi, chunk_rows)):
+                e = min(s + chunk_rows, hi)
+                buf = stage[i & 1]
+                if events[i & 1] is not None:
+                    events[i & 1].synchronize()          # the previous copy out of this buffer is done
+                np.copyto(buf[:e - s].numpy(), rows[s:e])
+                out[s - lo:e - lo].copy_(buf[:e - s], non_blocking=True)
+                events[i & 1] = torch.cuda.Event()
+                events[i & 1].record()
+            torch.cuda.current_stream().synchronize()
         return out
 
 

@@ -34,9 +34,34 @@ def get_similarities(P, get_embeddings, net, dataset):
     n = len(dataset)
     d, o = embeddings_device_dim(P, net, n, sim_matrix=True)
     embeddings = get_embeddings(net, dataset, d, o)
-    similarities = _place(mining.all_pairs_similarities(embeddings.cuda()), d)   # :53 torch.mm(E, E.t())
+    if d >= 0:
+        similarities = mining.all_pairs_similarities(embeddings.cuda())            # :53 torch.mm(E, E.t())
+    else:
+        # the reference keeps a matrix above P.embeddings_cuda_size on the host (:41-42): compute it
+        # in row blocks on the GPU and stream them out, the N x N matrix never exists in HBM
+        similarities = _similarities_to_host(embeddings.cuda())
     set_net_train(net, True, bn_train=P.train_bn)
     return similarities, d
+
+
+def _similarities_to_host(emb, block_rows=4096):
+    """S = E . E^T as a pinned host tensor, one [block_rows, N] slab at a time (split-operand
+    tcgen05 GEMM per slab, D2H copy of slab i overlapping the product of slab i + 1)."""
+    n = emb.size(0)
+    hi, lo = ops.to_bf16(emb, 0), ops.to_bf16(emb, 1)
+    out = torch.empty((n, n), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    for s in range(0, n, block_rows):
+        e = min(s + block_rows, n)
+        slab = ops.gemm_nt_split(hi[s:e], lo[s:e], hi, lo)
+        done = torch.cuda.Event()
+        done.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            out[s:e].copy_(slab, non_blocking=True)
+            slab.record_stream(copy_stream)
+    copy_stream.synchronize()
+    return out
 
 
 def test_descriptor_net(P, get_embeddings, net, test_set, test_ref_set, kth=1):

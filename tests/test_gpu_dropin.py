@@ -297,3 +297,23 @@ def test_siamese_regions_test_evaluate_matches_the_oracle(capsys):
     assert abs(mAP - oracle.mean_avg_precision(sim_d, test_set, ref_set, 1)) < 1e-6
     out = capsys.readouterr().out
     assert "Descriptor (TEST): " in out and "Descriptor (TEST DBA k=-1): " in out
+
+
+def test_get_similarities_streams_to_the_host_when_the_placement_rule_says_so():
+    # utils/train_siamese.py:30-43: a matrix above P.embeddings_cuda_size lives on the host; the
+    # product still runs on the GPU, in row blocks, and the N x N matrix never exists in HBM
+    from instance_search_b200.train.siamese_regions import get_embeddings
+    from instance_search_b200.utils import train_siamese as ts
+
+    class Small(_P):
+        embeddings_cuda_size = 1024        # 23 x 23 x 4 > 1024 -> device -1
+    net = _toy_region_net(4)
+    gen = torch.Generator().manual_seed(15)
+    ds = [(torch.randn(3, 32, 32, generator=gen), "L%d" % (i % 5), "im%d" % i) for i in range(23)]
+    S, dev = ts.get_similarities(Small, get_embeddings, net, ds)
+    assert dev == -1 and not S.is_cuda and S.shape == (23, 23)
+    net.eval()
+    emb = get_embeddings(net, ds, 0, 16).cpu()
+    assert torch.allclose(S, emb @ emb.t(), rtol=1e-5, atol=2e-6)
+    blocks = ts._similarities_to_host(emb.cuda(), block_rows=7)         # ragged last block
+    assert torch.allclose(blocks, S, rtol=0, atol=1e-6)

@@ -164,3 +164,33 @@ def test_region_eval_path_without_cls_out(R, B, C, H, W, ncls, D):
     d0, c0, i0, n0 = R.region_descriptors(x, hw, 6, (7, 7))
     d1, c1, i1, n1 = R.region_descriptors(x, hw, 6, (7, 7), want_cls_out=False)
     assert c1 is None and torch.equal(i1, i0) and torch.equal(n1, n0) and torch.equal(d1, d0)
+
+
+@pytest.mark.parametrize("H,W", [(13, 13), (16, 20)])
+def test_region_exact_line_is_complete_on_maps_with_more_than_32_windows(R, H, W):
+    # window scores separated by far less than the bf16 screen can see (a nearly constant map with a
+    # 1e-4 ramp) on a map with 49 / 140 windows: the first round's 32 candidates are an arbitrary
+    # subset, so the exact second line must keep scoring until its certificate holds -- it may
+    # never return a list it has flagged incomplete (round 1 did)
+    C, ncls, D, k = 32, 6, 16, 6
+    s = _synthetic(2, C, H, W, ncls, D, seed=9)
+    g = torch.Generator().manual_seed(H)
+    ramp = torch.rand(2, 1, H, W, generator=g)
+    s["x"] = 0.5 + 2e-4 * ramp + 1e-5 * torch.rand(2, C, H, W, generator=g)
+    hw = _hw(R, s)
+    x = s["x"].cuda()
+    od, oc, oi, on = oracle.region_descriptor_forward(s["x"], s["cls_w"], s["cls_b"], s["shift"], s["lin_w"],
+                                                      s["lin_b"], k, (7, 7))
+    # the oracle's own top-k must be decided well above fp32 noise for the comparison to mean anything
+    c = torch.nn.functional.conv2d(torch.nn.functional.avg_pool2d(s["x"], 7, stride=1),
+                                   s["cls_w"].view(ncls, C, 1, 1), s["cls_b"]).max(1).values.reshape(2, -1)
+    top = c.sort(dim=1, descending=True).values
+    assert float((top[:, :k] - top[:, 1:k + 1]).min()) > 2e-6
+    i2, n2, c2, wn2, _, _, n_unc = R.region_select(x, hw, k, (7, 7), exact_mode=True)
+    assert int(n_unc[0]) == 0                                   # complete by construction
+    assert torch.equal(i2.cpu(), oi)
+    assert torch.allclose(c2.cpu(), oc, rtol=CLS_RTOL, atol=CLS_ATOL)
+    stats = {}
+    d, c1, i1, n1 = R.region_descriptors(x, hw, k, (7, 7), stats=stats)       # the certified front door
+    assert torch.equal(i1.cpu(), oi)
+    check_descriptors(d, od)

@@ -7,7 +7,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from instance_search_b200 import regions  # noqa: E402
+from instance_search_b200 import _lib, regions  # noqa: E402
 
 dev = torch.device("cuda:0")
 peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
@@ -20,10 +20,8 @@ flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
 for size in (14, 32):
     x = torch.relu(torch.randn(B, C, size, size, device=dev, generator=g))
     for stages, gmax in ((3, 0), (3, 4), (3, 8), (3, 16), (3, 32), (2, 0)):   # 0: the plan's own choice
-        os.environ["ISB_POOL_STAGES"] = str(stages)
-        os.environ.pop("ISB_POOL_G", None)
-        if gmax:
-            os.environ["ISB_POOL_G"] = str(gmax)
+        _lib.set_option("pool_stages", stages)
+        _lib.set_option("pool_g", gmax if gmax else None)
         regions._PROBE_CACHE.clear()   # the workspace layout follows the plan
         ts = []
         for it in range(13):

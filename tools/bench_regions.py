@@ -12,7 +12,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from instance_search_b200 import regions  # noqa: E402
+from instance_search_b200 import _lib, regions  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--B", type=int, default=256)
@@ -25,8 +25,8 @@ ap.add_argument("--terms", type=int, default=3)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--cls-out", type=int, default=0, help="1: also produce cls_out (training); 0: eval, class-max only")
-ap.add_argument("--variants", default="", help="';'-separated tuning variants, each 'ENV=val,ENV=val' (ISB_POOL_STAGES, "
-                "ISB_GATHER_CW / _G / _STAGES); one JSON line per variant and map size")
+ap.add_argument("--variants", default="", help="';'-separated tuning variants, each 'option=val,option=val' (pool_stages, "
+                "pool_generic_geom, gather_cw / _g / _stages: _lib.OPTIONS); one JSON line per variant and map size")
 a = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -51,15 +51,15 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 
-TUNABLES = ("ISB_POOL_STAGES", "ISB_POOL_GENERIC_GEOM", "ISB_GATHER_CW", "ISB_GATHER_G", "ISB_GATHER_STAGES")
+TUNABLES = ("pool_stages", "pool_generic_geom", "gather_cw", "gather_g", "gather_stages")
 variants = [v for v in a.variants.split(";")] if a.variants else [""]
 for hw_size, variant in [(int(s), v) for s in a.sizes.split(",") for v in variants]:
     H = W = hw_size
     for name in (TUNABLES if a.variants else ()):
-        os.environ.pop(name, None)
+        _lib.set_option(name, None)
     for kv in [t for t in variant.split(",") if t]:
         name, val = kv.split("=")
-        os.environ[name] = val            # read by libisb's launch plans at every call
+        _lib.set_option(name, int(val))   # read by libisb's launch plans at every call
     x = torch.relu(torch.randn(a.B, a.C, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(77 + hw_size)))
     stages = {"select": [], "gather": [], "logits_fixup": [], "project": [], "total": []}
     changed_total = 0
