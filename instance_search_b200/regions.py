@@ -360,3 +360,29 @@ def global_descriptors(x, hw):
     u = ops.shift_rows(ops.l2norm_rows(flat), hw.shift)
     y = _project(ops.to_bf16(u, 0), ops.to_bf16(u, 1) if hw.terms == 3 else None, hw, B)
     return descriptor_finalize(y, hw.lin_b, None)
+
+
+def classif_embeddings(x, hw, fsize):
+    """Embeddings of the classification track's sub-window net (TuneClassifSub): for every image the
+    class scores at the window with the highest maximal activation, L2-normalised -- [B, ncls].
+    reference: train/classif_regions.py:107-132 (one image per forward there).  The window is the
+    head's exact top-1 selection (same certified path as region_descriptors with k = 1), the scores
+    are its true-fp32 logits."""
+    ops._need_cuda(x)
+    k = 1
+    ke = min(32, k + RUNNER_UPS)
+    idx_e, nsel_e, _, norm_e, approx_e, runner_up, n1 = region_select(x, hw, ke, fsize)
+    # exact means of the k + 2 best windows (the gather's by-product) -> true fp32 logits -> the top-1
+    gw = object.__new__(HeadWeights)
+    gw.terms, gw.shift = 1, torch.zeros(x.size(1) * fsize[0] * fsize[1], dtype=torch.float32, device=x.device)
+    gw.Kin = gw.shift.numel()
+    gw.KinP = (gw.Kin + 7) // 8 * 8
+    _, _, win_mean = region_gather(x, gw, ke, fsize, idx_e, nsel_e, norm_e, k_sum=k)
+    idx, _, nsel, cls_out, _, _, n2 = region_logits(win_mean, hw, k, nsel_e, idx_e, norm_e, approx_e, runner_up)
+    bad = uncertified_images(torch.stack([n1, n2]))
+    if bad:   # near-tied windows: the fp64-exact second line for those images
+        sel = torch.tensor(bad, dtype=torch.int64, device=x.device)
+        i2, _, c2, _, _, _, _ = region_select(x.index_select(0, sel).contiguous(), hw, k, fsize, exact_mode=True)
+        cls_out.index_copy_(0, sel, c2)
+        idx.index_copy_(0, sel, i2)
+    return ops.l2norm_rows(cls_out[:, :, 0].contiguous()), idx[:, 0]

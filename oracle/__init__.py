@@ -36,6 +36,7 @@ from .siamese import (  # noqa: F401
     region_descriptor_forward_single,
     region_descriptor_forward,
     descriptor_forward,
+    classif_regions_embedding,
 )
 from .search import similarity, topk_search, topk_search_f64  # noqa: F401
 from .metrics import precision1, avg_precision, mean_avg_precision  # noqa: F401

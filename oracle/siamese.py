@@ -97,3 +97,29 @@ def descriptor_forward(x, shift, lin_w, lin_b):
     x = shift_fn(x, shift)
     x = F.linear(x, lin_w, lin_b)
     return normalize_l2(x)
+
+
+def classif_regions_embedding(x, cls_w, cls_b, feature_size2d):
+    """Embedding of the classification track's sub-window net (TuneClassifSub): the class scores
+    at the window with the highest maximal activation, L2-normalised.  x: [1, C, H, W] trunk
+    feature map of ONE image.
+
+    reference: train/classif_regions.py:107-132 (``get_embeddings``' per-image body after
+    ``net(x)[0]``, i.e. after TuneClassifSub.forward_single, model/siamese.py:82-86), with the
+    torch-0.1 semantics its indexing relies on: ``max(dim)`` keeps the reduced dimension.
+    Not pinned against the reference run in the container (the body cannot execute on torch >= 1
+    because of those semantics); pinned by construction to the same avg-pool / 1x1-conv arithmetic
+    as region_descriptor_forward_single, which is.
+    Returns (embedding [1, ncls], flat window index).
+    """
+    assert x.size(0) == 1
+    fh, fw = feature_size2d
+    ncls, C = cls_w.shape
+    out = F.conv2d(F.avg_pool2d(x, (fh, fw), stride=1), cls_w.view(ncls, C, 1, 1), cls_b)   # net(x)[0]
+    max_pred, _ = out.max(1, keepdim=True)              # :119  [1, 1, H', W']
+    max_pred1, max_i1 = max_pred.max(2, keepdim=True)   # :120  best row of every column
+    _, max_i2 = max_pred1.max(3, keepdim=True)          # :121  best column
+    i2 = int(max_i2.view(-1)[0])
+    i1 = int(max_i1.view(-1)[i2])
+    vec = out[:, :, i1, i2]                              # :126
+    return normalize_l2(vec), i1 * out.size(3) + i2     # :127

@@ -317,3 +317,23 @@ def test_get_similarities_streams_to_the_host_when_the_placement_rule_says_so():
     assert torch.allclose(S, emb @ emb.t(), rtol=1e-5, atol=2e-6)
     blocks = ts._similarities_to_host(emb.cuda(), block_rows=7)         # ragged last block
     assert torch.allclose(blocks, S, rtol=0, atol=1e-6)
+
+
+def test_classif_regions_embeddings_match_the_oracle():
+    # the classification track's sub-window embedding (train/classif_regions.py:107-132) on the
+    # fused head: class scores at the window of highest maximal activation, L2-normalised
+    from instance_search_b200.model.siamese import TuneClassifSub
+    from instance_search_b200.train.classif_regions import get_embeddings
+    torch.manual_seed(6)
+    net = TuneClassifSub(ToyNet(8, 5), 7, (7, 7)).cuda().eval()          # last FC resized to 7 classes
+    gen = torch.Generator().manual_seed(16)
+    ds = [(torch.randn(3, 36, 40, generator=gen), "L%d" % (i % 3), "im%d" % i) for i in range(11)]
+    emb = get_embeddings(net, ds, 0, 7, batch_size=4)
+    assert emb.shape == (11, 7)
+    conv = net.classifier[0]
+    for i, (im, _, _) in enumerate(ds):
+        with torch.no_grad():
+            fmap = net.features(im.unsqueeze(0).cuda()).cpu()
+        want, _ = oracle.classif_regions_embedding(fmap, conv.weight.detach().cpu().view(7, -1),
+                                                   conv.bias.detach().cpu(), (7, 7))
+        assert torch.allclose(emb[i].cpu(), want[0], rtol=1e-5, atol=2e-6)
