@@ -42,6 +42,10 @@ class DescriptorIndex(object):
         self._db_lo = None            # lo bf16 term, built the first time a row needs resolving
         self.row_offset = int(row_offset)
         self._ws = None
+        self._ws_pipe = [None, None]  # deferred searches alternate between two workspaces ...
+        self._tail_done = [None, None]   # ... each guarded by the event that ends its re-rank
+        self._slot = 0
+        self._tail = None             # side stream of the deferred (pipelined) searches
         self.stats = {}               # rows searched / resolved fp32-grade / resolved exhaustively
 
     def __len__(self):
@@ -56,22 +60,32 @@ class DescriptorIndex(object):
             q = torch.nn.functional.pad(q, (0, self.pad))
         return q.contiguous()
 
-    def _workspace(self, Q, k, margin):
+    def _workspace(self, Q, k, margin, slot=None):
         need = ops._lib.lib().isb_topk_search_workspace_bytes(Q, len(self), self.db_f32.size(1), k, margin)
+        if slot is not None:
+            if self._ws_pipe[slot] is None or self._ws_pipe[slot].numel() < need:
+                self._ws_pipe[slot] = torch.empty(need, dtype=torch.uint8, device=self.db_f32.device)
+            return self._ws_pipe[slot]
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.db_f32.device)
         return self._ws
+
+    def tail_stream(self):
+        """Side stream on which a deferred search runs everything after its screen."""
+        if self._tail is None:
+            self._tail = torch.cuda.Stream(device=self.db_f32.device)
+        return self._tail
 
     def _lo(self):
         if self._db_lo is None:
             self._db_lo = ops.to_bf16(self.db_f32, 1, ld=self.db_bf16.size(1))
         return self._db_lo
 
-    def _screen(self, q, k_eff, margin, events=None):
+    def _screen(self, q, k_eff, margin, events=None, slot=None):
         """Stage 1 (isb_topk_screen): bf16 tcgen05 GEMM + streaming top-(k+margin) into the
         candidate pool of the workspace, which is returned.  q: padded fp32 queries."""
         Q = q.size(0)
-        ws = self._workspace(Q, k_eff, margin)
+        ws = self._workspace(Q, k_eff, margin, slot)
         L = ops._lib.lib()
         st = torch.cuda.current_stream().cuda_stream
         N, D = self.db_f32.shape
@@ -106,6 +120,9 @@ class DescriptorIndex(object):
         defer=True: returns (scores, idx, ticket) without any host synchronisation; the
         caller resolves the ticket (ops.ExactnessTicket) before it consumes the result --
         after it has queued the next batch, so the GPU never idles on the round trip.
+        The screen runs on the caller's stream, the exact re-rank (HBM gathers, no tensor
+        cores) on a side stream: queued back to back, the re-rank of batch i runs UNDER the
+        screen of batch i + 1 (two workspaces alternate).
 
         exact=True: rows whose candidate list the bf16 screen cannot certify
         complete are re-screened with fp32-grade operands / exhaustively
@@ -125,22 +142,52 @@ class DescriptorIndex(object):
         scores = torch.empty((Q, k_eff), dtype=torch.float32, device=q.device)
         idx = torch.empty((Q, k_eff), dtype=torch.int64, device=q.device)
         if Q == 0:
-            return scores, idx
-        ws = self._screen(q, k_eff, margin, events)
+            return (scores, idx, None) if defer else (scores, idx)
         L = ops._lib.lib()
-        st = torch.cuda.current_stream().cuda_stream
         N, D = self.db_f32.shape
-        unc_rows = torch.empty(Q, dtype=torch.int32, device=q.device) if exact else None
-        n_unc = torch.zeros(1, dtype=torch.int32, device=q.device) if exact else None
-        ops._lib.check(L.isb_topk_rerank(q.data_ptr(), Q, self.db_f32.data_ptr(), N, D, k_eff, margin,
-                                         self.row_offset, scores.data_ptr(), idx.data_ptr(),
-                                         ops._ptr(unc_rows), ops._ptr(n_unc),
-                                         ws.data_ptr(), ws.numel(), st), "isb_topk_rerank")
-        ticket = None
-        if exact:
-            ticket = ops.resolve_uncertified(q, self.db_f32, self.db_bf16, self._lo, k_eff, margin, self.row_offset,
-                                             scores, idx, unc_rows, n_unc, self.stats, defer=defer)
+        cur = torch.cuda.current_stream()
+        pipelined = defer and exact
+        slot = None
+        if pipelined:
+            slot = self._slot
+            self._slot ^= 1
+            if self._tail_done[slot] is not None:
+                cur.wait_event(self._tail_done[slot])      # the re-rank that last read this workspace
+        ws = self._screen(q, k_eff, margin, events, slot)
+        tail = cur
+        if pipelined:
+            screened = torch.cuda.Event()
+            screened.record(cur)
+            tail = self.tail_stream()
+            tail.wait_event(screened)
+            for t in (q, scores, idx):
+                t.record_stream(tail)
+        with torch.cuda.stream(tail):
+            unc_rows = torch.empty(Q, dtype=torch.int32, device=q.device) if exact else None
+            n_unc = torch.zeros(1, dtype=torch.int32, device=q.device) if exact else None
+            ops._lib.check(L.isb_topk_rerank(q.data_ptr(), Q, self.db_f32.data_ptr(), N, D, k_eff, margin,
+                                             self.row_offset, scores.data_ptr(), idx.data_ptr(),
+                                             ops._ptr(unc_rows), ops._ptr(n_unc),
+                                             ws.data_ptr(), ws.numel(), tail.cuda_stream), "isb_topk_rerank")
+            ticket = None
+            if exact:
+                ticket = ops.resolve_uncertified(q, self.db_f32, self.db_bf16, self._lo, k_eff, margin,
+                                                 self.row_offset, scores, idx, unc_rows, n_unc, self.stats,
+                                                 defer=defer)
+            if pipelined:
+                self._tail_done[slot] = torch.cuda.Event()
+                self._tail_done[slot].record(tail)
+                for t in (unc_rows, n_unc):
+                    t.record_stream(cur)                   # a fix-up at resolve() time runs on the caller's stream
         return (scores, idx, ticket) if defer else (scores, idx)
+
+
+class _NoStream(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
 
 
 class ShardedIndex(object):
@@ -237,9 +284,25 @@ class ShardedIndex(object):
         kk = min(k, self.n_total)
         kc = min(kk + ops.DEFAULT_MARGIN, ops.MAX_CANDIDATES)
         cand_screen, cand_col = self._local_candidates(q, kk, kc, events)
-        thr = self._global_threshold(self._gather(cand_screen))
-        packed = self._rerank_owned(q, kk, cand_screen, cand_col, thr)
-        ms, mi, unc_rows, n_unc = self._merge_certified(self._gather(packed), thr, kk)
+        # defer=True: everything after the screen (two all-gathers, threshold, re-rank of the owned
+        # candidates, merge: no tensor cores, ~1 ms) runs on a side stream, i.e. UNDER the screen
+        # of the next batch when searches are queued back to back
+        side = None
+        if defer and q.is_cuda:
+            cur = torch.cuda.current_stream()
+            screened = torch.cuda.Event()
+            screened.record(cur)
+            side = self.local.tail_stream()
+            side.wait_event(screened)
+            for t in (q, cand_screen, cand_col):
+                t.record_stream(side)
+        with (torch.cuda.stream(side) if side is not None else _NoStream()):
+            thr = self._global_threshold(self._gather(cand_screen))
+            packed = self._rerank_owned(q, kk, cand_screen, cand_col, thr)
+            ms, mi, unc_rows, n_unc = self._merge_certified(self._gather(packed), thr, kk)
+            if side is not None:
+                for t in (ms, mi, unc_rows, n_unc):
+                    t.record_stream(cur)
 
         def fixup(n_bad):
             self.stats["rows"] = self.stats.get("rows", 0) + q.size(0)
@@ -254,7 +317,8 @@ class ShardedIndex(object):
                 mi.index_copy_(0, rows, ri)
 
         # the one 4-byte D2H read of the exactness guarantee (deferred: off the critical path)
-        ticket = self._ticket(n_unc, fixup)
+        with (torch.cuda.stream(side) if side is not None else _NoStream()):
+            ticket = self._ticket(n_unc, fixup)
         if defer:
             return ms, mi, ticket
         ticket.resolve()

@@ -304,3 +304,24 @@ def test_topk_search_errors(ops):
     with pytest.raises(IsbError):
         ops.topk_search(q[:, :12].contiguous(), db[:, :12].contiguous(),
                         ops.to_bf16(db[:, :12].contiguous()), 2)  # D % 8 != 0
+
+
+def test_deferred_pipelined_searches_equal_the_plain_search(ops):
+    # defer=True: no host sync inside; the re-rank runs on a side stream under the next batch's
+    # screen, two workspaces alternate.  Four different batches queued back to back, resolved
+    # afterwards, must equal one-at-a-time searches (planted duplicates make one batch use the
+    # certificate's second line at resolve time).
+    from instance_search_b200.search import DescriptorIndex
+    N, D, k = 30000, 128, 50
+    db = oracle.normalize_l2(_randn(N, D, seed=61))
+    qs = [oracle.normalize_l2(_randn(300 + 17 * j, D, seed=62 + j)) for j in range(4)]
+    db[100:400] = qs[2][5]                      # batch 2, row 5: 300 exact duplicates -> exhaustive line
+    index = DescriptorIndex(db.cuda())
+    want = [index.search(q.cuda(), k) for q in qs]
+    torch.cuda.synchronize()
+    queued = [index.search(q.cuda(), k, defer=True) for q in qs]
+    n_bad = [t.resolve() for _, _, t in queued]
+    torch.cuda.synchronize()
+    assert n_bad[2] >= 1 and n_bad[0] == 0
+    for (s0, i0), (s1, i1, _) in zip(want, queued):
+        assert torch.equal(i0, i1) and torch.equal(s0, s1)
