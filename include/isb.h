@@ -65,7 +65,8 @@ enum {
   ISB_OPT_GATHER_CW = 9,         /* channels per warp unit of the gather kernel */
   ISB_OPT_GATHER_G = 10,         /* units per warp of the gather kernel */
   ISB_OPT_GATHER_STAGES = 11,    /* ring depth of the gather kernel */
-  ISB_OPT_COUNT_ = 12
+  ISB_OPT_GEMM_PAIR = 12,        /* 1 (default): CTA-pair kernel for isb_gemm_nt[_split] with >= 2 row blocks */
+  ISB_OPT_COUNT_ = 13
 };
 int isb_set_option(int option, int value);
 int isb_get_option(int option);

@@ -185,17 +185,24 @@ static int gemm_nt_impl(const char* fn, const uint16_t* A, const uint16_t* A_lo,
     set_error("%s: workspace too small (need %zu bytes, got %zu)", fn, need, workspace_bytes);
     return ISB_ERR_WORKSPACE;
   }
+  // CTA-pair kernel (one tcgen05.mma.cta_group::2 of M = 256 per pair, every B tile staged once
+  // per 256 output rows instead of once per 128: the single-CTA kernel is shared-memory-port
+  // bound) whenever there are at least two row blocks; ISB_OPT_GEMM_PAIR = 0 keeps
+  // the single-CTA kernel.
+  const int sms = device_sm_count();
+  const bool pair = m_blocks >= 2 && sms >= 2 && option(ISB_OPT_GEMM_PAIR, 1) != 0;
+  const int b_box = pair ? kPairBRows : kBN;
   CUtensorMap ta, tb, ta_lo, tb_lo;
   rc = make_tmap_bf16_k64(&ta, A, M, K, lda, kBM);
   if (rc) return rc;
-  rc = make_tmap_bf16_k64(&tb, B, N, K, ldb, kBN);
+  rc = make_tmap_bf16_k64(&tb, B, N, K, ldb, b_box);
   if (rc) return rc;
   ta_lo = ta;
   tb_lo = tb;
   if (split_ops) {
     rc = make_tmap_bf16_k64(&ta_lo, A_lo, M, K, lda, kBM);
     if (rc) return rc;
-    rc = make_tmap_bf16_k64(&tb_lo, B_lo, N, K, ldb, kBN);
+    rc = make_tmap_bf16_k64(&tb_lo, B_lo, N, K, ldb, b_box);
     if (rc) return rc;
   }
 
@@ -203,7 +210,8 @@ static int gemm_nt_impl(const char* fn, const uint16_t* A, const uint16_t* A_lo,
   const int kb_split = (k_blocks + splits - 1) / splits;
   const int n_chunks = (kb_split + kAccChunkKb - 1) / kAccChunkKb;
   const int chunk_kb = (kb_split + n_chunks - 1) / n_chunks;
-  PlainSched sched{m_blocks, n_tiles, k_blocks, splits, chunk_kb};
+  // the scheduler counts row blocks in the kernel's unit: 128 rows, or 256 for the pair kernel
+  PlainSched sched{pair ? (m_blocks + 1) / 2 : m_blocks, n_tiles, k_blocks, splits, chunk_kb};
   StoreEpiParams ep;
   ep.M = static_cast<int>(M);
   ep.N = static_cast<int>(N);
@@ -221,13 +229,20 @@ static int gemm_nt_impl(const char* fn, const uint16_t* A, const uint16_t* A_lo,
   ep.vec_ok = ((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 && ep.ldo % 4 == 0 &&
                (ep.bias == nullptr || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0)) ? 1 : 0;
 
-  const long long segs = static_cast<long long>(m_blocks) * n_tiles * splits;
-  const int sms = device_sm_count();
-  const int grid = static_cast<int>(segs < sms ? segs : sms);
-  auto kern = gemm_tc_kernel<PlainSched, StoreEpilogue>;
-  ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
-  kern<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, ta_lo, tb_lo, split_ops ? kb_term : kSingleTerm,
-                                                   sched, ep);
+  const long long segs = static_cast<long long>(sched.m_blocks) * n_tiles * splits;
+  if (pair) {
+    const int pairs = static_cast<int>(segs < sms / 2 ? segs : sms / 2);
+    auto kern = gemm_tc_pair_kernel<PlainSched, StoreEpilogue>;
+    ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    kern<<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ta, tb, ta_lo, tb_lo, split_ops ? kb_term : kSingleTerm,
+                                                         sched, ep);
+  } else {
+    const int grid = static_cast<int>(segs < sms ? segs : sms);
+    auto kern = gemm_tc_kernel<PlainSched, StoreEpilogue>;
+    ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    kern<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, ta_lo, tb_lo, split_ops ? kb_term : kSingleTerm,
+                                                     sched, ep);
+  }
   ISB_CUDA(cudaGetLastError());
   if (splits > 1) {
     const long long total = static_cast<long long>(M) * N;

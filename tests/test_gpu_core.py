@@ -325,3 +325,39 @@ def test_deferred_pipelined_searches_equal_the_plain_search(ops):
     assert n_bad[2] >= 1 and n_bad[0] == 0
     for (s0, i0), (s1, i1, _) in zip(want, queued):
         assert torch.equal(i0, i1) and torch.equal(s0, s1)
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(256, 512, 1024, 1), (300, 700, 6400, 3), (1536, 2048, 12544, 4),
+                                          (129, 256, 200, 1)])
+def test_gemm_pair_and_single_cta_kernels_agree(ops, M, N, K, splits):
+    # isb_gemm_nt[_split] runs the CTA-pair kernel (cta_group::2, M = 256) when there are >= 2 row
+    # blocks; option gemm_pair=0 keeps the single-CTA kernel: same products, same chunked fp32
+    # accumulation order -> identical results
+    from instance_search_b200 import _lib
+    a, b = _randn(M, K, seed=71).cuda(), _randn(N, K, seed=72).cuda()
+    a_hi, a_lo, b_hi, b_lo = ops.to_bf16(a, 0), ops.to_bf16(a, 1), ops.to_bf16(b, 0), ops.to_bf16(b, 1)
+    y2 = ops.gemm_nt_split(a_hi, a_lo, b_hi, b_lo, splits=splits, k=K)
+    p2 = ops.gemm_nt(a_hi, b_hi, splits=splits, k=K)
+    with _lib.options(gemm_pair=0):
+        y1 = ops.gemm_nt_split(a_hi, a_lo, b_hi, b_lo, splits=splits, k=K)
+        p1 = ops.gemm_nt(a_hi, b_hi, splits=splits, k=K)
+    assert torch.equal(y1, y2) and torch.equal(p1, p2)
+    want = a.double() @ b.double().t()
+    assert (y2.double() - want).abs().max().item() < 2e-5 * want.abs().max().item()
+
+
+def test_gemm_long_contraction_accumulates_in_chunks(ops):
+    # K = 100352 (the whitening projection): the tensor core's fp32 accumulator drifts on long chains
+    # (3.6e-4 relative on one 300k-step chain); chunked accumulation keeps the split-operand product at
+    # the 16-bit representation floor whatever the number of split-K partitions
+    M, N, K = 128, 256, 100352
+    g = torch.Generator().manual_seed(73)
+    a = torch.relu(torch.randn(M, K, generator=g)).cuda()
+    a = a / a.norm(dim=1, keepdim=True)
+    b = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    a_hi, a_lo, b_hi, b_lo = ops.to_bf16(a, 0), ops.to_bf16(a, 1), ops.to_bf16(b, 0), ops.to_bf16(b, 1)
+    want = a.double() @ b.double().t()
+    for splits in (1, 9, 37):
+        y = ops.gemm_nt_split(a_hi, a_lo, b_hi, b_lo, splits=splits, k=K)
+        rel = ((y.double() - want).norm(dim=1) / want.norm(dim=1)).max().item()
+        assert rel < 8e-6, (splits, rel)
