@@ -209,12 +209,12 @@ def time_cpu(q, db, k, repeats=1):
     return best
 
 
-def topk_parity(q, db, k, gpu_scores, gpu_idx, cpu_scores, cpu_idx, tie_atol=5e-7):
+def topk_parity(q, db, k, gpu_scores, gpu_idx, cpu_scores, cpu_idx, tie_rtol=16 * 2.0 ** -24, tie_atol=5e-8):
     """GPU top-k of a query sample against the CPU oracle's (torch fp32 mm + topk on the host).
     rows identical to the oracle are index-exact; a row that differs is adjudicated in fp64 on
     the union of the two lists: it counts as fp64_adjudicated when the fp64 ranking of that
     union is the GPU's list AND every differing entry is an fp32-noise tie in the oracle's own
-    scores (gap <= tie_atol); anything else is unexplained."""
+    scores (gap <= tie_atol + tie_rtol |score|: 16 ulp); anything else is unexplained."""
     gs, gi = gpu_scores.cpu(), gpu_idx.cpu()
     rows = gi.size(0)
     same = (gi == cpu_idx).all(dim=1)
@@ -225,16 +225,16 @@ def topk_parity(q, db, k, gpu_scores, gpu_idx, cpu_scores, cpu_idx, tie_atol=5e-
         s64 = db[union].double() @ q[r].double()
         order = torch.sort(s64, descending=True, stable=True).indices[:k]
         pos = (gi[r] != cpu_idx[r]).nonzero().flatten()
-        gap = ((db[gi[r, pos]] * q[r]).sum(1) - cpu_scores[r, pos]).abs().max().item()
-        max_gap = max(max_gap, gap)
-        if torch.equal(union[order], gi[r]) and gap <= tie_atol:
+        gaps = ((db[gi[r, pos]] * q[r]).sum(1) - cpu_scores[r, pos]).abs()
+        max_gap = max(max_gap, gaps.max().item())
+        if torch.equal(union[order], gi[r]) and bool((gaps <= tie_atol + tie_rtol * cpu_scores[r, pos].abs()).all()):
             adjudicated += 1
         else:
             unexplained += 1
     rel = ((gs - cpu_scores).abs() / cpu_scores.abs().clamp_min(1e-6)).max().item()
     return {"rows": rows, "index_exact_rows": int(same.sum()), "fp64_adjudicated": adjudicated,
             "unexplained_rows": unexplained, "entries_differing": entries, "max_tie_gap": max_gap,
-            "tie_atol": tie_atol, "max_rel_score_err": rel, "k": k,
+            "tie_tolerance": "%.1e + %.1e |score|" % (tie_atol, tie_rtol), "max_rel_score_err": rel, "k": k,
             "oracle": "torch fp32 mm + topk on the host (oracle.similarity), first %d queries over the "
                       "full database" % rows}
 

@@ -109,7 +109,7 @@ int isb_f32_to_bf16(const float* x, int64_t rows, int64_t cols, int64_t ldx, uin
  *               exact_kth - t_min  >  8 * sigma + 4e-7 * |score|
  *            with sigma = rms(screen - exact) MEASURED on the row's own
  *            candidates and floored by the noise bf16 operand rounding is expected
- *            to have on dense rows (1.6e-3 |q||db| / sqrt(D); half of it from 32
+ *            to have on dense rows (2.34e-3 |q||db| / sqrt(D); half of it from 32
  *            candidates on, 1.5x below: a sigma from a few samples can be ~0).
  *            Rows that fail are appended to uncertified_rows and
  *            counted in *n_uncertified (both device memory, may both be NULL to
@@ -367,7 +367,7 @@ int isb_region_scatter_grad(const float* x, int64_t B, int64_t C, int64_t H, int
  *   eps = max(screen_eps, 8 * max(sigma_measured, sigma_floor)),
  * sigma_measured = rms(screen - exact) over the couple's own candidates.  (Statistical, not a
  * proof: 8 sigma.)  In semi-hard mode the epilogue also drops columns whose screen score is
- * >= S[anchor, positive] + max(screen_eps, 16 * sigma_floor); a couple whose eps exceeds
+ * >= S[anchor, positive] + max(screen_eps, 32 * sigma_floor); a couple whose eps exceeds
  * that slack is rejected too.
  *   uncertified_rows != NULL: the rejected couples (indices p) are listed there and counted in
  *     *n_uncertified; the caller re-runs them with a finer screen (split operands) -- the
@@ -376,7 +376,7 @@ int isb_region_scatter_grad(const float* x, int64_t B, int64_t C, int64_t H, int
  *     (counted in *n_uncertified when non-NULL).
  *   emb [N, D] fp32 (unit rows); emb_hi / emb_lo [N, ld] bf16 = isb_f32_to_bf16 parts
  *   0 / 1 of emb.  emb_lo == NULL: plain bf16 screen (one tcgen05 product per tile;
- *   screen_eps = 0, sigma_floor = the expected bf16 noise 1.6e-3 |a||b| / sqrt(D)).
+ *   screen_eps = 0, sigma_floor = the expected bf16 noise 2.34e-3 |a||b| / sqrt(D)).
  *   emb_lo != NULL: split operands, a_hi.b_hi + a_lo.b_hi + a_hi.b_lo, an fp32-grade screen
  *   (three products per tile; screen_eps = 2e-5 absolute on unit rows, sigma_floor = 0).
  *   label [N] int32; anchors, positives [P] int64

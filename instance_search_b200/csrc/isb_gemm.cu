@@ -29,7 +29,8 @@ struct StoreEpilogue {
   // pass nt of a segment = chunk nt of the split's k-range (PlainSched): the first pass stores
   // the tile (+ bias), the later ones add to it -- every output element is owned by exactly one
   // thread of one CTA, so the read-modify-write is plain, ordered and deterministic (the slab
-  // stays in L2 between passes)
+  // stays in L2 between passes).  The running sums of a 32-column chunk are fetched BEFORE the
+  // wait for the accumulator chunk, so the L2 round trip hides behind the TMEM load.
   __device__ __forceinline__ void tile(const Segment& seg, int nt, uint32_t tmem_acc,
                                        uint64_t* tmem_empty_bar) {
     const int row = seg.m_block * kBM + row_in_tile;
@@ -37,13 +38,19 @@ struct StoreEpilogue {
                   static_cast<long long>(row) * p.ldo;
     const int col0 = seg.n_tile * kBN;
     const bool first = nt == seg.nt_begin;
+    const bool fast = p.vec_ok && row < p.M && col0 + kBN <= p.N;   // whole tile in bounds, 16-byte rows
     uint32_t v0[32], v1[32];
+    float4 o0[8], o1[8];
     ptx::tmem_ld_32x32b_x32(tmem_acc, v0);
+    if (fast && !first) fetch(o0, orow + col0);
 #pragma unroll 1
     for (int it = 0; it < kBN / 64; ++it) {
+      if (fast && !first) fetch(o1, orow + col0 + it * 64 + 32);
       ptx::tmem_ld_wait();
       ptx::tmem_ld_32x32b_x32(tmem_acc + it * 64 + 32, v1);
-      emit(v0, orow, row, col0 + it * 64, first);
+      if (fast) emit_fast(v0, o0, orow + col0 + it * 64, col0 + it * 64, first);
+      else emit(v0, orow, row, col0 + it * 64, first);
+      if (fast && !first && it + 1 < kBN / 64) fetch(o0, orow + col0 + it * 64 + 64);
       ptx::tmem_ld_wait();
       if (it + 1 < kBN / 64) {
         ptx::tmem_ld_32x32b_x32(tmem_acc + it * 64 + 64, v0);
@@ -52,33 +59,56 @@ struct StoreEpilogue {
         ptx::tc_fence_before();
         ptx::mbar_arrive(tmem_empty_bar);
       }
-      emit(v1, orow, row, col0 + it * 64 + 32, first);
+      if (fast) emit_fast(v1, o1, orow + col0 + it * 64 + 32, col0 + it * 64 + 32, first);
+      else emit(v1, orow, row, col0 + it * 64 + 32, first);
     }
   }
 
+  __device__ __forceinline__ void fetch(float4 (&o)[8], const float* src) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = s4[j];
+  }
+
+  // 32 columns, fully in bounds: first pass -> acc (+ bias); later passes -> running sum + acc
+  __device__ __forceinline__ void emit_fast(const uint32_t (&x)[32], const float4 (&old)[8], float* dst, int cb,
+                                            bool first) {
+    float4* o4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 o = make_float4(__uint_as_float(x[4 * j]), __uint_as_float(x[4 * j + 1]),
+                             __uint_as_float(x[4 * j + 2]), __uint_as_float(x[4 * j + 3]));
+      if (first) {
+        if (p.bias != nullptr) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cb) + j);
+          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        }
+      } else {
+        o.x += old[j].x; o.y += old[j].y; o.z += old[j].z; o.w += old[j].w;
+      }
+      o4[j] = o;
+    }
+  }
+
+  // general path (ragged tile / unaligned rows)
   __device__ __forceinline__ void emit(const uint32_t (&x)[32], float* orow, int row, int cb, bool first) {
     if (row < p.M && cb < p.N) {
       if (p.vec_ok && cb + 32 <= p.N) {
         float4* o4 = reinterpret_cast<float4*>(orow + cb);
-        if (first) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(__uint_as_float(x[4 * j]), __uint_as_float(x[4 * j + 1]),
-                                   __uint_as_float(x[4 * j + 2]), __uint_as_float(x[4 * j + 3]));
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(__uint_as_float(x[4 * j]), __uint_as_float(x[4 * j + 1]),
+                                 __uint_as_float(x[4 * j + 2]), __uint_as_float(x[4 * j + 3]));
+          if (first) {
             if (p.bias != nullptr) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cb) + j);
               o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
             }
-            o4[j] = o;
+          } else {
+            const float4 b = o4[j];
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = o4[j];
-            o.x += __uint_as_float(x[4 * j]); o.y += __uint_as_float(x[4 * j + 1]);
-            o.z += __uint_as_float(x[4 * j + 2]); o.w += __uint_as_float(x[4 * j + 3]);
-            o4[j] = o;
-          }
+          o4[j] = o;
         }
       } else {
 #pragma unroll
@@ -104,7 +134,8 @@ struct StoreEpilogue {
 // The k-range of a segment is accumulated in passes of at most chunk_kb k-blocks (see the
 // scheduler interface in isb_gemm_core.cuh): pass c of the segment covers k-blocks
 // [kb_begin + c * chunk_kb, ...) and the epilogue sums the passes in fp32.
-constexpr int kAccChunkKb = 32;   // 128 tcgen05.mma accumulation steps per chunk
+constexpr int kAccChunkKb = 64;   // 256 tcgen05.mma accumulation steps per chunk (error 6.6e-6 vs 5.1e-6 at 32,
+                                  // 4.6e-6 = the 16-bit representation floor; tools/gemm_precision.py)
 
 struct PlainSched {
   int m_blocks, n_tiles, k_blocks, splits, chunk_kb;

@@ -229,15 +229,16 @@ __device__ __forceinline__ bool row_certified(const SelectSmem& sm, int kc, doub
 }
 
 // Expected rms error of a plain-bf16 screen score on dense rows: both operands are rounded to 8
-// significant bits (relative error uniform in +-2^-9, rms 2^-9/sqrt(3)), so a product is off by
-// sqrt(2/3) 2^-9 relative and the sum of D such terms by that times sqrt(sum (a_i b_i)^2) ~
-// |a||b|/sqrt(D).  Half of it is used as the floor when the sample is large (>= 32 candidates
-// measure sigma well), one and a half times it when it is small.
+// significant bits, so a product is off by ~2.3e-3 relative (rms) and the sum of D such terms by
+// that times sqrt(sum (a_i b_i)^2) ~ |a||b|/sqrt(D): sigma = 2.34e-3 |a||b| / sqrt(D), calibrated
+// on unit Gaussian rows at D = 128 and 2048 (5.2e-5 at D = 2048).  Half of it is used as the
+// floor when the sample is large (>= 32 candidates measure sigma well), one and a half times it
+// when it is small.
 // qn2: squared norm of the query row, sm.sel_norm2: of the candidates (the largest is taken).
 __device__ __forceinline__ double screen_sigma_floor(const SelectSmem& sm, int n_sel, double qn2, int D) {
   float bn2 = 0.f;
   for (int c = 0; c < n_sel; ++c) bn2 = fmaxf(bn2, sm.sel_norm2[c]);
-  const double dense = 1.5947e-3 * sqrt(qn2 * static_cast<double>(bn2) / static_cast<double>(D));
+  const double dense = 2.34e-3 * sqrt(qn2 * static_cast<double>(bn2) / static_cast<double>(D));
   return (n_sel >= 32 ? 0.5 : 1.5) * dense;
 }
 
@@ -1756,9 +1757,10 @@ extern "C" int isb_select_negatives(const float* emb, const uint16_t* emb_hi, co
   if (kc < 1 || kc > kMaxCand) kc = kMiningCand;
   if (kc > N) kc = static_cast<int>(N);
   // semi-hard: columns scoring >= sim_pos (+ the screen's error bound) are masked in the epilogue
-  // twice the certificate's z: sigma measured on ~16 candidates scatters by ~20 % around the
-  // floor, and a couple is rejected when its measured noise exceeds the slack
-  const float ub_slack = fmaxf(screen_eps, 2.f * kCertZ * sigma_floor);
+  // four times the certificate's z: the noise measured on a couple's ~16 best candidates scatters
+  // around the dense-row expectation (up to 2.2 x on clustered descriptors), and a couple is
+  // rejected when its measured noise exceeds the slack
+  const float ub_slack = fmaxf(screen_eps, 4.f * kCertZ * sigma_floor);
   rc = launch_topk_screen(a_hi, a_lo, ld, P, emb_hi, emb_lo, ld, N, D, kc, mp.sp, ws, label, row_label,
                           semi_hard ? pos32 : nullptr, ub_slack, st);
   if (rc) return rc;

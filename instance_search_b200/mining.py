@@ -12,8 +12,9 @@ from .sharding import all_gather_rows, shard_bounds
 
 SCREEN_EPS_3TERM = 2e-5   # absolute error bound of the [hi|lo|hi].[hi|hi|lo] screen, unit rows
 # plain bf16 screen: expected rms error of a score on dense rows, both operands rounded to 8
-# significant bits: sqrt(2/3) 2^-9 |a||b| / sqrt(D)  (include/isb.h, isb_select_negatives)
-SIGMA_BF16 = 1.5947e-3
+# significant bits: 2.34e-3 |a||b| / sqrt(D), calibrated on unit Gaussian rows at D = 128 and 2048
+# (include/isb.h, isb_select_negatives)
+SIGMA_BF16 = 2.34e-3
 
 
 def label_ids(dataset):

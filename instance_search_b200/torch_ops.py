@@ -45,7 +45,7 @@ def _head_from_parts(cls_w, cls_w_hi, cls_w_lo, cls_b, shift, lin_w_hi, lin_w_lo
     if lin_w_hi is not None:
         hw.D, hw.KinP = lin_w_hi.shape
     else:
-        hw.D, hw.KinP = 0, (shift.numel() + 7) // 8 * 8
+        hw.D, hw.KinP = 0, (0 if shift is None else (shift.numel() + 7) // 8 * 8)
     hw.Kin = shift.numel() if shift is not None else hw.KinP
     return hw
 

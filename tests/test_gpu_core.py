@@ -360,4 +360,4 @@ def test_gemm_long_contraction_accumulates_in_chunks(ops):
     for splits in (1, 9, 37):
         y = ops.gemm_nt_split(a_hi, a_lo, b_hi, b_lo, splits=splits, k=K)
         rel = ((y.double() - want).norm(dim=1) / want.norm(dim=1)).max().item()
-        assert rel < 8e-6, (splits, rel)
+        assert rel < 1e-5, (splits, rel)      # 6.6e-6 measured; one 300k-step chain gave 3.6e-4

@@ -33,7 +33,8 @@ def test_row_ops_and_gemm_through_the_dispatcher():
     assert (o.gemm_nt(a_hi, b_hi, 1).double() - a_hi[:, :136].double() @ b_hi[:, :136].double().t()).abs().max() \
         < 1e-5 * want.abs().max()
     E = oracle.normalize_l2(_randn(300, 72, seed=6))
-    assert torch.allclose(o.all_pairs_similarities(E.cuda(), 3).cpu(), E @ E.t(), rtol=1e-5, atol=2e-6)
+    # (16-bit operands: 4e-6 / sqrt(D) rms per entry -> a few 1e-6 at the maximum over 90k entries at D = 72)
+    assert torch.allclose(o.all_pairs_similarities(E.cuda(), 3).cpu(), E @ E.t(), rtol=1e-5, atol=5e-6)
     with pytest.raises(NotImplementedError):
         o.l2norm_rows(x, 1e-10)                       # CPU tensor: no kernel, no fallback
 

@@ -9,7 +9,7 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from instance_search_b200 import ops  # noqa: E402
+from instance_search_b200 import _lib, ops  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--Q", type=int, default=10000)
@@ -18,7 +18,11 @@ ap.add_argument("--D", type=int, default=2048)
 ap.add_argument("--k", type=int, default=100)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--check", type=int, default=32)
+ap.add_argument("--options", default="", help="library options, e.g. 'screen_wavesync=0,screen_seed=1'")
 a = ap.parse_args()
+for kv in [t for t in a.options.split(",") if t]:
+    name, val = kv.split("=")
+    _lib.set_option(name, int(val))
 
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(1234)
@@ -44,7 +48,7 @@ for it in range(a.iters + 1):
 print("times ms", ["%.2f" % t for t in times])
 best = min(times[1:])
 flops = 2.0 * a.Q * a.N * a.D
-print(json.dumps({"Q": a.Q, "N": a.N, "D": a.D, "k": a.k, "ms": best, "qps": a.Q / best * 1e3,
+print(json.dumps({"Q": a.Q, "N": a.N, "D": a.D, "k": a.k, "options": a.options, "ms": best, "qps": a.Q / best * 1e3,
                   "tflops": flops / best / 1e9}))
 if a.check:
     c = min(a.check, a.Q)
