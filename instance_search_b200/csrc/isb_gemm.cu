@@ -38,7 +38,9 @@ struct StoreEpilogue {
                   static_cast<long long>(row) * p.ldo;
     const int col0 = seg.n_tile * kBN;
     const bool first = nt == seg.nt_begin;
-    const bool fast = p.vec_ok && row < p.M && col0 + kBN <= p.N;   // whole tile in bounds, 16-byte rows
+    // fast path: the tile's columns and ALL 32 rows of this warp in bounds, 16-byte rows -- the
+    // predicate must be warp-uniform (the general path ends in a __syncwarp)
+    const bool fast = p.vec_ok && (row | 31) < p.M && col0 + kBN <= p.N;
     uint32_t v0[32], v1[32];
     float4 o0[8], o1[8];
     ptx::tmem_ld_32x32b_x32(tmem_acc, v0);
