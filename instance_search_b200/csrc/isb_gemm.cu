@@ -90,6 +90,7 @@ struct StoreEpilogue {
       }
       o4[j] = o;
     }
+    __syncwarp();   // same convergence point as the general path: the next tcgen05.ld is .aligned
   }
 
   // general path (ragged tile / unaligned rows)
