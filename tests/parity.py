@@ -21,8 +21,12 @@ SCORE_RTOL = 1e-5
 # profiles/r02_parity_achieved.jsonl.
 FP32_TIE_RTOL = 16 * 2.0 ** -24
 FP32_TIE_ATOL = 5e-8
-# ... and such disagreements are rare: at most this fraction of the Q*k returned
-# entries (+2) may differ from the fp32 oracle
+# ... and a disagreement may only sit where the oracle's OWN ranking is undecided at that
+# tolerance: the oracle's score at that position is within the tie tolerance of one of its
+# neighbours in the oracle's sorted list (the oracle is asked for k+1 so the last position has a
+# right neighbour).  On data without near-ties that set is (almost) empty, on near-duplicate
+# clusters it is large.  On data WITHOUT planted near-duplicates the count is bounded too:
+# at most this fraction of the Q*k entries (+2); callers with clustered data pass None.
 FP32_TIE_MAX_FRACTION = 2e-3
 
 # region descriptors (unit-norm rows, split-operand fp32-grade projection): per-row L2
@@ -65,12 +69,18 @@ def check_descriptors(got, want, l2_tol=DESC_L2_TOL, cos_tol=DESC_COS_TOL, unit=
     return float(l2.max())
 
 
-def check_topk_against_oracle(q, db, k, scores, idx, f64_exact=True, oracle_result=None):
+def check_topk_against_oracle(q, db, k, scores, idx, f64_exact=True, oracle_result=None,
+                              max_mismatch_fraction=FP32_TIE_MAX_FRACTION):
     """q, db CPU fp32; scores/idx = result of the CUDA path (any device).  Returns the
     number of entries that differ from the fp32 oracle (all of them fp32-noise ties that
-    the fp64 ranking decides our way; bounded by FP32_TIE_MAX_FRACTION)."""
+    the fp64 ranking decides our way, each at a position the oracle's own ranking leaves undecided)."""
     scores, idx = scores.cpu(), idx.cpu()
-    o_s, o_i = oracle.topk_search(q, db, k) if oracle_result is None else oracle_result
+    if oracle_result is None and k < db.size(0):
+        o_s1, o_i1 = oracle.topk_search(q, db, k + 1)
+        o_s, o_i, o_next = o_s1[:, :k], o_i1[:, :k], o_s1[:, k:]
+    else:
+        o_s, o_i = oracle.topk_search(q, db, k) if oracle_result is None else oracle_result
+        o_next = o_s[:, -1:]                       # unknown (k+1)-th: last position counts as undecided
     # 1. index-exact against the fp64 adjudicator
     if f64_exact:
         a_s, a_i = oracle.topk_search_f64(q, db, k)
@@ -98,8 +108,15 @@ def check_topk_against_oracle(q, db, k, scores, idx, f64_exact=True, oracle_resu
         max_gap = float(gap.max())
         tol = FP32_TIE_ATOL + FP32_TIE_RTOL * o_s[rows, cols].abs()
         assert bool((gap <= tol).all()), "index mismatch not explained by fp32 noise: gap %g" % max_gap
-        assert n_mism <= FP32_TIE_MAX_FRACTION * idx.numel() + 2, \
-            "%d of %d entries differ from the fp32 oracle" % (n_mism, idx.numel())
+        ext = torch.cat([o_s[:, :1] + 1.0, o_s, o_next], dim=1)
+        near = torch.minimum(ext[:, :-2] - o_s, o_s - ext[:, 2:])          # gap to the closer neighbour
+        undecided = near <= FP32_TIE_ATOL + FP32_TIE_RTOL * o_s.abs()
+        assert bool(undecided[rows, cols].all()), \
+            "%d entries differ from the fp32 oracle where its own ranking is decided" % \
+            int((~undecided[rows, cols]).sum())
+        if max_mismatch_fraction is not None:
+            assert n_mism <= max_mismatch_fraction * idx.numel() + 2, \
+                "%d of %d entries differ from the fp32 oracle" % (n_mism, idx.numel())
     record("topk", Q=q.size(0), N=db.size(0), D=q.size(1), k=k, mismatches_vs_f32=n_mism, max_tie_gap=max_gap,
            max_rel_score_err=float(rel))
     return n_mism

@@ -207,7 +207,9 @@ def test_topk_search_clustered_and_planted(ops):
     s, i = _search(ops, q, db, k, stats=stats)
     assert torch.equal(i[:, 0].cpu(), planted)          # round trip: a row finds itself
     assert torch.allclose(s[:, 0].cpu(), torch.ones(Q), atol=1e-6)
-    check_topk_against_oracle(q, db, k, s, i)
+    # near-duplicate clusters: hundreds of fp32-undecided neighbours by construction, so only the
+    # per-position rule applies (each disagreement sits where the oracle's own ranking is undecided)
+    check_topk_against_oracle(q, db, k, s, i, max_mismatch_fraction=None)
     # ~100 near-duplicates per cluster, score spacing far below bf16 noise: the
     # certificate must have sent (most of) these rows to the fp32-grade re-screen
     assert stats["rows"] == Q and stats["resolved_fp32_grade"] > Q // 2

@@ -169,14 +169,18 @@ def test_region_eval_path_without_cls_out(R, B, C, H, W, ncls, D):
 @pytest.mark.parametrize("H,W", [(13, 13), (16, 20)])
 def test_region_exact_line_is_complete_on_maps_with_more_than_32_windows(R, H, W):
     # window scores separated by far less than the bf16 screen can see (a nearly constant map with a
-    # 1e-4 ramp) on a map with 49 / 140 windows: the first round's 32 candidates are an arbitrary
+    # 2e-3 ramp under one bf16 ulp) on a map with 49 / 140 windows: the first round's 32 candidates are an arbitrary
     # subset, so the exact second line must keep scoring until its certificate holds -- it may
     # never return a list it has flagged incomplete (round 1 did)
     C, ncls, D, k = 32, 6, 16, 6
     s = _synthetic(2, C, H, W, ncls, D, seed=9)
-    g = torch.Generator().manual_seed(H)
-    ramp = torch.rand(2, 1, H, W, generator=g)
-    s["x"] = 0.5 + 2e-4 * ramp + 1e-5 * torch.rand(2, C, H, W, generator=g)
+    # raster ramp of amplitude 1.8e-3 on 0.5 (below half a bf16 ulp of 0.5, so every pooled value
+    # rounds to the same bf16 number), ascending on image 0 and descending on image 1: consecutive
+    # windows differ by 1.8e-3 / (H*W) = 5e-6 .. 1e-5 in the fp32 pooled mean
+    ramp = (torch.arange(H * W, dtype=torch.float64) / (H * W)).view(1, 1, H, W)
+    ramp = torch.cat([ramp, 0.9 * (1.0 - ramp)], 0)
+    s["x"] = (0.5 + 1.8e-3 * ramp).float().expand(2, C, H, W).contiguous()
+    s["cls_w"] = s["cls_w"].abs() / s["cls_w"].abs().sum(1, keepdim=True)     # slope 1 for every class
     hw = _hw(R, s)
     x = s["x"].cuda()
     od, oc, oi, on = oracle.region_descriptor_forward(s["x"], s["cls_w"], s["cls_b"], s["shift"], s["lin_w"],
