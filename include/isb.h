@@ -66,7 +66,9 @@ enum {
   ISB_OPT_GATHER_G = 10,         /* units per warp of the gather kernel */
   ISB_OPT_GATHER_STAGES = 11,    /* ring depth of the gather kernel */
   ISB_OPT_GEMM_PAIR = 12,        /* 1 (default): CTA-pair kernel for isb_gemm_nt[_split] with >= 2 row blocks */
-  ISB_OPT_COUNT_ = 13
+  ISB_OPT_MINING_PROGRESSIVE = 13, /* exact re-check of a couple's candidates: 1 (default) progressive, 0 all of them, 2 progressive with the one-CTA-per-couple kernel */
+  ISB_OPT_GATHER_SMALL = 14,     /* 1 (default): plane-block gather kernel for maps of <= 256 pixels; 0: off */
+  ISB_OPT_COUNT_ = 15
 };
 int isb_set_option(int option, int value);
 int isb_get_option(int option);
@@ -360,7 +362,9 @@ int isb_region_scatter_grad(const float* x, int64_t B, int64_t C, int64_t H, int
  * semi_hard is the reference's `epoch < P.train_epoch_switch`.
  * The rows of a tcgen05 screen GEMM are the anchors; the masks are applied in its
  * streaming top-k epilogue; the survivors (ISB_OPT_MINING_KC per couple, default 16) are
- * re-scored exactly (fp64 accumulation) and the exact conditions re-applied.
+ * re-scored exactly (fp64 accumulation) and the exact conditions re-applied -- progressively:
+ * only the candidates the current exact winner does not exclude (screen score within eps of
+ * it, the certificate's own bound) are gathered, usually one or two of the 16.
  * Certificate per couple: every column outside the candidate list has a screen score <= the
  * worst candidate's (t_min), hence an exact score <= t_min + eps; the couple is certified when
  * the exact winner clears that, with

@@ -1565,6 +1565,191 @@ region_gather_kernel(const float* __restrict__ x, int C, int H, int W, int fh_, 
   }
 }
 
+// ------------------------------------------------------------------ 4b. gather, small maps (7 x 7 windows)
+// Maps of up to 256 pixels (14 x 14: the reference's 448-px input) with at most 8 listed windows.
+// The warp-per-channel-stream kernel above spends ~5 instructions per useful one on such maps
+// (117 M warp instructions per 256 x 2048 x 14 x 14 batch, issue-bound at 160 us: its units are 4
+// planes, so unit overhead and per-element index arithmetic dominate).  Here a CTA stages 32 whole
+// planes per step (ONE bulk copy: they are contiguous in NCHW; ring of NST steps) and every thread
+// owns one (channel, dx) column of the 7 x 7 output patch:
+//   for each listed window i: the 7 values x[c, h_i + dy, w_i + dx], dy = 0..6 -- ONE address add and
+//   seven ld.shared with immediate row offsets; their sum is the thread's share of the window mean,
+//   and for the summed windows they go into the seven accumulators u[c, dy, dx] with one FMA each.
+// The four channels of a warp are spaced so that its 28 active lanes (4 channels x 7 dx) hit 28
+// different banks.  The 32 x 49 outputs of a step are converted to bf16 hi / lo in a shared tile
+// and leave as 16-byte vectors (the block is one contiguous, 16-byte aligned range of the row).
+constexpr int kG7MaxWin = 8;
+constexpr int kG7MaxStages = 6;
+
+// WT = map width as a compile-time constant (14), 0 = runtime; SC = channels per step (16 or 32:
+// SC / 4 warps per CTA).  Smaller steps in a deeper ring keep more bytes in flight per SM.
+template <int WT, int SC>
+__global__ void __launch_bounds__(SC * 8)
+region_gather7_kernel(const float* __restrict__ x, int C, int H, int W_, int k, int k_sum, int CPB, int NST, int CM,
+                      const int* __restrict__ image_list, const int* __restrict__ n_list,
+                      const int64_t* __restrict__ idx, const int* __restrict__ nsel_in,
+                      const float* __restrict__ win_norm, const float* __restrict__ shift,
+                      uint16_t* __restrict__ U_hi, uint16_t* __restrict__ U_lo, int64_t ldu,
+                      float* __restrict__ win_mean) {
+  constexpr int kG7CsStride = SC + 4;   // colsum [window][dx][channel]: conflict-free both ways
+  extern __shared__ __align__(128) uint8_t g7_smem[];
+  __shared__ uint32_t s_off[kG7MaxWin];
+  __shared__ float s_inv[kG7MaxWin];
+  __shared__ __align__(8) uint64_t full[kG7MaxStages];
+  if (image_list != nullptr && static_cast<int>(blockIdx.y) >= *n_list) return;
+  const int b = (image_list != nullptr) ? image_list[blockIdx.y] : blockIdx.y;
+  const int W = WT ? WT : W_;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = H * W, Wo = W - 6;
+  const int nall = min(nsel_in[b], min(k, kG7MaxWin));
+  const int nsel = min(nall, k_sum);
+  const int S = HW;   // planes of a step are contiguous in NCHW: ONE bulk copy per step
+  float* planes = reinterpret_cast<float*>(g7_smem);                            // [NST][SC][HW]
+  uint16_t* out_hi = reinterpret_cast<uint16_t*>(planes + static_cast<size_t>(NST) * SC * S);   // [32 * 49]
+  uint16_t* out_lo = out_hi + SC * 49;
+  float* colsum = reinterpret_cast<float*>(out_lo + SC * 49);                // [8][7][36]
+  if (tid < kG7MaxWin) {
+    uint32_t off = 0u;
+    float inv = 0.f;
+    if (tid < nall) {
+      const int win = static_cast<int>(idx[static_cast<size_t>(b) * k + tid]);
+      const int h = win / Wo, w = win - h * Wo;
+      off = static_cast<uint32_t>(h * W + w) * 4u;
+      // reciprocal multiply instead of the reference's division (model/custom_modules.py:56): the
+      // operand is rounded to bf16 hi + lo (2^-17) below, nothing of the difference survives
+      inv = 1.f / win_norm[static_cast<size_t>(b) * k + tid];
+    }
+    s_off[tid] = off;
+    s_inv[tid] = inv;
+  }
+  if (tid == 0) {
+    for (int st = 0; st < NST; ++st) ptx::mbar_init(&full[st], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  const int c_begin = blockIdx.x * CPB, c_end = min(C, c_begin + CPB);
+  const int nstep = (c_end - c_begin + SC - 1) / SC;
+  const float* xb = x + static_cast<size_t>(b) * C * HW;
+  // thread 0 stages step st into slot st % NST: the SC planes are one contiguous range
+  auto issue = [&](int st) {
+    const int c0 = c_begin + st * SC;
+    const int nch = min(SC, c_end - c0);
+    uint64_t* bar = &full[st % NST];
+    const uint32_t bytes = static_cast<uint32_t>(nch) * HW * 4u;
+    ptx::fence_proxy_async();   // the slot was last read through the generic proxy
+    ptx::mbar_arrive_expect_tx(bar, bytes);
+    ptx::bulk_load_1d(planes + static_cast<size_t>(st % NST) * SC * S, xb + static_cast<size_t>(c0) * HW, bytes, bar);
+  };
+  if (tid == 0)
+    for (int st = 0; st < NST && st < nstep; ++st) issue(st);
+
+  // this thread's column: dx = lane % 7 of channel cl of the step.  The four channels of a warp are
+  // CM apart, CM * HW = 8 or 24 (mod 32) words (14 x 14: CM = 2), so that its 28 active lanes hit 28
+  // different banks although the planes are not padded; the warps tile the SC channels in groups
+  // of 4 * CM
+  const int c_sub = lane / 7, dx = lane - c_sub * 7;
+  const int cl = (warp / CM) * (4 * CM) + (warp % CM) + CM * c_sub;
+  uint32_t off[kG7MaxWin];
+  float inv[kG7MaxWin];
+#pragma unroll
+  for (int i = 0; i < kG7MaxWin; ++i) { off[i] = s_off[i]; inv[i] = s_inv[i]; }
+  const float fn = static_cast<float>(nsel);
+  const uint32_t RS = static_cast<uint32_t>(W) * 4u;
+  uint16_t* uh = U_hi + static_cast<size_t>(b) * ldu;
+  uint16_t* ul = (U_lo != nullptr) ? U_lo + static_cast<size_t>(b) * ldu : nullptr;
+  const int Kin = C * 49;
+
+  for (int st = 0; st < nstep; ++st) {
+    const int c0 = c_begin + st * SC;
+    const int nch = min(SC, c_end - c0);
+    ptx::mbar_wait(&full[st % NST], static_cast<uint32_t>((st / NST) & 1));
+    if (lane < 28 && cl < nch) {
+      const uint32_t base = ptx::smem_u32(planes + (static_cast<size_t>(st % NST) * SC + cl) * S) + dx * 4u;
+      float acc[7];
+#pragma unroll
+      for (int dy = 0; dy < 7; ++dy) acc[dy] = 0.f;
+      const float* sh = shift + static_cast<size_t>(c0 + cl) * 49 + dx;
+      float shv[7];
+#pragma unroll
+      for (int dy = 0; dy < 7; ++dy) shv[dy] = __ldg(sh + dy * 7);   // in flight under the shared-memory loads
+#pragma unroll
+      for (int i = 0; i < kG7MaxWin; ++i) {
+        if (i < nall) {   // CTA-uniform
+          const uint32_t a = base + off[i];
+          float v[7];
+          if (WT) {
+            v[0] = lds_f32_off<0>(a);           v[1] = lds_f32_off<4 * WT>(a);
+            v[2] = lds_f32_off<8 * WT>(a);      v[3] = lds_f32_off<12 * WT>(a);
+            v[4] = lds_f32_off<16 * WT>(a);     v[5] = lds_f32_off<20 * WT>(a);
+            v[6] = lds_f32_off<24 * WT>(a);
+          } else {
+#pragma unroll
+            for (int dy = 0; dy < 7; ++dy) v[dy] = lds_f32(a + dy * RS);
+          }
+          if (win_mean != nullptr)
+            colsum[(i * 7 + dx) * kG7CsStride + cl] = (((((v[0] + v[1]) + v[2]) + v[3]) + v[4]) + v[5]) + v[6];
+          if (i < nsel) {
+#pragma unroll
+            for (int dy = 0; dy < 7; ++dy) acc[dy] = fmaf(v[dy], inv[i], acc[dy]);
+          }
+        }
+      }
+      // + nsel * shift (Shift, model/custom_modules.py:16-18, once per summed window), then bf16 hi / lo
+      const int e0 = cl * 49 + dx;
+#pragma unroll
+      for (int dy = 0; dy < 7; dy += 2) {
+        const float u0 = fmaf(fn, shv[dy], acc[dy]);
+        const float u1 = (dy + 1 < 7) ? fmaf(fn, shv[dy + 1 < 7 ? dy + 1 : dy], acc[dy + 1 < 7 ? dy + 1 : dy]) : 0.f;
+        uint32_t hi2, lo2;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(u1), "f"(u0));
+        const float r0f = u0 - __uint_as_float(hi2 << 16);
+        const float r1f = u1 - __uint_as_float(hi2 & 0xFFFF0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(r1f), "f"(r0f));
+        out_hi[e0 + dy * 7] = static_cast<uint16_t>(hi2 & 0xFFFFu);
+        out_lo[e0 + dy * 7] = static_cast<uint16_t>(lo2 & 0xFFFFu);
+        if (dy + 1 < 7) {
+          out_hi[e0 + (dy + 1) * 7] = static_cast<uint16_t>(hi2 >> 16);
+          out_lo[e0 + (dy + 1) * 7] = static_cast<uint16_t>(lo2 >> 16);
+        }
+      }
+    }
+    __syncthreads();   // tile and column sums complete; nobody reads the slot any more
+    if (tid == 0 && st + NST < nstep) issue(st + NST);
+    // the step's 49 * nch outputs: one contiguous range of the row, 16-byte aligned (c0 % 32 == 0)
+    {
+      const int n_el = nch * 49;
+      const size_t g0 = static_cast<size_t>(c0) * 49;
+      const int nvec = n_el >> 3;
+      for (int v = tid; v < nvec; v += (SC * 8)) {
+        *reinterpret_cast<uint4*>(uh + g0 + 8 * v) = *reinterpret_cast<const uint4*>(out_hi + 8 * v);
+        if (ul != nullptr) *reinterpret_cast<uint4*>(ul + g0 + 8 * v) = *reinterpret_cast<const uint4*>(out_lo + 8 * v);
+      }
+      for (int e = (nvec << 3) + tid; e < n_el; e += (SC * 8)) {
+        uh[g0 + e] = out_hi[e];
+        if (ul != nullptr) ul[g0 + e] = out_lo[e];
+      }
+      // the CTA that holds the image's last channel also writes the zero padding [Kin, KinP)
+      if (c0 + nch >= C && tid < ((Kin + 7) & ~7) - Kin) {
+        uh[Kin + tid] = 0;
+        if (ul != nullptr) ul[Kin + tid] = 0;
+      }
+    }
+    // by-product: the fp32 mean of every listed window (AvgPool2d, model/siamese.py:187), the input of
+    // isb_region_logits: column sums (dy ascending) added left to right, / 49
+    if (win_mean != nullptr) {
+      for (int t = tid; t < nch * nall; t += (SC * 8)) {
+        const int i = t / nch, c = t - i * nch;   // consecutive lanes: consecutive channels of one window
+        const float* cs = colsum + (i * 7) * kG7CsStride + c;
+        float sum = cs[0];
+#pragma unroll
+        for (int d = 1; d < 7; ++d) sum += cs[d * kG7CsStride];
+        win_mean[(static_cast<size_t>(b) * k + i) * C + c0 + c] = sum / 49.f;
+      }
+    }
+    __syncthreads();   // tile and column sums are free for the next step
+  }
+}
+
 // ------------------------------------------------------------------ 5b. exact logits of the selected windows
 // cls_out[b, :, i] = Wc . mean_i + bc in fp32 from the exact window means
 // (model/siamese.py:188,216), one CTA per image: the k means sit in shared memory,
@@ -2098,6 +2283,36 @@ extern "C" int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H
   ISB_CHECK_ARG(ldu >= KinP && ldu % 8 == 0 && (reinterpret_cast<uintptr_t>(U_hi) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(U_lo) & 15) == 0, "isb_region_gather: bad ldu / alignment");
   const int64_t HW = H * W;
+  // small maps, 7 x 7 windows, <= 8 listed windows: the plane-block kernel (option gather_small = 0: off)
+  if (fh == 7 && fw == 7 && HW <= 256 && HW % 4 == 0 && k <= kG7MaxWin &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && option(ISB_OPT_GATHER_SMALL, 1) != 0) {
+    const int SC = option(ISB_OPT_GATHER_CW, 32) == 16 ? 16 : 32;    // channels per step
+    // channel spacing inside a warp that spreads its lanes over all banks (see the kernel); 1: none does
+    int CM = 1;
+    for (int m : {1, 2, 4})
+      if ((m * HW) % 32 == 8 || (m * HW) % 32 == 24) { CM = m; break; }
+    if (SC % (4 * CM) != 0) CM = 1;
+    int NST = option(ISB_OPT_GATHER_STAGES, 2);
+    if (NST < 1) NST = 1;
+    if (NST > kG7MaxStages) NST = kG7MaxStages;
+    // channels per CTA: a multiple of 32, >= 4 waves of CTAs when the batch allows
+    int CPB = 256;
+    while (CPB > 64 && B * ((C + CPB - 1) / CPB) < 148 * 4 * 4) CPB >>= 1;
+    {
+      const int g = option(ISB_OPT_GATHER_G, 0);
+      if (g >= 1 && g <= 64) CPB = 32 * g;
+    }
+    const size_t smem = static_cast<size_t>(NST) * SC * HW * 4 + 2 * SC * 49 * 2 + kG7MaxWin * 7 * (SC + 4) * 4;
+    dim3 grid(static_cast<unsigned>((C + CPB - 1) / CPB), static_cast<unsigned>(B));
+    auto kern = (W == 14) ? (SC == 32 ? region_gather7_kernel<14, 32> : region_gather7_kernel<14, 16>)
+                          : (SC == 32 ? region_gather7_kernel<0, 32> : region_gather7_kernel<0, 16>);
+    ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, SC * 8, smem, static_cast<cudaStream_t>(stream)>>>(
+        x, (int)C, (int)H, (int)W, k, k_sum, CPB, NST, CM, image_list, n_list, idx, nsel, win_norm, shift, U_hi,
+        U_lo, ldu, win_mean);
+    ISB_CUDA(cudaGetLastError());
+    return ISB_OK;
+  }
   // channels per warp unit: <= 4 KB of planes per ring slot (14 x 14: 4 channels, 32 x 32: 1)
   int CW = 1;
   for (int cw : {8, 4, 2, 1}) {

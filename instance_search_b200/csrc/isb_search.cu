@@ -835,54 +835,149 @@ __device__ __forceinline__ void block_best(double& s, int& c, double* red_s, int
   c = red_c[0];
 }
 
+// Error bound of a couple's screen scores from the candidates scored so far.  With >= 8 samples the
+// measured rms (floored by the expected noise) is a usable sigma; a sigma from one or two samples is
+// not (a single 4-sigma deviation, ~1 couple in 10^4, would read as a 4x noisier screen and reject
+// the couple), so small samples take 2.5 x the floor (measured noise scatters up to 2.2 x around the
+// dense-row expectation) and are only widened by an OBSERVED deviation: eps >= 2 max|screen - exact|.
+constexpr int kMiningSigmaSamples = 8;
+__device__ __forceinline__ double mining_eps(double d2_sum, int cnt, double max_abs_d, float screen_eps,
+                                             float sigma_floor) {
+  const double sigma = (cnt >= kMiningSigmaSamples)
+                           ? fmax(sqrt(d2_sum / static_cast<double>(cnt)), static_cast<double>(sigma_floor))
+                           : 2.5 * static_cast<double>(sigma_floor);
+  double eps = fmax(static_cast<double>(screen_eps), static_cast<double>(kCertZ) * sigma);
+  if (cnt < kMiningSigmaSamples) eps = fmax(eps, 2.0 * max_abs_d);
+  return eps;
+}
+
+// Exact score (fp32 products, fp64 accumulation) of candidate c of the row, by one warp.
+__device__ __forceinline__ double warp_exact_dot(const float* qs, const float* __restrict__ dbrow, int D) {
+  const int lane = threadIdx.x & 31;
+  const float4* dr = reinterpret_cast<const float4*>(dbrow);
+  double acc = 0.0;
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 b = __ldg(dr + i);
+    const float4 a = reinterpret_cast<const float4*>(qs)[i];
+    acc = fma(static_cast<double>(a.x), static_cast<double>(b.x), acc);
+    acc = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc);
+    acc = fma(static_cast<double>(a.z), static_cast<double>(b.z), acc);
+    acc = fma(static_cast<double>(a.w), static_cast<double>(b.w), acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+// One CTA per couple.  The kc best screen candidates of the couple are re-checked exactly
+// PROGRESSIVELY: only ONE negative is wanted, and a candidate whose screen score lies more than
+// eps below the best exact valid score found so far cannot win -- the statement the certificate
+// makes about the columns outside the candidate list (t_min + eps < winner), applied inside the
+// list.  Round 0 scores the candidates within 2 eps of the best screen score; every further
+// round scores the ones the current winner does not yet exclude (eps grows with the noise measured
+// on the candidates scored so far), until none is left.  On ordinary data one or two rows of D
+// floats are gathered per couple instead of kc (16 x 8 KB x 16 384 couples = 2.1 GB at the
+// BASELINE configs[2] size: 535 us of the 1.72 ms step).
 __global__ void __launch_bounds__(kRerankThreads)
 mining_rerank_kernel(const float* __restrict__ emb, int D, const int64_t* __restrict__ anchors,
                      int n_groups, const uint2* __restrict__ pool, const int* __restrict__ pool_cnt,
                      int kc, const double* __restrict__ pos64, int semi_hard, float screen_eps,
-                     float sigma_floor, float ub_slack, int64_t* __restrict__ neg_idx,
+                     float sigma_floor, float ub_slack, int progressive, int64_t* __restrict__ neg_idx,
                      float* __restrict__ neg_sim, int* __restrict__ flag, int* __restrict__ unc_rows,
-                     int* __restrict__ unc_count) {
+                     int* __restrict__ unc_count, unsigned long long* __restrict__ n_scored) {
   extern __shared__ __align__(16) uint8_t rr_smem[];
   float* qs = reinterpret_cast<float*>(rr_smem);
   __shared__ SelectSmem sm;
   __shared__ double red_s[kRerankThreads / 32];
   __shared__ int red_c[kRerankThreads / 32];
   __shared__ double s_sig2;
-  const int row = blockIdx.x, tid = threadIdx.x;
-  if (tid == 0) s_sig2 = 0.0;
+  __shared__ int s_cnt, s_more;
+  __shared__ uint32_t s_topkey, s_maxd;
+  __shared__ float s_thr;
+  __shared__ unsigned char s_done[kMaxCand];
+  const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
   const float* qrow = emb + anchors[row] * D;
   for (int i = tid; i < D / 4; i += kRerankThreads)
     reinterpret_cast<float4*>(qs)[i] = __ldg(reinterpret_cast<const float4*>(qrow) + i);
   const int n_sel = select_pool_candidates(sm, pool + static_cast<size_t>(row) * n_groups * kMaxCand,
                                            pool_cnt + static_cast<size_t>(row) * n_groups, n_groups, kc);
-  exact_scores(sm, qs, emb, D, n_sel);
-  // screen noise of this couple: sum over its candidates of (screen - exact)^2
-  {
-    double d2 = 0.0;
-    if (tid < n_sel) {
-      const double d = static_cast<double>(sm.sel_screen[tid]) - sm.sel_score[tid];
-      d2 = d * d;
+  const double eps0 = mining_eps(0.0, progressive ? 0 : kMiningSigmaSamples, 0.0, screen_eps, sigma_floor);
+  if (tid < kMaxCand) {
+    s_done[tid] = 0;
+    sm.sel_score[tid] = -INFINITY;
+    if (tid >= n_sel) sm.sel_col[tid] = 0x7FFFFFFF;
+  }
+  if (tid == 0) { s_topkey = 0u; s_thr = -INFINITY; }
+  __syncthreads();
+  if (progressive) {
+    if (tid < n_sel) atomicMax(&s_topkey, f2key(__float_as_uint(sm.sel_screen[tid])));
+    __syncthreads();
+    if (tid == 0 && n_sel > 0)
+      s_thr = static_cast<float>(static_cast<double>(__uint_as_float(key2f(s_topkey))) - 2.0 * eps0);
+    __syncthreads();
+  }
+  double s, eps = eps0;
+  int c, scored_total = 0;
+  for (;;) {
+    const float thr = s_thr;
+    for (int i = warp; i < n_sel; i += kRerankThreads / 32) {   // warp-uniform
+      if (s_done[i] || !(sm.sel_screen[i] >= thr)) continue;
+      const double v = warp_exact_dot(qs, emb + static_cast<size_t>(sm.sel_col[i]) * D, D);
+      if ((tid & 31) == 0) { sm.sel_score[i] = v; s_done[i] = 1; }
     }
+    if (tid == 0) { s_sig2 = 0.0; s_cnt = 0; s_more = 0; s_maxd = 0u; }
+    __syncthreads();
+    // screen noise of this couple: rms(screen - exact) over the candidates scored so far
+    {
+      double d2 = 0.0;
+      int n1 = 0;
+      if (tid < n_sel && s_done[tid]) {
+        const double d = static_cast<double>(sm.sel_screen[tid]) - sm.sel_score[tid];
+        d2 = d * d;
+        n1 = 1;
+        atomicMax(&s_maxd, __float_as_uint(fabsf(static_cast<float>(d)) * 1.000001f));
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-    if ((tid & 31) == 0 && tid < kMaxCand) atomicAdd(&s_sig2, d2);
+      for (int o = 16; o > 0; o >>= 1) {
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+      }
+      if ((tid & 31) == 0 && n1) { atomicAdd(&s_sig2, d2); atomicAdd(&s_cnt, n1); }
+    }
+    // reference: excluded if S[i1, j] >= S[i1, i2]  (train/siamese_regions.py:111)
+    s = -INFINITY;
+    c = 0x7FFFFFFF;
+    if (tid < n_sel && s_done[tid]) {
+      const double v = sm.sel_score[tid];
+      if (!semi_hard || v < pos64[row]) { s = v; c = sm.sel_col[tid]; }
+    }
+    block_best(s, c, red_s, red_c);   // (its barriers also order the atomics above)
+    scored_total = s_cnt;
+    eps = mining_eps(s_sig2, scored_total, static_cast<double>(__uint_as_float(s_maxd)), screen_eps, sigma_floor);
+    // which of the candidates not yet scored can the current winner not exclude?
+    double bound = (c != 0x7FFFFFFF) ? s - eps : -INFINITY;
+    uint32_t my_key = 0u;
+    if (tid < n_sel && !s_done[tid]) {
+      if (static_cast<double>(sm.sel_screen[tid]) >= bound) atomicOr(&s_more, 1);
+      my_key = f2key(__float_as_uint(sm.sel_screen[tid]));
+    }
+    if (tid == 0) s_topkey = 0u;
+    __syncthreads();
+    if (!s_more) break;
+    if (c == 0x7FFFFFFF) {
+      // no valid winner yet (semi-hard: everything scored so far is >= sim_pos): go down the list
+      if (my_key) atomicMax(&s_topkey, my_key);
+      __syncthreads();
+      bound = static_cast<double>(__uint_as_float(key2f(s_topkey))) - 2.0 * eps;
+    }
+    if (tid == 0) s_thr = static_cast<float>(bound) - 1e-7f * fabsf(static_cast<float>(bound));  // never above the fp64 bound
+    __syncthreads();
   }
-  // reference: excluded if S[i1, j] >= S[i1, i2]  (train/siamese_regions.py:111)
-  double s = -INFINITY;
-  int c = 0x7FFFFFFF;
-  if (tid < n_sel) {
-    const double v = sm.sel_score[tid];
-    if (!semi_hard || v < pos64[row]) { s = v; c = sm.sel_col[tid]; }
-  }
-  block_best(s, c, red_s, red_c);   // (its barriers also order the s_sig2 atomics)
   if (tid == 0) {
     const bool found = c != 0x7FFFFFFF;
     // Certificate: every column NOT selected has a screen score <= the worst selected one,
     // hence an exact score <= that + eps, with eps = max(the caller's absolute bound,
-    // kCertZ x the screen noise: measured on this couple's candidates, floored by sigma_floor).
-    const double sigma = fmax(sqrt(s_sig2 / static_cast<double>(n_sel > 0 ? n_sel : 1)),
-                              static_cast<double>(sigma_floor));
-    const double eps = fmax(static_cast<double>(screen_eps), static_cast<double>(kCertZ) * sigma);
+    // kCertZ x the screen noise: mining_eps over this couple's scored candidates).
     bool certified = true;
     if (sm.total > kc) {
       const float t_min = __uint_as_float(key2f(sm.min_key));
@@ -895,6 +990,106 @@ mining_rerank_kernel(const float* __restrict__ emb, int D, const int64_t* __rest
     neg_sim[row] = found ? static_cast<float>(s) : -2.f;  // the reference's fill value (:124)
     flag[row] = certified ? 0 : 1;
     if (!certified && unc_rows != nullptr) unc_rows[atomicAdd(unc_count, 1)] = row;
+    if (n_scored != nullptr) atomicAdd(n_scored, static_cast<unsigned long long>(scored_total));
+  }
+}
+
+// The same re-check with ONE WARP per couple, for kc <= 32 (lane = candidate): the candidates come
+// from pool_candidates_kernel (warp-level radix select), so no CTA-wide barrier and no serial
+// histogram scan sits on the couple's critical path -- the one-CTA-per-couple kernel above spent
+// ~35 us of latency per couple on its selection (16 384 couples = 14 waves = 0.5 ms), far more than
+// the gathers.  cand_screen / cand_col [P, kc]: unsorted, (-inf, -1) beyond the couple's entries.
+constexpr int kMineWarps = 8;
+
+__global__ void __launch_bounds__(32 * kMineWarps)
+mining_rerank_warp_kernel(const float* __restrict__ emb, int D, const int64_t* __restrict__ anchors, int64_t P,
+                          const float* __restrict__ cand_screen, const int* __restrict__ cand_col, int kc,
+                          const double* __restrict__ pos64, int semi_hard, float screen_eps, float sigma_floor,
+                          float ub_slack, int progressive, int64_t* __restrict__ neg_idx,
+                          float* __restrict__ neg_sim, int* __restrict__ flag, int* __restrict__ unc_rows,
+                          int* __restrict__ unc_count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kMineWarps + (threadIdx.x >> 5);
+  if (row >= P) return;   // warp-uniform
+  const float my_screen = (lane < kc) ? cand_screen[row * kc + lane] : -INFINITY;
+  const int my_col = (lane < kc) ? cand_col[row * kc + lane] : -1;
+  const bool valid = my_col >= 0;
+  const int n_valid = __popc(__ballot_sync(0xffffffffu, valid));
+  const float* arow = emb + anchors[row] * D;
+  const double ub = semi_hard ? pos64[row] : 0.0;
+  // screen range of the candidates
+  float t_min = valid ? my_screen : INFINITY, top = valid ? my_screen : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    t_min = fminf(t_min, __shfl_xor_sync(0xffffffffu, t_min, o));
+    top = fmaxf(top, __shfl_xor_sync(0xffffffffu, top, o));
+  }
+  const double eps0 = mining_eps(0.0, progressive ? 0 : kMiningSigmaSamples, 0.0, screen_eps, sigma_floor);
+  float thr = progressive ? static_cast<float>(static_cast<double>(top) - 2.0 * eps0) : -INFINITY;
+  double my_exact = -INFINITY;
+  bool done = false;
+  double s, eps;
+  int c;
+  for (;;) {
+    uint32_t todo = __ballot_sync(0xffffffffu, valid && !done && my_screen >= thr);
+    while (todo) {
+      const int i = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int col = __shfl_sync(0xffffffffu, my_col, i);
+      const double v = warp_exact_dot(arow, emb + static_cast<size_t>(col) * D, D);
+      if (lane == i) { my_exact = v; done = true; }
+    }
+    // screen noise of this couple: rms(screen - exact) over the candidates scored so far
+    double d2 = 0.0, dmax = 0.0;
+    if (done) {
+      const double d = static_cast<double>(my_screen) - my_exact;
+      d2 = d * d;
+      dmax = fabs(d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+      dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    const int cnt = __popc(__ballot_sync(0xffffffffu, done));
+    eps = mining_eps(d2, cnt, dmax, screen_eps, sigma_floor);
+    // reference: excluded if S[i1, j] >= S[i1, i2]  (train/siamese_regions.py:111); larger first, ties -> lower column
+    s = -INFINITY;
+    c = 0x7FFFFFFF;
+    if (done && (!semi_hard || my_exact < ub)) { s = my_exact; c = my_col; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double os = __shfl_xor_sync(0xffffffffu, s, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, c, o);
+      if (os > s || (os == s && oc < c)) { s = os; c = oc; }
+    }
+    const bool found = c != 0x7FFFFFFF;
+    double bound = found ? s - eps : -INFINITY;
+    const bool open = valid && !done;
+    if (!__ballot_sync(0xffffffffu, open && static_cast<double>(my_screen) >= bound)) break;
+    if (!found) {
+      // no valid winner yet (semi-hard: everything scored so far is >= sim_pos): go down the list
+      float top2 = open ? my_screen : -INFINITY;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) top2 = fmaxf(top2, __shfl_xor_sync(0xffffffffu, top2, o));
+      bound = static_cast<double>(top2) - 2.0 * eps;
+    }
+    thr = static_cast<float>(bound);
+    thr -= 1e-7f * fabsf(thr);   // never above the fp64 bound
+  }
+  if (lane == 0) {
+    const bool found = c != 0x7FFFFFFF;
+    // Certificate: a column outside the list has a screen score <= the worst listed one (only a full
+    // list can have dropped anything), hence an exact score <= t_min + eps
+    bool certified = true;
+    if (n_valid >= kc) certified = found && (static_cast<double>(t_min) + eps < s);
+    // semi-hard: the epilogue dropped the columns with screen >= sim_pos + ub_slack as "surely
+    // excluded"; that holds only while the screen noise stays within the slack
+    if (semi_hard && eps > static_cast<double>(ub_slack)) certified = false;
+    neg_idx[row] = found ? static_cast<int64_t>(c) : -1;
+    neg_sim[row] = found ? static_cast<float>(s) : -2.f;  // the reference's fill value (:124)
+    flag[row] = certified ? 0 : 1;
+    if (!certified && unc_rows != nullptr) unc_rows[atomicAdd(unc_count, 1)] = static_cast<int>(row);
   }
 }
 
@@ -1682,7 +1877,7 @@ extern "C" int isb_topk_merge_certified(const uint32_t* packed_all, const int64_
 // ------------------------------------------------------------------ a13 entry point
 struct MiningPlan {
   SearchPlan sp;
-  size_t off_row_label, off_pos64, off_pos32, off_flag, total;
+  size_t off_row_label, off_pos64, off_pos32, off_flag, off_cand_screen, off_cand_col, total;
 };
 
 static MiningPlan make_mining_plan(int64_t P, int64_t N, int64_t D, int split) {
@@ -1693,6 +1888,8 @@ static MiningPlan make_mining_plan(int64_t P, int64_t N, int64_t D, int split) {
   m.off_pos64 = off;     off = align_up(off + static_cast<size_t>(P) * 8, 1024);
   m.off_pos32 = off;     off = align_up(off + static_cast<size_t>(P) * 4, 1024);
   m.off_flag = off;      off = align_up(off + static_cast<size_t>(P) * 4, 1024);
+  m.off_cand_screen = off; off = align_up(off + static_cast<size_t>(P) * 32 * 4, 1024);   // warp path: kc <= 32
+  m.off_cand_col = off;    off = align_up(off + static_cast<size_t>(P) * 32 * 4, 1024);
   m.total = off;
   return m;
 }
@@ -1766,14 +1963,35 @@ extern "C" int isb_select_negatives(const float* emb, const uint16_t* emb_hi, co
   if (rc) return rc;
   const size_t smem = static_cast<size_t>(D) * 4;
   ISB_CHECK_ARG(smem <= 160 * 1024, "isb_select_negatives: D too large");
-  if (smem > 48 * 1024) {
-    ISB_CUDA(cudaFuncSetAttribute(mining_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024)
     ISB_CUDA(cudaFuncSetAttribute(mining_bruteforce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int progressive = option(ISB_OPT_MINING_PROGRESSIVE, 1) != 0 ? 1 : 0;
+  const uint2* pool = reinterpret_cast<const uint2*>(ws + mp.sp.off_pool);
+  const int* pool_cnt = reinterpret_cast<const int*>(ws + mp.sp.off_pool_cnt);
+  // warp path (kc <= 32 and a row's pool fits a warp's share of shared memory): warp-level candidate
+  // selection, then one warp per couple; otherwise one CTA per couple
+  const size_t per_warp = (static_cast<size_t>(mp.sp.n_groups) * kMaxCand * 2 + 256 + mp.sp.n_groups + 1) * 4;
+  int wpc = kSelWarps;
+  while (wpc > 1 && per_warp * wpc > 96 * 1024) wpc >>= 1;
+  if (kc <= 32 && per_warp * wpc <= 200 * 1024 && option(ISB_OPT_MINING_PROGRESSIVE, 1) != 2) {
+    float* cand_screen = reinterpret_cast<float*>(ws + mp.off_cand_screen);
+    int* cand_col = reinterpret_cast<int*>(ws + mp.off_cand_col);
+    const size_t psmem = per_warp * wpc;
+    if (psmem > 48 * 1024)
+      ISB_CUDA(cudaFuncSetAttribute(pool_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    pool_candidates_kernel<<<static_cast<unsigned>((P + wpc - 1) / wpc), 32 * wpc, psmem, st>>>(
+        P, mp.sp.n_groups, pool, pool_cnt, kc, kc, cand_screen, cand_col);
+    ISB_CUDA(cudaGetLastError());
+    mining_rerank_warp_kernel<<<static_cast<unsigned>((P + kMineWarps - 1) / kMineWarps), 32 * kMineWarps, 0, st>>>(
+        emb, (int)D, anchors, P, cand_screen, cand_col, kc, pos64, semi_hard, screen_eps, sigma_floor, ub_slack,
+        progressive, neg_idx, neg_sim, flag, uncertified_rows, n_uncertified);
+  } else {
+    if (smem > 48 * 1024)
+      ISB_CUDA(cudaFuncSetAttribute(mining_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mining_rerank_kernel<<<static_cast<unsigned>(P), kRerankThreads, smem, st>>>(
+        emb, (int)D, anchors, mp.sp.n_groups, pool, pool_cnt, kc, pos64, semi_hard, screen_eps, sigma_floor,
+        ub_slack, progressive, neg_idx, neg_sim, flag, uncertified_rows, n_uncertified, nullptr);
   }
-  mining_rerank_kernel<<<static_cast<unsigned>(P), kRerankThreads, smem, st>>>(
-      emb, (int)D, anchors, mp.sp.n_groups, reinterpret_cast<const uint2*>(ws + mp.sp.off_pool),
-      reinterpret_cast<const int*>(ws + mp.sp.off_pool_cnt), kc, pos64, semi_hard, screen_eps, sigma_floor,
-      ub_slack, neg_idx, neg_sim, flag, uncertified_rows, n_uncertified);
   ISB_CUDA(cudaGetLastError());
   if (uncertified_rows == nullptr) {   // no second line requested: resolve the rejected couples here
     mining_bruteforce_kernel<<<static_cast<unsigned>(P), kRerankThreads, smem, st>>>(

@@ -125,6 +125,40 @@ def test_select_negatives_dense_neighbourhoods_fall_to_the_second_line(M):
     assert idx.last_second_line > 0
 
 
+@pytest.mark.parametrize("semi", [False, True])
+def test_progressive_recheck_equals_the_full_recheck(M, semi):
+    # only the candidates the current exact winner cannot exclude are gathered (option
+    # mining_progressive, default on); the negatives must be those of the full re-check of all 16 --
+    # on ordinary clustered rows, on rows whose best negatives are packed inside the screen noise
+    # (many rounds), and in semi-hard mode where the best screen candidates sit at sim_pos (invalid:
+    # the list has to be walked down)
+    from instance_search_b200 import _lib
+    g = torch.Generator().manual_seed(31 + semi)
+    N, D, per = 6000, 192, 6
+    lab = torch.arange(N) // per
+    centers = torch.randn(N // per, D, generator=g)
+    E = centers[lab] + 0.5 * torch.randn(N, D, generator=g)
+    # a tight bundle: 300 rows of different labels within 2e-4 of one direction
+    E[::20] = torch.randn(1, D, generator=g) * D ** 0.5 + 2e-3 * torch.randn(300, D, generator=g)
+    E = oracle.normalize_l2(E)
+    anchors = torch.arange(0, N, 3)[:900]
+    positives = (anchors // per) * per + (anchors % per + 1) % per
+    idx = M.MiningIndex(E.cuda(), lab)
+    with _lib.options(mining_progressive=0):
+        n0, s0, _ = idx.select_negatives(anchors, positives, semi)
+        second0 = idx.last_second_line
+    n1, s1, _ = idx.select_negatives(anchors, positives, semi)
+    assert torch.equal(n0, n1) and torch.equal(s0, s1)
+    assert idx.last_second_line == second0
+    with _lib.options(mining_progressive=2):      # the one-CTA-per-couple kernel (what kc > 32 uses)
+        n2, s2, _ = idx.select_negatives(anchors, positives, semi)
+    assert torch.equal(n0, n2) and torch.equal(s0, s2)
+    with _lib.options(mining_kc=40):              # ... and with a list longer than a warp
+        n3, s3, _ = idx.select_negatives(anchors, positives, semi)
+    assert torch.equal(n0, n3) and torch.equal(s0, s3)
+    _check_negs(E, lab, anchors, positives, semi, n1, s1)
+
+
 def test_lab_indicators_and_device_rule(M):
     ds = [(None, "b", "0"), (None, "a", "1"), (None, "b", "2")]
     ind = M.get_lab_indicators(ds, 0)

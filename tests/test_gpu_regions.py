@@ -75,6 +75,9 @@ def _synthetic(B, C, H, W, ncls, D, seed):
     (2, 2048, 14, 14, 464, 64, 6),   # the reference's ResNet-152 head shape (config 2a), small D
     (2, 256, 32, 32, 464, 32, 6),    # 676 windows per image (config 2b map size)
     (4, 64, 9, 9, 10, 16, 12),       # k larger than the number of windows (9)
+    (3, 100, 14, 14, 12, 24, 6),     # small-map gather kernel, C not a multiple of its 32-channel step
+    (3, 72, 12, 16, 9, 16, 5),       # small-map gather kernel, run-time map width
+    (2, 40, 7, 8, 5, 16, 6),         # 2 windows, 56 pixels
 ])
 def test_region_random_vs_oracle(R, B, C, H, W, ncls, D, k):
     s = _synthetic(B, C, H, W, ncls, D, seed=B * 1000 + C)
@@ -198,3 +201,39 @@ def test_region_exact_line_is_complete_on_maps_with_more_than_32_windows(R, H, W
     d, c1, i1, n1 = R.region_descriptors(x, hw, k, (7, 7), stats=stats)       # the certified front door
     assert torch.equal(i1.cpu(), oi)
     check_descriptors(d, od)
+
+
+@pytest.mark.parametrize("B,C,H,W,k,k_sum", [(5, 200, 14, 14, 8, 6), (3, 64, 12, 16, 5, 5), (4, 2048, 14, 14, 8, 6),
+                                             (2, 96, 8, 8, 8, 3)])
+def test_small_map_gather_kernel_equals_the_channel_stream_kernel(R, B, C, H, W, k, k_sum):
+    # the plane-block kernel for maps of <= 256 pixels (option gather_small, default on) against the
+    # general kernel: the operand sums the same terms in the same order -> bit-identical bf16 hi / lo;
+    # the window means add their 49 terms column-wise instead of row-wise -> equal to fp32 rounding
+    from instance_search_b200 import _lib
+    g = torch.Generator().manual_seed(B * 100 + C)
+    x = torch.relu(torch.randn(B, C, H, W, generator=g)).cuda()
+    nwin = (H - 6) * (W - 6)
+    hw = R.HeadWeights(None, None, 0.01 * torch.randn(C * 49, generator=g).cuda(),
+                       torch.randn(8, C * 49, generator=g).cuda(), None)
+    idx = torch.stack([torch.randperm(nwin, generator=g)[:k] if nwin >= k else
+                       torch.arange(k) % nwin for _ in range(B)]).cuda()
+    nsel = torch.tensor([min(k, nwin) - (b % 2) for b in range(B)], dtype=torch.int32).cuda()
+    norm = (1.0 + torch.rand(B, k, generator=g)).cuda()
+    with _lib.options(gather_small=0):
+        h0, l0, m0 = R.region_gather(x, hw, k, (7, 7), idx, nsel, norm, k_sum=k_sum)
+    h1, l1, m1 = R.region_gather(x, hw, k, (7, 7), idx, nsel, norm, k_sum=k_sum)
+    assert torch.equal(h0.view(torch.int16), h1.view(torch.int16))
+    assert torch.equal(l0.view(torch.int16), l1.view(torch.int16))
+    for b in range(B):
+        n = int(nsel[b])
+        assert torch.allclose(m0[b, :n], m1[b, :n], rtol=2e-6, atol=1e-7)
+    # ... and the fix-up form (image list, no means) rewrites exactly the listed rows
+    lst = torch.tensor([B - 1, 0] + [0] * (B - 2), dtype=torch.int32).cuda()
+    n_list = torch.tensor([2], dtype=torch.int32).cuda()
+    h2, l2 = torch.zeros_like(h1), torch.zeros_like(l1)
+    R.region_gather(x, hw, k, (7, 7), idx, nsel, norm, k_sum=k_sum, want_means=False, out=(h2, l2),
+                    image_list=lst, n_list=n_list)
+    assert torch.equal(h2[0].view(torch.int16), h1[0].view(torch.int16))
+    assert torch.equal(l2[B - 1].view(torch.int16), l1[B - 1].view(torch.int16))
+    if B > 2:
+        assert int(h2[1].view(torch.int16).abs().sum()) == 0
