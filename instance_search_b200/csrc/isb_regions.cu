@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include "isb_host.cuh"
 #include "isb_gemm_core.cuh"
+#include "isb_topk.cuh"
 
 namespace isb {
 
@@ -914,6 +915,7 @@ struct RowSched {
 // ------------------------------------------------------------------ 3. candidates
 constexpr int kSelThreads = 256;
 constexpr int kRankSelectMaxWin = 1024;   // maps with more windows select by repeated arg-max
+constexpr int kRankSelectSmallWin = 128;  // up to here every window ranks itself against all others
 constexpr int kSelMaxCand = 32;   // k + margin
 
 __device__ __forceinline__ void block_argmax(float v, int i, float* s_val, int* s_idx, float& out_v,
@@ -965,7 +967,7 @@ region_candidates_kernel(const float* __restrict__ screen, int nwin, int ncand, 
     sc[i] = (v == v) ? v : -INFINITY;   // a NaN never outranks anything
   }
   __syncthreads();
-  if (nwin <= kRankSelectMaxWin) {
+  if (nwin <= kRankSelectSmallWin) {
     // rank selection: every window counts the windows that come before it in the order
     // (value desc, index asc); the ncand first write themselves to their slot.  One pass and
     // one barrier instead of ncand block-wide arg-max rounds (27 us per batch at 14 x 14).
@@ -982,6 +984,52 @@ region_candidates_kernel(const float* __restrict__ screen, int nwin, int ncand, 
           cand_out[b * ncand_max + rank] = i;
           cand_screen[b * ncand_max + rank] = v;
         }
+      }
+    }
+    __syncthreads();
+  } else if (nwin <= kRankSelectMaxWin) {
+    // larger maps (32 x 32: 676 windows -- the all-pairs ranking above cost 115 us per batch there):
+    // the ncand-th largest key by a warp radix select, the windows above it (and the lowest-indexed
+    // ties) compacted into a list, and the ranking done inside that list of ncand
+    uint32_t* skey = reinterpret_cast<uint32_t*>(sc + ((nwin + 3) & ~3));   // [nwin]
+    __shared__ int hist[256];
+    __shared__ int list[kSelMaxCand];
+    __shared__ uint32_t s_T;
+    __shared__ int s_ngt;
+    for (int i = tid; i < nwin; i += kSelThreads) skey[i] = f2key(__float_as_uint(sc[i]));
+    if (tid == 0) s_ngt = 0;
+    __syncthreads();
+    if (tid < 32) {
+      const uint32_t T = warp_kth_largest(skey, nwin, ncand, hist);
+      if (tid == 0) s_T = T;
+    }
+    __syncthreads();
+    const uint32_t T = s_T;
+    for (int i = tid; i < nwin; i += kSelThreads)
+      if (skey[i] > T) list[atomicAdd(&s_ngt, 1)] = i;      // fewer than ncand by construction
+    __syncthreads();
+    const int n_gt = s_ngt;
+    for (int i = tid; i < nwin; i += kSelThreads) {
+      if (skey[i] == T) {
+        int before = 0;
+        for (int j = 0; j < i; ++j) before += (skey[j] == T) ? 1 : 0;
+        if (n_gt + before < ncand) list[n_gt + before] = i;
+      }
+    }
+    __syncthreads();
+    if (tid < ncand) {
+      const int i = list[tid];
+      const float v = sc[i];
+      int rank = 0;
+      for (int u = 0; u < ncand; ++u) {
+        const int j = list[u];
+        const float s2 = sc[j];
+        rank += (s2 > v || (s2 == v && j < i)) ? 1 : 0;
+      }
+      cand[rank] = i;
+      if (blockIdx.y == 0) {
+        cand_out[b * ncand_max + rank] = i;
+        cand_screen[b * ncand_max + rank] = v;
       }
     }
     __syncthreads();
@@ -2119,7 +2167,7 @@ static bool make_region_plan(RegionPlan& p, int64_t B, int C, int H, int W, int 
   }
   p.off_partials = off; off = align_up(off + p.partials_bytes, 1024);
   p.total = off;
-  p.cand_smem = static_cast<size_t>((p.nwin + 3) & ~3) * 4;
+  p.cand_smem = static_cast<size_t>((p.nwin + 3) & ~3) * 4 * 2;   // scores + radix keys
   return true;
 }
 

@@ -352,62 +352,6 @@ constexpr int kSelWarps = 4;   // rows per CTA (launches may use fewer when a ro
 
 __host__ __device__ __forceinline__ size_t align_up_dev(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// k-th largest of n keys in shared memory by a 4 x 8-bit radix select; hist: 256 ints of
-// the warp's own scratch.  Precondition n >= kth >= 1; all 32 lanes call it together.
-__device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t* keys, int n, int kth, int* hist) {
-  const int lane = threadIdx.x & 31;
-  uint32_t prefix = 0u;
-  int remaining = kth;
-#pragma unroll 1
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    const uint32_t pmask = (pass == 0) ? 0u : (0xFFFFFFFFu << (shift + 8));
-    for (int b = lane; b < 256; b += 32) hist[b] = 0;
-    __syncwarp();
-    for (int e = lane; e < n; e += 32) {
-      const uint32_t key = keys[e];
-      if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
-    }
-    __syncwarp();
-    // lane L owns bins 255 - 8L ... 248 - 8L; running count from the top bin downwards
-    int c[8], local = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      c[j] = hist[255 - 8 * lane - j];
-      local += c[j];
-    }
-    int incl = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    const int excl = incl - local;
-    const bool mine = excl < remaining && remaining <= incl;
-    const uint32_t bal = __ballot_sync(0xffffffffu, mine);
-    if (bal == 0u) return 0u;   // n < kth (precondition violated): everything qualifies
-    const int src = __ffs(bal) - 1;
-    int d = 0, above = 0;
-    if (mine) {
-      int run = excl;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (run + c[j] >= remaining) {
-          d = 255 - 8 * lane - j;
-          above = run;
-          break;
-        }
-        run += c[j];
-      }
-    }
-    d = __shfl_sync(0xffffffffu, d, src);
-    above = __shfl_sync(0xffffffffu, above, src);
-    prefix |= static_cast<uint32_t>(d) << shift;
-    remaining -= above;
-    __syncwarp();
-  }
-  return prefix;
-}
 
 // Threshold seeding.  A row that starts its stream from -inf passes ~kc ln(N / kc) values and
 // the rows of a warp compact their buffers at the same tiles while they warm up -- a fixed
