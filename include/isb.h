@@ -35,7 +35,7 @@ extern "C" {
 #define ISB_ERR_WORKSPACE 3
 #define ISB_ERR_UNSUPPORTED_DEVICE 4
 
-#define ISB_ABI_VERSION 5
+#define ISB_ABI_VERSION 6
 
 /* Largest k (after the screening margin is added) one search call supports. */
 #define ISB_MAX_CANDIDATES 128
@@ -183,8 +183,8 @@ int isb_topk_merge(const float* cand_scores, const int64_t* cand_idx, int R, int
  *                                 cand_screen [Q, kc_out] fp32 (-inf = none), cand_col [Q, kc_out]
  *                                 int32 local row (-1 = none); `k`, `margin` as passed to the screen
  *      -- all-gather of cand_screen (4 bytes per candidate) --
- *   2. isb_topk_global_threshold  thr [Q] = the kc-th best screen score over all shards
- *                                 (all_screen [R, Q, kc]); -inf when fewer than kc exist
+ *   2. isb_topk_global_threshold  thr [Q] = the kth-best screen score over all shards
+ *                                 (all_screen [R, Q, kc]; kth <= 0: kth = kc); -inf when fewer exist
  *   3. isb_topk_rerank_owned      exact fp64-accumulated scores of ITS candidates >= thr, sorted
  *                                 best first into ONE packed row of 2k + 2 32-bit words per query:
  *                                 k scores (fp32, -inf padded) | k local rows (int32, -1 padded) |
@@ -198,11 +198,16 @@ int isb_topk_merge(const float* cand_scores, const int64_t* cand_idx, int R, int
  *                                 rows that fail are listed (resolve them with isb_topk_search on
  *                                 every shard + isb_topk_merge).
  * In total k + margin database rows are gathered per query, independent of R.
+ * Reduced lists: the global top (k + margin) spreads over the shards, so a shard may list fewer
+ * candidates than that (screen with k' + margin' = kc < k + margin; kth = k + margin in step 2; kc
+ * may be smaller than k in step 3): its screen keeps fewer rows per query and warms its thresholds
+ * up faster.  A shard whose FULL list lies entirely above thr may have been cut above it; step 3
+ * then reports infinite noise for the row and step 4 lists it as uncertified.
  * Replaces the same reference lines as isb_topk_search; the reference is single-device. */
 int isb_topk_candidates(int64_t Q, int64_t N, int64_t D, int k, int margin, int kc_out,
                         float* cand_screen, int32_t* cand_col, void* workspace,
                         size_t workspace_bytes, void* stream);
-int isb_topk_global_threshold(const float* all_screen, int R, int64_t Q, int kc, float* thr,
+int isb_topk_global_threshold(const float* all_screen, int R, int64_t Q, int kc, int kth, float* thr,
                               void* stream);
 int isb_topk_rerank_owned(const float* q, int64_t Q, const float* db_f32, int64_t N, int64_t D,
                           int k, int kc, const float* cand_screen, const int32_t* cand_col,

@@ -16,7 +16,7 @@ c_f32 = ctypes.c_float
 c_ptr = ctypes.c_void_p
 c_size = ctypes.c_size_t
 
-ABI_VERSION = 5   # == ISB_ABI_VERSION in include/isb.h
+ABI_VERSION = 6   # == ISB_ABI_VERSION in include/isb.h
 
 # name -> (restype, argtypes); mirrors include/isb.h one to one
 SIGNATURES = {
@@ -44,7 +44,7 @@ SIGNATURES = {
     "isb_topk_merge": (c_int, [c_ptr, c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
     "isb_topk_candidates": (c_int, [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_size,
                                     c_ptr]),
-    "isb_topk_global_threshold": (c_int, [c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr]),
+    "isb_topk_global_threshold": (c_int, [c_ptr, c_int, c_i64, c_int, c_int, c_ptr, c_ptr]),
     "isb_topk_rerank_owned": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr,
                                       c_ptr, c_ptr]),
     "isb_topk_merge_certified": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr,

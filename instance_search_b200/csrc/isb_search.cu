@@ -500,11 +500,12 @@ pool_candidates_cta_kernel(int n_groups, const uint2* __restrict__ pool, const i
   }
 }
 
-// (2) thr[row] = the kc-th largest of the row's R * kc gathered screen scores
-// (all_screen [R, Q, kc], -inf = no entry); -inf when fewer than kc entries exist, i.e.
-// when no shard dropped anything that could matter.
+// (2) thr[row] = the kth-largest of the row's R * kc gathered screen scores
+// (all_screen [R, Q, kc], -inf = no entry); -inf when fewer than kth entries exist, i.e.
+// when no shard dropped anything that could matter.  kth = kc: every shard lists as many
+// candidates as the result needs; kth > kc: reduced lists (see isb_topk_rerank_owned).
 __global__ void __launch_bounds__(32 * kSelWarps)
-global_threshold_kernel(const float* __restrict__ all_screen, int R, int64_t Q, int kc,
+global_threshold_kernel(const float* __restrict__ all_screen, int R, int64_t Q, int kc, int kth,
                         float* __restrict__ thr) {
   extern __shared__ __align__(16) uint8_t gt_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -523,7 +524,16 @@ global_threshold_kernel(const float* __restrict__ all_screen, int R, int64_t Q, 
   valid = __reduce_add_sync(0xffffffffu, valid);
   __syncwarp();
   float t = -INFINITY;
-  if (valid >= kc) t = __uint_as_float(key2f(warp_kth_largest(keys, n, kc, hist)));
+  if (valid >= kth) {
+    t = __uint_as_float(key2f(warp_kth_largest(keys, n, kth, hist)));
+  } else if (kth > kc) {
+    // reduced lists: fewer than kth entries overall, yet a shard whose list is FULL (its last slot
+    // is taken) may have dropped rows -- nothing can be concluded: +inf sends the row to the
+    // second line (nothing is re-ranked, the merge cannot certify)
+    bool full = false;
+    for (int r = lane; r < R; r += 32) full |= keys[r * kc + kc - 1] > kKeyNegInf;
+    if (__any_sync(0xffffffffu, full)) t = INFINITY;
+  }
   if (lane == 0) thr[row] = t;
 }
 
@@ -544,17 +554,26 @@ rerank_owned_kernel(const float* __restrict__ q, const float* __restrict__ db, i
     reinterpret_cast<float4*>(qs)[i] = __ldg(reinterpret_cast<const float4*>(q + static_cast<size_t>(row) * D) + i);
   __syncthreads();
   const float t = thr[row];
+  int n_above = 0;   // listed entries strictly above the threshold
   for (int j = tid; j < kc; j += kRerankThreads) {
     const float s = cand_screen[static_cast<size_t>(row) * kc + j];
     const int c = cand_col[static_cast<size_t>(row) * kc + j];
+    n_above += (c >= 0 && s > t) ? 1 : 0;
     if (c >= 0 && s >= t) {
       const int pos = atomicAdd(&sm.sel, 1);
       sm.sel_col[pos] = c;
       sm.sel_screen[pos] = s;
     }
   }
-  __syncthreads();
+  n_above = __syncthreads_count(n_above);   // kc <= 128 < kRerankThreads: one entry per thread at most
   const int n_sel = sm.sel;
+  // Reduced lists (kc shorter than the k + margin the threshold is the rank of): a FULL list whose
+  // every entry lies strictly above the threshold may have been cut above it -- rows of this shard
+  // that were not listed could still score above thr, and the global certificate would not cover
+  // them.  The row is then handed to the merge as uncertifiable (infinite noise).  With full-length
+  // lists the condition cannot occur: thr is the kc-th best overall, so no shard holds kc entries
+  // strictly above it.
+  const bool cut_above_thr = n_above == kc;
   exact_scores(sm, qs, db, D, n_sel);
   double d2 = 0.0;
   if (tid < n_sel) {
@@ -574,7 +593,7 @@ rerank_owned_kernel(const float* __restrict__ q, const float* __restrict__ db, i
     out[k + j] = static_cast<uint32_t>(ok ? sm.sel_col[j] : -1);
   }
   if (tid == 0) {
-    out[2 * k] = __float_as_uint(static_cast<float>(s_sig2));
+    out[2 * k] = __float_as_uint(cut_above_thr ? INFINITY : static_cast<float>(s_sig2));
     out[2 * k + 1] = __float_as_uint(static_cast<float>(n_sel));
   }
 }
@@ -1342,7 +1361,12 @@ static int pick_n_groups(int m_blocks, int n_tiles, int grid) {
   auto efficiency = [&](int ng) {
     const long long segs = static_cast<long long>(m_blocks) * ng;
     const long long waves = (segs + grid - 1) / grid;
-    return static_cast<double>(segs) / static_cast<double>(waves * grid);
+    // the waves run in step (wave barrier), so a wave lasts as long as its longest segment: groups of
+    // unequal tile counts cost mean / max (64 n-tiles in 15 groups of 4 or 5: 0.85 -- the mining
+    // configuration; immaterial for the search, whose groups hold ~100 tiles)
+    const double balance = static_cast<double>(n_tiles) / static_cast<double>(ng) /
+                           static_cast<double>((n_tiles + ng - 1) / ng);
+    return balance * static_cast<double>(segs) / static_cast<double>(waves * grid);
   };
   double best_eff = -1.0;
   for (int ng = lo; ng <= hi; ++ng) best_eff = efficiency(ng) > best_eff ? efficiency(ng) : best_eff;
@@ -1767,17 +1791,20 @@ extern "C" int isb_topk_candidates(int64_t Q, int64_t N, int64_t D, int k, int m
   return ISB_OK;
 }
 
-extern "C" int isb_topk_global_threshold(const float* all_screen, int R, int64_t Q, int kc, float* thr,
+extern "C" int isb_topk_global_threshold(const float* all_screen, int R, int64_t Q, int kc, int kth, float* thr,
                                          void* stream) {
   ISB_CHECK_ARG(all_screen && thr, "isb_topk_global_threshold: null pointer");
   ISB_CHECK_ARG(R >= 1 && Q >= 0 && kc >= 1 && kc <= ISB_MAX_CANDIDATES, "isb_topk_global_threshold: bad shape");
+  if (kth <= 0) kth = kc;
+  ISB_CHECK_ARG(kth >= kc && kth <= ISB_MAX_CANDIDATES, "isb_topk_global_threshold: need kc <= kth <= %d",
+                ISB_MAX_CANDIDATES);
   if (Q == 0) return ISB_OK;
   const size_t smem = static_cast<size_t>(kSelWarps) * (static_cast<size_t>(R) * kc + 256) * 4;
   ISB_CHECK_ARG(smem <= 200 * 1024, "isb_topk_global_threshold: R * kc (%d) too large", R * kc);
   if (smem > 48 * 1024)
     ISB_CUDA(cudaFuncSetAttribute(global_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   global_threshold_kernel<<<static_cast<unsigned>((Q + kSelWarps - 1) / kSelWarps), 32 * kSelWarps, smem,
-                            static_cast<cudaStream_t>(stream)>>>(all_screen, R, Q, kc, thr);
+                            static_cast<cudaStream_t>(stream)>>>(all_screen, R, Q, kc, kth, thr);
   ISB_CUDA(cudaGetLastError());
   return ISB_OK;
 }
@@ -1787,8 +1814,8 @@ extern "C" int isb_topk_rerank_owned(const float* q, int64_t Q, const float* db_
                                      const float* thr, uint32_t* packed, void* stream) {
   ISB_CHECK_ARG(q && db_f32 && cand_screen && cand_col && thr && packed, "isb_topk_rerank_owned: null pointer");
   ISB_CHECK_ARG(Q >= 0 && N > 0 && D > 0 && D % 8 == 0, "isb_topk_rerank_owned: bad shape");
-  ISB_CHECK_ARG(k >= 1 && kc >= k && kc <= ISB_MAX_CANDIDATES, "isb_topk_rerank_owned: need 1 <= k <= kc <= %d",
-                ISB_MAX_CANDIDATES);
+  ISB_CHECK_ARG(k >= 1 && k <= ISB_MAX_CANDIDATES && kc >= 1 && kc <= ISB_MAX_CANDIDATES,
+                "isb_topk_rerank_owned: need 1 <= k, kc <= %d", ISB_MAX_CANDIDATES);
   ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(db_f32) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(packed) & 3) == 0, "isb_topk_rerank_owned: misaligned input");
   if (Q == 0) return ISB_OK;

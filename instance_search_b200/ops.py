@@ -310,14 +310,15 @@ def topk_merge(cand_scores, cand_idx):
     return scores, idx
 
 
-def topk_global_threshold(all_screen):
+def topk_global_threshold(all_screen, kth=0):
     """all_screen [R, Q, kc] fp32 (the all-gathered screen scores of every shard's
-    candidates, -inf = none) -> thr [Q]: the kc-th best per query, -inf when fewer exist."""
+    candidates, -inf = none) -> thr [Q]: the kth-best per query (kth <= 0: kc), -inf when
+    fewer exist."""
     _need_cuda(all_screen)
     all_screen = _f32c(all_screen)
     R, Q, kc = all_screen.shape
     thr = torch.empty((Q,), dtype=torch.float32, device=all_screen.device)
-    _lib.check(_lib.lib().isb_topk_global_threshold(all_screen.data_ptr(), R, Q, kc, thr.data_ptr(), _stream()),
+    _lib.check(_lib.lib().isb_topk_global_threshold(all_screen.data_ptr(), R, Q, kc, int(kth), thr.data_ptr(), _stream()),
                "isb_topk_global_threshold")
     return thr
 

@@ -208,6 +208,10 @@ class ShardedIndex(object):
         self.device = local_db.device
         self.stats = {}
         self._row_offsets = None
+        # reduced candidate lists (see list_length); switched off by the first batch whose rows
+        # the reduction sends to the second line in numbers (a database sorted by instance puts a
+        # query's neighbours on ONE shard)
+        self.reduce_lists = True
         self.local = self._make_local(local_db, self.lo)
 
     # hooks (the gloo CPU tests replace them to exercise the plumbing)
@@ -223,8 +227,22 @@ class ShardedIndex(object):
     def _local_candidates(self, q, k, kc, events=None):
         return self.local.candidates(q, k, kc, events)
 
-    def _global_threshold(self, all_screen):
-        return ops.topk_global_threshold(all_screen)
+    def _global_threshold(self, all_screen, kth):
+        return ops.topk_global_threshold(all_screen, kth)
+
+    def list_length(self, kc):
+        """Candidates a shard lists per query.  The global top kc = k + margin spreads over the R
+        shards (kc / R per shard on average when rows are placed independently of their content),
+        so a shard lists mean + 6 sigma + 8 of them instead of kc: its screen keeps fewer rows
+        per query -- 48 instead of 128 at R = 8, which is 9 % of the screen's time on a 125k-row
+        shard (threshold warm-up, buffer compactions).  A list that turns out to have been cut
+        above the global threshold is detected (isb_topk_rerank_owned) and the row goes to the
+        second line, so the result does not depend on the assumption -- only the speed does."""
+        R = self.world_size
+        if R == 1 or not self.reduce_lists:
+            return kc
+        mean = kc / float(R)
+        return min(kc, int(mean + 6.0 * mean ** 0.5 + 0.999) + 8)
 
     def _rerank_owned(self, q, k, cand_screen, cand_col, thr):
         return self.local.rerank_owned(q, k, cand_screen, cand_col, thr)
@@ -282,8 +300,9 @@ class ShardedIndex(object):
             r = self._search_replicated_rerank(q, k, events)
             return r + (None,) if defer else r
         kk = min(k, self.n_total)
-        kc = min(kk + ops.DEFAULT_MARGIN, ops.MAX_CANDIDATES)
-        cand_screen, cand_col = self._local_candidates(q, kk, kc, events)
+        kc = min(kk + ops.DEFAULT_MARGIN, ops.MAX_CANDIDATES)   # rank of the global threshold
+        kl = self.list_length(kc)                               # entries listed per shard
+        cand_screen, cand_col = self._local_candidates(q, min(kk, kl), kl, events)
         # defer=True: everything after the screen (two all-gathers, threshold, re-rank of the owned
         # candidates, merge: no tensor cores, ~1 ms) runs on a side stream, i.e. UNDER the screen
         # of the next batch when searches are queued back to back
@@ -297,7 +316,7 @@ class ShardedIndex(object):
             for t in (q, cand_screen, cand_col):
                 t.record_stream(side)
         with (torch.cuda.stream(side) if side is not None else _NoStream()):
-            thr = self._global_threshold(self._gather(cand_screen))
+            thr = self._global_threshold(self._gather(cand_screen), kc)
             packed = self._rerank_owned(q, kk, cand_screen, cand_col, thr)
             ms, mi, unc_rows, n_unc = self._merge_certified(self._gather(packed), thr, kk)
             if side is not None:
@@ -307,6 +326,8 @@ class ShardedIndex(object):
         def fixup(n_bad):
             self.stats["rows"] = self.stats.get("rows", 0) + q.size(0)
             self.stats["resolved_locally_exact"] = self.stats.get("resolved_locally_exact", 0) + n_bad
+            if kl < kc and n_bad > max(2, q.size(0) // 50):
+                self.reduce_lists = False   # n_bad is the same on every rank: so is the switch
             if n_bad:
                 # rows the global certificate rejects (the same on every rank): every shard answers
                 # them with its own certified search (fp32-grade re-screen / exhaustive as needed),

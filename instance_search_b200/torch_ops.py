@@ -117,9 +117,9 @@ def topk_candidates(q: T, db_bf16: T, k: int, kc: int) -> Tuple[T, T]:
     return _ops.topk_candidates(q, db_bf16, k, kc)
 
 
-@_op("topk_global_threshold", lambda all_screen: all_screen.new_empty((all_screen.size(1),)))
-def topk_global_threshold(all_screen: T) -> T:
-    return _ops.topk_global_threshold(all_screen)
+@_op("topk_global_threshold", lambda all_screen, kth=0: all_screen.new_empty((all_screen.size(1),)))
+def topk_global_threshold(all_screen: T, kth: int = 0) -> T:
+    return _ops.topk_global_threshold(all_screen, kth)
 
 
 @_op("topk_rerank_owned",

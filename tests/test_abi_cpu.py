@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported_and_bound(L):
 
 
 def test_abi_version(L):
-    assert L.isb_abi_version() == 5
+    assert L.isb_abi_version() == 6
 
 
 def test_argument_errors_need_no_gpu(L):

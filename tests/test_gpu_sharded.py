@@ -22,8 +22,9 @@ def _rows(n, d, seed):
     return oracle.normalize_l2(torch.randn(n, d, generator=g))
 
 
-def _lockstep_search(q, db, k, R, kc=None):
-    """What R ranks compute, on one device.  Returns (scores, idx, n_uncertified, stats)."""
+def _lockstep_search(q, db, k, R, kc=None, kl=None):
+    """What R ranks compute, on one device.  Returns (scores, idx, n_uncertified, stats).
+    kl: entries listed per shard (None: kc, full lists; ShardedIndex.list_length reduces it)."""
     from instance_search_b200 import ops
     from instance_search_b200.search import DescriptorIndex, shard_bounds
     dev = torch.device("cuda:0")
@@ -32,9 +33,10 @@ def _lockstep_search(q, db, k, R, kc=None):
     if kc is None:
         kc = min(kk + ops.DEFAULT_MARGIN, ops.MAX_CANDIDATES)
     shards = [DescriptorIndex(db[lo:hi].to(dev), lo) for lo, hi in shard_bounds(db.size(0), R)]
-    cands = [sh.candidates(qd, kk, kc) for sh in shards]
+    kl = kc if kl is None else kl
+    cands = [sh.candidates(qd, min(kk, kl), kl) for sh in shards]
     all_screen = torch.stack([c[0] for c in cands])                 # all-gather 1
-    thr = ops.topk_global_threshold(all_screen)
+    thr = ops.topk_global_threshold(all_screen, kc)
     packed_all = torch.stack([sh.rerank_owned(qd, kk, c[0], c[1], thr) for sh, c in zip(shards, cands)])  # all-gather 2
     offs = torch.tensor([lo for lo, _ in shard_bounds(db.size(0), R)], dtype=torch.int64, device=dev)
     s, i, unc_rows, n_unc = ops.topk_merge_certified(packed_all, offs, thr, kk)
@@ -64,6 +66,54 @@ def test_candidate_exchange_equals_oracle(R, Q, N, D, k):
     assert int(st["scored"].max()) <= min(kc, N) + 4
 
 
+@pytest.mark.parametrize("R,Q,N,D,k", [(8, 60, 40000, 128, 100), (4, 33, 20011, 256, 100), (2, 20, 9000, 64, 100),
+                                       (3, 12, 2000, 64, 100)])
+def test_reduced_candidate_lists_equal_full_lists(R, Q, N, D, k):
+    # every shard lists mean + 6 sigma + 8 candidates instead of k + margin (ShardedIndex.list_length):
+    # same result, same number of exact re-ranks in total, and no row needs the second line when
+    # the rows are placed at random
+    from instance_search_b200.search import ShardedIndex
+    q, db = _rows(Q, D, 31), _rows(N, D, 32)
+    kc = min(k + 28, 128)
+    probe = ShardedIndex.__new__(ShardedIndex)
+    probe.world_size, probe.reduce_lists = R, True
+    kl = probe.list_length(kc)
+    assert kl < kc and R * kl >= kc
+    s0, i0, n0, st0 = _lockstep_search(q, db, k, R)
+    s1, i1, n1, st1 = _lockstep_search(q, db, k, R, kl=kl)
+    assert n0 == 0 and n1 == 0
+    assert torch.equal(i0, i1) and torch.equal(s0, s1)
+    assert torch.equal(st0["thr"], st1["thr"]) and torch.equal(st0["scored"], st1["scored"])
+    check_topk_against_oracle(q, db, k, s1, i1)
+
+
+def test_reduced_list_cut_above_the_threshold_is_reported():
+    # a database sorted by content: the queries' neighbours all sit on shard 0, whose reduced list
+    # (48 of the 128 wanted) is cut far above the global threshold -> every such row must be
+    # reported as uncertified (never answered from the incomplete lists); rows whose neighbours are
+    # spread out stay certified
+    R, N, D, k = 8, 16000, 64, 100
+    g = torch.Generator().manual_seed(5)
+    centre = torch.randn(1, D, generator=g)
+    db = oracle.normalize_l2(torch.randn(N, D, generator=g))
+    db[:600] = oracle.normalize_l2(centre + 0.2 * torch.randn(600, D, generator=g))   # one tight cluster on shard 0
+    q = torch.cat([oracle.normalize_l2(centre + 0.2 * torch.randn(10, D, generator=g)),      # near the cluster
+                   oracle.normalize_l2(torch.randn(10, D, generator=g))])                    # anywhere
+    s, i, n_unc, st = _lockstep_search(q, db, k, R, kl=48)
+    bad = set(st["unc_rows"][:n_unc].tolist())
+    assert set(range(10)) <= bad                       # cut lists detected
+    ok = [r for r in range(20) if r not in bad]
+    assert len(ok) >= 8
+    o_s, o_i = oracle.topk_search(q, db, k)
+    assert torch.equal(i.cpu()[ok], o_i[ok])
+    # with full lists no list is cut: whatever the certificate still rejects there is the dense
+    # neighbourhood itself (600 near-duplicates within bf16 noise), not the exchange
+    s2, i2, n2, st2 = _lockstep_search(q, db, k, R)
+    ok2 = [r for r in range(20) if r not in set(st2["unc_rows"][:n2].tolist())]
+    assert set(range(10, 20)) <= set(ok2)
+    assert torch.equal(i2.cpu()[ok2], o_i[ok2])
+
+
 def test_candidate_exchange_matches_single_index():
     from instance_search_b200.search import DescriptorIndex
     q, db = _rows(64, 512, 21), _rows(30000, 512, 22)
@@ -86,6 +136,16 @@ def test_global_threshold_kernel_is_the_kc_th_best():
     x[:, 6, :] = 0.25                             # all tied
     x[2, 7, :] = x[3, 7, :]                       # duplicated values across shards
     thr = ops.topk_global_threshold(x.cuda()).cpu()
+    # a rank beyond the list length (reduced lists): the 20th best of 3 x 9 entries
+    x9 = torch.randn(3, 11, 9)
+    want = x9.permute(1, 0, 2).reshape(11, 27).sort(dim=1, descending=True).values[:, 19]
+    assert torch.equal(ops.topk_global_threshold(x9.cuda(), 20).cpu(), want)
+    # ... fewer than that exist while a list is full: nothing can be concluded -> +inf
+    x9[:, 4, 3:] = float("-inf")
+    x9[1, 4] = torch.arange(9.0)
+    assert ops.topk_global_threshold(x9.cuda(), 20).cpu()[4] == float("inf")
+    x9[1, 4, 8] = float("-inf")
+    assert ops.topk_global_threshold(x9.cuda(), 20).cpu()[4] == float("-inf")
     flat = x.permute(1, 0, 2).reshape(Q, R * kc)
     want = flat.sort(dim=1, descending=True).values[:, kc - 1]
     assert torch.equal(thr, want)

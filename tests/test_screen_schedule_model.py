@@ -15,7 +15,8 @@ def pick_n_groups(m_blocks, n_tiles, grid):
     def eff(ng):
         segs = m_blocks * ng
         waves = (segs + grid - 1) // grid
-        return segs / (waves * grid)
+        balance = (n_tiles / ng) / ((n_tiles + ng - 1) // ng)    # waves run in step: mean / max tiles per group
+        return balance * segs / (waves * grid)
     best = max(eff(ng) for ng in range(lo, hi + 1))
     for ng in range(lo, hi + 1):
         if eff(ng) >= best - 0.01:
@@ -75,3 +76,5 @@ def test_headline_plans():
     shard = plan(10000, 125000)              # the per-GPU shard of the 8-GPU run
     assert shard["pair"] and shard["n_groups"] == 11
     assert not plan(64, 70000)["pair"]       # a single row block: the single-CTA kernel
+    mining = plan(16384, 16384)              # BASELINE configs[2]: 64 n-tiles -> 16 groups of 4, not 15 of 4 or 5
+    assert mining["pair"] and mining["n_tiles"] % mining["n_groups"] == 0

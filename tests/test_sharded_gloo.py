@@ -79,11 +79,18 @@ def _worker(rank, world, port, n_total, k, out_dir):
             cs[:, :n], cc[:, :n] = v, c.int()
             return cs, cc
 
-        def _global_threshold(self, all_screen):
+        def _global_threshold(self, all_screen, kth_rank):
             R, Q, kc = all_screen.shape
+            assert kth_rank >= kc
             flat = all_screen.permute(1, 0, 2).reshape(Q, R * kc)
-            kth = flat.sort(dim=1, descending=True).values[:, kc - 1]
-            return torch.where((flat > float("-inf")).sum(1) >= kc, kth, torch.full_like(kth, float("-inf")))
+            srt = flat.sort(dim=1, descending=True).values
+            kth = srt[:, kth_rank - 1] if kth_rank <= R * kc else torch.full((Q,), float("-inf"))
+            enough = (flat > float("-inf")).sum(1) >= kth_rank
+            # reduced lists: too few entries overall but some shard's list is full -> +inf (nothing
+            # can be concluded; the merge cannot certify)
+            full = (all_screen[:, :, kc - 1] > float("-inf")).any(0) & (kth_rank > kc)
+            short = torch.where(full, torch.full_like(kth, float("inf")), torch.full_like(kth, float("-inf")))
+            return torch.where(enough, kth, short)
 
         def _rerank_owned(self, q, k, cand_screen, cand_col, thr):
             sim = oracle.similarity(q, self.local.rows)
@@ -103,6 +110,9 @@ def _worker(rank, world, port, n_total, k, out_dir):
             s[:, :n], i[:, :n] = e2[:, :n], g2[:, :n]
             d = torch.where(own, cand_screen - sim.gather(1, cand_col.clamp(min=0).long()), torch.zeros_like(exact))
             stat = torch.stack([(d * d).sum(1), own.sum(1).float()], 1)
+            # a full list that lies entirely above the threshold may have been cut above it
+            cut = ((cand_col >= 0) & (cand_screen > thr[:, None])).sum(1) == kc
+            stat[cut, 0] = float("inf")
             # packed row (include/isb.h): k scores | k LOCAL rows | 2 stat words, 32 bits each
             col = torch.where(i >= 0, i - self.local.off, i).int()
             return torch.cat([s.view(torch.int32), col, stat.view(torch.int32)], 1)
@@ -118,7 +128,7 @@ def _worker(rank, world, port, n_total, k, out_dir):
             # every candidate >= thr was re-ranked by exactly one shard
             total = stat[:, :, 1].sum(0)
             kc = min(k + 28, 128)
-            assert bool(((total >= min(kc, n_total)) | (thr == float("-inf"))).all())
+            assert bool(((total >= min(kc, n_total)) | (thr == float("-inf")) | (thr == float("inf"))).all())
             s, i = self._merge(cs, ci)
             # pretend the certificate rejects every 5th row (listed in a rank-dependent order,
             # like the device's atomicAdd): the resolve path must reproduce them exactly

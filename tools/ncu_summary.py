@@ -17,7 +17,7 @@ KEEP = re.compile(
     r"sm__warps_active\.avg\.pct_of_peak_sustained_active|launch__registers_per_thread|"
     r"launch__grid_size|launch__block_size|launch__shared_mem_per_block_dynamic|"
     r"launch__occupancy_limit_\w+|lts__t_sector_hit_rate\.pct|lts__t_bytes\.sum|"
-    r"l1tex__t_bytes\.sum|smsp__inst_executed\.sum|sm__inst_executed_pipe_uniform\.sum|"
+    r"l1tex__t_bytes\.sum|lts__throughput\.avg\.pct_of_peak_sustained_elapsed|l1tex__throughput\.avg\.pct_of_peak_sustained_elapsed|lts__t_sectors_srcunit_tex\.sum|sm__inst_executed_pipe_tma\.sum|smsp__inst_executed\.sum|sm__inst_executed_pipe_uniform\.sum|"
     r"smsp__average_warps_issue_stalled_\w+_per_issue_active\.ratio|"
     r"smsp__cycles_active\.avg)$")
 
