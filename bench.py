@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--k", type=int, default=K_DEFAULT)
     ap.add_argument("--cpu-sample-queries", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-upload", default="auto", choices=["auto", "split", "full"],
+                    help="N > 1: how the pinned host queries reach every rank -- split: 1/N of the rows per rank + an "
+                         "NVLink all-gather (on the search stream); full: every rank copies all rows over its own "
+                         "PCIe link (copy engine only, hidden under the previous batch's screen); auto = full")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the side measurements: region descriptors / mining (N=1 only) and the "
                          "end-to-end configs[4] leg (every N)")
@@ -351,9 +355,11 @@ def run_b200(a, rank, world, local_rank):
     copy_in, copy_out = torch.cuda.Stream(), torch.cuda.Stream()
     inflight = {"q": None, "ready": None, "out": []}
 
+    upload_full = world > 1 and a.e2e_upload in ("auto", "full")
+
     def start_upload():
         with torch.cuda.stream(copy_in):
-            lo_q, hi_q = shard_bounds(a.queries, world)[rank] if world > 1 else (0, a.queries)
+            lo_q, hi_q = shard_bounds(a.queries, world)[rank] if (world > 1 and not upload_full) else (0, a.queries)
             part = q_host[lo_q:hi_q].to(dev, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
@@ -365,7 +371,7 @@ def run_b200(a, rank, world, local_rank):
         torch.cuda.current_stream().wait_event(inflight["ready"])
         part = inflight["q"]
         part.record_stream(torch.cuda.current_stream())
-        q = index.gather_queries(part, a.queries) if world > 1 else part
+        q = index.gather_queries(part, a.queries) if (world > 1 and not upload_full) else part
         start_upload()                             # next batch's H2D overlaps this batch's search
         s, i, t = index.search(q, a.k, defer=True)
         done = torch.cuda.Event()
@@ -463,11 +469,14 @@ def run_b200(a, rank, world, local_rank):
             "data": "synthetic (seeded unit-norm Gaussian rows)", "config": workload_config(a, world),
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT,
+                    # bytes every rank copies per step (full: all rows on each rank; split: 1/N each)
                     "h2d_bytes_per_step": q_host.numel() * 4,
+                    "h2d_mode": ("full rows on every rank over its own PCIe link" if upload_full else
+                                 "1/N of the rows per rank + NVLink all-gather") if world > 1 else "single GPU",
                     "d2h_bytes_per_step": out_s_host.numel() * 4 + out_i_host.numel() * 8,
                     "ms_per_step": ms_e2e / a.steps,
                     "pipeline": "double-buffered serving loop: pinned-host queries of batch i+1 are copied H2D "
-                                "(1/N of the rows per rank, all-gathered over NVLink) and the results of batch "
+                                "(see h2d_mode) and the results of batch "
                                 "i-1 D2H on copy streams while batch i is searched; all copies of all %d batches "
                                 "and the wait for the last results are inside the timed region" % a.steps},
             "gpu_launches": launches_per_step * a.steps * 2,  # resident + e2e timed regions

@@ -68,7 +68,8 @@ enum {
   ISB_OPT_GEMM_PAIR = 12,        /* 1 (default): CTA-pair kernel for isb_gemm_nt[_split] with >= 2 row blocks */
   ISB_OPT_MINING_PROGRESSIVE = 13, /* exact re-check of a couple's candidates: 1 (default) progressive, 0 all of them, 2 progressive with the one-CTA-per-couple kernel */
   ISB_OPT_GATHER_SMALL = 14,     /* 1 (default): plane-block gather kernel for maps of <= 256 pixels; 0: off */
-  ISB_OPT_COUNT_ = 15
+  ISB_OPT_SCREEN_GROUPS = 15,    /* n-groups of the screen's work decomposition (default 0: chosen for whole waves) */
+  ISB_OPT_COUNT_ = 16
 };
 int isb_set_option(int option, int value);
 int isb_get_option(int option);

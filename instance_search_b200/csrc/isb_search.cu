@@ -1350,32 +1350,36 @@ struct SearchPlan {
   bool seed;   // thresholds seeded from the first kSeedRows database rows
 };
 
-// Pick the number of n-groups so that m_blocks * n_groups segments fill whole
-// waves of the persistent grid (segments are handed out round-robin).
+// Pick the number of n-groups.  Cost model of a decomposition (in n-tile times): the segments are
+// handed out round-robin and the waves run in step (wave barrier), so the screen lasts
+//     waves x (tiles of the longest segment + kSegOverheadTiles),
+// the overhead being what every segment pays before its MMA pipe runs full: the wave gate, the
+// refill of the operand ring and a threshold warm-up (compactions).  Fitted on the mining
+// configuration (16 384 x 16 384: 64 row-block pairs x 64 n-tiles on 74 CTA pairs), where ONE group
+// on 64 of the 74 pairs (0.99 ms) beats 8 groups in 7 full waves (1.08 ms) and 22 groups (1.41 ms):
+// 2.7 tiles per segment.  For the search (hundreds of tiles per segment) the term is immaterial and
+// the choice is the one that fills whole waves, as before.
+constexpr double kSegOverheadTiles = 3.0;
+
 static int pick_n_groups(int m_blocks, int n_tiles, int grid) {
-  int lo = (grid + m_blocks - 1) / m_blocks;
-  if (lo < 1) lo = 1;
-  if (lo > n_tiles) lo = n_tiles;
-  int hi = lo * 8 + 8;
+  int hi = ((grid + m_blocks - 1) / m_blocks) * 8 + 8;
   if (hi > n_tiles) hi = n_tiles;
+  if (hi < 1) hi = 1;
   auto efficiency = [&](int ng) {
     const long long segs = static_cast<long long>(m_blocks) * ng;
     const long long waves = (segs + grid - 1) / grid;
-    // the waves run in step (wave barrier), so a wave lasts as long as its longest segment: groups of
-    // unequal tile counts cost mean / max (64 n-tiles in 15 groups of 4 or 5: 0.85 -- the mining
-    // configuration; immaterial for the search, whose groups hold ~100 tiles)
-    const double balance = static_cast<double>(n_tiles) / static_cast<double>(ng) /
-                           static_cast<double>((n_tiles + ng - 1) / ng);
-    return balance * static_cast<double>(segs) / static_cast<double>(waves * grid);
+    const double longest = static_cast<double>((n_tiles + ng - 1) / ng) + kSegOverheadTiles;
+    const double ideal = static_cast<double>(m_blocks) * n_tiles / grid;
+    return ideal / (static_cast<double>(waves) * longest);
   };
   double best_eff = -1.0;
-  for (int ng = lo; ng <= hi; ++ng) best_eff = efficiency(ng) > best_eff ? efficiency(ng) : best_eff;
-  // the FEWEST groups within 1 % of the best wave efficiency: longer segments mean fewer wave
-  // barriers, fewer threshold warm-ups, fewer groups straddling a wave boundary (each straddle
-  // streams the group's database range from HBM again) and a smaller candidate pool
-  for (int ng = lo; ng <= hi; ++ng)
+  for (int ng = 1; ng <= hi; ++ng) best_eff = efficiency(ng) > best_eff ? efficiency(ng) : best_eff;
+  // the FEWEST groups within 1 % of the best: longer segments mean fewer wave barriers, fewer
+  // groups straddling a wave boundary (each straddle streams the group's database range from HBM
+  // again) and a smaller candidate pool
+  for (int ng = 1; ng <= hi; ++ng)
     if (efficiency(ng) >= best_eff - 0.01) return ng;
-  return lo;
+  return 1;
 }
 
 // ISB_OPT_SCREEN_PAIR = 0 keeps the single-CTA 128 x 256 kernel (A/B switch; the workspace layout
@@ -1399,6 +1403,10 @@ static SearchPlan make_search_plan(int64_t Q, int64_t N, int64_t D, int terms = 
     p.n_groups = pick_n_groups(pair_m, p.n_tiles, p.grid / 2);
   } else {
     p.n_groups = pick_n_groups(p.m_blocks, p.n_tiles, p.grid);
+  }
+  {
+    const int g = option(ISB_OPT_SCREEN_GROUPS, 0);   // experiment switch (changes the workspace layout)
+    if (g >= 1) p.n_groups = g < p.n_tiles ? g : p.n_tiles;
   }
   p.ldq = static_cast<int64_t>(align_up(static_cast<size_t>(D), 8));
   size_t off = 0;
