@@ -588,6 +588,17 @@ def side_regions(dev, pk, cpu_baseline=True):
         # written as bf16 hi + lo; CUDA events around the one kernel, L2 flushed before every launch
         ms_pool = _median_ms(lambda: regions.region_pool_probe(x, hw, k + regions.RUNNER_UPS, (7, 7)), flush=flush)
         rd, wr = regions.region_pool_probe(x, hw, k + regions.RUNNER_UPS, (7, 7))
+        # the gather pass alone: crops of the k + 2 scored windows read, U = sum crop/|crop| + n shift
+        # written as bf16 hi + lo, window means as a by-product
+        ke = k + regions.RUNNER_UPS
+        idx_e, nsel_e, _, norm_e, _, _, _ = regions.region_select(x, hw, ke, (7, 7))
+        ms_gather = _median_ms(lambda: regions.region_gather(x, hw, ke, (7, 7), idx_e, nsel_e, norm_e, k_sum=k),
+                               flush=flush)
+        win_rows = idx_e.clamp(min=0) // (hwsize - 6)
+        rows_read = (win_rows.max(1).values + 7 - win_rows.min(1).values).clamp(max=hwsize).double().mean().item()
+        # bytes the kernel touches: small maps stage whole planes, larger ones the row range of the windows
+        g_rd = 4 * B * C * hwsize * (hwsize if hwsize * hwsize <= 256 else rows_read)
+        g_wr = 2 * 2 * B * Kin + 4 * B * ke * C
         # streamed: 8 batches queued back to back over two alternating inputs (each larger than
         # L2, so no batch finds its map cached), certificates read once at the end -- what a
         # pipelined embedding loop sees once launch latency is hidden
@@ -632,6 +643,10 @@ def side_regions(dev, pk, cpu_baseline=True):
                                "algorithmic_bytes": rd + wr, "achieved": (rd + wr) / (ms_pool * 1e-3) / 1e9,
                                "peak": pk["hbm_gbs"], "unit": "GB/s",
                                "frac": (rd + wr) / (ms_pool * 1e-3) / 1e9 / pk["hbm_gbs"]},
+            "gather_kernel": {"kernel": "region_gather7_kernel" if hwsize * hwsize <= 256 else "region_gather_kernel",
+                              "bound": "hbm", "ms": ms_gather, "bytes_touched": g_rd + g_wr,
+                              "achieved": (g_rd + g_wr) / (ms_gather * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                              "unit": "GB/s", "frac": (g_rd + g_wr) / (ms_gather * 1e-3) / 1e9 / pk["hbm_gbs"]},
             "projection_ms": ms - ms_head,
             "streamed": {"ms_per_batch": ms_stream, "region_descriptors_per_s": units / (ms_stream * 1e-3),
                          "batches_in_flight": nstream, "uncertified_images_last_pass": n_unc_stream},

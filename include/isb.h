@@ -69,7 +69,8 @@ enum {
   ISB_OPT_MINING_PROGRESSIVE = 13, /* exact re-check of a couple's candidates: 1 (default) progressive, 0 all of them, 2 progressive with the one-CTA-per-couple kernel */
   ISB_OPT_GATHER_SMALL = 14,     /* 1 (default): plane-block gather kernel for maps of <= 256 pixels; 0: off */
   ISB_OPT_SCREEN_GROUPS = 15,    /* n-groups of the screen's work decomposition (default 0: chosen for whole waves) */
-  ISB_OPT_COUNT_ = 16
+  ISB_OPT_RESC_SPLITS = 16,      /* split-K of the region head's candidate re-score GEMM (default 0: fills the machine) */
+  ISB_OPT_COUNT_ = 17
 };
 int isb_set_option(int option, int value);
 int isb_get_option(int option);

@@ -2163,6 +2163,10 @@ static bool make_region_plan(RegionPlan& p, int64_t B, int C, int H, int W, int 
     p.resc_splits = static_cast<int>(148 / (tiles > 0 ? tiles : 1));
     if (p.resc_splits < 1) p.resc_splits = 1;
     if (p.resc_splits > 4) p.resc_splits = 4;
+    {
+      const int o = option(ISB_OPT_RESC_SPLITS, 0);   // experiment switch (changes the workspace layout)
+      if (o >= 1 && o <= 8) p.resc_splits = o;
+    }
     p.partials_bytes = p.resc_splits > 1 ? isb_gemm_nt_workspace_bytes(Mr, ncls, C, p.resc_splits) : 0;
   }
   p.off_partials = off; off = align_up(off + p.partials_bytes, 1024);
