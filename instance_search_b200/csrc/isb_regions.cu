@@ -1798,6 +1798,227 @@ region_gather7_kernel(const float* __restrict__ x, int C, int H, int W_, int k, 
   }
 }
 
+// ------------------------------------------------------------------ 4c. gather, larger maps (7 x 7 windows)
+// Maps of 257 .. 1024 pixels with W % 4 == 0 (32 x 32: the 1024-px input) and at most 8 listed
+// windows.  A plane is up to 4 KB here, so a step stages the ROW RANGE that covers the image's
+// windows for 8 channels (one bulk copy per channel), one channel per warp.  The channel-stream kernel
+// gives such a map ONE channel per warp-unit: 49 outputs and 8 window means per unit, i.e. passes with
+// 8 of 32 lanes busy -- 286 M warp instructions per 256 x 2048 x 32 x 32 batch, bound by the L1 /
+// shared-memory pipe (83 %) at 36 % of the DRAM throughput (profiles/r02_ncu_regions_32x32.txt).
+// Here a lane owns the (dx, window pair) column slice of its warp's channel: lane = 4 dx + wg handles
+// windows wg and wg + 4 -- seven ld.shared with immediate row offsets per window, their sum is the
+// lane's share of that window's mean -- and the seven accumulators u[c, dy, dx] are completed by two
+// xor-shuffles over wg.  (The terms of a sum are therefore added pairwise, not in window order as the
+// other two kernels do: equal to fp32 rounding, not bit for bit.)
+constexpr int kGLThreads = 256;
+constexpr int kGLSC = 8;          // channels per step = warps per CTA
+constexpr int kGLCsStride = 12;   // colsum [window][dx][channel]
+
+template <int WT>   // WT = map width as a compile-time constant (32), 0 = runtime
+__global__ void __launch_bounds__(kGLThreads)
+region_gatherL_kernel(const float* __restrict__ x, int C, int H, int W_, int k, int k_sum, int CPB, int NST,
+                      const int* __restrict__ image_list, const int* __restrict__ n_list,
+                      const int64_t* __restrict__ idx, const int* __restrict__ nsel_in,
+                      const float* __restrict__ win_norm, const float* __restrict__ shift,
+                      uint16_t* __restrict__ U_hi, uint16_t* __restrict__ U_lo, int64_t ldu,
+                      float* __restrict__ win_mean) {
+  extern __shared__ __align__(128) uint8_t gl_smem[];
+  __shared__ uint32_t s_off[kG7MaxWin];
+  __shared__ float s_inv[kG7MaxWin];
+  __shared__ int s_r0, s_r1;
+  __shared__ __align__(8) uint64_t full[kG7MaxStages];
+  if (image_list != nullptr && static_cast<int>(blockIdx.y) >= *n_list) return;
+  const int b = (image_list != nullptr) ? image_list[blockIdx.y] : blockIdx.y;
+  const int W = WT ? WT : W_;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = H * W, Wo = W - 6;
+  const int nall = min(nsel_in[b], min(k, kG7MaxWin));
+  const int nsel = min(nall, k_sum);
+  // row range of the image's windows (warp 0), barriers
+  if (tid < 32) {
+    int r0 = H, r1 = 0;
+    if (tid < nall) {
+      const int h = static_cast<int>(idx[static_cast<size_t>(b) * k + tid]) / Wo;
+      r0 = h;
+      r1 = h + 7;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      r0 = min(r0, __shfl_xor_sync(0xffffffffu, r0, o));
+      r1 = max(r1, __shfl_xor_sync(0xffffffffu, r1, o));
+    }
+    if (tid == 0) {
+      if (nall == 0) { r0 = 0; r1 = 0; }
+      s_r0 = r0; s_r1 = r1;
+      for (int st = 0; st < NST; ++st) ptx::mbar_init(&full[st], 1);
+      ptx::fence_barrier_init();
+    }
+  }
+  __syncthreads();
+  const int r0 = s_r0, pl = (s_r1 - s_r0) * W;   // floats staged per plane (a multiple of 4: W % 4 == 0)
+  if (tid < kG7MaxWin) {
+    uint32_t off = 0u;
+    float inv = 0.f;
+    if (tid < nall) {
+      const int win = static_cast<int>(idx[static_cast<size_t>(b) * k + tid]);
+      const int h = win / Wo, w = win - h * Wo;
+      off = static_cast<uint32_t>((h - r0) * W + w) * 4u;
+      inv = 1.f / win_norm[static_cast<size_t>(b) * k + tid];   // see region_gather7_kernel
+    }
+    s_off[tid] = off;
+    s_inv[tid] = inv;
+  }
+  __syncthreads();
+  float* planes = reinterpret_cast<float*>(gl_smem);                                         // [NST][8][HW]
+  uint16_t* out_hi = reinterpret_cast<uint16_t*>(planes + static_cast<size_t>(NST) * kGLSC * HW);   // [8 * 49]
+  uint16_t* out_lo = out_hi + kGLSC * 49;
+  float* colsum = reinterpret_cast<float*>(out_lo + kGLSC * 49);                              // [8][7][12]
+  const int c_begin = blockIdx.x * CPB, c_end = min(C, c_begin + CPB);
+  const int nstep = (pl > 0) ? (c_end - c_begin + kGLSC - 1) / kGLSC : 0;
+  const float* xb = x + static_cast<size_t>(b) * C * HW + r0 * W;
+  // warp 0 stages step st into slot st % NST: the row range of one channel per lane
+  auto issue = [&](int st) {
+    const int c0 = c_begin + st * kGLSC;
+    const int nch = min(kGLSC, c_end - c0);
+    uint64_t* bar = &full[st % NST];
+    if (lane == 0) {
+      ptx::fence_proxy_async();   // the slot was last read through the generic proxy
+      ptx::mbar_arrive_expect_tx(bar, static_cast<uint32_t>(nch) * pl * 4u);
+    }
+    __syncwarp();
+    if (lane < nch)
+      ptx::bulk_load_1d(planes + (static_cast<size_t>(st % NST) * kGLSC + lane) * HW,
+                        xb + static_cast<size_t>(c0 + lane) * HW, static_cast<uint32_t>(pl) * 4u, bar);
+  };
+  if (warp == 0)
+    for (int st = 0; st < NST && st < nstep; ++st) issue(st);
+
+  // lane = 4 dx + wg: column dx of the patch, windows wg and wg + 4; the warp's channel is cl = warp
+  const int dx = lane >> 2, wg = lane & 3;
+  const bool col = lane < 28;
+  const int cl = warp;
+  const uint32_t off0 = s_off[wg], off1 = s_off[wg + 4];
+  const float inv0 = s_inv[wg], inv1 = s_inv[wg + 4];
+  const bool have0 = wg < nall, have1 = wg + 4 < nall, sum0 = wg < nsel, sum1 = wg + 4 < nsel;
+  const float fn = static_cast<float>(nsel);
+  const uint32_t RS = static_cast<uint32_t>(W) * 4u;
+  uint16_t* uh = U_hi + static_cast<size_t>(b) * ldu;
+  uint16_t* ul = (U_lo != nullptr) ? U_lo + static_cast<size_t>(b) * ldu : nullptr;
+  const int Kin = C * 49;
+
+  for (int st = 0; st < nstep; ++st) {
+    const int c0 = c_begin + st * kGLSC;
+    const int nch = min(kGLSC, c_end - c0);
+    ptx::mbar_wait(&full[st % NST], static_cast<uint32_t>((st / NST) & 1));
+    float acc[7];
+#pragma unroll
+    for (int dy = 0; dy < 7; ++dy) acc[dy] = 0.f;
+    const bool act = col && cl < nch;
+    float shv[7];
+    if (act && wg == 0) {
+      const float* sh = shift + static_cast<size_t>(c0 + cl) * 49 + dx;
+#pragma unroll
+      for (int dy = 0; dy < 7; ++dy) shv[dy] = __ldg(sh + dy * 7);   // in flight under the shared-memory loads
+    }
+    if (act) {
+      const uint32_t base = ptx::smem_u32(planes + (static_cast<size_t>(st % NST) * kGLSC + cl) * HW) + dx * 4u;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (t == 0 ? have0 : have1) {
+          const uint32_t a = base + (t == 0 ? off0 : off1);
+          float v[7];
+          if (WT) {
+            v[0] = lds_f32_off<0>(a);           v[1] = lds_f32_off<4 * WT>(a);
+            v[2] = lds_f32_off<8 * WT>(a);      v[3] = lds_f32_off<12 * WT>(a);
+            v[4] = lds_f32_off<16 * WT>(a);     v[5] = lds_f32_off<20 * WT>(a);
+            v[6] = lds_f32_off<24 * WT>(a);
+          } else {
+#pragma unroll
+            for (int dy = 0; dy < 7; ++dy) v[dy] = lds_f32(a + dy * RS);
+          }
+          if (win_mean != nullptr)
+            colsum[((wg + 4 * t) * 7 + dx) * kGLCsStride + cl] =
+                (((((v[0] + v[1]) + v[2]) + v[3]) + v[4]) + v[5]) + v[6];
+          if (t == 0 ? sum0 : sum1) {
+            const float iv = (t == 0) ? inv0 : inv1;
+#pragma unroll
+            for (int dy = 0; dy < 7; ++dy) acc[dy] = fmaf(v[dy], iv, acc[dy]);
+          }
+        }
+      }
+    }
+    // the four window groups of a column: lanes 4 dx .. 4 dx + 3 (all 32 lanes take part in the shuffles)
+#pragma unroll
+    for (int dy = 0; dy < 7; ++dy) {
+      acc[dy] += __shfl_xor_sync(0xffffffffu, acc[dy], 1);
+      acc[dy] += __shfl_xor_sync(0xffffffffu, acc[dy], 2);
+    }
+    if (act && wg == 0) {
+      // + nsel * shift (Shift, model/custom_modules.py:16-18, once per summed window), then bf16 hi / lo
+      const int e0 = cl * 49 + dx;
+#pragma unroll
+      for (int dy = 0; dy < 7; dy += 2) {
+        const int d1 = dy + 1 < 7 ? dy + 1 : dy;
+        const float u0 = fmaf(fn, shv[dy], acc[dy]);
+        const float u1 = (dy + 1 < 7) ? fmaf(fn, shv[d1], acc[d1]) : 0.f;
+        uint32_t hi2, lo2;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(u1), "f"(u0));
+        const float r0f = u0 - __uint_as_float(hi2 << 16);
+        const float r1f = u1 - __uint_as_float(hi2 & 0xFFFF0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(r1f), "f"(r0f));
+        out_hi[e0 + dy * 7] = static_cast<uint16_t>(hi2 & 0xFFFFu);
+        out_lo[e0 + dy * 7] = static_cast<uint16_t>(lo2 & 0xFFFFu);
+        if (dy + 1 < 7) {
+          out_hi[e0 + (dy + 1) * 7] = static_cast<uint16_t>(hi2 >> 16);
+          out_lo[e0 + (dy + 1) * 7] = static_cast<uint16_t>(lo2 >> 16);
+        }
+      }
+    }
+    __syncthreads();   // tile and column sums complete; nobody reads the slot any more
+    if (warp == 0 && st + NST < nstep) issue(st + NST);
+    {
+      const int n_el = nch * 49;                       // 8 channels: 392 elements = 49 16-byte vectors
+      const size_t g0 = static_cast<size_t>(c0) * 49;  // c0 % 8 == 0: 16-byte aligned
+      const int nvec = n_el >> 3;
+      for (int v = tid; v < nvec; v += kGLThreads) {
+        *reinterpret_cast<uint4*>(uh + g0 + 8 * v) = *reinterpret_cast<const uint4*>(out_hi + 8 * v);
+        if (ul != nullptr) *reinterpret_cast<uint4*>(ul + g0 + 8 * v) = *reinterpret_cast<const uint4*>(out_lo + 8 * v);
+      }
+      for (int e = (nvec << 3) + tid; e < n_el; e += kGLThreads) {
+        uh[g0 + e] = out_hi[e];
+        if (ul != nullptr) ul[g0 + e] = out_lo[e];
+      }
+      if (c0 + nch >= C && tid < ((Kin + 7) & ~7) - Kin) {
+        uh[Kin + tid] = 0;
+        if (ul != nullptr) ul[Kin + tid] = 0;
+      }
+    }
+    if (win_mean != nullptr) {
+      for (int t = tid; t < nch * nall; t += kGLThreads) {
+        const int i = t / nch, c = t - i * nch;
+        const float* cs = colsum + (i * 7) * kGLCsStride + c;
+        float sum = cs[0];
+#pragma unroll
+        for (int d = 1; d < 7; ++d) sum += cs[d * kGLCsStride];
+        win_mean[(static_cast<size_t>(b) * k + i) * C + c0 + c] = sum / 49.f;
+      }
+    }
+    __syncthreads();   // tile and column sums are free for the next step
+  }
+  // an image without windows (nsel = 0) still owns its operand row: u = 0 * shift
+  if (nstep == 0) {
+    const size_t g0 = static_cast<size_t>(c_begin) * 49;
+    for (int e = tid; e < (c_end - c_begin) * 49; e += kGLThreads) {
+      uh[g0 + e] = 0;
+      if (ul != nullptr) ul[g0 + e] = 0;
+    }
+    if (c_end >= C && tid < ((Kin + 7) & ~7) - Kin) {
+      uh[Kin + tid] = 0;
+      if (ul != nullptr) ul[Kin + tid] = 0;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ 5b. exact logits of the selected windows
 // cls_out[b, :, i] = Wc . mean_i + bc in fp32 from the exact window means
 // (model/siamese.py:188,216), one CTA per image: the k means sit in shared memory,
@@ -2362,6 +2583,29 @@ extern "C" int isb_region_gather(const float* x, int64_t B, int64_t C, int64_t H
     kern<<<grid, SC * 8, smem, static_cast<cudaStream_t>(stream)>>>(
         x, (int)C, (int)H, (int)W, k, k_sum, CPB, NST, CM, image_list, n_list, idx, nsel, win_norm, shift, U_hi,
         U_lo, ldu, win_mean);
+    ISB_CUDA(cudaGetLastError());
+    return ISB_OK;
+  }
+  // larger maps (up to 1024 pixels, 16-byte rows), <= 8 listed windows: the row-range kernel
+  // (option gather_small = 0 switches both plane / row-range kernels off)
+  if (fh == 7 && fw == 7 && HW > 256 && HW <= 1024 && W % 4 == 0 && k <= kG7MaxWin &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && option(ISB_OPT_GATHER_SMALL, 1) != 0) {
+    int NST = option(ISB_OPT_GATHER_STAGES, 2);
+    if (NST < 1) NST = 1;
+    if (NST > kG7MaxStages) NST = kG7MaxStages;
+    while (NST > 1 && static_cast<size_t>(NST) * kGLSC * HW * 4 > 96 * 1024) --NST;
+    int CPB = 128;
+    {
+      const int g = option(ISB_OPT_GATHER_G, 0);
+      if (g >= 1 && g <= 64) CPB = 8 * g;
+    }
+    const size_t smem = static_cast<size_t>(NST) * kGLSC * HW * 4 + 2 * kGLSC * 49 * 2 + kG7MaxWin * 7 * kGLCsStride * 4;
+    dim3 grid(static_cast<unsigned>((C + CPB - 1) / CPB), static_cast<unsigned>(B));
+    auto kern = (W == 32) ? region_gatherL_kernel<32> : region_gatherL_kernel<0>;
+    ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kGLThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        x, (int)C, (int)H, (int)W, k, k_sum, CPB, NST, image_list, n_list, idx, nsel, win_norm, shift, U_hi, U_lo,
+        ldu, win_mean);
     ISB_CUDA(cudaGetLastError());
     return ISB_OK;
   }
