@@ -70,7 +70,8 @@ enum {
   ISB_OPT_GATHER_SMALL = 14,     /* 1 (default): plane-block gather kernel for maps of <= 256 pixels; 0: off */
   ISB_OPT_SCREEN_GROUPS = 15,    /* n-groups of the screen's work decomposition (default 0: chosen for whole waves) */
   ISB_OPT_RESC_SPLITS = 16,      /* split-K of the region head's candidate re-score GEMM (default 0: fills the machine) */
-  ISB_OPT_COUNT_ = 17
+  ISB_OPT_REGION_TOP_SELECT = 17, /* 1 (default): one-kernel candidate re-score from the screen's best classes; 0: re-score GEMM */
+  ISB_OPT_COUNT_ = 18
 };
 int isb_set_option(int option, int value);
 int isb_get_option(int option);

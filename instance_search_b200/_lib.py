@@ -89,7 +89,7 @@ SIGNATURES = {
 OPTIONS = {
     "screen_pair": 0, "screen_seed": 1, "screen_wavesync": 2, "mining_kc": 3, "pool_stages": 4, "pool_g": 5,
     "pool_generic_geom": 6, "region_pool_tc": 7, "tc_debug": 8, "gather_cw": 9, "gather_g": 10,
-    "gather_stages": 11, "gemm_pair": 12, "mining_progressive": 13, "gather_small": 14, "screen_groups": 15, "resc_splits": 16,
+    "gather_stages": 11, "gemm_pair": 12, "mining_progressive": 13, "gather_small": 14, "screen_groups": 15, "resc_splits": 16, "region_top_select": 17,
 }
 
 

@@ -897,6 +897,88 @@ struct RowMaxEpilogue {
   }
 };
 
+// The same epilogue, additionally keeping the FOUR best class values of every row and their classes
+// (row_top [M][8]: m1 m2 m3 m4 | c1 c2 c3 c4): what region_select_top_kernel needs to re-score a
+// window's class-max without the logits of all classes.  Branch-free: the class index (< 512)
+// replaces the low 9 mantissa bits of the value (a 2^-14 relative perturbation of a bf16-noise screen
+// value, still an ordinary float), and the packed value is inserted into the sorted four by a
+// min / max chain -- 7 FMNMX + 1 LOP3 per accumulator value, no divergence (a compare-and-shift
+// insertion behind `if (x > m4)` doubled the classifier GEMM's time: its branch is taken by some lane
+// of the warp on most columns).  row_max keeps the exact maximum.
+constexpr uint32_t kTopIdxBits = 9;                       // ncls <= 512
+constexpr uint32_t kTopIdxMask = (1u << kTopIdxBits) - 1u;
+constexpr float kTopNone = -3.0e38f;                      // "no class": below any logit
+
+struct RowTopEpiParams {
+  float* row_max;      // [M]
+  uint32_t* row_top;   // [M][8]
+  const float* bias;   // [N]
+  int M, N;
+};
+
+struct RowTopEpilogue {
+  using Params = RowTopEpiParams;
+  const Params& p;
+  const int row_in_tile;
+  float m, m1, m2, m3, m4;
+  __device__ RowTopEpilogue(const Params& p_, int r) : p(p_), row_in_tile(r) { m = m1 = m2 = m3 = m4 = 0.f; }
+  __device__ __forceinline__ void begin_segment(const Segment&) {
+    m = -INFINITY;
+    m1 = m2 = m3 = m4 = kTopNone;
+  }
+  __device__ __forceinline__ void tile(const Segment& seg, int nt, uint32_t tmem_acc,
+                                       uint64_t* tmem_empty_bar) {
+    const int col0 = nt * kBN;
+    uint32_t v0[32], v1[32];
+    ptx::tmem_ld_32x32b_x32(tmem_acc, v0);
+#pragma unroll 1
+    for (int it = 0; it < kBN / 64; ++it) {
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_32x32b_x32(tmem_acc + it * 64 + 32, v1);
+      scan(v0, col0 + it * 64);
+      ptx::tmem_ld_wait();
+      if (it + 1 < kBN / 64) {
+        ptx::tmem_ld_32x32b_x32(tmem_acc + it * 64 + 64, v0);
+      } else {
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(tmem_empty_bar);
+      }
+      scan(v1, col0 + it * 64 + 32);
+    }
+  }
+  __device__ __forceinline__ void scan(const uint32_t (&v)[32], int cb) {
+    if (cb >= p.N) return;  // warp-uniform
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = cb + j;
+      const float x = (col < p.N) ? __uint_as_float(v[j]) + __ldg(p.bias + col) : kTopNone;
+      m = fmaxf(m, x);
+      float t = __uint_as_float((__float_as_uint(x) & ~kTopIdxMask) | static_cast<uint32_t>(col));
+      float n = fmaxf(m1, t); t = fminf(m1, t); m1 = n;
+      n = fmaxf(m2, t); t = fminf(m2, t); m2 = n;
+      n = fmaxf(m3, t); t = fminf(m3, t); m3 = n;
+      m4 = fmaxf(m4, t);
+    }
+  }
+  __device__ __forceinline__ void end_segment(const Segment& seg) {
+    const int row = seg.m_block * kBM + row_in_tile;
+    if (row < p.M) {
+      p.row_max[row] = m;
+      const float mm[4] = {m1, m2, m3, m4};
+      uint32_t val[4], cls[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool none = mm[i] <= kTopNone * 0.5f;
+        val[i] = none ? __float_as_uint(-INFINITY) : (__float_as_uint(mm[i]) & ~kTopIdxMask);
+        cls[i] = none ? 0xFFFFFFFFu : (__float_as_uint(mm[i]) & kTopIdxMask);
+      }
+      uint4* o = reinterpret_cast<uint4*>(p.row_top + static_cast<size_t>(row) * 8);
+      o[0] = make_uint4(val[0], val[1], val[2], val[3]);
+      o[1] = make_uint4(cls[0], cls[1], cls[2], cls[3]);
+    }
+  }
+};
+
 // one segment = one m-block x ALL n-tiles (the max runs over every class)
 struct RowSched {
   ISB_PLAIN_SEGMENT_PASSES
@@ -947,26 +1029,13 @@ __device__ __forceinline__ void block_argmax(float v, int i, float* s_val, int* 
   __syncthreads();
 }
 
-// One CTA per image: the ncand best windows of the bf16 screen (value desc, index
-// asc), and their pooled rows copied out of P_hi / P_lo into the operand of the
-// fp32-grade re-score GEMM: A_hi / A_lo [B * ncand_max, ldp], rows beyond the
-// image's candidates zeroed.
-__global__ void __launch_bounds__(kSelThreads)
-region_candidates_kernel(const float* __restrict__ screen, int nwin, int ncand, int ncand_max,
-                         const uint16_t* __restrict__ P_hi, const uint16_t* __restrict__ P_lo, int ldp,
-                         int* __restrict__ cand_out, float* __restrict__ cand_screen,
-                         uint16_t* __restrict__ A_hi, uint16_t* __restrict__ A_lo) {
-  extern __shared__ __align__(16) uint8_t sel_smem_raw[];
-  float* sc = reinterpret_cast<float*>(sel_smem_raw);   // [nwin]
-  __shared__ float s_val[kSelThreads / 32];
-  __shared__ int s_idx[kSelThreads / 32];
-  __shared__ int cand[kSelMaxCand];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  for (int i = tid; i < nwin; i += kSelThreads) {
-    const float v = screen[static_cast<size_t>(b) * nwin + i];
-    sc[i] = (v == v) ? v : -INFINITY;   // a NaN never outranks anything
-  }
-  __syncthreads();
+// The ncand best windows of one image's screen (value desc, index asc) into cand[] / cand_val[]
+// (shared memory, ncand <= kSelMaxCand entries), by all kSelThreads threads of the CTA.
+// sc [nwin] holds the screen scores (NaN already mapped to -inf) and is followed by nwin words of
+// scratch for the radix keys; on maps of more than kRankSelectMaxWin windows sc is consumed.
+__device__ __forceinline__ void select_best_windows(float* sc, int nwin, int ncand, int* cand, float* cand_val,
+                                                    float* s_val, int* s_idx) {
+  const int tid = threadIdx.x;
   if (nwin <= kRankSelectSmallWin) {
     // rank selection: every window counts the windows that come before it in the order
     // (value desc, index asc); the ncand first write themselves to their slot.  One pass and
@@ -980,10 +1049,7 @@ region_candidates_kernel(const float* __restrict__ screen, int nwin, int ncand, 
       }
       if (rank < ncand) {
         cand[rank] = i;
-        if (blockIdx.y == 0) {
-          cand_out[b * ncand_max + rank] = i;
-          cand_screen[b * ncand_max + rank] = v;
-        }
+        cand_val[rank] = v;
       }
     }
     __syncthreads();
@@ -1027,10 +1093,7 @@ region_candidates_kernel(const float* __restrict__ screen, int nwin, int ncand, 
         rank += (s2 > v || (s2 == v && j < i)) ? 1 : 0;
       }
       cand[rank] = i;
-      if (blockIdx.y == 0) {
-        cand_out[b * ncand_max + rank] = i;
-        cand_screen[b * ncand_max + rank] = v;
-      }
+      cand_val[rank] = v;
     }
     __syncthreads();
   } else {
@@ -1045,12 +1108,39 @@ region_candidates_kernel(const float* __restrict__ screen, int nwin, int ncand, 
       block_argmax(v, vi, s_val, s_idx, bv, bi);
       if (tid == 0) {
         cand[c] = bi;
-        cand_out[b * ncand_max + c] = bi;
-        cand_screen[b * ncand_max + c] = bv;
+        cand_val[c] = bv;
         sc[bi] = -INFINITY;
       }
       __syncthreads();
     }
+  }
+}
+
+// One CTA per image: the ncand best windows of the bf16 screen (value desc, index
+// asc), and their pooled rows copied out of P_hi / P_lo into the operand of the
+// fp32-grade re-score GEMM: A_hi / A_lo [B * ncand_max, ldp], rows beyond the
+// image's candidates zeroed.
+__global__ void __launch_bounds__(kSelThreads)
+region_candidates_kernel(const float* __restrict__ screen, int nwin, int ncand, int ncand_max,
+                         const uint16_t* __restrict__ P_hi, const uint16_t* __restrict__ P_lo, int ldp,
+                         int* __restrict__ cand_out, float* __restrict__ cand_screen,
+                         uint16_t* __restrict__ A_hi, uint16_t* __restrict__ A_lo) {
+  extern __shared__ __align__(16) uint8_t sel_smem_raw[];
+  float* sc = reinterpret_cast<float*>(sel_smem_raw);   // [nwin] + [nwin] radix keys
+  __shared__ float s_val[kSelThreads / 32];
+  __shared__ int s_idx[kSelThreads / 32];
+  __shared__ int cand[kSelMaxCand];
+  __shared__ float cand_val[kSelMaxCand];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < nwin; i += kSelThreads) {
+    const float v = screen[static_cast<size_t>(b) * nwin + i];
+    sc[i] = (v == v) ? v : -INFINITY;   // a NaN never outranks anything
+  }
+  __syncthreads();
+  select_best_windows(sc, nwin, ncand, cand, cand_val, s_val, s_idx);
+  if (blockIdx.y == 0 && tid < ncand) {
+    cand_out[b * ncand_max + tid] = cand[tid];
+    cand_screen[b * ncand_max + tid] = cand_val[tid];
   }
   if (tid < ncand_max - ncand) {
     cand_out[b * ncand_max + ncand + tid] = -1;
@@ -1149,6 +1239,256 @@ region_finalize_select_kernel(const float* __restrict__ logits, int ldl, int ncl
   }
   // ||crop||: sqrt(sum over the window of the per-pixel energy + eps)
   for (int i = warp; i < k; i += kSelThreads / 32) {
+    if (i < nsel) {
+      const int win = cand[order[i]];
+      const int h = win / Wo, w = win - h * Wo;
+      double s = 0.0;
+#pragma unroll 8
+      for (int t = lane; t < fh * fw * ngroups; t += 32) {   // unrolled: eight loads in flight per lane
+        const int g = t / (fh * fw), r = t - g * (fh * fw);
+        const int dy = r / fw, dx = r - dy * fw;
+        s += static_cast<double>(__ldg(e_part + (static_cast<size_t>(b) * ngroups + g) * HW + (h + dy) * W + w + dx));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) win_norm[static_cast<size_t>(b) * k + i] = sqrtf(static_cast<float>(s) + eps);
+    } else if (lane == 0) {
+      win_norm[static_cast<size_t>(b) * k + i] = 1.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ 4a. candidates + re-score + final selection in one kernel
+// What region_candidates_kernel -> isb_gemm_nt_split -> splitk_reduce -> region_finalize_select_kernel
+// compute (four launches, 79 us per 256 x 2048 x 14 x 14 batch of which the tensor-core GEMM is 30),
+// for the class-max only: the screen GEMM's epilogue (RowTopEpilogue) has kept the four best class
+// values of every window and the classes of the best three, so a window's class-max needs the
+// fp32-grade logits of THREE classes, not 464 -- 3 * ncand dot products of C per image, done here
+// on the CUDA cores from the window's pooled row (hi + lo = the fp32 mean to 2^-17) and the fp32
+// weights.  One CTA per image.
+//   A class outside the best three has a screen logit <= m4; the window is certified when its
+//   re-scored class-max clears m4 by 8 sigma, sigma = max(rms(screen - re-scored) over the image's
+//   3 * ncand pairs, half the bf16 noise expected for the rows at hand: 2.34e-3 |p| |w| / sqrt(C)).
+//   An image with a window that fails is listed in n_uncertified (second line), like one whose
+//   candidate list the completeness certificate rejects.
+// cls_out [B, ncls, k] receives the re-scored logits of those classes and -inf elsewhere (isb_region_logits
+// prunes on it: only classes within its tolerance of the maximum are scored in true fp32).
+constexpr int kTopChunk = 8;   // candidates whose pooled rows sit in shared memory at a time
+
+__global__ void __launch_bounds__(kSelThreads)
+region_select_top_kernel(const float* __restrict__ screen, const uint32_t* __restrict__ row_top, int nwin,
+                         int ncand, const uint16_t* __restrict__ P_hi, const uint16_t* __restrict__ P_lo, int ldp,
+                         int C, const float* __restrict__ cls_w, const float* __restrict__ cls_b, int ncls,
+                         const float* __restrict__ e_part, int ngroups, int H, int W, int fh, int fw, int k,
+                         float eps, int chunk, int dbg, int64_t* __restrict__ idx, int* __restrict__ nsel_out,
+                         float* __restrict__ cls_out, float* __restrict__ win_norm,
+                         float* __restrict__ approx_max, float* __restrict__ runner_up,
+                         int* __restrict__ n_uncertified) {
+  extern __shared__ __align__(16) uint8_t sel_smem_raw[];
+  float* sc = reinterpret_cast<float*>(sel_smem_raw);                  // [nwin] + [nwin] radix keys
+  float* prow = sc + 2 * ((nwin + 3) & ~3);                            // [chunk][ldp]
+  __shared__ float s_val[kSelThreads / 32];
+  __shared__ int s_idx[kSelThreads / 32];
+  __shared__ int cand[kSelMaxCand];
+  __shared__ float cand_val[kSelMaxCand];
+  __shared__ float cand_max[kSelMaxCand];
+  __shared__ int order[kSelMaxCand];
+  __shared__ float t_scr[kSelMaxCand][4];    // m1 .. m4 of the candidate's window (screen)
+  __shared__ int t_cls[kSelMaxCand][3];      // classes of m1 .. m3
+  __shared__ float t_log[kSelMaxCand][3];    // their re-scored logits
+  __shared__ int t_wn2[kSelMaxCand];         // largest squared norm of the weight rows used (float bits)
+  __shared__ float t_pn2[kSelMaxCand];       // squared norm of the pooled row
+  __shared__ float s_d2;
+  __shared__ int s_nv, s_bad;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Wo = W - fw + 1, HW = H * W;
+  for (int i = tid; i < nwin; i += kSelThreads) {
+    const float v = screen[static_cast<size_t>(b) * nwin + i];
+    sc[i] = (v == v) ? v : -INFINITY;   // a NaN never outranks anything
+  }
+  if (tid == 0) { s_d2 = 0.f; s_nv = 0; s_bad = 0; }
+  __syncthreads();
+  select_best_windows(sc, nwin, ncand, cand, cand_val, s_val, s_idx);
+  if (tid < ncand) {
+    const uint4* rt = reinterpret_cast<const uint4*>(row_top + (static_cast<size_t>(b) * nwin + cand[tid]) * 8);
+    const uint4 a = __ldg(rt), c = __ldg(rt + 1);
+    t_scr[tid][0] = __uint_as_float(a.x); t_scr[tid][1] = __uint_as_float(a.y);
+    t_scr[tid][2] = __uint_as_float(a.z); t_scr[tid][3] = __uint_as_float(a.w);
+    t_cls[tid][0] = static_cast<int>(c.x); t_cls[tid][1] = static_cast<int>(c.y); t_cls[tid][2] = static_cast<int>(c.z);
+    t_wn2[tid] = 0;
+    t_pn2[tid] = 0.f;
+  }
+  __syncthreads();
+  const int vec = ldp / 8;   // 16-byte chunks of a pooled row (zero padded beyond C)
+  const bool w4 = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(cls_w) & 15) == 0;
+  for (int c0 = 0; c0 < ((dbg & 1) ? 0 : ncand); c0 += chunk) {
+    const int nc = min(chunk, ncand - c0);
+    // pooled rows of the chunk: hi + lo -> fp32; four 16-byte loads of each term in flight per thread
+    for (int i0 = tid; i0 < nc * vec; i0 += 4 * kSelThreads) {
+      uint4 h[4], l[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kSelThreads;
+        if (i < nc * vec) {
+          const int c = i / vec, j = i - c * vec;
+          const size_t srcrow = (static_cast<size_t>(b) * nwin + cand[c0 + c]) * ldp;
+          h[u] = __ldg(reinterpret_cast<const uint4*>(P_hi + srcrow) + j);
+          l[u] = __ldg(reinterpret_cast<const uint4*>(P_lo + srcrow) + j);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kSelThreads;
+        if (i < nc * vec) {
+          const int c = i / vec, j = i - c * vec;
+          float* d = prow + static_cast<size_t>(c) * ldp + 8 * j;
+          const uint32_t hw_[4] = {h[u].x, h[u].y, h[u].z, h[u].w}, lw_[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
+          float4 lo4, hi4;
+          lo4.x = __uint_as_float(hw_[0] << 16) + __uint_as_float(lw_[0] << 16);
+          lo4.y = __uint_as_float(hw_[0] & 0xFFFF0000u) + __uint_as_float(lw_[0] & 0xFFFF0000u);
+          lo4.z = __uint_as_float(hw_[1] << 16) + __uint_as_float(lw_[1] << 16);
+          lo4.w = __uint_as_float(hw_[1] & 0xFFFF0000u) + __uint_as_float(lw_[1] & 0xFFFF0000u);
+          hi4.x = __uint_as_float(hw_[2] << 16) + __uint_as_float(lw_[2] << 16);
+          hi4.y = __uint_as_float(hw_[2] & 0xFFFF0000u) + __uint_as_float(lw_[2] & 0xFFFF0000u);
+          hi4.z = __uint_as_float(hw_[3] << 16) + __uint_as_float(lw_[3] << 16);
+          hi4.w = __uint_as_float(hw_[3] & 0xFFFF0000u) + __uint_as_float(lw_[3] & 0xFFFF0000u);
+          reinterpret_cast<float4*>(d)[0] = lo4;
+          reinterpret_cast<float4*>(d)[1] = hi4;
+        }
+      }
+    }
+    __syncthreads();
+    // one warp per candidate: its pooled row against the weight rows of its three classes at once
+    // (three independent load streams; the row is read from shared memory once).  Keeping one
+    // class's weight row in registers and visiting the candidates that share it was tried and is
+    // slower (62 vs 47 us at 14 x 14): on the benchmark's maps an image's 3 * ncand pairs name
+    // more than eight distinct classes, so the pooled rows were staged twice or more.
+    for (int c = warp; c < nc; c += kSelThreads / 32) {
+      const int j0 = t_cls[c0 + c][0], j1 = t_cls[c0 + c][1], j2 = t_cls[c0 + c][2];
+      const float* pr = prow + static_cast<size_t>(c) * ldp;
+      // a missing class (fewer than three) reads row 0 and is discarded below
+      const float* w0 = cls_w + static_cast<size_t>(j0 < 0 ? 0 : j0) * C;
+      const float* w1 = cls_w + static_cast<size_t>(j1 < 0 ? 0 : j1) * C;
+      const float* w2 = cls_w + static_cast<size_t>(j2 < 0 ? 0 : j2) * C;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, pn = 0.f;
+      if (w4) {
+#pragma unroll 4
+        for (int i = lane; i < C / 4; i += 32) {
+          const float4 x0 = __ldg(reinterpret_cast<const float4*>(w0) + i);
+          const float4 x1 = __ldg(reinterpret_cast<const float4*>(w1) + i);
+          const float4 x2 = __ldg(reinterpret_cast<const float4*>(w2) + i);
+          const float4 pv = reinterpret_cast<const float4*>(pr)[i];
+          a0 = fmaf(x0.x, pv.x, a0); a0 = fmaf(x0.y, pv.y, a0); a0 = fmaf(x0.z, pv.z, a0); a0 = fmaf(x0.w, pv.w, a0);
+          a1 = fmaf(x1.x, pv.x, a1); a1 = fmaf(x1.y, pv.y, a1); a1 = fmaf(x1.z, pv.z, a1); a1 = fmaf(x1.w, pv.w, a1);
+          a2 = fmaf(x2.x, pv.x, a2); a2 = fmaf(x2.y, pv.y, a2); a2 = fmaf(x2.z, pv.z, a2); a2 = fmaf(x2.w, pv.w, a2);
+          n0 = fmaf(x0.x, x0.x, fmaf(x0.y, x0.y, fmaf(x0.z, x0.z, fmaf(x0.w, x0.w, n0))));
+          n1 = fmaf(x1.x, x1.x, fmaf(x1.y, x1.y, fmaf(x1.z, x1.z, fmaf(x1.w, x1.w, n1))));
+          n2 = fmaf(x2.x, x2.x, fmaf(x2.y, x2.y, fmaf(x2.z, x2.z, fmaf(x2.w, x2.w, n2))));
+          pn = fmaf(pv.x, pv.x, fmaf(pv.y, pv.y, fmaf(pv.z, pv.z, fmaf(pv.w, pv.w, pn))));
+        }
+      } else {
+        for (int i = lane; i < C; i += 32) {
+          const float x0 = __ldg(w0 + i), x1 = __ldg(w1 + i), x2 = __ldg(w2 + i), pv = pr[i];
+          a0 = fmaf(x0, pv, a0); a1 = fmaf(x1, pv, a1); a2 = fmaf(x2, pv, a2);
+          n0 = fmaf(x0, x0, n0); n1 = fmaf(x1, x1, n1); n2 = fmaf(x2, x2, n2);
+          pn = fmaf(pv, pv, pn);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o); n0 += __shfl_xor_sync(0xffffffffu, n0, o);
+        n1 += __shfl_xor_sync(0xffffffffu, n1, o); n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        pn += __shfl_xor_sync(0xffffffffu, pn, o);
+      }
+      if (lane == 0) {
+        t_log[c0 + c][0] = (j0 < 0) ? -INFINITY : a0 + __ldg(cls_b + j0);
+        t_log[c0 + c][1] = (j1 < 0) ? -INFINITY : a1 + __ldg(cls_b + j1);
+        t_log[c0 + c][2] = (j2 < 0) ? -INFINITY : a2 + __ldg(cls_b + j2);
+        t_wn2[c0 + c] = __float_as_int(fmaxf(j0 < 0 ? 0.f : n0, fmaxf(j1 < 0 ? 0.f : n1, j2 < 0 ? 0.f : n2)));
+        t_pn2[c0 + c] = pn;
+      }
+    }
+    __syncthreads();
+  }
+  // class-max of every candidate, screen noise over all re-scored pairs
+  if (tid < ncand) {
+    float m = -INFINITY, d2 = 0.f;
+    int nv = 0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      if (t_cls[tid][t] >= 0) {
+        const float lg = t_log[tid][t];
+        m = fmaxf(m, lg);
+        const float d = t_scr[tid][t] - lg;
+        d2 += d * d;
+        ++nv;
+      }
+    }
+    cand_max[tid] = m;
+    atomicAdd(&s_d2, d2);
+    atomicAdd(&s_nv, nv);
+  }
+  __syncthreads();
+  if (tid < ncand) {
+    // classes outside the best three: screen logit <= m4
+    const float sigma_meas = sqrtf(s_d2 / static_cast<float>(s_nv > 0 ? s_nv : 1));
+    const float sigma_exp = 2.34e-3f * sqrtf(t_pn2[tid] * __int_as_float(t_wn2[tid]) / static_cast<float>(C));
+    const float sigma = fmaxf(sigma_meas, 0.5f * sigma_exp);
+    const float m4 = t_scr[tid][3], cm = cand_max[tid];
+    if (m4 > -INFINITY && !(cm - m4 > 8.f * sigma + 4e-7f * fmaxf(fabsf(cm), fabsf(m4)))) atomicOr(&s_bad, 1);
+  }
+  const int nsel = min(nwin, k);
+  // order of the <= 32 candidates (class-max desc, window asc): every candidate counts the ones
+  // before it and writes itself to that slot
+  if (tid < ncand) {
+    const float v = cand_max[tid];
+    const int w = cand[tid];
+    int rank = 0;
+    for (int j = 0; j < ncand; ++j) {
+      const float s = cand_max[j];
+      rank += (s > v || (s == v && cand[j] < w)) ? 1 : 0;
+    }
+    order[rank] = tid;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    nsel_out[b] = nsel;
+    if (approx_max != nullptr) {
+      for (int i = 0; i < k; ++i) approx_max[static_cast<size_t>(b) * k + i] = (i < nsel) ? cand_max[order[i]] : 0.f;
+      runner_up[b] = (ncand > nsel) ? cand_max[order[nsel]] : -INFINITY;
+    }
+    bool bad = s_bad != 0;
+    // completeness of the candidate list (as region_finalize_select_kernel)
+    if (nwin > ncand && !bad) {
+      float t_min = INFINITY, s2 = 0.f;
+      for (int c = 0; c < ncand; ++c) {
+        const float sv = cand_val[c];
+        t_min = fminf(t_min, sv);
+        const float d = sv - cand_max[c];
+        s2 += d * d;
+      }
+      const float sigma = sqrtf(s2 / static_cast<float>(ncand));
+      const float kth = cand_max[order[nsel - 1]];
+      bad = !(kth - t_min > 8.f * sigma + 4e-7f * fmaxf(fabsf(kth), fabsf(t_min)));
+    }
+    if (bad && n_uncertified != nullptr) n_uncertified[1 + atomicAdd(n_uncertified, 1)] = b;
+  }
+  for (int i = tid; i < k; i += kSelThreads)
+    idx[static_cast<size_t>(b) * k + i] = (i < nsel) ? static_cast<int64_t>(cand[order[i]]) : -1;
+  // cls_out[b, cls, i]: -inf for the classes not re-scored, zero beyond nsel (model/siamese.py:207-208)
+  for (int t = tid; t < ((dbg & 4) ? 0 : ncls * k); t += kSelThreads) {
+    const int i = t % k;
+    cls_out[static_cast<size_t>(b) * ncls * k + t] = (i < nsel) ? -INFINITY : 0.f;
+  }
+  __syncthreads();
+  if (tid < nsel * 3) {
+    const int i = tid / 3, t = tid - i * 3, o = order[i];
+    const int j = t_cls[o][t];
+    if (j >= 0) cls_out[(static_cast<size_t>(b) * ncls + j) * k + i] = t_log[o][t];
+  }
+  // ||crop||: sqrt(sum over the window of the per-pixel energy + eps)
+  for (int i = warp; i < ((dbg & 2) ? 0 : k); i += kSelThreads / 32) {
     if (i < nsel) {
       const int win = cand[order[i]];
       const int h = win / Wo, w = win - h * Wo;
@@ -2252,7 +2592,7 @@ struct RegionPlan {
   FastGeom geom;
   int64_t ldp;
   size_t off_Phi, off_Plo, off_epart, off_screen, off_cand, off_cscreen, off_Ahi, off_Alo, off_logits, off_partials,
-      partials_bytes, total;
+      off_rowtop, partials_bytes, total;
   int resc_splits;   // split-K of the candidates' re-score GEMM (its tiles alone do not fill the machine)
   size_t pool_smem, cand_smem;
   int fast_threads;   // block size of region_pool_fast_kernel
@@ -2391,6 +2731,7 @@ static bool make_region_plan(RegionPlan& p, int64_t B, int C, int H, int W, int 
     p.partials_bytes = p.resc_splits > 1 ? isb_gemm_nt_workspace_bytes(Mr, ncls, C, p.resc_splits) : 0;
   }
   p.off_partials = off; off = align_up(off + p.partials_bytes, 1024);
+  p.off_rowtop = off;   off = align_up(off + static_cast<size_t>(B) * p.nwin * 8 * 4, 1024);
   p.total = off;
   p.cand_smem = static_cast<size_t>((p.nwin + 3) & ~3) * 4 * 2;   // scores + radix keys
   return true;
@@ -2498,12 +2839,40 @@ extern "C" int isb_region_select(const float* x, int64_t B, int64_t C, int64_t H
   if (rc) return rc;
   RowSched sched{static_cast<int>((M + kBM - 1) / kBM), static_cast<int>((ncls + kBN - 1) / kBN),
                  static_cast<int>((C + kBK - 1) / kBK)};
-  RowMaxEpiParams ep{screen, cls_b, static_cast<int>(M), static_cast<int>(ncls)};
-  auto kern = gemm_tc_kernel<RowSched, RowMaxEpilogue>;
-  ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+  // option region_top_select (default 1): the epilogue also keeps the four best classes of every window and
+  // ONE kernel does candidates + re-score + final selection (region_select_top_kernel); 0: four launches with
+  // the re-score of all classes on the tensor cores
+  const size_t top_smem_fixed = static_cast<size_t>(2) * ((p.nwin + 3) & ~3) * 4;
+  int top_chunk = kTopChunk;
+  while (top_chunk > 1 && top_smem_fixed + static_cast<size_t>(top_chunk) * p.ldp * 4 > 160 * 1024) top_chunk >>= 1;
+  const bool top_select = !exact_mode && option(ISB_OPT_REGION_TOP_SELECT, 1) != 0 && p.nwin <= kRankSelectMaxWin &&
+                          ncls <= (1 << kTopIdxBits) &&
+                          top_smem_fixed + static_cast<size_t>(top_chunk) * p.ldp * 4 <= 200 * 1024;
+  uint32_t* row_top = reinterpret_cast<uint32_t*>(ws + p.off_rowtop);
   const int sms = device_sm_count();
-  kern<<<sched.m_blocks < sms ? sched.m_blocks : sms, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, ta, tb, kSingleTerm, sched, ep);
+  if (top_select) {
+    RowTopEpiParams ep{screen, row_top, cls_b, static_cast<int>(M), static_cast<int>(ncls)};
+    auto kern = gemm_tc_kernel<RowSched, RowTopEpilogue>;
+    ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    kern<<<sched.m_blocks < sms ? sched.m_blocks : sms, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, ta, tb, kSingleTerm, sched, ep);
+  } else {
+    RowMaxEpiParams ep{screen, cls_b, static_cast<int>(M), static_cast<int>(ncls)};
+    auto kern = gemm_tc_kernel<RowSched, RowMaxEpilogue>;
+    ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    kern<<<sched.m_blocks < sms ? sched.m_blocks : sms, kGemmThreads, kGemmSmemBytes, st>>>(ta, tb, ta, tb, kSingleTerm, sched, ep);
+  }
   ISB_CUDA(cudaGetLastError());
+
+  if (top_select) {
+    const size_t smem = top_smem_fixed + static_cast<size_t>(top_chunk) * p.ldp * 4;
+    ISB_CUDA(cudaFuncSetAttribute(region_select_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    region_select_top_kernel<<<static_cast<unsigned>(B), kSelThreads, smem, st>>>(
+        screen, row_top, p.nwin, p.ncand, P_hi, P_lo, (int)p.ldp, (int)C, cls_w, cls_b, (int)ncls, e_part,
+        p.ngroups * p.eplanes, (int)H, (int)W, fh, fw, k, 1e-10f, top_chunk, option(ISB_OPT_TC_DEBUG, 0), idx, nsel, cls_out, win_norm, approx_max,
+        runner_up, n_uncertified);
+    ISB_CUDA(cudaGetLastError());
+    return ISB_OK;
+  }
 
   if (exact_mode) {
     // second line: fp64-exact re-score of the candidates straight from the fp32 inputs

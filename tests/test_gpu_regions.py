@@ -245,3 +245,53 @@ def test_small_map_gather_kernel_equals_the_channel_stream_kernel(R, B, C, H, W,
     assert torch.equal(l2[B - 1].view(torch.int16), l1[B - 1].view(torch.int16))
     if B > 2:
         assert int(h2[1].view(torch.int16).abs().sum()) == 0
+
+
+@pytest.mark.parametrize("B,C,H,W,ncls,k", [(6, 128, 14, 14, 40, 6), (3, 64, 20, 24, 464, 6), (4, 96, 12, 12, 2, 4),
+                                            (2, 256, 32, 32, 100, 6)])
+def test_one_kernel_reselect_equals_the_four_launch_chain(R, B, C, H, W, ncls, k):
+    # option region_top_select (default on): candidates + fp32-grade re-score of each window's best three
+    # classes + final selection in ONE kernel, against the chain with the tensor-core re-score of all
+    # classes: same windows, same certificates, descriptors equal to fp32 rounding, and the oracle's
+    from instance_search_b200 import _lib
+    s = _synthetic(B, C, H, W, ncls, 24, seed=B * 7 + ncls)
+    hw = _hw(R, s)
+    x = s["x"].cuda()
+    with _lib.options(region_top_select=0):
+        d0, c0, i0, n0 = R.region_descriptors(x, hw, k, (7, 7), want_cls_out=False)
+        e0 = R.region_select(x, hw, k + 2, (7, 7))
+    st = {}
+    d1, c1, i1, n1 = R.region_descriptors(x, hw, k, (7, 7), want_cls_out=False, stats=st)
+    e1 = R.region_select(x, hw, k + 2, (7, 7))
+    assert torch.equal(i0, i1) and torch.equal(n0, n1)
+    assert torch.equal(e0[0], e1[0])                                    # the k + 2 windows handed to the gather
+    assert torch.allclose(e0[3], e1[3], rtol=1e-6)                      # crop norms
+    assert torch.allclose(e0[4], e1[4], rtol=1e-5, atol=2e-6)           # fp32-grade class-max
+    assert int(e1[6][0]) == 0 and st.get("images_resolved_exactly", 0) == 0
+    check_descriptors(d1, d0)
+    od, oc, oi, on = oracle.region_descriptor_forward(s["x"], s["cls_w"], s["cls_b"], s["shift"], s["lin_w"],
+                                                      s["lin_b"], k, (7, 7))
+    assert torch.equal(i1.cpu(), oi)
+    check_descriptors(d1, od)
+
+
+def test_one_kernel_reselect_reports_windows_with_more_than_three_contending_classes(R):
+    # five identical classifier rows: the four best classes of every window are tied, so the class-max
+    # cannot be settled from the best three -> every image is listed, the exact second line answers,
+    # and the result is still the oracle's
+    s = _synthetic(4, 64, 14, 14, 12, 16, seed=41)
+    s["cls_w"][1:6] = s["cls_w"][0] * 3.0
+    s["cls_b"][0:6] = 0.5
+    hw = _hw(R, s)
+    x = s["x"].cuda()
+    n_unc = R.region_select(x, hw, 8, (7, 7))[6]
+    assert int(n_unc[0]) == 4
+    st = {}
+    d, c, i, n = R.region_descriptors(x, hw, 6, (7, 7), stats=st)
+    assert st["images_resolved_exactly"] == 4
+    od, oc, oi, on = oracle.region_descriptor_forward(s["x"], s["cls_w"], s["cls_b"], s["shift"], s["lin_w"],
+                                                      s["lin_b"], 6, (7, 7))
+    o_max = oc.max(1).values
+    assert torch.allclose(c.cpu().max(1).values, o_max, rtol=CLS_RTOL, atol=CLS_ATOL)
+    assert torch.equal(i.cpu(), oi)
+    check_descriptors(d, od)

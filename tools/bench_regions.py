@@ -51,7 +51,7 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 
-TUNABLES = ("pool_stages", "pool_generic_geom", "gather_cw", "gather_g", "gather_stages", "gather_small", "resc_splits")
+TUNABLES = ("pool_stages", "pool_generic_geom", "gather_cw", "gather_g", "gather_stages", "gather_small", "resc_splits", "tc_debug", "region_top_select")
 variants = [v for v in a.variants.split(";")] if a.variants else [""]
 for hw_size, variant in [(int(s), v) for s in a.sizes.split(",") for v in variants]:
     H = W = hw_size
