@@ -276,12 +276,12 @@ def test_one_kernel_reselect_equals_the_four_launch_chain(R, B, C, H, W, ncls, k
 
 
 def test_one_kernel_reselect_reports_windows_with_more_than_three_contending_classes(R):
-    # five identical classifier rows: the four best classes of every window are tied, so the class-max
+    # five identical, dominant classifier rows: the four best classes of every window are tied, so the class-max
     # cannot be settled from the best three -> every image is listed, the exact second line answers,
     # and the result is still the oracle's
     s = _synthetic(4, 64, 14, 14, 12, 16, seed=41)
-    s["cls_w"][1:6] = s["cls_w"][0] * 3.0
-    s["cls_b"][0:6] = 0.5
+    s["cls_w"][0:5] = s["cls_w"][0].abs() * 3.0      # positive on relu features: these five classes win, tied
+    s["cls_b"][0:5] = 0.5
     hw = _hw(R, s)
     x = s["x"].cuda()
     n_unc = R.region_select(x, hw, 8, (7, 7))[6]
