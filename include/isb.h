@@ -264,6 +264,13 @@ int isb_gemm_nt_split(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda, c
  * approx_max [B, k] (class-max of the selected windows as seen here) and
  * runner_up [B] (class-max of the best window NOT selected, -inf if none) feed it;
  * both may be NULL.
+ * Default (ISB_OPT_REGION_TOP_SELECT = 1, up to 512 classes and 1024 windows per image): the
+ * screen keeps the four best classes of every window and only the best THREE of each candidate
+ * are re-scored (a class outside them has a screen logit <= the fourth best, m4; a window whose
+ * re-scored class-max does not clear m4 by 8 sigma puts its image on the n_uncertified list).
+ * cls_out then holds the re-scored logits of those classes and -inf for every other class --
+ * a class-max preview, which is all isb_region_logits needs from it.  With the option at 0 the
+ * candidates are re-scored against all classes (split-operand tensor-core GEMM).
  * exact_mode < 0: measurement probe -- only the pooling pass runs (window means as bf16
  * hi / lo into the workspace, energy partials); no output is written.
  * exact_mode > 0: second line for uncertified batches -- the candidates (use
