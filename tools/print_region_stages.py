@@ -1,4 +1,4 @@
-"""Print (variant, stage times) of tools/bench_regions.py JSON lines read from stdin (dev helper)."""
+"""Print (variant, stage times) of tools/bench_regions.py JSON lines read from stdin (development helper for option sweeps)."""
 import json
 import sys
 
