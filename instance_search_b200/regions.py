@@ -115,7 +115,8 @@ def region_select(x, hw, k, fsize, margin=WINDOW_MARGIN, exact_mode=False):
     win_norm = torch.empty((B, k), dtype=torch.float32, device=dev)
     approx_max = torch.empty((B, k), dtype=torch.float32, device=dev)
     runner_up = torch.empty((B,), dtype=torch.float32, device=dev)
-    n_unc = torch.zeros(1 + B, dtype=torch.int32, device=dev)   # count, then the uncertified images
+    # count, then the uncertified images; the library zeroes the count, entries beyond it are never read
+    n_unc = torch.empty(1 + B, dtype=torch.int32, device=dev)
     L = _lib.lib()
     nbytes = L.isb_region_select_workspace_bytes(B, C, H, W, ncls, fh, fw, k, margin)
     ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
@@ -169,8 +170,8 @@ def region_logits(win_mean, hw, k, nsel_in, idx_in, norm_in, approx_max, runner_
     nsel = torch.empty((B,), dtype=torch.int32, device=dev)
     cls_out = torch.empty((B, ncls, k), dtype=torch.float32, device=dev) if approx_cls is None else None
     changed = torch.empty((B,), dtype=torch.int32, device=dev)
-    n_changed = torch.zeros(1, dtype=torch.int32, device=dev)
-    n_unc = torch.zeros(1 + B, dtype=torch.int32, device=dev)   # count, then the uncertified images
+    n_changed = torch.empty(1, dtype=torch.int32, device=dev)        # zeroed by the library
+    n_unc = torch.empty(1 + B, dtype=torch.int32, device=dev)        # count (zeroed by the library), then the images
     _lib.check(_lib.lib().isb_region_logits(win_mean.data_ptr(), hw.cls_w.data_ptr(), hw.cls_b.data_ptr(), B, C,
                                             ncls, ke, k, nsel_in.data_ptr(), approx_max.data_ptr(),
                                             runner_up.data_ptr(), idx_in.data_ptr(), norm_in.data_ptr(),
