@@ -440,6 +440,19 @@ def run_b200(a, rank, world, local_rank):
     # the result every rank holds after the timed steps (identical on all ranks), for the parity check
     res_s, res_i = index.search(q_dev, a.k)
     torch.cuda.synchronize()
+    # the same kernel with nothing running beside it (in the timed region the exact re-rank / candidate
+    # exchange of the previous batch runs on a side stream under it and takes part of the SMs and of the
+    # power budget): three plain searches, outside the timed region, for the record only
+    alone_events = []
+    for _ in range(3):
+        index.search(q_dev, a.k, events=alone_events)
+    torch.cuda.synchronize()
+    alone_ms = min(e0.elapsed_time(e1) for e0, e1 in alone_events) if alone_events else None
+    if alone_ms:
+        roofline["kernel_ms_alone"] = alone_ms
+        roofline["frac_alone"] = flops / (alone_ms * 1e-3) / 1e12 / peak
+        roofline["note"] = ("achieved / frac: the screen as timed inside the steps, with the previous batch's tail "
+                            "running concurrently on a side stream; *_alone: the same launch with nothing beside it")
 
     line = None
     if rank == 0:
