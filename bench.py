@@ -483,7 +483,8 @@ def run_b200(a, rank, world, local_rank):
             "data": "synthetic (seeded unit-norm Gaussian rows)", "config": workload_config(a, world),
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    # bytes every rank copies per step (full: all rows on each rank; split: 1/N each)
+                    # query bytes that cross PCIe per step over the whole job in split mode (1/N of the rows per rank);
+                    # in full mode every rank copies all of them
                     "h2d_bytes_per_step": q_host.numel() * 4,
                     "h2d_mode": ("full rows on every rank over its own PCIe link" if upload_full else
                                  "1/N of the rows per rank + NVLink all-gather") if world > 1 else "single GPU",
