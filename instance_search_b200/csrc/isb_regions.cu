@@ -953,7 +953,8 @@ struct RowTopEpilogue {
       const int col = cb + j;
       const float x = (col < p.N) ? __uint_as_float(v[j]) + __ldg(p.bias + col) : kTopNone;
       m = fmaxf(m, x);
-      float t = __uint_as_float((__float_as_uint(x) & ~kTopIdxMask) | static_cast<uint32_t>(col));
+      // fmaxf also maps a NaN logit to "no class": a NaN would otherwise duplicate m1 down the chain
+      float t = __uint_as_float((__float_as_uint(fmaxf(x, kTopNone)) & ~kTopIdxMask) | static_cast<uint32_t>(col));
       float n = fmaxf(m1, t); t = fminf(m1, t); m1 = n;
       n = fmaxf(m2, t); t = fminf(m2, t); m2 = n;
       n = fmaxf(m3, t); t = fminf(m3, t); m3 = n;

@@ -295,3 +295,18 @@ def test_one_kernel_reselect_reports_windows_with_more_than_three_contending_cla
     assert torch.allclose(c.cpu().max(1).values, o_max, rtol=CLS_RTOL, atol=CLS_ATOL)
     assert torch.equal(i.cpu(), oi)
     check_descriptors(d, od)
+
+
+def test_nan_features_do_not_leak_into_other_images(R):
+    # a NaN in one image's map poisons that image's logits only: the windows chosen for the other
+    # images are those of the clean batch (the top-class epilogue maps a NaN logit to "no class")
+    s = _synthetic(3, 64, 14, 14, 20, 16, seed=77)
+    hw = _hw(R, s)
+    clean = R.region_select(s["x"].cuda(), hw, 8, (7, 7))
+    dirty_x = s["x"].clone()
+    dirty_x[1, 5, 3, 4] = float("nan")
+    dirty = R.region_select(dirty_x.cuda(), hw, 8, (7, 7))
+    torch.cuda.synchronize()
+    for b in (0, 2):
+        assert torch.equal(clean[0][b], dirty[0][b])
+        assert torch.equal(clean[4][b], dirty[4][b])
