@@ -598,6 +598,10 @@ def side_regions(dev, pk, cpu_baseline=True):
         ms = _median_ms(lambda: regions.region_descriptors(x, hw, k, (7, 7), want_cls_out=False, stats=stats),
                         flush=flush)
         ms_head = _median_ms(lambda: regions.region_head(x, hw, k, (7, 7), want_cls_out=False), flush=flush)
+        # the same chain (+ projection) replayed from ONE CUDA graph (regions.GraphedRegionDescriptors)
+        graphed = regions.GraphedRegionDescriptors(x, hw, k, (7, 7))
+        ms_graph = _median_ms(graphed.replay, flush=flush)
+        del graphed
         # the pooling pass alone (north_star: >= 70 % of HBM bandwidth): x read once, window means
         # written as bf16 hi + lo; CUDA events around the one kernel, L2 flushed before every launch
         ms_pool = _median_ms(lambda: regions.region_pool_probe(x, hw, k + regions.RUNNER_UPS, (7, 7)), flush=flush)
@@ -661,6 +665,9 @@ def side_regions(dev, pk, cpu_baseline=True):
                               "bound": "hbm", "ms": ms_gather, "bytes_touched": g_rd + g_wr,
                               "achieved": (g_rd + g_wr) / (ms_gather * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                               "unit": "GB/s", "frac": (g_rd + g_wr) / (ms_gather * 1e-3) / 1e9 / pk["hbm_gbs"]},
+            "cuda_graph_replay": {"ms_per_batch": ms_graph, "region_descriptors_per_s": units / (ms_graph * 1e-3),
+                                  "what": "head + projection captured once (regions.GraphedRegionDescriptors), one "
+                                          "graph launch per batch; certificates read by the caller"},
             "projection_ms": ms - ms_head,
             "streamed": {"ms_per_batch": ms_stream, "region_descriptors_per_s": units / (ms_stream * 1e-3),
                          "batches_in_flight": nstream, "uncertified_images_last_pass": n_unc_stream},

@@ -240,6 +240,42 @@ def region_descriptors_async(x, hw, k, fsize, margin=WINDOW_MARGIN, want_cls_out
     return desc, cls_out, idx, nsel, n_unc
 
 
+class GraphedRegionDescriptors(object):
+    """The certified fast path (region_descriptors_async) captured ONCE into a CUDA graph for a fixed
+    input buffer: every replay() re-runs the whole chain (pool -> classifier screen -> reselect ->
+    gather -> logits -> fix-up -> projection -> finalize: ~10 launches and 3 memsets) with one
+    graph launch on whatever ``x`` holds by then.  The chain is launch-bound at small maps (35 us of
+    its 350 at 14 x 14 are gaps between kernels); a replay is 3-4 % faster than the eager calls and
+    costs the host one call instead of six.  Outputs are the SAME tensors on every replay: consume
+    (or copy) them before the next one.  The caller checks ``n_uncertified[:, 0]`` as after
+    region_descriptors_async and patches the listed images with region_descriptors_fix.
+
+        graphed = GraphedRegionDescriptors(x_buffer, hw, k, (7, 7))
+        for batch in loader:
+            x_buffer.copy_(trunk(batch))          # or have the trunk write into x_buffer
+            desc, cls_out, idx, nsel, n_unc = graphed.replay()
+    """
+
+    def __init__(self, x, hw, k, fsize, margin=WINDOW_MARGIN, want_cls_out=False, warmup=2):
+        ops._need_cuda(x)
+        if not x.is_contiguous() or x.dtype != torch.float32:
+            raise IsbError("GraphedRegionDescriptors: x must be a contiguous fp32 CUDA tensor (the graph reads it in place)")
+        self.x = x
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.cuda.stream(side):             # warm-up outside the capture: allocator, function attributes
+            for _ in range(max(1, warmup)):
+                region_descriptors_async(x, hw, k, fsize, margin, want_cls_out)
+        torch.cuda.current_stream(x.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = region_descriptors_async(x, hw, k, fsize, margin, want_cls_out)
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs
+
+
 def uncertified_images(n_unc):
     """Sorted image indices listed by the certificates (host sync).  n_unc: [2, 1 + B]."""
     host = n_unc.cpu()

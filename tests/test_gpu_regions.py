@@ -310,3 +310,23 @@ def test_nan_features_do_not_leak_into_other_images(R):
     for b in (0, 2):
         assert torch.equal(clean[0][b], dirty[0][b])
         assert torch.equal(clean[4][b], dirty[4][b])
+
+
+def test_graphed_region_descriptors_replay_equals_the_eager_path(R):
+    # the whole chain captured into one CUDA graph: bit-identical to the eager calls, also after
+    # the input buffer has been refilled
+    s = _synthetic(6, 128, 14, 14, 40, 32, seed=5)
+    hw = _hw(R, s)
+    x = s["x"].cuda().contiguous()
+    graphed = R.GraphedRegionDescriptors(x, hw, 6, (7, 7))
+    for seed in (5, 6):
+        x.copy_(_synthetic(6, 128, 14, 14, 40, 32, seed=seed)["x"])
+        d, c, i, n, unc = graphed.replay()
+        torch.cuda.synchronize()
+        d0, c0, i0, n0, unc0 = R.region_descriptors_async(x, hw, 6, (7, 7), want_cls_out=False)
+        assert torch.equal(d, d0) and torch.equal(i, i0) and torch.equal(n, n0)
+        assert int(unc[:, 0].sum()) == int(unc0[:, 0].sum()) == 0
+        od, oc, oi, on = oracle.region_descriptor_forward(x.cpu(), s["cls_w"], s["cls_b"], s["shift"], s["lin_w"],
+                                                          s["lin_b"], 6, (7, 7))
+        assert torch.equal(i.cpu(), oi)
+        check_descriptors(d, od)
